@@ -1,0 +1,180 @@
+/* vhr_b200.h — C-ABI of the B200-native ray-traced lighting + SVGF/SSAO chain.
+ *
+ * Drop-in boundary for the hybrid render path of RMichelsen/VulkanHybridRenderer: every entry point replaces one
+ * call the reference's RenderGraph / ResourceManager / execution contexts make into the Vulkan driver for this path.
+ * Citations are relative to the reference tree. Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative vhr_status otherwise (the reference asserts / prints instead:
+ *     src/rendering_backend/vulkan_common.h:4-7); vhr_last_error() holds the message of the last failure on the
+ *     calling thread.
+ *   - one context = one GPU + one CUDA stream; all work is enqueued on that stream in call order (the reference
+ *     records everything into one command buffer on one queue, src/rendering_backend/renderer.cpp:135). A context is
+ *     not thread-safe, like the reference's single-threaded recording (src/main.cpp:111-127).
+ *   - images are linear, dense row-major device buffers in the reference's texel formats; row 0 is NDC y = -1.
+ *   - there is NO CPU fallback: every compute entry point fails with VHR_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef VHR_B200_H
+#define VHR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vhr_context vhr_context;
+
+typedef enum vhr_status {
+    VHR_OK = 0,
+    VHR_ERR_INVALID = -1,      /* bad argument / unknown name / size mismatch (reference: assert) */
+    VHR_ERR_CUDA = -2,         /* CUDA runtime failure or no usable device */
+    VHR_ERR_EXHAUSTED = -3,    /* no free storage-image slot (reference: resource_manager.cpp:876-877) */
+    VHR_ERR_STATE = -4         /* call order violated (e.g. trace before geometry upload) */
+} vhr_status;
+
+/* VkFormat values accepted for images (src/render_paths/hybrid_render_path.cpp:16-19,109-110,247-261). */
+enum {
+    VHR_FORMAT_B8G8R8A8_UNORM = 44,
+    VHR_FORMAT_R16G16_SFLOAT = 83,
+    VHR_FORMAT_R16G16B16A16_SFLOAT = 97,
+    VHR_FORMAT_D32_SFLOAT = 126
+};
+
+#define VHR_MAX_GLOBAL_RESOURCES 2048   /* src/rendering_backend/resource_manager.h:13 */
+#define VHR_MAX_PASS_BINDINGS 16
+
+/* ---- context (replaces VulkanContext device/queue creation, src/rendering_backend/vulkan_context.cpp:44) -------- */
+
+/* `cuda_stream` may be NULL (the context creates its own non-blocking stream) or an existing cudaStream_t / CUstream
+ * of `device` (e.g. torch.cuda.current_stream().cuda_stream) so callers can time the passes with their own events.
+ * width/height = the swapchain extent every "swapchain-sized" (0,0) transient image takes
+ * (src/render_graph/render_graph.cpp:962-966). */
+int vhr_context_create(int device, void *cuda_stream, uint32_t width, uint32_t height, vhr_context **out);
+void vhr_context_destroy(vhr_context *ctx);
+const char *vhr_last_error(void);
+/* Blocks until everything enqueued on the context's stream has finished (reference: vkWaitForFences, renderer.cpp:107). */
+int vhr_context_synchronize(vhr_context *ctx);
+/* ComputeExecutionContext::GetDisplaySize (src/render_graph/compute_execution_context.cpp:8-10). */
+int vhr_get_display_size(vhr_context *ctx, uint32_t *width, uint32_t *height);
+/* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t vhr_kernel_launch_count(vhr_context *ctx);
+
+/* ---- ResourceManager ------------------------------------------------------------------------------------------- */
+
+/* ResourceManager::UpdateGeometry + UpdateBLAS + UpdateTLAS (src/rendering_backend/resource_manager.cpp:291-360,
+ * 593-801): uploads the flat Vertex[] (56 B), uint32 indices[] and Primitive[] (120 B) arrays
+ * (src/rendering_backend/glsl_common.h:74-99) and builds the acceleration structure on the GPU — an LBVH (Morton
+ * codes, radix sort, Karras hierarchy, SAH refit) collapsed into 8-wide quantised nodes — in place of
+ * vkCmdBuildAccelerationStructuresKHR. One world-space, opaque, two-sided triangle soup; geometry index = index
+ * into `primitives`. Host pointers; returns after the build has been enqueued. */
+int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_vertices, const uint32_t *indices,
+                        uint32_t n_indices, const void *primitives, uint32_t n_primitives);
+
+/* ResourceManager::UpdatePerFrameUBO (resource_manager.cpp:362-364): `per_frame_data` is the 584-byte PerFrameData
+ * of glsl_common.h:59-72. Copied by value; used by every later dispatch until the next call. */
+int vhr_update_per_frame_ubo(vhr_context *ctx, const void *per_frame_data, size_t size);
+
+/* ResourceManager::UploadNewStorageImage (resource_manager.cpp:230-263,866-878): returns the first free slot of
+ * storage_images[2048] (>= 0) or a negative status. Contents are zero-initialised (documented deviation: the
+ * reference leaves them undefined). */
+int vhr_upload_new_storage_image(vhr_context *ctx, uint32_t width, uint32_t height, int vk_format);
+/* ResourceManager::DestroyStorageImage (resource_manager.cpp:265-269). */
+int vhr_destroy_storage_image(vhr_context *ctx, int slot);
+
+/* ---- RenderGraph transient images ------------------------------------------------------------------------------ */
+
+/* RenderGraph::ActualizeResource (src/render_graph/render_graph.cpp:921-977): creates the named image on first
+ * mention; width = height = 0 means swapchain-sized. Re-declaring an existing name with another size/format fails
+ * (RenderGraph::SanityCheck, render_graph.cpp:980-1021). */
+int vhr_actualize_image(vhr_context *ctx, const char *name, uint32_t width, uint32_t height, int vk_format);
+/* RenderGraph::DestroyResources (render_graph.cpp:16-68): frees every transient image and the pass/kernel registry. */
+int vhr_destroy_transient_resources(vhr_context *ctx);
+
+/* Host <-> device copies of whole images (dense rows). These are the harness' stand-in for the passes outside the
+ * hot path (the rasterised G-buffer producer and the composition consumer); `bytes` must equal w*h*texel size.
+ * Pinned host memory makes them asynchronous on the context's stream. */
+int vhr_image_upload(vhr_context *ctx, const char *name, const void *host, size_t bytes);
+int vhr_image_download(vhr_context *ctx, const char *name, void *host, size_t bytes);
+int vhr_storage_image_upload(vhr_context *ctx, int slot, const void *host, size_t bytes);
+int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t bytes);
+/* Device pointer of a named image (zero-copy interop, e.g. NCCL halo exchange); NULL if unknown. */
+void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format);
+void *vhr_storage_image_device_ptr(vhr_context *ctx, int slot, uint32_t *width, uint32_t *height, int *vk_format);
+
+/* ---- pass execution (RenderGraph::Execute*, execution contexts) ------------------------------------------------- */
+
+/* Binds descriptor set 3 of the pass about to execute: the pass' dependencies followed by its outputs, indexed by
+ * their `binding` (render_graph.cpp:603-664 CreateComputePass, :893-907/:914-919 vkCmdBindDescriptorSets). */
+int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, uint32_t count);
+
+/* ComputeExecutionContext::Dispatch (src/render_graph/compute_execution_context.cpp:12-29, .h:20-27). Kernels are
+ * looked up by the reference's shader path: "hybrid_render_path/svgf.comp", ".../svgf_atrous_filter.comp",
+ * ".../ssao.comp", ".../ssao_blur.comp". Group size is the shaders' 8x8 (svgf.comp:6): the launcher covers
+ * x_groups*8 by y_groups*8 pixels clipped to the image. `push_constants` is SVGFPushConstants (24 B,
+ * glsl_common.h:31-39) for the two SVGF kernels and SSAOPushConstants (4 B, :48-50) or NULL (radius 0.75) for SSAO;
+ * a size that does not match fails like the reference's assert (compute_execution_context.h:23). */
+int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
+                 const void *push_constants, size_t push_constants_size);
+
+/* RaytracingExecutionContext::TraceRays (src/render_graph/raytracing_execution_context.cpp:4-13) of the pipeline
+ * raygen.rgen + miss.rmiss + reflection_miss.rmiss + reflection_hit.rchit (hybrid_render_path.cpp:111-123).
+ * Bound images: 0 normals/object ids, 1 depth, 2 shadow+AO (RG16F), 3 reflections (RGBA16F). */
+int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height);
+
+/* ComputeExecutionContext::Blit* (compute_execution_context.cpp:31-211): same-size, same-format image copies. */
+int vhr_blit_storage_to_transient(vhr_context *ctx, int src_slot, const char *dst_name);
+int vhr_blit_transient_to_storage(vhr_context *ctx, const char *src_name, int dst_slot);
+int vhr_blit_storage_to_storage(vhr_context *ctx, int src_slot, int dst_slot);
+
+/* Per-pass GPU timestamps (render_graph.cpp:143-148 vkCreateQueryPool, :167-182 vkCmdWriteTimestamp, :189-201
+ * vkGetQueryPoolResults): a pool of `count` CUDA events recorded on the context's stream. */
+int vhr_create_query_pool(vhr_context *ctx, uint32_t count);
+int vhr_write_timestamp(vhr_context *ctx, uint32_t query);
+/* Blocks until query `last` has been reached, then writes the elapsed milliseconds between `first` and `last`. */
+int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms);
+
+/* ---- options that have no counterpart in the reference (documented in DESIGN.md) -------------------------------- */
+
+typedef enum vhr_option {
+    VHR_OPT_AO_SPP = 1,            /* AO rays per pixel; reference is hard-wired to 2 (raygen.rgen:45,55) */
+    VHR_OPT_TRACE_SHADOWS = 2,     /* 1 (reference) / 0: skip the shadow ray, write 1.0 */
+    VHR_OPT_TRACE_AO = 3,          /* 1 (reference) / 0 */
+    VHR_OPT_TRACE_REFLECTIONS = 4, /* 1 (reference) / 0: skip the closest-hit ray, write 0 */
+    VHR_OPT_ROW_BEGIN = 5,         /* row band [begin, end) this context renders (multi-GPU split); default 0 */
+    VHR_OPT_ROW_END = 6,           /* default = image height */
+    VHR_OPT_SVGF_FUSED = 7,        /* 1: temporal pass also produces a-trous iteration 0 (fused kernel) */
+    VHR_OPT_ATROUS_VARIANT = 8     /* 0: direct-load kernel (the reference's dataflow); 1 (default): tiled kernel */
+} vhr_option;
+int vhr_set_option(vhr_context *ctx, int option, int64_t value);
+int64_t vhr_get_option(vhr_context *ctx, int option);
+
+/* Extra outputs of the acceleration-structure build and of the ray pass for tests and profiling. */
+typedef struct vhr_bvh_stats {
+    uint32_t n_triangles;
+    uint32_t n_bvh2_nodes;
+    uint32_t n_wide_nodes;
+    uint32_t max_leaf_size;
+    float sah_cost;              /* SAH cost of the wide tree (node cost 1, triangle cost 1) */
+    float scene_min[3];
+    float scene_max[3];
+    float build_ms;              /* device time of the last build */
+} vhr_bvh_stats;
+int vhr_get_bvh_stats(vhr_context *ctx, vhr_bvh_stats *out);
+
+/* Debug/test entry point: traces `n` explicit rays (origin xyz, tmin, dir xyz, tmax = 8 floats each, host memory).
+ * any_hit != 0: out_t[i] = 1 if anything is hit in (tmin, tmax) else 0. Otherwise closest hit: out_t[i] = t or -1,
+ * out_ids (optional, 2 x uint32 per ray) = (geometry index, primitive id), out_uv (optional, 2 floats per ray). */
+int vhr_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
+                       float *out_uv);
+
+/* G-buffer producer as a CUDA primary-ray pass (stand-in for the rasterised "G-Buffer Pass",
+ * hybrid_render_path.cpp:13-56; encodings of gbuf.frag:33,43,46-58). Bound images: 0 albedo (BGRA8), 1 normals/ids,
+ * 2 motion/metallic-roughness, 3 depth. */
+int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VHR_B200_H */

@@ -1,0 +1,117 @@
+"""Shared helpers for the parity tests: synthetic inputs, error metrics, the C-ABI SVGF pass body."""
+import functools
+
+import numpy as np
+
+from vulkanhybridrenderer_b200 import camera, scenes
+from vulkanhybridrenderer_b200 import types as T
+
+# Parity bar from BASELINE.json north_star: max abs 1e-3 on linear values, PSNR >= 60 dB vs the reference restatement.
+MAX_ABS_TOL = 1e-3
+PSNR_MIN_DB = 60.0
+
+
+def psnr(a, b, peak=1.0):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    mse = np.mean((a - b) ** 2)
+    return 200.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def compare(gpu, ref, what=""):
+    g = np.asarray(gpu, np.float32); r = np.asarray(ref, np.float32)
+    assert g.shape == r.shape, (g.shape, r.shape)
+    both_nan = np.isnan(g) & np.isnan(r)
+    d = np.where(both_nan, 0.0, np.abs(g - r))
+    stats = dict(max_abs=float(np.nanmax(d)) if d.size else 0.0, psnr=psnr(np.nan_to_num(g), np.nan_to_num(r)),
+                 exact=float(np.mean((g == r) | both_nan)) if d.size else 1.0, nan_mismatch=int(np.sum(np.isnan(g) != np.isnan(r))))
+    return stats
+
+
+def assert_parity(gpu, ref, what, max_abs=MAX_ABS_TOL, min_psnr=PSNR_MIN_DB):
+    s = compare(gpu, ref, what)
+    print(f"[parity] {what}: max_abs={s['max_abs']:.3e} psnr={s['psnr']:.1f}dB exact={s['exact']*100:.3f}% nan_mismatch={s['nan_mismatch']}")
+    assert s["nan_mismatch"] == 0, (what, s)
+    assert s["max_abs"] <= max_abs, (what, s)
+    assert s["psnr"] >= min_psnr, (what, s)
+    return s
+
+
+@functools.lru_cache(maxsize=8)
+def scene_and_gbuffer(width, height, tris=20000, seed=3, moving=False):
+    """Scene + oracle G-buffers of two consecutive frames (CPU primary rays; test scaffolding)."""
+    import oracle_lib as O
+    sc = scenes.sponza_like(tris, seed=seed, width=width, height=height, n_clutter=40)
+    osc = O.OracleScene(sc)
+    seq = camera.FrameSequencer(width, height, sc.light)
+    frames = []
+    cam = sc.camera
+    for f in range(3):
+        if moving and f > 0:
+            pos = cam.position + np.array([0.05, 0.0, 0.01])
+            cam.set_pose(pos, cam.yaw + 0.002, cam.pitch)
+        pfd = seq.next(cam)
+        frames.append((pfd, osc.gbuffer(pfd, width, height)))
+    return sc, osc, frames
+
+
+def noise_integrated(H, W, seed):
+    """(shadow, ao, var_s, var_ao) noise image: worst case for the edge-stopping weights."""
+    rng = np.random.default_rng(seed)
+    a = np.empty((H, W, 4), np.float32)
+    a[..., 0] = rng.integers(0, 2, (H, W))
+    a[..., 1] = rng.integers(0, 3, (H, W)) * 0.5
+    a[..., 2] = rng.uniform(0, 0.25, (H, W)) * (rng.uniform(size=(H, W)) > 0.3)
+    a[..., 3] = rng.uniform(0, 0.25, (H, W))
+    return a.astype(np.float16)
+
+
+GBUF_IMAGES = {
+    "Albedo": T.VK_FORMAT_B8G8R8A8_UNORM,
+    "World Space Normals and Object IDs": T.VK_FORMAT_R16G16B16A16_SFLOAT,
+    "Motion Vectors and Metallic Roughness": T.VK_FORMAT_R16G16B16A16_SFLOAT,
+    "Depth": T.VK_FORMAT_D32_SFLOAT,
+}
+N_NORMALS = "World Space Normals and Object IDs"
+N_MOTION = "Motion Vectors and Metallic Roughness"
+N_DEPTH = "Depth"
+N_RT = "Raytraced Shadows and Ambient Occlusion"
+N_REFL = "Raytraced Reflections"
+N_DENOISED = "Denoised Raytraced Shadows and Ambient Occlusion"
+N_SSAO_RAW = "Screen Space Ambient Occlusion Raw"
+N_SSAO = "Screen Space Ambient Occlusion"
+
+
+class SvgfPassCABI:
+    """The SVGF Denoise Pass body of hybrid_render_path.cpp:245-331 issued call by call through the C-ABI."""
+
+    def __init__(self, ctx, W, H):
+        self.ctx, self.W, self.H = ctx, W, H
+        F4, F2 = T.VK_FORMAT_R16G16B16A16_SFLOAT, T.VK_FORMAT_R16G16_SFLOAT
+        for name, fmt in ((N_NORMALS, F4), (N_MOTION, F4), (N_DEPTH, T.VK_FORMAT_D32_SFLOAT), (N_RT, F2), (N_DENOISED, F4)):
+            ctx.actualize_image(name, fmt)
+        pc = np.zeros((), T.SVGFPushConstants)
+        pc["integrated_shadow_and_ao"] = (ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F4))
+        pc["prev_frame_normals_and_object_ids"] = ctx.upload_new_storage_image(W, H, F4)
+        pc["shadow_and_ao_history"] = ctx.upload_new_storage_image(W, H, F4)
+        pc["shadow_and_ao_moments_history"] = ctx.upload_new_storage_image(W, H, F2)
+        self.pc = pc
+
+    def run(self, want_iters=False):
+        ctx, pc = self.ctx, self.pc
+        gx, gy = self.W // 8 + (self.W % 8 != 0), self.H // 8 + (self.H % 8 != 0)
+        ctx.bind_pass_images([N_NORMALS, N_MOTION, N_DEPTH, N_RT, N_DENOISED])
+        ctx.dispatch("hybrid_render_path/svgf.comp", gx, gy, 1, pc)
+        temporal = ctx.storage_image_download(int(pc["integrated_shadow_and_ao"][0])) if want_iters else None
+        iters = []
+        for i in range(5):
+            pc["atrous_step"] = 1 << i
+            ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", gx, gy, 1, pc)
+            if want_iters:
+                iters.append(ctx.storage_image_download(int(pc["integrated_shadow_and_ao"][1])))
+            if i == 0:
+                ctx.blit_storage_to_storage(int(pc["integrated_shadow_and_ao"][1]), int(pc["shadow_and_ao_history"]))
+            pc["integrated_shadow_and_ao"] = pc["integrated_shadow_and_ao"][::-1].copy()
+        ctx.blit_transient_to_storage(N_NORMALS, int(pc["prev_frame_normals_and_object_ids"]))
+        ctx.blit_storage_to_transient(int(pc["integrated_shadow_and_ao"][1]), N_DENOISED)
+        pc["integrated_shadow_and_ao"] = pc["integrated_shadow_and_ao"][::-1].copy()
+        return ctx.image_download(N_DENOISED), (np.stack(iters) if want_iters else None), temporal

@@ -1,0 +1,122 @@
+"""GPU parity: SVGF temporal + à-trous kernels (through the C-ABI) vs the CPU oracle on identical inputs."""
+import numpy as np
+import pytest
+
+import helpers as Hh
+import oracle_lib as O
+from vulkanhybridrenderer_b200 import capi
+from vulkanhybridrenderer_b200 import types as T
+
+pytestmark = pytest.mark.gpu
+
+F4, F2 = T.VK_FORMAT_R16G16B16A16_SFLOAT, T.VK_FORMAT_R16G16_SFLOAT
+
+
+def _groups(n):
+    return n // 8 + (n % 8 != 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("size", [(320, 184), (333, 171)])   # second one is ragged (not a multiple of 8 / 64)
+def test_atrous_all_steps_noise(variant, size):
+    W, H = size
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H)
+    pfd, g = frames[0]
+    integ = Hh.noise_integrated(H, W, seed=2)
+    with capi.Context(W, H) as ctx:
+        ctx.set_option(capi.OPT_ATROUS_VARIANT, variant)
+        ctx.update_per_frame_ubo(pfd)
+        ctx.actualize_image(Hh.N_NORMALS, F4)
+        ctx.image_upload(Hh.N_NORMALS, g["normals"])
+        a, b = ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F4)
+        ctx.bind_pass_images([Hh.N_NORMALS])
+        for step in (1, 2, 4, 8, 16):
+            ctx.storage_image_upload(a, integ)
+            pc = np.zeros((), T.SVGFPushConstants)
+            pc["integrated_shadow_and_ao"] = (a, b)
+            pc["atrous_step"] = step
+            ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", _groups(W), _groups(H), 1, pc)
+            got = ctx.storage_image_download(b)
+            ref = O.svgf_atrous(pfd, g["normals"], integ, step)
+            Hh.assert_parity(got, ref, f"atrous v{variant} step {step} {W}x{H}")
+
+
+def test_atrous_untiled_step_and_errors():
+    W, H = 96, 64
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H)
+    pfd, g = frames[0]
+    integ = Hh.noise_integrated(H, W, seed=5)
+    with capi.Context(W, H) as ctx:
+        ctx.update_per_frame_ubo(pfd)
+        ctx.actualize_image(Hh.N_NORMALS, F4)
+        ctx.image_upload(Hh.N_NORMALS, g["normals"])
+        a, b = ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F4)
+        ctx.storage_image_upload(a, integ)
+        ctx.bind_pass_images([Hh.N_NORMALS])
+        pc = np.zeros((), T.SVGFPushConstants)
+        pc["integrated_shadow_and_ao"] = (a, b)
+        pc["atrous_step"] = 3   # not a power of two: falls back to the direct kernel
+        ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", _groups(W), _groups(H), 1, pc)
+        Hh.assert_parity(ctx.storage_image_download(b), O.svgf_atrous(pfd, g["normals"], integ, 3), "atrous step 3")
+        # reference asserts sizeof(T) == declared push-constant size (compute_execution_context.h:23)
+        with pytest.raises(capi.VhrError):
+            ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", 1, 1, 1, np.zeros(5, np.int32))
+        with pytest.raises(capi.VhrError):
+            ctx.dispatch("hybrid_render_path/does_not_exist.comp", 1, 1, 1)
+        pc["integrated_shadow_and_ao"] = (a, 77)   # unknown storage slot
+        with pytest.raises(capi.VhrError):
+            ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", 1, 1, 1, pc)
+
+
+@pytest.mark.parametrize("size", [(320, 184), (203, 117)])
+def test_temporal_single_frame(size):
+    W, H = size
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, moving=True)
+    (pfd0, g0), (pfd1, g1) = frames[0], frames[1]
+    rng = np.random.default_rng(7)
+    rt = np.stack([rng.integers(0, 2, (H, W)), rng.integers(0, 3, (H, W)) * 0.5], -1).astype(np.float16)
+    history = rng.uniform(0, 1, (H, W, 4)).astype(np.float16)
+    moments = rng.uniform(0, 1, (H, W, 2)).astype(np.float16)
+    ref_i, ref_m = O.svgf_temporal(pfd1, g1["normals"], g1["motion"], rt, g0["normals"], history, moments)
+    with capi.Context(W, H) as ctx:
+        ctx.update_per_frame_ubo(pfd1)
+        for name, fmt in ((Hh.N_NORMALS, F4), (Hh.N_MOTION, F4), (Hh.N_DEPTH, T.VK_FORMAT_D32_SFLOAT), (Hh.N_RT, F2), (Hh.N_DENOISED, F4)):
+            ctx.actualize_image(name, fmt)
+        ctx.image_upload(Hh.N_NORMALS, g1["normals"])
+        ctx.image_upload(Hh.N_MOTION, g1["motion"])
+        ctx.image_upload(Hh.N_RT, rt)
+        pc = np.zeros((), T.SVGFPushConstants)
+        i0, i1 = ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F4)
+        pn, hi, mo = ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F2)
+        ctx.storage_image_upload(pn, g0["normals"]); ctx.storage_image_upload(hi, history); ctx.storage_image_upload(mo, moments)
+        pc["integrated_shadow_and_ao"] = (i0, i1)
+        pc["prev_frame_normals_and_object_ids"] = pn; pc["shadow_and_ao_history"] = hi; pc["shadow_and_ao_moments_history"] = mo
+        ctx.bind_pass_images([Hh.N_NORMALS, Hh.N_MOTION, Hh.N_DEPTH, Hh.N_RT, Hh.N_DENOISED])
+        ctx.dispatch("hybrid_render_path/svgf.comp", _groups(W), _groups(H), 1, pc)
+        got_i, got_m = ctx.storage_image_download(i0), ctx.storage_image_download(mo)
+    valid_frac = float(np.mean(ref_i[..., 3].astype(np.float32) > 0.5))   # valid reprojection => ao variance ~0.8+ (Q2)
+    print(f"[temporal] valid-reprojection fraction ~{valid_frac:.3f}")
+    assert valid_frac > 0.3, "test inputs should exercise the reprojection branch"
+    s = Hh.assert_parity(got_i, ref_i, f"temporal integrated {W}x{H}")
+    Hh.assert_parity(got_m, ref_m, f"temporal moments {W}x{H}")
+    assert s["exact"] > 0.999   # the temporal kernel mirrors the oracle's fp32 op order: expect bit-exact almost everywhere
+
+
+def test_svgf_pass_sequence_three_frames():
+    """Full pass body (temporal + 5 à-trous + blits + ping-pong) over three frames with a moving camera."""
+    W, H = 256, 144
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, moving=True)
+    state = O.SvgfState(W, H)
+    with capi.Context(W, H) as ctx:
+        p = Hh.SvgfPassCABI(ctx, W, H)
+        for f, (pfd, g) in enumerate(frames):
+            rt = osc.raygen(pfd, g["depth"], g["normals"], flags=3)["shadow_ao"]
+            ref_den, ref_iters, ref_temporal = state.run(pfd, g["normals"], g["motion"], rt)
+            ctx.update_per_frame_ubo(pfd)
+            ctx.image_upload(Hh.N_NORMALS, g["normals"]); ctx.image_upload(Hh.N_MOTION, g["motion"]); ctx.image_upload(Hh.N_RT, rt)
+            den, iters, temporal = p.run(want_iters=True)
+            Hh.assert_parity(temporal, ref_temporal, f"frame {f} temporal")
+            for i in range(5):
+                Hh.assert_parity(iters[i], ref_iters[i], f"frame {f} atrous it{i}")
+            Hh.assert_parity(den, ref_den, f"frame {f} denoised (= it3, SURVEY Q1)")
+            assert np.array_equal(den.view(np.uint16), iters[3].view(np.uint16))

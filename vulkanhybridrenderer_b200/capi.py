@@ -1,0 +1,262 @@
+"""ctypes binding of the C-ABI (include/vhr_b200.h -> vulkanhybridrenderer_b200/libvhr_b200.so).
+
+This is the stub a maintainer of a Python harness would write; INTEGRATION.md shows the C++ one. There is no
+fallback: a missing library or a missing sm_100 device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvhr_b200.so")
+
+# every symbol include/vhr_b200.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "vhr_context_create", "vhr_context_destroy", "vhr_last_error", "vhr_context_synchronize", "vhr_get_display_size",
+    "vhr_kernel_launch_count", "vhr_update_geometry", "vhr_update_per_frame_ubo", "vhr_upload_new_storage_image",
+    "vhr_destroy_storage_image", "vhr_actualize_image", "vhr_destroy_transient_resources", "vhr_image_upload",
+    "vhr_image_download", "vhr_storage_image_upload", "vhr_storage_image_download", "vhr_image_device_ptr",
+    "vhr_storage_image_device_ptr", "vhr_bind_pass_images", "vhr_dispatch", "vhr_trace_rays",
+    "vhr_blit_storage_to_transient", "vhr_blit_transient_to_storage", "vhr_blit_storage_to_storage", "vhr_set_option",
+    "vhr_get_option", "vhr_get_bvh_stats", "vhr_trace_explicit", "vhr_gbuffer_pass", "vhr_create_query_pool",
+    "vhr_write_timestamp", "vhr_get_query_elapsed_ms",
+]
+
+OPT_AO_SPP, OPT_TRACE_SHADOWS, OPT_TRACE_AO, OPT_TRACE_REFLECTIONS = 1, 2, 3, 4
+OPT_ROW_BEGIN, OPT_ROW_END, OPT_SVGF_FUSED, OPT_ATROUS_VARIANT = 5, 6, 7, 8
+
+
+class BvhStats(C.Structure):
+    _fields_ = [("n_triangles", C.c_uint32), ("n_bvh2_nodes", C.c_uint32), ("n_wide_nodes", C.c_uint32),
+                ("max_leaf_size", C.c_uint32), ("sah_cost", C.c_float), ("scene_min", C.c_float * 3),
+                ("scene_max", C.c_float * 3), ("build_ms", C.c_float)]
+
+
+class VhrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VhrError(f"{LIB_PATH} is missing: run `python -m vulkanhybridrenderer_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
+        L.vhr_context_create.argtypes = [i32, vp, u32, u32, C.POINTER(vp)]
+        L.vhr_context_destroy.argtypes = [vp]
+        L.vhr_context_destroy.restype = None
+        L.vhr_last_error.restype = C.c_char_p
+        L.vhr_context_synchronize.argtypes = [vp]
+        L.vhr_get_display_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+        L.vhr_kernel_launch_count.argtypes = [vp]
+        L.vhr_kernel_launch_count.restype = C.c_uint64
+        L.vhr_update_geometry.argtypes = [vp, vp, u32, vp, u32, vp, u32]
+        L.vhr_update_per_frame_ubo.argtypes = [vp, vp, sz]
+        L.vhr_upload_new_storage_image.argtypes = [vp, u32, u32, i32]
+        L.vhr_destroy_storage_image.argtypes = [vp, i32]
+        L.vhr_actualize_image.argtypes = [vp, C.c_char_p, u32, u32, i32]
+        L.vhr_destroy_transient_resources.argtypes = [vp]
+        L.vhr_image_upload.argtypes = [vp, C.c_char_p, vp, sz]
+        L.vhr_image_download.argtypes = [vp, C.c_char_p, vp, sz]
+        L.vhr_storage_image_upload.argtypes = [vp, i32, vp, sz]
+        L.vhr_storage_image_download.argtypes = [vp, i32, vp, sz]
+        L.vhr_image_device_ptr.argtypes = [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(i32)]
+        L.vhr_image_device_ptr.restype = vp
+        L.vhr_storage_image_device_ptr.argtypes = [vp, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(i32)]
+        L.vhr_storage_image_device_ptr.restype = vp
+        L.vhr_bind_pass_images.argtypes = [vp, C.POINTER(C.c_char_p), u32]
+        L.vhr_dispatch.argtypes = [vp, C.c_char_p, u32, u32, u32, vp, sz]
+        L.vhr_trace_rays.argtypes = [vp, C.c_char_p, u32, u32]
+        L.vhr_blit_storage_to_transient.argtypes = [vp, i32, C.c_char_p]
+        L.vhr_blit_transient_to_storage.argtypes = [vp, C.c_char_p, i32]
+        L.vhr_blit_storage_to_storage.argtypes = [vp, i32, i32]
+        L.vhr_set_option.argtypes = [vp, i32, C.c_int64]
+        L.vhr_get_option.argtypes = [vp, i32]
+        L.vhr_get_option.restype = C.c_int64
+        L.vhr_get_bvh_stats.argtypes = [vp, C.POINTER(BvhStats)]
+        L.vhr_trace_explicit.argtypes = [vp, vp, u32, i32, vp, vp, vp]
+        L.vhr_gbuffer_pass.argtypes = [vp, u32, u32]
+        L.vhr_create_query_pool.argtypes = [vp, u32]
+        L.vhr_write_timestamp.argtypes = [vp, u32]
+        L.vhr_get_query_elapsed_ms.argtypes = [vp, u32, u32, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise VhrError(f"vhr status {rc}: {lib().vhr_last_error().decode()}")
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _addr(buf):
+    """Host address of a numpy array or a (pinned) torch CPU tensor."""
+    if isinstance(buf, np.ndarray):
+        return C.c_void_p(buf.ctypes.data), buf.nbytes
+    return C.c_void_p(buf.data_ptr()), buf.numel() * buf.element_size()
+
+
+class Context:
+    """Thin object wrapper over vhr_context: one GPU, one stream."""
+
+    def __init__(self, width, height, device=0, stream=None):
+        self._h = C.c_void_p()
+        _check(lib().vhr_context_create(int(device), C.c_void_p(stream) if stream else None, int(width), int(height), C.byref(self._h)))
+        self.width, self.height = int(width), int(height)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vhr_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- ResourceManager --
+    def update_geometry(self, vertices, indices, primitives):
+        v = np.ascontiguousarray(vertices); i = np.ascontiguousarray(indices, np.uint32); p = np.ascontiguousarray(primitives)
+        assert v.dtype == T.Vertex and p.dtype == T.Primitive
+        _check(lib().vhr_update_geometry(self._h, _ptr(v), len(v), _ptr(i), len(i), _ptr(p), len(p)))
+
+    def update_per_frame_ubo(self, pfd):
+        pfd = np.ascontiguousarray(pfd)
+        _check(lib().vhr_update_per_frame_ubo(self._h, _ptr(pfd), pfd.nbytes))
+
+    def upload_new_storage_image(self, width, height, fmt):
+        return _check(lib().vhr_upload_new_storage_image(self._h, width, height, fmt))
+
+    def destroy_storage_image(self, slot):
+        _check(lib().vhr_destroy_storage_image(self._h, slot))
+
+    # -- RenderGraph images --
+    def actualize_image(self, name, fmt, width=0, height=0):
+        _check(lib().vhr_actualize_image(self._h, name.encode(), width, height, fmt))
+
+    def destroy_transient_resources(self):
+        _check(lib().vhr_destroy_transient_resources(self._h))
+
+    def image_upload(self, name, host):
+        pageable = isinstance(host, np.ndarray)
+        if pageable:
+            host = np.ascontiguousarray(host)
+        a, n = _addr(host)
+        _check(lib().vhr_image_upload(self._h, name.encode(), a, n))
+        if pageable:
+            self.synchronize()   # pageable source: do not let the caller free it mid-copy
+
+    def image_download_into(self, name, host):
+        a, n = _addr(host)
+        _check(lib().vhr_image_download(self._h, name.encode(), a, n))
+
+    def image_info(self, name):
+        w, h, f = C.c_uint32(), C.c_uint32(), C.c_int()
+        p = lib().vhr_image_device_ptr(self._h, name.encode(), C.byref(w), C.byref(h), C.byref(f))
+        if not p:
+            raise VhrError(f"unknown image {name!r}")
+        return p, w.value, h.value, f.value
+
+    def storage_image_info(self, slot):
+        w, h, f = C.c_uint32(), C.c_uint32(), C.c_int()
+        p = lib().vhr_storage_image_device_ptr(self._h, slot, C.byref(w), C.byref(h), C.byref(f))
+        if not p:
+            raise VhrError(f"unknown storage image {slot}")
+        return p, w.value, h.value, f.value
+
+    @staticmethod
+    def _host_array(w, h, fmt):
+        dt, ch = T.FORMAT_NUMPY[fmt]
+        return np.empty((h, w) if ch == 1 else (h, w, ch), dt)
+
+    def image_download(self, name):
+        _, w, h, f = self.image_info(name)
+        out = self._host_array(w, h, f)
+        self.image_download_into(name, out)
+        self.synchronize()
+        return out
+
+    def storage_image_upload(self, slot, host):
+        host = np.ascontiguousarray(host)
+        _check(lib().vhr_storage_image_upload(self._h, slot, _ptr(host), host.nbytes))
+        self.synchronize()
+
+    def storage_image_download(self, slot):
+        _, w, h, f = self.storage_image_info(slot)
+        out = self._host_array(w, h, f)
+        _check(lib().vhr_storage_image_download(self._h, slot, _ptr(out), out.nbytes))
+        self.synchronize()
+        return out
+
+    # -- pass execution --
+    def bind_pass_images(self, names):
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        _check(lib().vhr_bind_pass_images(self._h, arr, len(names)))
+
+    def dispatch(self, shader, xg, yg, zg=1, push_constants=None):
+        if push_constants is None:
+            _check(lib().vhr_dispatch(self._h, shader.encode(), xg, yg, zg, None, 0))
+        else:
+            pc = np.ascontiguousarray(push_constants)
+            _check(lib().vhr_dispatch(self._h, shader.encode(), xg, yg, zg, _ptr(pc), pc.nbytes))
+
+    def trace_rays(self, width, height, pipeline="Raytrace Pipeline"):
+        _check(lib().vhr_trace_rays(self._h, pipeline.encode(), width, height))
+
+    def gbuffer_pass(self, width, height):
+        _check(lib().vhr_gbuffer_pass(self._h, width, height))
+
+    def blit_storage_to_transient(self, src, dst):
+        _check(lib().vhr_blit_storage_to_transient(self._h, src, dst.encode()))
+
+    def blit_transient_to_storage(self, src, dst):
+        _check(lib().vhr_blit_transient_to_storage(self._h, src.encode(), dst))
+
+    def blit_storage_to_storage(self, src, dst):
+        _check(lib().vhr_blit_storage_to_storage(self._h, src, dst))
+
+    def set_option(self, opt, value):
+        _check(lib().vhr_set_option(self._h, opt, int(value)))
+
+    def get_option(self, opt):
+        return lib().vhr_get_option(self._h, opt)
+
+    def synchronize(self):
+        _check(lib().vhr_context_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return lib().vhr_kernel_launch_count(self._h)
+
+    def bvh_stats(self):
+        s = BvhStats()
+        _check(lib().vhr_get_bvh_stats(self._h, C.byref(s)))
+        return s
+
+    def trace_explicit(self, rays, any_hit):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = len(rays)
+        t = np.empty(n, np.float32)
+        ids = np.empty((n, 2), np.uint32)
+        uv = np.empty((n, 2), np.float32)
+        _check(lib().vhr_trace_explicit(self._h, _ptr(rays), n, int(bool(any_hit)), _ptr(t), _ptr(ids), _ptr(uv)))
+        return t, ids, uv

@@ -1,0 +1,406 @@
+// vhr_api.cu — the C-ABI of include/vhr_b200.h: context, image tables, per-frame constants, pass dispatch.
+// Each entry point cites the reference call it replaces in the header.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vhr_internal.h"
+
+namespace vhr {
+
+static thread_local char g_error[512] = "";
+
+int fail(int status, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+static int alloc_image(vhr_context *ctx, Image &im, uint32_t w, uint32_t h, int fmt) {
+    int tb = format_texel_bytes(fmt);
+    if (!tb) return fail(VHR_ERR_INVALID, "unsupported VkFormat %d", fmt);
+    if (w == 0 || h == 0) return fail(VHR_ERR_INVALID, "image size %ux%u", w, h);
+    im.width = w; im.height = h; im.format = fmt;
+    im.bytes = (size_t)w * h * tb;
+    VHR_CUDA_CHECK(cudaMalloc(&im.ptr, im.bytes));
+    VHR_CUDA_CHECK(cudaMemsetAsync(im.ptr, 0, im.bytes, ctx->stream));
+    im.twin = nullptr;
+    im.used = true;
+    return VHR_OK;
+}
+static void free_image(Image &im) {
+    if (im.ptr) cudaFree(im.ptr);
+    if (im.twin) cudaFree(im.twin);
+    im = Image();
+}
+static Image *find_transient(vhr_context *ctx, const char *name) {
+    if (!name) return nullptr;
+    auto it = ctx->transient.find(name);
+    return it == ctx->transient.end() ? nullptr : &it->second;
+}
+static int copy_in(vhr_context *ctx, Image *im, const void *host, size_t bytes, const char *what) {
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
+    if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", what, bytes, im->bytes);
+    VHR_CUDA_CHECK(cudaMemcpyAsync(im->ptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return VHR_OK;
+}
+static int copy_out(vhr_context *ctx, Image *im, void *host, size_t bytes, const char *what) {
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
+    if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", what, bytes, im->bytes);
+    VHR_CUDA_CHECK(cudaMemcpyAsync(host, im->ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return VHR_OK;
+}
+static int blit(vhr_context *ctx, Image *src, Image *dst, const char *what) {
+    if (!src || !dst) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
+    // compute_execution_context.cpp:128-129,179-180 assert equal extents; the blit is NEAREST same-size = copy
+    if (src->width != dst->width || src->height != dst->height || src->bytes != dst->bytes)
+        return fail(VHR_ERR_INVALID, "%s: extents/formats differ (%ux%u fmt %d -> %ux%u fmt %d)", what, src->width,
+                    src->height, src->format, dst->width, dst->height, dst->format);
+    VHR_CUDA_CHECK(cudaMemcpyAsync(dst->ptr, src->ptr, src->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return VHR_OK;
+}
+
+}  // namespace vhr
+
+using namespace vhr;
+
+extern "C" {
+
+const char *vhr_last_error(void) { return g_error; }
+
+int vhr_context_create(int device, void *cuda_stream, uint32_t width, uint32_t height, vhr_context **out) {
+    if (!out) return fail(VHR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (width == 0 || height == 0) return fail(VHR_ERR_INVALID, "display size %ux%u", width, height);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(VHR_ERR_CUDA, "no CUDA device (%s) — this library has no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(VHR_ERR_INVALID, "device %d of %d", device, n);
+    VHR_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VHR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(VHR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    vhr_context *ctx = new vhr_context();
+    ctx->device = device;
+    ctx->width = width; ctx->height = height;
+    ctx->storage.resize(VHR_MAX_GLOBAL_RESOURCES);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return fail(VHR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return VHR_OK;
+}
+
+void vhr_context_destroy(vhr_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->transient) free_image(kv.second);
+    for (auto &im : ctx->storage) if (im.used) free_image(im);
+    free_bvh(ctx);
+    if (ctx->d_vertices) cudaFree(ctx->d_vertices);
+    if (ctx->d_indices) cudaFree(ctx->d_indices);
+    if (ctx->d_primitives) cudaFree(ctx->d_primitives);
+    for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int vhr_context_synchronize(vhr_context *ctx) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VHR_OK;
+}
+
+int vhr_get_display_size(vhr_context *ctx, uint32_t *width, uint32_t *height) {
+    if (!ctx || !width || !height) return fail(VHR_ERR_INVALID, "NULL argument");
+    *width = ctx->width; *height = ctx->height;
+    return VHR_OK;
+}
+
+uint64_t vhr_kernel_launch_count(vhr_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_vertices, const uint32_t *indices,
+                        uint32_t n_indices, const void *primitives, uint32_t n_primitives) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if ((n_vertices && !vertices) || (n_indices && !indices) || (n_primitives && !primitives))
+        return fail(VHR_ERR_INVALID, "NULL geometry array");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    free_bvh(ctx);
+    if (ctx->d_vertices) { cudaFree(ctx->d_vertices); ctx->d_vertices = nullptr; }
+    if (ctx->d_indices) { cudaFree(ctx->d_indices); ctx->d_indices = nullptr; }
+    if (ctx->d_primitives) { cudaFree(ctx->d_primitives); ctx->d_primitives = nullptr; }
+    ctx->n_vertices = n_vertices; ctx->n_indices = n_indices; ctx->n_primitives = n_primitives;
+    // validate index ranges on the host: an out-of-range index would read outside the vertex buffer on the device
+    const Primitive *prims = (const Primitive *)primitives;
+    for (uint32_t g = 0; g < n_primitives; ++g) {
+        const Primitive &p = prims[g];
+        if ((uint64_t)p.index_offset + p.index_count > n_indices)
+            return fail(VHR_ERR_INVALID, "primitive %u: indices [%u, +%u) exceed %u", g, p.index_offset, p.index_count, n_indices);
+        if (p.vertex_offset > n_vertices) return fail(VHR_ERR_INVALID, "primitive %u: vertex_offset %u exceeds %u", g, p.vertex_offset, n_vertices);
+        uint32_t lim = n_vertices - p.vertex_offset;
+        for (uint32_t k = 0; k < p.index_count; ++k)
+            if (indices[p.index_offset + k] >= lim)
+                return fail(VHR_ERR_INVALID, "primitive %u: index %u (+offset %u) exceeds %u vertices", g, indices[p.index_offset + k], p.vertex_offset, n_vertices);
+    }
+    if (n_vertices) {
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_vertices, (size_t)n_vertices * sizeof(Vertex)));
+        VHR_CUDA_CHECK(cudaMemcpyAsync(ctx->d_vertices, vertices, (size_t)n_vertices * sizeof(Vertex), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n_indices) {
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_indices, (size_t)n_indices * sizeof(uint32_t)));
+        VHR_CUDA_CHECK(cudaMemcpyAsync(ctx->d_indices, indices, (size_t)n_indices * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n_primitives) {
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_primitives, (size_t)n_primitives * sizeof(Primitive)));
+        VHR_CUDA_CHECK(cudaMemcpyAsync(ctx->d_primitives, primitives, (size_t)n_primitives * sizeof(Primitive), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = build_bvh(ctx);
+    if (rc) return rc;
+    // host arrays may be pageable: make sure the async copies have consumed them before returning
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VHR_OK;
+}
+
+int vhr_update_per_frame_ubo(vhr_context *ctx, const void *per_frame_data, size_t size) {
+    if (!ctx || !per_frame_data) return fail(VHR_ERR_INVALID, "NULL argument");
+    if (size != sizeof(PerFrameData)) return fail(VHR_ERR_INVALID, "PerFrameData is %zu bytes, got %zu", sizeof(PerFrameData), size);
+    memcpy(&ctx->pfd, per_frame_data, sizeof(PerFrameData));
+    ctx->pfd_set = true;
+    return VHR_OK;
+}
+
+int vhr_upload_new_storage_image(vhr_context *ctx, uint32_t width, uint32_t height, int vk_format) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < VHR_MAX_GLOBAL_RESOURCES; ++i) {
+        if (!ctx->storage[i].used) {
+            int rc = alloc_image(ctx, ctx->storage[i], width, height, vk_format);
+            return rc ? rc : i;
+        }
+    }
+    return fail(VHR_ERR_EXHAUSTED, "No free storage image slots left!");
+}
+
+int vhr_destroy_storage_image(vhr_context *ctx, int slot) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    Image *im = storage_slot(ctx, slot);
+    if (!im) return fail(VHR_ERR_INVALID, "storage image %d does not exist", slot);
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    free_image(*im);
+    return VHR_OK;
+}
+
+int vhr_actualize_image(vhr_context *ctx, const char *name, uint32_t width, uint32_t height, int vk_format) {
+    if (!ctx || !name) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (width == 0 && height == 0) { width = ctx->width; height = ctx->height; }
+    Image *im = find_transient(ctx, name);
+    if (im) {
+        if (im->width != width || im->height != height || im->format != vk_format)
+            return fail(VHR_ERR_INVALID, "image '%s' re-declared as %ux%u fmt %d (is %ux%u fmt %d)", name, width, height,
+                        vk_format, im->width, im->height, im->format);
+        return VHR_OK;
+    }
+    Image fresh;
+    int rc = alloc_image(ctx, fresh, width, height, vk_format);
+    if (rc) return rc;
+    ctx->transient[name] = fresh;
+    return VHR_OK;
+}
+
+int vhr_destroy_transient_resources(vhr_context *ctx) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (auto &kv : ctx->transient) free_image(kv.second);
+    ctx->transient.clear();
+    ctx->n_bound = 0;
+    return VHR_OK;
+}
+
+int vhr_image_upload(vhr_context *ctx, const char *name, const void *host, size_t bytes) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return copy_in(ctx, find_transient(ctx, name), host, bytes, name ? name : "(null)");
+}
+int vhr_image_download(vhr_context *ctx, const char *name, void *host, size_t bytes) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return copy_out(ctx, find_transient(ctx, name), host, bytes, name ? name : "(null)");
+}
+int vhr_storage_image_upload(vhr_context *ctx, int slot, const void *host, size_t bytes) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return copy_in(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
+}
+int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t bytes) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return copy_out(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
+}
+void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format) {
+    Image *im = ctx ? find_transient(ctx, name) : nullptr;
+    if (!im) return nullptr;
+    if (width) *width = im->width;
+    if (height) *height = im->height;
+    if (vk_format) *vk_format = im->format;
+    return im->ptr;
+}
+void *vhr_storage_image_device_ptr(vhr_context *ctx, int slot, uint32_t *width, uint32_t *height, int *vk_format) {
+    Image *im = ctx ? storage_slot(ctx, slot) : nullptr;
+    if (!im) return nullptr;
+    if (width) *width = im->width;
+    if (height) *height = im->height;
+    if (vk_format) *vk_format = im->format;
+    return im->ptr;
+}
+
+int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, uint32_t count) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (count > VHR_MAX_PASS_BINDINGS) return fail(VHR_ERR_INVALID, "%u bindings (max %d)", count, VHR_MAX_PASS_BINDINGS);
+    for (uint32_t i = 0; i < count; ++i) {
+        Image *im = names_by_binding ? find_transient(ctx, names_by_binding[i]) : nullptr;
+        if (!im) return fail(VHR_ERR_INVALID, "binding %u: unknown image '%s'", i, (names_by_binding && names_by_binding[i]) ? names_by_binding[i] : "(null)");
+        ctx->bound[i] = im;
+    }
+    ctx->n_bound = count;
+    return VHR_OK;
+}
+
+int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
+                 const void *push_constants, size_t push_constants_size) {
+    if (!ctx || !shader_path) return fail(VHR_ERR_INVALID, "NULL argument");
+    if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
+    if (z_groups != 1) return fail(VHR_ERR_INVALID, "z_groups = %u (the hot-path kernels are 2D)", z_groups);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const bool is_temporal = !strcmp(shader_path, "hybrid_render_path/svgf.comp");
+    const bool is_atrous = !strcmp(shader_path, "hybrid_render_path/svgf_atrous_filter.comp");
+    if (is_temporal || is_atrous) {
+        // compute_execution_context.h:23: assert(sizeof(T) == pipeline.push_constant_description.size)
+        if (!push_constants || push_constants_size != sizeof(SVGFPushConstants))
+            return fail(VHR_ERR_INVALID, "%s: push constants are %zu bytes, got %zu", shader_path, sizeof(SVGFPushConstants), push_constants_size);
+        SVGFPushConstants pc;
+        memcpy(&pc, push_constants, sizeof(pc));
+        return is_temporal ? launch_svgf_temporal(ctx, x_groups, y_groups, pc) : launch_svgf_atrous(ctx, x_groups, y_groups, pc);
+    }
+    if (!strcmp(shader_path, "hybrid_render_path/ssao.comp")) {
+        // the reference never pushes the radius to this kernel; intent 0.75 (hybrid_render_path.cpp:139-141)
+        float radius = 0.75f;
+        if (push_constants) {
+            if (push_constants_size != sizeof(SSAOPushConstants))
+                return fail(VHR_ERR_INVALID, "%s: push constants are %zu bytes, got %zu", shader_path, sizeof(SSAOPushConstants), push_constants_size);
+            memcpy(&radius, push_constants, sizeof(float));
+        }
+        return launch_ssao(ctx, x_groups, y_groups, radius);
+    }
+    if (!strcmp(shader_path, "hybrid_render_path/ssao_blur.comp")) {
+        // the reference pushes SSAOPushConstants here although the shader has no push-constant block (Q15): accepted, ignored
+        if (push_constants && push_constants_size != sizeof(SSAOPushConstants))
+            return fail(VHR_ERR_INVALID, "%s: push constants are %zu bytes, got %zu", shader_path, sizeof(SSAOPushConstants), push_constants_size);
+        return launch_ssao_blur(ctx, x_groups, y_groups);
+    }
+    return fail(VHR_ERR_INVALID, "unknown compute kernel '%s'", shader_path);
+}
+
+int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height) {
+    if (!ctx || !pipeline_name) return fail(VHR_ERR_INVALID, "NULL argument");
+    if (strcmp(pipeline_name, "Raytrace Pipeline")) return fail(VHR_ERR_INVALID, "unknown ray-tracing pipeline '%s'", pipeline_name);
+    if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_trace_rays(ctx, width, height);
+}
+
+int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_gbuffer(ctx, width, height);
+}
+
+int vhr_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
+                       float *out_uv) {
+    if (!ctx || (n && (!rays || !out_t))) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_trace_explicit(ctx, rays, n, any_hit, out_t, out_ids, out_uv);
+}
+
+int vhr_blit_storage_to_transient(vhr_context *ctx, int src_slot, const char *dst_name) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return blit(ctx, storage_slot(ctx, src_slot), find_transient(ctx, dst_name), "BlitImageStorageToTransient");
+}
+int vhr_blit_transient_to_storage(vhr_context *ctx, const char *src_name, int dst_slot) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return blit(ctx, find_transient(ctx, src_name), storage_slot(ctx, dst_slot), "BlitImageTransientToStorage");
+}
+int vhr_blit_storage_to_storage(vhr_context *ctx, int src_slot, int dst_slot) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    return blit(ctx, storage_slot(ctx, src_slot), storage_slot(ctx, dst_slot), "BlitImageStorageToStorage");
+}
+
+int vhr_create_query_pool(vhr_context *ctx, uint32_t count) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
+    ctx->queries.assign(count, nullptr);
+    for (uint32_t i = 0; i < count; ++i) VHR_CUDA_CHECK(cudaEventCreate(&ctx->queries[i]));
+    return VHR_OK;
+}
+int vhr_write_timestamp(vhr_context *ctx, uint32_t query) {
+    if (!ctx || query >= ctx->queries.size()) return fail(VHR_ERR_INVALID, "timestamp query %u out of range", query);
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->queries[query], ctx->stream));
+    return VHR_OK;
+}
+int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms) {
+    if (!ctx || !out_ms || first >= ctx->queries.size() || last >= ctx->queries.size())
+        return fail(VHR_ERR_INVALID, "timestamp query range [%u, %u] invalid", first, last);
+    VHR_CUDA_CHECK(cudaEventSynchronize(ctx->queries[last]));
+    float ms = 0.0f;
+    VHR_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->queries[first], ctx->queries[last]));
+    *out_ms = ms;
+    return VHR_OK;
+}
+
+int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    switch (option) {
+        case VHR_OPT_AO_SPP:
+            if (value < 0 || value > 64) return fail(VHR_ERR_INVALID, "ao_spp %lld out of [0, 64]", (long long)value);
+            ctx->opt.ao_spp = (int)value; return VHR_OK;
+        case VHR_OPT_TRACE_SHADOWS: ctx->opt.trace_shadows = value != 0; return VHR_OK;
+        case VHR_OPT_TRACE_AO: ctx->opt.trace_ao = value != 0; return VHR_OK;
+        case VHR_OPT_TRACE_REFLECTIONS: ctx->opt.trace_reflections = value != 0; return VHR_OK;
+        case VHR_OPT_ROW_BEGIN: ctx->opt.row_begin = (int)value; return VHR_OK;
+        case VHR_OPT_ROW_END: ctx->opt.row_end = (int)value; return VHR_OK;
+        case VHR_OPT_SVGF_FUSED: ctx->opt.svgf_fused = value != 0; return VHR_OK;
+        case VHR_OPT_ATROUS_VARIANT:
+            if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
+            ctx->opt.atrous_variant = (int)value; return VHR_OK;
+    }
+    return fail(VHR_ERR_INVALID, "unknown option %d", option);
+}
+
+int64_t vhr_get_option(vhr_context *ctx, int option) {
+    if (!ctx) return -1;
+    switch (option) {
+        case VHR_OPT_AO_SPP: return ctx->opt.ao_spp;
+        case VHR_OPT_TRACE_SHADOWS: return ctx->opt.trace_shadows;
+        case VHR_OPT_TRACE_AO: return ctx->opt.trace_ao;
+        case VHR_OPT_TRACE_REFLECTIONS: return ctx->opt.trace_reflections;
+        case VHR_OPT_ROW_BEGIN: return ctx->opt.row_begin;
+        case VHR_OPT_ROW_END: return ctx->opt.row_end;
+        case VHR_OPT_SVGF_FUSED: return ctx->opt.svgf_fused;
+        case VHR_OPT_ATROUS_VARIANT: return ctx->opt.atrous_variant;
+    }
+    return -1;
+}
+
+int vhr_get_bvh_stats(vhr_context *ctx, vhr_bvh_stats *out) {
+    if (!ctx || !out) return fail(VHR_ERR_INVALID, "NULL argument");
+    *out = ctx->bvh.stats;
+    return VHR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// vhr_internal.h — host-side context of the C-ABI (not installed; include/vhr_b200.h is the public surface).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vhr_b200.h"
+#include "vhr_common.cuh"
+
+namespace vhr {
+
+struct Image {
+    void *ptr = nullptr;
+    void *twin = nullptr;      // second buffer of a double-buffered storage image (moments history)
+    uint32_t width = 0, height = 0;
+    int format = 0;
+    size_t bytes = 0;
+    bool used = false;
+};
+
+inline int format_texel_bytes(int fmt) {
+    switch (fmt) {
+        case VHR_FORMAT_B8G8R8A8_UNORM: return 4;
+        case VHR_FORMAT_R16G16_SFLOAT: return 4;
+        case VHR_FORMAT_R16G16B16A16_SFLOAT: return 8;
+        case VHR_FORMAT_D32_SFLOAT: return 4;
+    }
+    return 0;
+}
+
+// Device-side acceleration structure (bvh_build.cu / trace_kernels.cu)
+struct Bvh {
+    uint32_t n_tris = 0;
+    uint32_t n_nodes2 = 0;         // binary nodes
+    uint32_t n_wide = 0;           // 8-wide nodes
+    void *wide_nodes = nullptr;    // WideNode[n_wide]
+    float4 *tri_verts = nullptr;   // 3 float4 per triangle, leaf order (w of v0 = geometry index bits, w of v1 = primitive id bits)
+    void *scratch = nullptr;       // everything else allocated by the build (freed with the Bvh)
+    vhr_bvh_stats stats = {};
+};
+
+struct Options {
+    int ao_spp = 2;
+    int trace_shadows = 1;
+    int trace_ao = 1;
+    int trace_reflections = 1;
+    int row_begin = 0;
+    int row_end = -1;            // -1 = image height
+    int svgf_fused = 0;
+    int atrous_variant = 1;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel
+};
+
+}  // namespace vhr
+
+struct vhr_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t width = 0, height = 0;
+    std::unordered_map<std::string, vhr::Image> transient;
+    std::vector<vhr::Image> storage;               // VHR_MAX_GLOBAL_RESOURCES slots
+    vhr::Image *bound[VHR_MAX_PASS_BINDINGS] = {};
+    uint32_t n_bound = 0;
+    vhr::PerFrameData pfd = {};
+    bool pfd_set = false;
+    // geometry (global vertex / index / primitive buffers, resource_manager.cpp:13-28)
+    vhr::Vertex *d_vertices = nullptr;
+    uint32_t *d_indices = nullptr;
+    vhr::Primitive *d_primitives = nullptr;
+    uint32_t n_vertices = 0, n_indices = 0, n_primitives = 0;
+    vhr::Bvh bvh;
+    vhr::Options opt;
+    uint64_t launches = 0;
+    std::vector<cudaEvent_t> queries;              // timestamp query pool
+};
+
+namespace vhr {
+
+// error plumbing (vhr_api.cu)
+int fail(int status, const char *fmt, ...);
+#define VHR_CUDA_CHECK(expr)                                                                            \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) return vhr::fail(VHR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                                                 cudaGetErrorString(e__), __FILE__, __LINE__);           \
+    } while (0)
+
+// kernel launchers (svgf_kernels.cu, ssao_kernels.cu, trace_kernels.cu, bvh_build.cu); all return a vhr_status
+int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
+int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
+int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius);
+int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg);
+int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height);
+int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height);
+int launch_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
+                          float *out_uv);
+int build_bvh(vhr_context *ctx);
+void free_bvh(vhr_context *ctx);
+
+inline Image *storage_slot(vhr_context *ctx, int slot) {
+    if (slot < 0 || slot >= VHR_MAX_GLOBAL_RESOURCES) return nullptr;
+    Image &im = ctx->storage[slot];
+    return im.used ? &im : nullptr;
+}
+
+}  // namespace vhr
