@@ -145,7 +145,8 @@ typedef enum vhr_option {
     VHR_OPT_ROW_BEGIN = 5,         /* row band [begin, end) this context renders (multi-GPU split); default 0 */
     VHR_OPT_ROW_END = 6,           /* default = image height */
     VHR_OPT_SVGF_FUSED = 7,        /* 1: temporal pass also produces a-trous iteration 0 (fused kernel) */
-    VHR_OPT_ATROUS_VARIANT = 8     /* 0: direct-load kernel (the reference's dataflow); 1 (default): tiled kernel */
+    VHR_OPT_ATROUS_VARIANT = 8,    /* 0: direct-load kernel (the reference's dataflow); 1 (default): tiled kernel */
+    VHR_OPT_DEBUG_REFLECTION_T = 9 /* 1: the ray pass also records the reflection ray's closest-hit distance */
 } vhr_option;
 int vhr_set_option(vhr_context *ctx, int option, int64_t value);
 int64_t vhr_get_option(vhr_context *ctx, int option);
@@ -160,6 +161,7 @@ typedef struct vhr_bvh_stats {
     float scene_min[3];
     float scene_max[3];
     float build_ms;              /* device time of the last build */
+    uint32_t wide_depth;         /* levels of the wide tree (bounds the traversal stack) */
 } vhr_bvh_stats;
 int vhr_get_bvh_stats(vhr_context *ctx, vhr_bvh_stats *out);
 
@@ -168,6 +170,11 @@ int vhr_get_bvh_stats(vhr_context *ctx, vhr_bvh_stats *out);
  * out_ids (optional, 2 x uint32 per ray) = (geometry index, primitive id), out_uv (optional, 2 floats per ray). */
 int vhr_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
                        float *out_uv);
+
+/* Downloads the per-pixel closest-hit distance of the reflection ray written by the last vhr_trace_rays when
+ * VHR_OPT_DEBUG_REFLECTION_T is set (float32 per pixel of the display size; -1 = miss or sky). The reference never
+ * outputs hit distances (its payloads are 0/1 and radiance); this exists for the hit-distance parity check. */
+int vhr_debug_download_reflection_t(vhr_context *ctx, float *host, size_t bytes);
 
 /* G-buffer producer as a CUDA primary-ray pass (stand-in for the rasterised "G-Buffer Pass",
  * hybrid_render_path.cpp:13-56; encodings of gbuf.frag:33,43,46-58). Bound images: 0 albedo (BGRA8), 1 normals/ids,

@@ -115,3 +115,44 @@ class SvgfPassCABI:
         ctx.blit_storage_to_transient(int(pc["integrated_shadow_and_ao"][1]), N_DENOISED)
         pc["integrated_shadow_and_ao"] = pc["integrated_shadow_and_ao"][::-1].copy()
         return ctx.image_download(N_DENOISED), (np.stack(iters) if want_iters else None), temporal
+
+
+def world_triangles(sc):
+    """World-space triangle soup (float32, same evaluation order as the builders): (n, 3, 3) array."""
+    out = []
+    for p in sc.primitives:
+        m = p["transform"].astype(np.float32)          # m[c][r]
+        idx = sc.indices[int(p["index_offset"]): int(p["index_offset"]) + int(p["index_count"])].astype(np.int64) + int(p["vertex_offset"])
+        pos = sc.vertices["pos"][idx].astype(np.float32)
+        w = np.empty_like(pos)
+        for r in range(3):
+            w[:, r] = ((m[0, r] * pos[:, 0] + m[1, r] * pos[:, 1]) + m[2, r] * pos[:, 2]) + m[3, r]
+        out.append(w.reshape(-1, 3, 3))
+    return np.concatenate(out) if out else np.zeros((0, 3, 3), np.float32)
+
+
+def brute_force_hits(tris, o, d, tmin, tmax):
+    """Exact-ish (float64 Moller-Trumbore) test of one ray against every triangle.
+    Returns (any_hit, closest_t, edge_margin) where edge_margin is the smallest normalised barycentric distance to an
+    edge or to the [tmin, tmax] interval among triangles whose plane the ray crosses nearby — small values mean the
+    ray grazes an edge / the interval end (an epsilon case)."""
+    t64 = tris.astype(np.float64)
+    o = np.asarray(o, np.float64); d = np.asarray(d, np.float64)
+    e1 = t64[:, 1] - t64[:, 0]; e2 = t64[:, 2] - t64[:, 0]
+    pv = np.cross(d[None, :], e2)
+    det = np.einsum("ij,ij->i", e1, pv)
+    ok = np.abs(det) > 0
+    inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+    tv = o[None, :] - t64[:, 0]
+    u = np.einsum("ij,ij->i", tv, pv) * inv
+    qv = np.cross(tv, e1)
+    v = np.einsum("j,ij->i", d, qv) * inv
+    t = np.einsum("ij,ij->i", e2, qv) * inv
+    w = 1.0 - u - v
+    inside = ok & (u >= 0) & (v >= 0) & (w >= 0) & (t > tmin) & (t < tmax)
+    # margin: how far the nearest candidate is from flipping its classification
+    bary_margin = np.minimum(np.minimum(np.abs(u), np.abs(v)), np.abs(w))
+    t_margin = np.minimum(np.abs(t - tmin), np.abs(t - tmax)) / np.maximum(1.0, np.abs(t))
+    near = ok & (u > -1e-3) & (v > -1e-3) & (w > -1e-3) & (t > tmin - 1e-3) & (t < tmax + 1e-3)
+    margin = float(np.min(np.minimum(bary_margin, t_margin)[near])) if near.any() else 1.0
+    return bool(inside.any()), (float(t[inside].min()) if inside.any() else -1.0), margin

@@ -22,17 +22,17 @@ SYMBOLS = [
     "vhr_storage_image_device_ptr", "vhr_bind_pass_images", "vhr_dispatch", "vhr_trace_rays",
     "vhr_blit_storage_to_transient", "vhr_blit_transient_to_storage", "vhr_blit_storage_to_storage", "vhr_set_option",
     "vhr_get_option", "vhr_get_bvh_stats", "vhr_trace_explicit", "vhr_gbuffer_pass", "vhr_create_query_pool",
-    "vhr_write_timestamp", "vhr_get_query_elapsed_ms",
+    "vhr_write_timestamp", "vhr_get_query_elapsed_ms", "vhr_debug_download_reflection_t",
 ]
 
 OPT_AO_SPP, OPT_TRACE_SHADOWS, OPT_TRACE_AO, OPT_TRACE_REFLECTIONS = 1, 2, 3, 4
-OPT_ROW_BEGIN, OPT_ROW_END, OPT_SVGF_FUSED, OPT_ATROUS_VARIANT = 5, 6, 7, 8
+OPT_ROW_BEGIN, OPT_ROW_END, OPT_SVGF_FUSED, OPT_ATROUS_VARIANT, OPT_DEBUG_REFLECTION_T = 5, 6, 7, 8, 9
 
 
 class BvhStats(C.Structure):
     _fields_ = [("n_triangles", C.c_uint32), ("n_bvh2_nodes", C.c_uint32), ("n_wide_nodes", C.c_uint32),
                 ("max_leaf_size", C.c_uint32), ("sah_cost", C.c_float), ("scene_min", C.c_float * 3),
-                ("scene_max", C.c_float * 3), ("build_ms", C.c_float)]
+                ("scene_max", C.c_float * 3), ("build_ms", C.c_float), ("wide_depth", C.c_uint32)]
 
 
 class VhrError(RuntimeError):
@@ -84,6 +84,7 @@ def lib():
         L.vhr_get_bvh_stats.argtypes = [vp, C.POINTER(BvhStats)]
         L.vhr_trace_explicit.argtypes = [vp, vp, u32, i32, vp, vp, vp]
         L.vhr_gbuffer_pass.argtypes = [vp, u32, u32]
+        L.vhr_debug_download_reflection_t.argtypes = [vp, vp, sz]
         L.vhr_create_query_pool.argtypes = [vp, u32]
         L.vhr_write_timestamp.argtypes = [vp, u32]
         L.vhr_get_query_elapsed_ms.argtypes = [vp, u32, u32, C.POINTER(C.c_double)]
@@ -251,6 +252,11 @@ class Context:
         s = BvhStats()
         _check(lib().vhr_get_bvh_stats(self._h, C.byref(s)))
         return s
+
+    def download_reflection_t(self):
+        out = np.empty((self.height, self.width), np.float32)
+        _check(lib().vhr_debug_download_reflection_t(self._h, _ptr(out), out.nbytes))
+        return out
 
     def trace_explicit(self, rays, any_hit):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)

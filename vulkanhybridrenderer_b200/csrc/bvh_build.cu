@@ -1,0 +1,524 @@
+// bvh_build.cu — GPU acceleration-structure build (sm_100a), in place of the driver's BLAS/TLAS build
+// (/root/reference/src/rendering_backend/resource_manager.cpp:593-801 UpdateBLAS / UpdateTLAS).
+//
+//   1. extract   world-space triangle soup: Primitive.transform applied per geometry (resource_manager.cpp:608-617,
+//                636-641), indices relative to vertex_offset, geometry index = flat primitive index
+//   2. morton    63-bit Morton code of the triangle-box centre inside the scene box
+//   3. sort      CUB radix sort of (code, triangle)
+//   4. karras    binary radix tree over the sorted codes (Karras 2012)
+//   5. refit     bottom-up AABBs + SAH cost; subtrees of <= 3 triangles collapse into leaves when SAH prefers it
+//   6. widen     level-synchronous collapse of the binary tree into 8-wide nodes (largest-area child opened first),
+//                child boxes quantised to 8 bits (conservative), leaf triangles rewritten contiguously per node
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "bvh.cuh"
+#include "vhr_internal.h"
+
+namespace vhr {
+
+namespace {
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ordered_to_float(int i) {
+    int b = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// ---- 1. extract ------------------------------------------------------------------------------------------------
+__global__ void extract_triangles_kernel(const Vertex *__restrict__ verts, const uint32_t *__restrict__ indices,
+                                         const Primitive *__restrict__ prims, const uint32_t *__restrict__ prefix,
+                                         uint32_t n_prims, uint32_t n_tris, TriRef *__restrict__ out, int *scene_bounds) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    if (t < n_tris) {
+        // largest g with prefix[g] <= t
+        uint32_t lo = 0, hi = n_prims;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (prefix[mid] <= t) lo = mid; else hi = mid;
+        }
+        const uint32_t g = lo, k = t - prefix[g];
+        const Primitive &p = prims[g];
+        float3 v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t vi = p.vertex_offset + indices[p.index_offset + 3 * k + c];
+            const Vertex &vx = verts[vi];
+            v[c] = xform_point_rn(p.transform, vx.pos[0], vx.pos[1], vx.pos[2]);
+        }
+        TriRef r;
+        r.v0 = make_float4(v[0].x, v[0].y, v[0].z, __uint_as_float(g));
+        r.v1 = make_float4(v[1].x, v[1].y, v[1].z, __uint_as_float(k));
+        r.v2 = make_float4(v[2].x, v[2].y, v[2].z, 0.0f);
+        out[t] = r;
+        mn[0] = fminf(v[0].x, fminf(v[1].x, v[2].x)); mx[0] = fmaxf(v[0].x, fmaxf(v[1].x, v[2].x));
+        mn[1] = fminf(v[0].y, fminf(v[1].y, v[2].y)); mx[1] = fmaxf(v[0].y, fmaxf(v[1].y, v[2].y));
+        mn[2] = fminf(v[0].z, fminf(v[1].z, v[2].z)); mx[2] = fmaxf(v[0].z, fmaxf(v[1].z, v[2].z));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float lo = mn[a], hi = mx[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0 && lo <= hi) {
+            atomicMin(&scene_bounds[a], float_to_ordered(lo));
+            atomicMax(&scene_bounds[3 + a], float_to_ordered(hi));
+        }
+    }
+}
+
+// ---- 2. morton -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t expand21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void morton_kernel(const TriRef *__restrict__ tris, uint32_t n, const int *__restrict__ scene_bounds,
+                              uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float smin[3], inv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        smin[a] = ordered_to_float(scene_bounds[a]);
+        float ext = ordered_to_float(scene_bounds[3 + a]) - smin[a];
+        inv[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+    }
+    const TriRef r = tris[t];
+    float c[3];
+    c[0] = 0.5f * (fminf(r.v0.x, fminf(r.v1.x, r.v2.x)) + fmaxf(r.v0.x, fmaxf(r.v1.x, r.v2.x)));
+    c[1] = 0.5f * (fminf(r.v0.y, fminf(r.v1.y, r.v2.y)) + fmaxf(r.v0.y, fmaxf(r.v1.y, r.v2.y)));
+    c[2] = 0.5f * (fminf(r.v0.z, fminf(r.v1.z, r.v2.z)) + fmaxf(r.v0.z, fmaxf(r.v1.z, r.v2.z)));
+    uint64_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float f = (c[a] - smin[a]) * inv[a];
+        f = fminf(fmaxf(f, 0.0f), 2097151.0f);
+        q[a] = (uint64_t)f;
+    }
+    keys[t] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    vals[t] = t;
+}
+
+// ---- 4. karras -------------------------------------------------------------------------------------------------
+struct Tree2 {
+    uint32_t n;              // number of leaves (triangles)
+    uint32_t *child_l;       // [n-1] unified ids: < n-1 internal, >= n-1 leaf (id - (n-1) = sorted position)
+    uint32_t *child_r;
+    uint32_t *parent;        // [2n-1]
+    uint32_t *range_first;   // [n-1] first sorted position covered
+    float4 *bmin;            // [2n-1] xyz = box min, w = SAH cost of the subtree
+    float4 *bmax;            // [2n-1] xyz = box max, w = triangle count (as uint bits)
+    uint8_t *cluster;        // [n-1] 1: subtree is emitted as one leaf (<= kMaxLeafTris triangles)
+    int *visit;              // [n-1]
+};
+
+__device__ __forceinline__ int delta(const uint64_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void karras_kernel(const uint64_t *__restrict__ keys, Tree2 t) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (int)t.n;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int s = lmax >> 1; s >= 1; s >>= 1)
+        if (delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int tt = l;
+    do {
+        tt = (tt + 1) >> 1;
+        if (delta(keys, n, i, i + (s + tt) * d) > dnode) s += tt;
+    } while (tt > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    uint32_t left = (lo == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+    uint32_t right = (hi == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+    t.child_l[i] = left;
+    t.child_r[i] = right;
+    t.parent[left] = (uint32_t)i;
+    t.parent[right] = (uint32_t)i;
+    t.range_first[i] = (uint32_t)lo;
+    if (i == 0) t.parent[0] = 0xffffffffu;
+}
+
+// ---- 5. refit + SAH --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float box_half_area(float3 mn, float3 mx) {
+    float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__restrict__ order, Tree2 t) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.n) return;
+    const TriRef r = tris[order[j]];
+    float3 mn = make_float3(fminf(r.v0.x, fminf(r.v1.x, r.v2.x)), fminf(r.v0.y, fminf(r.v1.y, r.v2.y)), fminf(r.v0.z, fminf(r.v1.z, r.v2.z)));
+    float3 mx = make_float3(fmaxf(r.v0.x, fmaxf(r.v1.x, r.v2.x)), fmaxf(r.v0.y, fmaxf(r.v1.y, r.v2.y)), fmaxf(r.v0.z, fmaxf(r.v1.z, r.v2.z)));
+    uint32_t id = t.n - 1 + j;
+    t.bmin[id] = make_float4(mn.x, mn.y, mn.z, box_half_area(mn, mx));      // leaf cost = area * 1 triangle
+    t.bmax[id] = make_float4(mx.x, mx.y, mx.z, __uint_as_float(1u));
+    if (t.n == 1) return;
+    __threadfence();
+    uint32_t p = t.parent[id];
+    while (p != 0xffffffffu) {
+        if (atomicAdd(&t.visit[p], 1) == 0) return;   // the sibling subtree is not finished: its thread continues
+        __threadfence();
+        uint32_t l = t.child_l[p], rr = t.child_r[p];
+        float4 lmn = __ldcg(&t.bmin[l]), lmx = __ldcg(&t.bmax[l]);
+        float4 rmn = __ldcg(&t.bmin[rr]), rmx = __ldcg(&t.bmax[rr]);
+        mn = make_float3(fminf(lmn.x, rmn.x), fminf(lmn.y, rmn.y), fminf(lmn.z, rmn.z));
+        mx = make_float3(fmaxf(lmx.x, rmx.x), fmaxf(lmx.y, rmx.y), fmaxf(lmx.z, rmx.z));
+        uint32_t cnt = __float_as_uint(lmx.w) + __float_as_uint(rmx.w);
+        float area = box_half_area(mn, mx);
+        float cost_inner = area * 1.0f + lmn.w + rmn.w;       // node cost 1, triangle cost 1
+        float cost_leaf = area * (float)cnt;
+        bool cl = cnt <= (uint32_t)kMaxLeafTris && cost_leaf <= cost_inner;
+        t.cluster[p] = cl ? 1 : 0;
+        t.bmin[p] = make_float4(mn.x, mn.y, mn.z, cl ? cost_leaf : cost_inner);
+        t.bmax[p] = make_float4(mx.x, mx.y, mx.z, __uint_as_float(cnt));
+        __threadfence();
+        p = t.parent[p];
+    }
+}
+
+// ---- 6. widen --------------------------------------------------------------------------------------------------
+struct WidenArgs {
+    Tree2 t;
+    const TriRef *tris;          // unsorted triangles
+    const uint32_t *order;       // sorted position -> unsorted triangle
+    WideNode *wide;
+    TriRef *tris_out;            // final triangle array (leaf order)
+    const uint2 *queue_in;       // (binary node, wide node index)
+    uint2 *queue_out;
+    uint32_t n_in;
+    uint32_t *counters;          // [0] wide nodes allocated, [1] triangles emitted, [2] queue_out size
+    float *sah;                  // accumulated SAH numerator
+};
+
+__device__ __forceinline__ bool leaf_like(const Tree2 &t, uint32_t id) { return id >= t.n - 1 || t.cluster[id]; }
+
+__device__ void emit_wide_node(const WidenArgs &a, uint32_t wide_idx, const uint32_t *kids, int nk, float3 nmn, float3 nmx) {
+    const Tree2 &t = a.t;
+    int n_inner = 0, n_leaf_tris = 0;
+    for (int c = 0; c < nk; ++c) {
+        if (leaf_like(t, kids[c])) n_leaf_tris += (int)__float_as_uint(t.bmax[kids[c]].w);
+        else n_inner++;
+    }
+    uint32_t child_base = n_inner ? atomicAdd(&a.counters[0], (uint32_t)n_inner) : 0u;
+    uint32_t tri_base = n_leaf_tris ? atomicAdd(&a.counters[1], (uint32_t)n_leaf_tris) : 0u;
+    uint32_t q_base = n_inner ? atomicAdd(&a.counters[2], (uint32_t)n_inner) : 0u;
+
+    WideNode w;
+    w.origin[0] = nmn.x; w.origin[1] = nmn.y; w.origin[2] = nmn.z;
+    float ext[3] = {nmx.x - nmn.x, nmx.y - nmn.y, nmx.z - nmn.z};
+    float scale[3];
+    for (int ax = 0; ax < 3; ++ax) {
+        // smallest power of two with ext / scale <= 254 (one step of slack for the conservative fix-ups below)
+        int e = 1;
+        if (ext[ax] > 0.0f) {
+            int ex;
+            float m = frexpf(ext[ax] / 254.0f, &ex);   // ext/254 = m * 2^ex, m in [0.5,1)
+            (void)m;
+            e = ex + 127;                              // 2^ex >= ext/254
+            e = max(1, min(254, e));
+        }
+        w.e[ax] = (uint8_t)e;
+        scale[ax] = __uint_as_float((uint32_t)e << 23);
+    }
+    w.imask = 0;
+    w.child_base = child_base;
+    w.tri_base = tri_base;
+    for (int s = 0; s < 8; ++s) {
+        w.meta[s] = 0;
+        for (int ax = 0; ax < 3; ++ax) { w.qlo[ax][s] = 255; w.qhi[ax][s] = 0; }
+    }
+    int k_inner = 0, tri_off = 0;
+    float sah = box_half_area(nmn, nmx);
+    for (int c = 0; c < nk; ++c) {
+        uint32_t id = kids[c];
+        float4 cmn = t.bmin[id], cmx = t.bmax[id];
+        float lo[3] = {cmn.x, cmn.y, cmn.z}, hi[3] = {cmx.x, cmx.y, cmx.z};
+        for (int ax = 0; ax < 3; ++ax) {
+            float org = w.origin[ax];
+            float ql = floorf((lo[ax] - org) / scale[ax]);
+            float qh = ceilf((hi[ax] - org) / scale[ax]);
+            ql = fminf(fmaxf(ql, 0.0f), 255.0f);
+            qh = fminf(fmaxf(qh, 0.0f), 255.0f);
+            // conservative fix-ups against rounding in the two lines above
+            while (ql > 0.0f && __fmaf_rn(ql, scale[ax], org) > lo[ax]) ql -= 1.0f;
+            while (qh < 255.0f && __fmaf_rn(qh, scale[ax], org) < hi[ax]) qh += 1.0f;
+            w.qlo[ax][c] = (uint8_t)ql;
+            w.qhi[ax][c] = (uint8_t)qh;
+        }
+        if (leaf_like(t, id)) {
+            uint32_t cnt = __float_as_uint(cmx.w);
+            uint32_t first = id >= t.n - 1 ? id - (t.n - 1) : t.range_first[id];
+            w.meta[c] = (uint8_t)((cnt << 5) | (uint32_t)tri_off);
+            for (uint32_t k = 0; k < cnt; ++k) a.tris_out[tri_base + tri_off + k] = a.tris[a.order[first + k]];
+            tri_off += (int)cnt;
+            sah += box_half_area(make_float3(cmn.x, cmn.y, cmn.z), make_float3(cmx.x, cmx.y, cmx.z)) * (float)cnt;
+        } else {
+            w.imask |= (uint8_t)(1u << c);
+            w.meta[c] = (uint8_t)(0x80u | (uint32_t)k_inner);
+            a.queue_out[q_base + k_inner] = make_uint2(id, child_base + k_inner);
+            k_inner++;
+        }
+    }
+    a.wide[wide_idx] = w;
+    atomicAdd(a.sah, sah);
+}
+
+__global__ void widen_kernel(const __grid_constant__ WidenArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_in) return;
+    const Tree2 &t = a.t;
+    const uint2 item = a.queue_in[i];
+    uint32_t kids[8];
+    int nk = 2;
+    kids[0] = t.child_l[item.x];
+    kids[1] = t.child_r[item.x];
+    while (nk < 8) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int c = 0; c < nk; ++c) {
+            if (leaf_like(t, kids[c])) continue;
+            float4 mn = t.bmin[kids[c]], mx = t.bmax[kids[c]];
+            float ar = box_half_area(make_float3(mn.x, mn.y, mn.z), make_float3(mx.x, mx.y, mx.z));
+            if (ar > best_area) { best_area = ar; best = c; }
+        }
+        if (best < 0) break;
+        uint32_t id = kids[best];
+        kids[best] = t.child_l[id];
+        kids[nk++] = t.child_r[id];
+    }
+    float4 nmn = t.bmin[item.x], nmx = t.bmax[item.x];
+    emit_wide_node(a, item.y, kids, nk, make_float3(nmn.x, nmn.y, nmn.z), make_float3(nmx.x, nmx.y, nmx.z));
+}
+
+// the whole tree is a single leaf (<= kMaxLeafTris triangles, or the root collapsed)
+__global__ void widen_single_leaf_kernel(const __grid_constant__ WidenArgs a, uint32_t root_id) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t kids[1] = {root_id};
+    float4 nmn = a.t.bmin[root_id], nmx = a.t.bmax[root_id];
+    emit_wide_node(a, 0, kids, 1, make_float3(nmn.x, nmn.y, nmn.z), make_float3(nmx.x, nmx.y, nmx.z));
+}
+
+template <typename T>
+int dmalloc(T **p, size_t count) {
+    VHR_CUDA_CHECK(cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return VHR_OK;
+}
+
+}  // namespace
+
+void free_bvh(vhr_context *ctx) {
+    Bvh &b = ctx->bvh;
+    if (b.wide_nodes) cudaFree(b.wide_nodes);
+    if (b.tri_verts) cudaFree(b.tri_verts);
+    b = Bvh();
+}
+
+int build_bvh(vhr_context *ctx) {
+    Bvh &bvh = ctx->bvh;
+    bvh = Bvh();
+    cudaStream_t st = ctx->stream;
+    // per-primitive triangle prefix (host copy of the primitives is what the caller just handed us; re-read from device
+    // would need a sync anyway)
+    std::vector<Primitive> prims(ctx->n_primitives);
+    if (ctx->n_primitives) {
+        VHR_CUDA_CHECK(cudaMemcpyAsync(prims.data(), ctx->d_primitives, prims.size() * sizeof(Primitive), cudaMemcpyDeviceToHost, st));
+        VHR_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    std::vector<uint32_t> prefix(ctx->n_primitives + 1, 0);
+    uint64_t total = 0;
+    for (uint32_t g = 0; g < ctx->n_primitives; ++g) {
+        prefix[g] = (uint32_t)total;
+        total += prims[g].index_count / 3;
+    }
+    prefix[ctx->n_primitives] = (uint32_t)total;
+    if (total >= 0x7fffffffull) return fail(VHR_ERR_INVALID, "too many triangles (%llu)", (unsigned long long)total);
+    const uint32_t n = (uint32_t)total;
+    bvh.n_tris = n;
+    bvh.stats.n_triangles = n;
+    bvh.stats.max_leaf_size = kMaxLeafTris;
+    if (n == 0) return VHR_OK;
+
+    cudaEvent_t ev0, ev1;
+    VHR_CUDA_CHECK(cudaEventCreate(&ev0));
+    VHR_CUDA_CHECK(cudaEventCreate(&ev1));
+    VHR_CUDA_CHECK(cudaEventRecord(ev0, st));
+
+    uint32_t *d_prefix = nullptr;
+    TriRef *d_tris = nullptr;
+    int *d_scene = nullptr;
+    uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+    uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
+    void *d_tmp = nullptr;
+    Tree2 t = {};
+    t.n = n;
+    uint2 *d_q[2] = {nullptr, nullptr};
+    uint32_t *d_counters = nullptr;
+    float *d_sah = nullptr;
+    WideNode *d_wide = nullptr;
+    TriRef *d_tris_out = nullptr;
+    int rc = VHR_OK;
+    std::vector<void *> scratch;
+    auto track = [&](void *p) { scratch.push_back(p); };
+#define TRY(x) do { rc = (x); if (rc) goto done; } while (0)
+#define TRYCUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail(VHR_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e__)); goto done; } } while (0)
+
+    {
+        TRY(dmalloc(&d_prefix, prefix.size())); track(d_prefix);
+        TRY(dmalloc(&d_tris, n)); track(d_tris);
+        TRY(dmalloc(&d_scene, 6)); track(d_scene);
+        TRYCUDA(cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+        TRYCUDA(cudaMemcpyAsync(d_scene, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        const int B = 256;
+        const uint32_t G = (n + B - 1) / B;
+        extract_triangles_kernel<<<G, B, 0, st>>>(ctx->d_vertices, ctx->d_indices, ctx->d_primitives, d_prefix, ctx->n_primitives, n, d_tris, d_scene);
+        TRYCUDA(cudaGetLastError()); ctx->launches++;
+
+        TRY(dmalloc(&d_keys, n)); track(d_keys);
+        TRY(dmalloc(&d_keys2, n)); track(d_keys2);
+        TRY(dmalloc(&d_vals, n)); track(d_vals);
+        TRY(dmalloc(&d_vals2, n)); track(d_vals2);
+        morton_kernel<<<G, B, 0, st>>>(d_tris, n, d_scene, d_keys, d_vals);
+        TRYCUDA(cudaGetLastError()); ctx->launches++;
+        size_t tmp_bytes = 0;
+        TRYCUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
+        TRYCUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16))); track(d_tmp);
+        TRYCUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
+        ctx->launches += 8;   // CUB radix sort passes (upsweep/scan/downsweep per digit; approximate)
+
+        const uint32_t n_inner = n > 1 ? n - 1 : 0;
+        TRY(dmalloc(&t.child_l, n_inner)); track(t.child_l);
+        TRY(dmalloc(&t.child_r, n_inner)); track(t.child_r);
+        TRY(dmalloc(&t.parent, 2 * (size_t)n)); track(t.parent);
+        TRY(dmalloc(&t.range_first, n_inner)); track(t.range_first);
+        TRY(dmalloc(&t.bmin, 2 * (size_t)n)); track(t.bmin);
+        TRY(dmalloc(&t.bmax, 2 * (size_t)n)); track(t.bmax);
+        TRY(dmalloc(&t.cluster, n_inner)); track(t.cluster);
+        TRY(dmalloc(&t.visit, n_inner)); track(t.visit);
+        TRYCUDA(cudaMemsetAsync(t.visit, 0, std::max<size_t>(n_inner, 1) * sizeof(int), st));
+        TRYCUDA(cudaMemsetAsync(t.cluster, 0, std::max<size_t>(n_inner, 1), st));
+        if (n_inner) {
+            karras_kernel<<<(n_inner + B - 1) / B, B, 0, st>>>(d_keys2, t);
+            TRYCUDA(cudaGetLastError()); ctx->launches++;
+        }
+        refit_kernel<<<G, B, 0, st>>>(d_tris, d_vals2, t);
+        TRYCUDA(cudaGetLastError()); ctx->launches++;
+
+        // widen
+        TRY(dmalloc(&d_wide, (size_t)n)); track(d_wide);
+        TRY(dmalloc(&d_tris_out, (size_t)n));   // kept on success
+        TRY(dmalloc(&d_q[0], (size_t)n)); track(d_q[0]);
+        TRY(dmalloc(&d_q[1], (size_t)n)); track(d_q[1]);
+        TRY(dmalloc(&d_counters, 4)); track(d_counters);
+        TRY(dmalloc(&d_sah, 1)); track(d_sah);
+        uint32_t counters[4] = {1, 0, 0, 0};
+        TRYCUDA(cudaMemcpyAsync(d_counters, counters, sizeof(counters), cudaMemcpyHostToDevice, st));
+        TRYCUDA(cudaMemsetAsync(d_sah, 0, sizeof(float), st));
+        WidenArgs a;
+        a.t = t; a.tris = d_tris; a.order = d_vals2; a.wide = d_wide; a.tris_out = d_tris_out;
+        a.counters = d_counters; a.sah = d_sah;
+        uint8_t root_cluster = 0;
+        if (n_inner) {
+            TRYCUDA(cudaMemcpyAsync(&root_cluster, t.cluster, 1, cudaMemcpyDeviceToHost, st));
+            TRYCUDA(cudaStreamSynchronize(st));
+        }
+        if (n_inner == 0 || root_cluster) {
+            a.queue_in = d_q[0]; a.queue_out = d_q[1]; a.n_in = 0;
+            bvh.stats.wide_depth = 1;
+            widen_single_leaf_kernel<<<1, 32, 0, st>>>(a, 0u);
+            TRYCUDA(cudaGetLastError()); ctx->launches++;
+        } else {
+            uint2 root_item = make_uint2(0u, 0u);
+            TRYCUDA(cudaMemcpyAsync(d_q[0], &root_item, sizeof(uint2), cudaMemcpyHostToDevice, st));
+            uint32_t n_in = 1;
+            int cur = 0;
+            for (int level = 0; n_in > 0 && level < 256; ++level) {
+                bvh.stats.wide_depth = (uint32_t)level + 1;
+                TRYCUDA(cudaMemsetAsync(d_counters + 2, 0, sizeof(uint32_t), st));
+                a.queue_in = d_q[cur]; a.queue_out = d_q[cur ^ 1]; a.n_in = n_in;
+                widen_kernel<<<(n_in + 127) / 128, 128, 0, st>>>(a);
+                TRYCUDA(cudaGetLastError()); ctx->launches++;
+                TRYCUDA(cudaMemcpyAsync(&n_in, d_counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                TRYCUDA(cudaStreamSynchronize(st));
+                cur ^= 1;
+            }
+            if (n_in) { rc = fail(VHR_ERR_CUDA, "BVH widening did not terminate"); goto done; }
+        }
+        TRYCUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+        float sah_num = 0.0f;
+        TRYCUDA(cudaMemcpyAsync(&sah_num, d_sah, sizeof(float), cudaMemcpyDeviceToHost, st));
+        int scene[6];
+        TRYCUDA(cudaMemcpyAsync(scene, d_scene, sizeof(scene), cudaMemcpyDeviceToHost, st));
+        TRYCUDA(cudaStreamSynchronize(st));
+        if (counters[1] != n) { rc = fail(VHR_ERR_CUDA, "BVH build emitted %u of %u triangles", counters[1], n); goto done; }
+        bvh.n_wide = counters[0];
+        bvh.n_nodes2 = 2 * n - 1;
+        // shrink the node array to its final size
+        WideNode *final_nodes = nullptr;
+        TRYCUDA(cudaMalloc((void **)&final_nodes, (size_t)bvh.n_wide * sizeof(WideNode)));
+        TRYCUDA(cudaMemcpyAsync(final_nodes, d_wide, (size_t)bvh.n_wide * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        bvh.wide_nodes = final_nodes;
+        bvh.tri_verts = reinterpret_cast<float4 *>(d_tris_out);
+        d_tris_out = nullptr;
+        for (int k = 0; k < 3; ++k) {
+            bvh.stats.scene_min[k] = ordered_to_float(scene[k]);
+            bvh.stats.scene_max[k] = ordered_to_float(scene[3 + k]);
+        }
+        float ex = bvh.stats.scene_max[0] - bvh.stats.scene_min[0], ey = bvh.stats.scene_max[1] - bvh.stats.scene_min[1],
+              ez = bvh.stats.scene_max[2] - bvh.stats.scene_min[2];
+        float root_area = ex * ey + ey * ez + ez * ex;
+        bvh.stats.sah_cost = root_area > 0.0f ? sah_num / root_area : 0.0f;
+        bvh.stats.n_bvh2_nodes = bvh.n_nodes2;
+        bvh.stats.n_wide_nodes = bvh.n_wide;
+        TRYCUDA(cudaEventRecord(ev1, st));
+        TRYCUDA(cudaEventSynchronize(ev1));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        bvh.stats.build_ms = ms;
+    }
+done:
+    cudaStreamSynchronize(st);
+    for (void *p : scratch) cudaFree(p);
+    if (d_tris_out) cudaFree(d_tris_out);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (rc) free_bvh(ctx);
+    return rc;
+#undef TRY
+#undef TRYCUDA
+}
+
+}  // namespace vhr

@@ -1,0 +1,533 @@
+// trace_kernels.cu — software ray traversal over the 8-wide quantised BVH and the ray-traced passes (sm_100a).
+//
+//   raygen_kernel   <- /root/reference/data/shaders/hybrid_render_path/raygen.rgen:14-66, miss.rmiss:6-8,
+//                      reflection_miss.rmiss:6-8, reflection_hit.rchit:10-72 (one thread per pixel; the ray buffer
+//                      is never materialised)
+//   gbuffer_kernel  <- G-buffer encodings of gbuf.vert:19-28 / gbuf.frag:33,43,46-58 with primary rays standing in
+//                      for the rasteriser ("G-Buffer Pass", hybrid_render_path.cpp:13-56)
+//   trace_explicit  <- test/debug entry: explicit rays, any-hit or closest-hit
+//
+// traceRayEXT semantics restated from the Vulkan ray-tracing spec (the reference's traversal lives in the driver):
+// opaque triangles, no culling (TLAS instance flag TRIANGLE_FACING_CULL_DISABLE, resource_manager.cpp:704-718),
+// a triangle counts when tMin < t < tMax, shared edges are watertight (Woop/Benthin/Wald 2013 with the double
+// fallback for zero edge functions).
+#include <algorithm>
+#include <vector>
+
+#include "bvh.cuh"
+#include "vhr_internal.h"
+
+namespace vhr {
+
+namespace {
+
+constexpr int kStackSize = 40;
+
+struct Ray {
+    float3 o, d;
+    float tmin, tmax;
+};
+
+struct RayPre {
+    float3 o;
+    float3 idir;          // 1/d with zero components replaced by a huge finite value
+    int kx, ky, kz;       // Woop permutation
+    float Sx, Sy, Sz;
+    uint32_t neg;         // bit a set: d[a] < 0
+};
+
+__device__ __forceinline__ float comp(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+__device__ __forceinline__ float comp4(float4 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+__device__ __forceinline__ RayPre prepare(const Ray &r) {
+    RayPre p;
+    p.o = r.o;
+    float3 d = r.d;
+    const float tiny = 1e-30f;
+    float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
+    float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
+    float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
+    p.idir = make_float3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+    // sign of the *adjusted* component: -0.0 becomes -tiny, so near/far must swap for it too
+    p.neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    p.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+    p.kx = p.kz + 1; if (p.kx == 3) p.kx = 0;
+    p.ky = p.kx + 1; if (p.ky == 3) p.ky = 0;
+    float dkz = comp(d, p.kz);
+    if (dkz < 0.0f) { int t = p.kx; p.kx = p.ky; p.ky = t; }
+    p.Sx = comp(d, p.kx) / dkz;
+    p.Sy = comp(d, p.ky) / dkz;
+    p.Sz = 1.0f / dkz;
+    return p;
+}
+
+// Watertight ray/triangle test, two-sided. Returns true and (t, u, v) when tmin < t < tmax.
+__device__ __forceinline__ bool intersect_tri(const RayPre &r, float tmin, float tmax, float4 v0, float4 v1, float4 v2,
+                                              float &t_out, float &u_out, float &v_out) {
+    const float3 A = make_float3(v0.x - r.o.x, v0.y - r.o.y, v0.z - r.o.z);
+    const float3 B = make_float3(v1.x - r.o.x, v1.y - r.o.y, v1.z - r.o.z);
+    const float3 C = make_float3(v2.x - r.o.x, v2.y - r.o.y, v2.z - r.o.z);
+    const float Akz = comp(A, r.kz), Bkz = comp(B, r.kz), Ckz = comp(C, r.kz);
+    const float Ax = comp(A, r.kx) - r.Sx * Akz, Ay = comp(A, r.ky) - r.Sy * Akz;
+    const float Bx = comp(B, r.kx) - r.Sx * Bkz, By = comp(B, r.ky) - r.Sy * Bkz;
+    const float Cx = comp(C, r.kx) - r.Sx * Ckz, Cy = comp(C, r.ky) - r.Sy * Ckz;
+    // Edge functions: each product rounded on its own (no FMA contraction). With a fused multiply-add the two
+    // triangles sharing an edge would see rn(p - rn(q)) and rn(q - rn(p)), which can have the SAME sign when p ~ q —
+    // a crack. rn(p) - rn(q) and rn(q) - rn(p) are exact negations, which is what watertightness needs.
+    float U = sub_rn(mul_rn(Cx, By), mul_rn(Cy, Bx));
+    float V = sub_rn(mul_rn(Ax, Cy), mul_rn(Ay, Cx));
+    float W = sub_rn(mul_rn(Bx, Ay), mul_rn(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    const float rdet = 1.0f / det;
+    const float t = T * rdet;
+    if (!(t > tmin && t < tmax)) return false;
+    t_out = t;
+    u_out = V * rdet;
+    v_out = W * rdet;
+    return true;
+}
+
+__device__ __forceinline__ float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+
+struct Hit {
+    float t, u, v;
+    uint32_t tri;
+};
+
+// Intersects the ray with the 8 quantised child boxes of node `idx`. Returns the hit internal children as an 8-bit
+// mask over child ordinals and the triangles of the hit leaf children as a 24-bit mask over [tri_base, tri_base+24).
+__device__ __forceinline__ void intersect_node(const WideNode *__restrict__ nodes, uint32_t idx, const RayPre &r, float tmin,
+                                               float tmax, uint32_t &child_base, uint32_t &child_hits, uint32_t &tri_base,
+                                               uint32_t &tri_hits) {
+    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + idx);
+    const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
+                sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+    const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
+    const float bx = (__uint_as_float(n0.x) - r.o.x) * r.idir.x;
+    const float by = (__uint_as_float(n0.y) - r.o.y) * r.idir.y;
+    const float bz = (__uint_as_float(n0.z) - r.o.z) * r.idir.z;
+    // qlo: x = n2.xy, y = n2.zw, z = n3.xy ; qhi: x = n3.zw, y = n4.xy, z = n4.zw
+    const bool nx = r.neg & 1u, ny = r.neg & 2u, nz = r.neg & 4u;
+    const uint32_t nearx[2] = {nx ? n3.z : n2.x, nx ? n3.w : n2.y}, farx[2] = {nx ? n2.x : n3.z, nx ? n2.y : n3.w};
+    const uint32_t neary[2] = {ny ? n4.x : n2.z, ny ? n4.y : n2.w}, fary[2] = {ny ? n2.z : n4.x, ny ? n2.w : n4.y};
+    const uint32_t nearz[2] = {nz ? n4.z : n3.x, nz ? n4.w : n3.y}, farz[2] = {nz ? n3.x : n4.z, nz ? n3.y : n4.w};
+    const uint32_t meta[2] = {n1.z, n1.w};
+    child_base = n1.x;
+    tri_base = n1.y;
+    child_hits = 0;
+    tri_hits = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int w = s >> 2, b = s & 3;
+        const float tnx = fmaf(byte_f(nearx[w], b), ax, bx), tfx = fmaf(byte_f(farx[w], b), ax, bx);
+        const float tny = fmaf(byte_f(neary[w], b), ay, by), tfy = fmaf(byte_f(fary[w], b), ay, by);
+        const float tnz = fmaf(byte_f(nearz[w], b), az, bz), tfz = fmaf(byte_f(farz[w], b), az, bz);
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+        // Ize 2013: inflate the exit distance by a few ulps so rounding never culls a box the exact test would enter
+        const float tf = fminf(fminf(tfx, tfy), tfz) * 1.0000004f;
+        const uint32_t m = (meta[w] >> (8 * b)) & 0xffu;
+        if (tn <= fminf(tf, tmax) && m != 0u) {
+            if (m & 0x80u) child_hits |= 1u << (m & 7u);
+            else tri_hits |= ((1u << (m >> 5)) - 1u) << (m & 31u);
+        }
+    }
+}
+
+template <bool ANY>
+__device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
+                                      const Ray &ray, Hit &hit) {
+    if (n_wide == 0) return false;
+    const RayPre r = prepare(ray);
+    float tmax = ray.tmax;
+    bool found = false;
+    uint2 stack[kStackSize];
+    int sp = 0;
+    uint2 group = make_uint2(0u, 1u);   // (child_base, hit mask over child ordinals): the root
+    while (true) {
+        if (group.y == 0u) {
+            if (sp == 0) break;
+            group = stack[--sp];
+        }
+        const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
+        group.y &= group.y - 1u;
+        if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
+        uint32_t child_base, child_hits, tri_base, tri_hits;
+        intersect_node(nodes, group.x + k, r, ray.tmin, tmax, child_base, child_hits, tri_base, tri_hits);
+        group = make_uint2(child_base, child_hits);
+        while (tri_hits) {
+            const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
+            tri_hits &= tri_hits - 1u;
+            const float4 *tp = tris + (size_t)(tri_base + j) * 3;
+            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+            float t, u, v;
+            if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v)) {
+                if (ANY) return true;
+                tmax = t;
+                hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
+                found = true;
+            }
+        }
+    }
+    return found;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shading of the reflection ray: reflection_hit.rchit:10-72 (constant materials; texture indices treated as -1)
+// ---------------------------------------------------------------------------------------------------------------
+struct SceneRefs {
+    const Vertex *verts;
+    const uint32_t *indices;
+    const Primitive *prims;
+    const float *normal_mats;     // 9 floats per primitive, column-major inverseTranspose(mat3(transform))
+    const WideNode *nodes;
+    const float4 *tris;
+    uint32_t n_wide;
+};
+
+__device__ __forceinline__ float3 f3(const float *p) { return make_float3(p[0], p[1], p[2]); }
+__device__ __forceinline__ float3 bary3(float3 a, float3 b, float3 c, float b0, float b1, float b2) {
+    // (a*b0 + b*b1) + c*b2, componentwise, products and sums rounded like the oracle
+    return make_float3(add_rn(add_rn(mul_rn(a.x, b0), mul_rn(b.x, b1)), mul_rn(c.x, b2)),
+                       add_rn(add_rn(mul_rn(a.y, b0), mul_rn(b.y, b1)), mul_rn(c.y, b2)),
+                       add_rn(add_rn(mul_rn(a.z, b0), mul_rn(b.z, b1)), mul_rn(c.z, b2)));
+}
+__device__ __forceinline__ float mixf_rn(float a, float b, float t) { return add_rn(mul_rn(a, sub_rn(1.0f, t)), mul_rn(b, t)); }
+
+__device__ float4 reflection_hit(const SceneRefs &s, const PerFrameData &pfd, const Hit &h) {
+    const float4 *tp = s.tris + (size_t)h.tri * 3;
+    const uint32_t g = __float_as_uint(__ldg(tp).w), pid = __float_as_uint(__ldg(tp + 1).w);
+    const Primitive &prim = s.prims[g];
+    const uint32_t i0 = s.indices[prim.index_offset + 3 * pid + 0], i1 = s.indices[prim.index_offset + 3 * pid + 1],
+                   i2 = s.indices[prim.index_offset + 3 * pid + 2];
+    const Vertex &v0 = s.verts[prim.vertex_offset + i0], &v1 = s.verts[prim.vertex_offset + i1], &v2 = s.verts[prim.vertex_offset + i2];
+    const float b1 = h.u, b2 = h.v, b0 = sub_rn(sub_rn(1.0f, b1), b2);
+    const float3 normal = bary3(f3(v0.normal), f3(v1.normal), f3(v2.normal), b0, b1, b2);
+    const float3 pobj = bary3(f3(v0.pos), f3(v1.pos), f3(v2.pos), b0, b1, b2);
+    const float4 pw = mul44_rn(prim.transform, make_float4(pobj.x, pobj.y, pobj.z, 1.0f));
+    const float3 position = make_float3(pw.x, pw.y, pw.z);
+    const float3 albedo = make_float3(prim.material.base_color[0], prim.material.base_color[1], prim.material.base_color[2]);
+    float metallic = prim.material.metallic_factor, roughness = prim.material.roughness_factor;
+    const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
+    const float3 V = normalize_rn(make_float3(sub_rn(cam.x, position.x), sub_rn(cam.y, position.y), sub_rn(cam.z, position.z)));
+    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+    const float3 N = normal;
+    const float3 H = normalize_rn(make_float3(add_rn(L.x, V.x), add_rn(L.y, V.y), add_rn(L.z, V.z)));
+    roughness = fminf(fmaxf(roughness, 0.04f), 1.0f);
+    metallic = fminf(fmaxf(metallic, 0.0f), 1.0f);
+    const float ambient_factor = mul_rn(VHR_PI_INVERSE, 0.2f);
+    const float3 f0 = make_float3(mixf_rn(0.04f, albedo.x, metallic), mixf_rn(0.04f, albedo.y, metallic), mixf_rn(0.04f, albedo.z, metallic));
+    // fresnel_schlick (common.glsl:117-120)
+    const float hv = fmaxf(dot3_rn(H, V), 0.0f);
+    const float o = sub_rn(1.0f, hv);
+    auto fres = [&](float f) { return add_rn(f, mul_rn(mul_rn(mul_rn(mul_rn(mul_rn(sub_rn(1.0f, f), o), o), o), o), o)); };
+    const float3 F = make_float3(fres(f0.x), fres(f0.y), fres(f0.z));
+    // diffuse_brdf (common.glsl:146-150)
+    const float sdm = sub_rn(1.0f, metallic);
+    const float3 diffuse = make_float3(__fdiv_rn(mul_rn(mul_rn(sub_rn(1.0f, F.x), sdm), albedo.x), VHR_PI),
+                                       __fdiv_rn(mul_rn(mul_rn(sub_rn(1.0f, F.y), sdm), albedo.y), VHR_PI),
+                                       __fdiv_rn(mul_rn(mul_rn(sub_rn(1.0f, F.z), sdm), albedo.z), VHR_PI));
+    // specular_brdf (common.glsl:123-144)
+    const float a2 = mul_rn(roughness, roughness);
+    const float nh = fmaxf(dot3_rn(N, H), 0.0f);
+    const float ff = add_rn(mul_rn(mul_rn(nh, nh), sub_rn(a2, 1.0f)), 1.0f);
+    const float D = __fdiv_rn(a2, mul_rn(mul_rn(VHR_PI, ff), ff));
+    const float kk = mul_rn(mul_rn(add_rn(roughness, 1.0f), add_rn(roughness, 1.0f)), 0.125f);
+    const float nv = fmaxf(dot3_rn(N, V), 0.0f), nl = fmaxf(dot3_rn(N, L), 0.0f);
+    const float g_nvk = __fdiv_rn(nv, add_rn(mul_rn(nv, sub_rn(1.0f, kk)), kk));
+    const float g_nlk = __fdiv_rn(nl, add_rn(mul_rn(nl, sub_rn(1.0f, kk)), kk));
+    const float dg = mul_rn(D, mul_rn(g_nvk, g_nlk));
+    const float denom = fmaxf(mul_rn(mul_rn(4.0f, nv), nl), 1e-6f);
+    const float3 specular = make_float3(__fdiv_rn(mul_rn(dg, F.x), denom), __fdiv_rn(mul_rn(dg, F.y), denom), __fdiv_rn(mul_rn(dg, F.z), denom));
+    const float ndl = fmaxf(dot3_rn(N, L), 0.0f);
+    const float *li = pfd.directional_light.intensity, *lc = pfd.directional_light.color;
+    auto lit = [&](float amb, float dif, float spec, float i, float c) {
+        return add_rn(amb, mul_rn(mul_rn(mul_rn(add_rn(dif, spec), ndl), i), c));
+    };
+    return make_float4(lit(mul_rn(albedo.x, ambient_factor), diffuse.x, specular.x, li[0], lc[0]),
+                       lit(mul_rn(albedo.y, ambient_factor), diffuse.y, specular.y, li[1], lc[1]),
+                       lit(mul_rn(albedo.z, ambient_factor), diffuse.z, specular.z, li[2], lc[2]), 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// raygen
+// ---------------------------------------------------------------------------------------------------------------
+struct RaygenParams {
+    int W, H;                 // launch size (gl_LaunchSizeEXT)
+    int y_begin, y_end;
+    int ao_spp;
+    int flags;                // bit0 shadows, bit1 AO, bit2 reflections
+    const uint2 *normals;     // binding 0
+    const float *depth;       // binding 1
+    uint32_t *shadow_ao;      // binding 2 (RG16F)
+    uint2 *reflections;       // binding 3 (RGBA16F)
+    float *refl_t;            // optional debug output: closest-hit distance of the reflection ray (-1 = miss/sky)
+    SceneRefs scene;
+};
+
+// 8x4-pixel warp tiles inside a 16x8 block: neighbouring lanes trace neighbouring pixels.
+__device__ __forceinline__ void tile_coords(int &x, int &y) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+}
+
+__global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
+    int x, y;
+    tile_coords(x, y);
+    y += p.y_begin;
+    if (x >= p.W || y >= p.y_end) return;
+    const size_t pix = (size_t)y * p.W + x;
+    const float u = __fdiv_rn(add_rn((float)x, 0.5f), (float)p.W), v = __fdiv_rn(add_rn((float)y, 0.5f), (float)p.H);
+    uint32_t rng = seed_thread(((uint32_t)y * (uint32_t)p.H + (uint32_t)x) * pfd.frame_index);   // raygen.rgen:17 (Q4)
+    const float depth = __ldg(&p.depth[pix]);                                                    // texel centre: exact texel (Q17)
+    if (depth == 0.0f) {
+        p.shadow_ao[pix] = pack_rg16f(1.0f, 1.0f);
+        p.reflections[pix] = make_uint2(0u, 0u);
+        if (p.refl_t) p.refl_t[pix] = -1.0f;
+        return;
+    }
+    const float3 P = unproject_rn(pfd.camera_viewproj_inverse, depth, u, v);
+    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+    const float4 n4 = unpack_rgba16f(__ldg(&p.normals[pix]));
+    const float3 N = make_float3(n4.x, n4.y, n4.z);
+    Ray ray;
+    ray.o = make_float3(add_rn(P.x, mul_rn(N.x, 0.1f)), add_rn(P.y, mul_rn(N.y, 0.1f)), add_rn(P.z, mul_rn(N.z, 0.1f)));
+    ray.tmin = 0.01f;
+    Hit hit;
+
+    // shadow (raygen.rgen:32-41; the 4x loop re-traces one ray, Q3)
+    float rnd1 = random01(rng), rnd2 = random01(rng);
+    float shadow = 1.0f;
+    if (p.flags & 1) {
+        const float3 cone = normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f));
+        ray.d = onb_apply(L, cone);
+        ray.tmax = 10000.0f;
+        shadow = trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, hit) ? 0.0f : 1.0f;
+    }
+    // ambient occlusion (raygen.rgen:44-55)
+    float ao = 0.0f;
+    for (int i = 0; i < p.ao_spp; ++i) {
+        rnd1 = random01(rng);
+        rnd2 = random01(rng);
+        if (p.flags & 2) {
+            ray.d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
+            ray.tmax = 5.0f;
+            ao = add_rn(ao, trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, hit) ? 0.0f : 1.0f);
+        } else {
+            ao = add_rn(ao, 1.0f);
+        }
+    }
+    ao = __fdiv_rn(ao, (float)p.ao_spp);
+    p.shadow_ao[pix] = pack_rg16f(shadow, ao);
+
+    // mirror reflection (raygen.rgen:59-65)
+    float4 payload = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float rt = -1.0f;
+    if (p.flags & 4) {
+        const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
+        const float3 I = normalize_rn(make_float3(sub_rn(P.x, cam.x), sub_rn(P.y, cam.y), sub_rn(P.z, cam.z)));
+        const float k2 = mul_rn(2.0f, dot3_rn(N, I));
+        ray.d = make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2)));
+        ray.tmax = 10000.0f;
+        if (trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, hit)) {
+            payload = reflection_hit(p.scene, pfd, hit);
+            rt = hit.t;
+        }
+    }
+    p.reflections[pix] = pack_rgba16f(payload);
+    if (p.refl_t) p.refl_t[pix] = rt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G-buffer producer (primary rays)
+// ---------------------------------------------------------------------------------------------------------------
+struct GbufferParams {
+    int W, H;
+    int y_begin, y_end;
+    uint32_t *albedo;      // BGRA8
+    uint2 *normals;
+    uint2 *motion;
+    float *depth;
+    SceneRefs scene;
+};
+
+__device__ __forceinline__ uint32_t unorm8(float f) {
+    f = fminf(fmaxf(f, 0.0f), 1.0f);
+    return (uint32_t)__float2int_rn(f * 255.0f);
+}
+
+__global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ GbufferParams p, const __grid_constant__ PerFrameData pfd) {
+    int x, y;
+    tile_coords(x, y);
+    y += p.y_begin;
+    if (x >= p.W || y >= p.y_end) return;
+    const size_t pix = (size_t)y * p.W + x;
+    const float u = mul_rn(add_rn((float)x, 0.5f), pfd.display_size_inverse[0]);
+    const float v = mul_rn(add_rn((float)y, 0.5f), pfd.display_size_inverse[1]);
+    const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
+    const float3 pn = unproject_rn(pfd.camera_viewproj_inverse, 1.0f, u, v);   // near plane (reverse-Z: depth 1)
+    Ray ray;
+    ray.o = cam;
+    ray.d = make_float3(sub_rn(pn.x, cam.x), sub_rn(pn.y, cam.y), sub_rn(pn.z, cam.z));
+    ray.tmin = 1.0f;
+    ray.tmax = 3.0e38f;
+    Hit h;
+    if (!trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, h)) {
+        // clear values of hybrid_render_path.cpp:16-19
+        if (p.albedo) p.albedo[pix] = 0u;
+        p.normals[pix] = make_uint2(0u, 0u);
+        p.motion[pix] = pack_rgba16f(make_float4(0.0f, 0.0f, -1.0f, -1.0f));
+        p.depth[pix] = 0.0f;
+        return;
+    }
+    const SceneRefs &s = p.scene;
+    const float4 *tp = s.tris + (size_t)h.tri * 3;
+    const uint32_t g = __float_as_uint(__ldg(tp).w), pid = __float_as_uint(__ldg(tp + 1).w);
+    const Primitive &prim = s.prims[g];
+    const Vertex &v0 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 0]];
+    const Vertex &v1 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 1]];
+    const Vertex &v2 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 2]];
+    const float b1 = h.u, b2 = h.v, b0 = sub_rn(sub_rn(1.0f, b1), b2);
+    const float3 nobj = bary3(f3(v0.normal), f3(v1.normal), f3(v2.normal), b0, b1, b2);
+    const float3 pobj = bary3(f3(v0.pos), f3(v1.pos), f3(v2.pos), b0, b1, b2);
+    const float *nm = s.normal_mats + (size_t)g * 9;
+    float3 nw = make_float3(add_rn(add_rn(mul_rn(nm[0], nobj.x), mul_rn(nm[3], nobj.y)), mul_rn(nm[6], nobj.z)),
+                            add_rn(add_rn(mul_rn(nm[1], nobj.x), mul_rn(nm[4], nobj.y)), mul_rn(nm[7], nobj.z)),
+                            add_rn(add_rn(mul_rn(nm[2], nobj.x), mul_rn(nm[5], nobj.y)), mul_rn(nm[8], nobj.z)));
+    nw = normalize_rn(nw);
+    const float4 pw = mul44_rn(prim.transform, make_float4(pobj.x, pobj.y, pobj.z, 1.0f));
+    const float4 clip = mul44_rn(pfd.camera_proj, mul44_rn(pfd.camera_view, pw));
+    const float4 pclip = mul44_rn(pfd.camera_proj_prev_frame, mul44_rn(pfd.camera_view_prev_frame, pw));
+    const float pu = add_rn(mul_rn(__fdiv_rn(pclip.x, pclip.w), 0.5f), 0.5f);
+    const float pv = add_rn(mul_rn(__fdiv_rn(pclip.y, pclip.w), 0.5f), 0.5f);
+    if (p.albedo) {
+        const float *bc = prim.material.base_color;
+        p.albedo[pix] = unorm8(bc[2]) | (unorm8(bc[1]) << 8) | (unorm8(bc[0]) << 16) | (unorm8(bc[3]) << 24);
+    }
+    p.normals[pix] = pack_rgba16f(make_float4(nw.x, nw.y, nw.z, (float)g));
+    p.motion[pix] = pack_rgba16f(make_float4(sub_rn(u, pu), sub_rn(v, pv), prim.material.metallic_factor, prim.material.roughness_factor));
+    p.depth[pix] = __fdiv_rn(clip.z, clip.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// explicit rays (tests)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void trace_explicit_kernel(const float *__restrict__ rays, uint32_t n, int any_hit, SceneRefs s, float *out_t,
+                                      uint32_t *out_ids, float *out_uv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = make_float3(rays[8 * i + 0], rays[8 * i + 1], rays[8 * i + 2]);
+    r.tmin = rays[8 * i + 3];
+    r.d = make_float3(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6]);
+    r.tmax = rays[8 * i + 7];
+    Hit h;
+    h.t = -1.0f; h.u = 0.0f; h.v = 0.0f; h.tri = 0xffffffffu;
+    if (any_hit) {
+        out_t[i] = trace<true>(s.nodes, s.tris, s.n_wide, r, h) ? 1.0f : 0.0f;
+        return;
+    }
+    bool found = trace<false>(s.nodes, s.tris, s.n_wide, r, h);
+    out_t[i] = found ? h.t : -1.0f;
+    if (out_ids) {
+        out_ids[2 * i] = found ? __float_as_uint(s.tris[(size_t)h.tri * 3].w) : 0xffffffffu;
+        out_ids[2 * i + 1] = found ? __float_as_uint(s.tris[(size_t)h.tri * 3 + 1].w) : 0xffffffffu;
+    }
+    if (out_uv) { out_uv[2 * i] = h.u; out_uv[2 * i + 1] = h.v; }
+}
+
+SceneRefs scene_refs(vhr_context *ctx) {
+    SceneRefs s;
+    s.verts = ctx->d_vertices; s.indices = ctx->d_indices; s.prims = ctx->d_primitives;
+    s.normal_mats = ctx->d_normal_mats;
+    s.nodes = (const WideNode *)ctx->bvh.wide_nodes; s.tris = ctx->bvh.tri_verts; s.n_wide = ctx->bvh.n_wide;
+    return s;
+}
+
+bool band(vhr_context *ctx, uint32_t height, int &y0, int &y1) {
+    y0 = std::max(0, ctx->opt.row_begin);
+    y1 = ctx->opt.row_end < 0 ? (int)height : std::min((int)height, ctx->opt.row_end);
+    return y1 > y0;
+}
+
+}  // namespace
+
+int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
+    // descriptor set 3 of the "Raytrace Pass" (hybrid_render_path.cpp:102-110): 0 normals, 1 depth, 2 shadow/AO, 3 reflections
+    if (ctx->n_bound < 4) return fail(VHR_ERR_STATE, "TraceRays: pass images not bound (need bindings 0..3)");
+    if (!ctx->d_primitives && ctx->bvh.n_tris) return fail(VHR_ERR_STATE, "TraceRays: geometry not uploaded");
+    Image *normals = ctx->bound[0], *depth = ctx->bound[1], *sa = ctx->bound[2], *refl = ctx->bound[3];
+    if (normals->format != VHR_FORMAT_R16G16B16A16_SFLOAT || depth->format != VHR_FORMAT_D32_SFLOAT ||
+        sa->format != VHR_FORMAT_R16G16_SFLOAT || refl->format != VHR_FORMAT_R16G16B16A16_SFLOAT)
+        return fail(VHR_ERR_INVALID, "TraceRays: unexpected image formats");
+    for (Image *im : {normals, depth, sa, refl})
+        if (im->width != width || im->height != height)
+            return fail(VHR_ERR_INVALID, "TraceRays: launch size %ux%u differs from image %ux%u", width, height, im->width, im->height);
+    RaygenParams p;
+    p.W = (int)width; p.H = (int)height;
+    if (!band(ctx, height, p.y_begin, p.y_end)) return VHR_OK;
+    p.ao_spp = ctx->opt.ao_spp;
+    p.flags = (ctx->opt.trace_shadows ? 1 : 0) | (ctx->opt.trace_ao ? 2 : 0) | (ctx->opt.trace_reflections ? 4 : 0);
+    p.normals = (const uint2 *)normals->ptr; p.depth = (const float *)depth->ptr;
+    p.shadow_ao = (uint32_t *)sa->ptr; p.reflections = (uint2 *)refl->ptr;
+    p.refl_t = ctx->opt.debug_refl_t ? ctx->d_refl_t : nullptr;
+    p.scene = scene_refs(ctx);
+    dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
+    raygen_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
+int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height) {
+    if (ctx->n_bound < 4) return fail(VHR_ERR_STATE, "G-buffer pass: images not bound (need bindings 0..3)");
+    Image *albedo = ctx->bound[0], *normals = ctx->bound[1], *motion = ctx->bound[2], *depth = ctx->bound[3];
+    if (albedo->format != VHR_FORMAT_B8G8R8A8_UNORM || normals->format != VHR_FORMAT_R16G16B16A16_SFLOAT ||
+        motion->format != VHR_FORMAT_R16G16B16A16_SFLOAT || depth->format != VHR_FORMAT_D32_SFLOAT)
+        return fail(VHR_ERR_INVALID, "G-buffer pass: unexpected image formats");
+    for (Image *im : {albedo, normals, motion, depth})
+        if (im->width != width || im->height != height) return fail(VHR_ERR_INVALID, "G-buffer pass: image size mismatch");
+    GbufferParams p;
+    p.W = (int)width; p.H = (int)height;
+    if (!band(ctx, height, p.y_begin, p.y_end)) return VHR_OK;
+    p.albedo = (uint32_t *)albedo->ptr; p.normals = (uint2 *)normals->ptr; p.motion = (uint2 *)motion->ptr; p.depth = (float *)depth->ptr;
+    p.scene = scene_refs(ctx);
+    dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
+    gbuffer_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
+int launch_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids, float *out_uv) {
+    if (n == 0) return VHR_OK;
+    float *d_rays = nullptr, *d_t = nullptr, *d_uv = nullptr;
+    uint32_t *d_ids = nullptr;
+    VHR_CUDA_CHECK(cudaMalloc(&d_rays, (size_t)n * 8 * sizeof(float)));
+    VHR_CUDA_CHECK(cudaMalloc(&d_t, (size_t)n * sizeof(float)));
+    VHR_CUDA_CHECK(cudaMalloc(&d_ids, (size_t)n * 2 * sizeof(uint32_t)));
+    VHR_CUDA_CHECK(cudaMalloc(&d_uv, (size_t)n * 2 * sizeof(float)));
+    VHR_CUDA_CHECK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    trace_explicit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_rays, n, any_hit, scene_refs(ctx), d_t, d_ids, d_uv);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    VHR_CUDA_CHECK(cudaMemcpyAsync(out_t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ids) VHR_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_uv) VHR_CUDA_CHECK(cudaMemcpyAsync(out_uv, d_uv, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_rays); cudaFree(d_t); cudaFree(d_ids); cudaFree(d_uv);
+    return VHR_OK;
+}
+
+}  // namespace vhr

@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "vhr_internal.h"
 
 namespace vhr {
@@ -108,6 +110,8 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->d_vertices) cudaFree(ctx->d_vertices);
     if (ctx->d_indices) cudaFree(ctx->d_indices);
     if (ctx->d_primitives) cudaFree(ctx->d_primitives);
+    if (ctx->d_normal_mats) cudaFree(ctx->d_normal_mats);
+    if (ctx->d_refl_t) cudaFree(ctx->d_refl_t);
     for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -137,6 +141,7 @@ int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_verti
     if (ctx->d_vertices) { cudaFree(ctx->d_vertices); ctx->d_vertices = nullptr; }
     if (ctx->d_indices) { cudaFree(ctx->d_indices); ctx->d_indices = nullptr; }
     if (ctx->d_primitives) { cudaFree(ctx->d_primitives); ctx->d_primitives = nullptr; }
+    if (ctx->d_normal_mats) { cudaFree(ctx->d_normal_mats); ctx->d_normal_mats = nullptr; }
     ctx->n_vertices = n_vertices; ctx->n_indices = n_indices; ctx->n_primitives = n_primitives;
     // validate index ranges on the host: an out-of-range index would read outside the vertex buffer on the device
     const Primitive *prims = (const Primitive *)primitives;
@@ -161,6 +166,25 @@ int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_verti
     if (n_primitives) {
         VHR_CUDA_CHECK(cudaMalloc(&ctx->d_primitives, (size_t)n_primitives * sizeof(Primitive)));
         VHR_CUDA_CHECK(cudaMemcpyAsync(ctx->d_primitives, primitives, (size_t)n_primitives * sizeof(Primitive), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n_primitives) {
+        // normal_matrix = glm::inverseTranspose(mat3(transform)) (hybrid_render_path.cpp:45) = cofactor(M) / det(M),
+        // evaluated in double like the oracle's G-buffer scaffolding, stored column-major
+        std::vector<float> nm((size_t)n_primitives * 9);
+        for (uint32_t g = 0; g < n_primitives; ++g) {
+            const float *m = prims[g].transform;
+            double a00 = m[0], a10 = m[1], a20 = m[2], a01 = m[4], a11 = m[5], a21 = m[6], a02 = m[8], a12 = m[9], a22 = m[10];
+            double c00 = a11 * a22 - a21 * a12, c01 = -(a10 * a22 - a20 * a12), c02 = a10 * a21 - a20 * a11;
+            double c10 = -(a01 * a22 - a21 * a02), c11 = a00 * a22 - a20 * a02, c12 = -(a00 * a21 - a20 * a01);
+            double c20 = a01 * a12 - a11 * a02, c21 = -(a00 * a12 - a10 * a02), c22 = a00 * a11 - a10 * a01;
+            double det = a00 * c00 + a01 * c01 + a02 * c02;
+            float *o = &nm[(size_t)g * 9];
+            o[0] = (float)(c00 / det); o[1] = (float)(c10 / det); o[2] = (float)(c20 / det);
+            o[3] = (float)(c01 / det); o[4] = (float)(c11 / det); o[5] = (float)(c21 / det);
+            o[6] = (float)(c02 / det); o[7] = (float)(c12 / det); o[8] = (float)(c22 / det);
+        }
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_normal_mats, nm.size() * sizeof(float)));
+        VHR_CUDA_CHECK(cudaMemcpy(ctx->d_normal_mats, nm.data(), nm.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     int rc = build_bvh(ctx);
     if (rc) return rc;
@@ -378,6 +402,17 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
         case VHR_OPT_ATROUS_VARIANT:
             if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
+        case VHR_OPT_DEBUG_REFLECTION_T:
+            ctx->opt.debug_refl_t = value != 0;
+            if (ctx->opt.debug_refl_t && !ctx->d_refl_t) {
+                VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+                VHR_CUDA_CHECK(cudaMalloc(&ctx->d_refl_t, (size_t)ctx->width * ctx->height * sizeof(float)));
+            } else if (!ctx->opt.debug_refl_t && ctx->d_refl_t) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(ctx->d_refl_t);
+                ctx->d_refl_t = nullptr;
+            }
+            return VHR_OK;
     }
     return fail(VHR_ERR_INVALID, "unknown option %d", option);
 }
@@ -393,8 +428,19 @@ int64_t vhr_get_option(vhr_context *ctx, int option) {
         case VHR_OPT_ROW_END: return ctx->opt.row_end;
         case VHR_OPT_SVGF_FUSED: return ctx->opt.svgf_fused;
         case VHR_OPT_ATROUS_VARIANT: return ctx->opt.atrous_variant;
+        case VHR_OPT_DEBUG_REFLECTION_T: return ctx->opt.debug_refl_t;
     }
     return -1;
+}
+
+int vhr_debug_download_reflection_t(vhr_context *ctx, float *host, size_t bytes) {
+    if (!ctx || !host) return fail(VHR_ERR_INVALID, "NULL argument");
+    if (!ctx->d_refl_t) return fail(VHR_ERR_STATE, "VHR_OPT_DEBUG_REFLECTION_T is not enabled");
+    size_t need = (size_t)ctx->width * ctx->height * sizeof(float);
+    if (bytes != need) return fail(VHR_ERR_INVALID, "reflection-t image is %zu bytes, got %zu", need, bytes);
+    VHR_CUDA_CHECK(cudaMemcpyAsync(host, ctx->d_refl_t, need, cudaMemcpyDeviceToHost, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VHR_OK;
 }
 
 int vhr_get_bvh_stats(vhr_context *ctx, vhr_bvh_stats *out) {

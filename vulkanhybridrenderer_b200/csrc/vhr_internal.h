@@ -51,6 +51,7 @@ struct Options {
     int row_end = -1;            // -1 = image height
     int svgf_fused = 0;
     int atrous_variant = 1;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel
+    int debug_refl_t = 0;        // 1: the ray pass also writes the reflection ray's hit distance (tests)
 };
 
 }  // namespace vhr
@@ -71,6 +72,8 @@ struct vhr_context {
     uint32_t *d_indices = nullptr;
     vhr::Primitive *d_primitives = nullptr;
     uint32_t n_vertices = 0, n_indices = 0, n_primitives = 0;
+    float *d_normal_mats = nullptr;                // 9 floats per primitive: inverseTranspose(mat3(transform)), column-major
+    float *d_refl_t = nullptr;                     // optional debug image: reflection-ray hit distance per pixel
     vhr::Bvh bvh;
     vhr::Options opt;
     uint64_t launches = 0;
