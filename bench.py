@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native ray-traced lighting + SVGF chain.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one frame of the hybrid render path's hot chain on synthetic input:
+    Raytrace Pass (shadow 1 spp + AO 1 spp per non-sky pixel)  ->  SVGF Denoise Pass (temporal + variance + 5 a-trous
+    iterations, the reference's blits and ping-pong), 1920x1080, ~3M-triangle procedural scene (BASELINE.json north_star
+    target configuration). The G-buffer (depth / normals+ids / motion) is an INPUT of the path.
+
+metric  : shadow+AO Mrays/s over the whole frame (unique rays / frame time; the SVGF ms/frame and the ray pass' own
+          Mrays/s ride along as extra keys). N > 1: every rank renders its own view of the replicated scene (BASELINE
+          config 5 style, no data-path collective) => weak scaling; value = rays of all ranks / max-over-ranks time.
+value   : inputs resident in HBM, CUDA-event timed.      e2e: same frames through the C-ABI with HOST G-buffers in
+          pinned memory (H2D inside the timed region) and the denoised + raw shadow/AO images read back (D2H).
+--impl reference : the CPU restatement of the reference shaders (oracle/, OpenMP on all host cores) on a bounded
+          row-band sample of the same frame. The reference itself (Win32 + Vulkan + GLSL) cannot run here.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (width, height, triangles, ao_spp, reflections)
+    "hybrid_frame_1080p_3Mtri": (1920, 1080, 3_000_000, 1, 0),       # north_star target (default)
+    "shadows_1080p_260ktri": (1920, 1080, 260_000, 0, 0),            # BASELINE config 2
+    "ao4_temporal_1080p_1Mtri": (1920, 1080, 1_000_000, 4, 0),       # BASELINE config 3
+    "full_frame_4k_3Mtri": (3840, 2160, 3_000_000, 2, 1),            # BASELINE config 4 on one GPU (reference's 2 spp + reflections)
+    "tiny": (320, 184, 20_000, 1, 0),                                # CPU-sized self-test of this script
+}
+SCENE_SEED = 3
+LIGHT_DIR = (-0.3, -1.0, 0.2)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_scene(wl, view=0):
+    from vulkanhybridrenderer_b200 import camera, scenes
+    W, H, tris, _, _ = WORKLOADS[wl]
+    sc = scenes.sponza_like(tris, seed=SCENE_SEED, width=W, height=H)
+    sc.light = camera.directional_light(LIGHT_DIR)
+    cam = sc.camera
+    # two camera poses the bench oscillates between (non-trivial reprojection every frame); per-rank view offset
+    base = cam.position + np.array([0.9 * view, 0.0, 0.0])
+    poses = [(base, cam.yaw + 0.01 * view, cam.pitch), (base + np.array([0.05, 0.0, 0.01]), cam.yaw + 0.01 * view + 0.002, cam.pitch)]
+    return sc, poses
+
+
+class ClockSampler:
+    """nvidia-smi style clock / throttle-reason samples taken DURING the timed region (pynvml, 10 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement on a bounded row band (cpu_baseline of the default run and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuArm:
+    def __init__(self, wl, band_rows):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_lib as O
+        from vulkanhybridrenderer_b200 import camera
+        self.O = O
+        self.W, self.H, _, self.ao_spp, self.refl = WORKLOADS[wl]
+        self.sc, self.poses = make_scene(wl)
+        t0 = time.time()
+        self.osc = O.OracleScene(self.sc)
+        self.bvh_s = time.time() - t0
+        self.seq = camera.FrameSequencer(self.W, self.H, self.sc.light)
+        self.rows = min(band_rows, self.H)
+        self.y0 = (self.H - self.rows) // 2
+        self.state = O.SvgfState(self.W, self.rows)
+        self.cores = os.cpu_count()
+        self.g = None
+        self.k = 0
+
+    def prepare(self):
+        """G-buffer of the band for both camera poses (CPU primary rays; set-up, untimed)."""
+        cam = self.sc.camera
+        self.frames = []
+        for pose in (self.poses[1], self.poses[0], self.poses[1]):
+            cam.set_pose(*pose)
+            pfd = self.seq.next(cam)
+            self.frames.append((pfd, self.osc.gbuffer(pfd, self.W, self.H)))
+        self.frames = self.frames[1:]
+
+    def step(self):
+        """One bounded sample: raygen on rows [y0, y0+rows) + the SVGF pass on that band. Returns (seconds, rays)."""
+        pfd, g = self.frames[self.k & 1]
+        pfd = pfd.copy()
+        pfd["frame_index"] = 3 + self.k
+        self.k += 1
+        y0, y1 = self.y0, self.y0 + self.rows
+        flags = 1 | (2 if self.ao_spp else 0) | (4 if self.refl else 0)
+        t0 = time.perf_counter()
+        out = self.osc.raygen(pfd, g["depth"], g["normals"], ao_spp=max(self.ao_spp, 1), flags=flags, rows=(y0, y1))
+        t1 = time.perf_counter()
+        band_pfd = pfd.copy()
+        band_pfd["display_size"] = (self.W, self.rows)
+        band_pfd["display_size_inverse"] = (np.float32(1) / np.float32(self.W), np.float32(1) / np.float32(self.rows))
+        self.state.run(band_pfd, np.ascontiguousarray(g["normals"][y0:y1]), np.ascontiguousarray(g["motion"][y0:y1]),
+                       np.ascontiguousarray(out["shadow_ao"][y0:y1]), want_iters=False)
+        t2 = time.perf_counter()
+        nonsky = int((g["depth"][y0:y1] > 0).sum())
+        rays = nonsky * (1 + self.ao_spp + self.refl)
+        return t2 - t0, rays, t1 - t0, t2 - t1
+
+    def sample_desc(self):
+        return (f"rows [{self.y0},{self.y0 + self.rows}) of the {self.W}x{self.H} frame: oracle raygen (shadow 1 + AO {self.ao_spp} spp"
+                f"{' + reflection' if self.refl else ''}) + oracle SVGF pass on that band, OpenMP {self.cores} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm(args.workload, args.cpu_rows)
+    arm.prepare()
+    for _ in range(args.warmup):
+        arm.step()
+    tot_s, tot_rays, rt_s, svgf_s = 0.0, 0, 0.0, 0.0
+    for _ in range(args.steps):
+        s, r, a, b = arm.step()
+        tot_s += s; tot_rays += r; rt_s += a; svgf_s += b
+    val = tot_rays / tot_s / 1e6
+    W, H, tris, ao, refl = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.workload, arm.sc.num_triangles),
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": arm.cores, "kind": "port", "sample": arm.sample_desc(),
+                         "raygen_s_per_step": rt_s / args.steps, "svgf_s_per_step": svgf_s / args.steps,
+                         "svgf_ms_per_full_frame_extrapolated": svgf_s / args.steps * 1e3 * H / arm.rows},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the reference GLSL (oracle/); the reference itself needs Win32+Vulkan+glslang and cannot run here",
+    }
+    print(json.dumps(line))
+
+
+METRIC = "shadow+AO Mrays/s (frame = RT shadow+AO pass + SVGF temporal + 5 a-trous)"
+
+
+def config_dict(wl, n_tris):
+    W, H, _, ao, refl = WORKLOADS[wl]
+    return {"workload": wl, "width": W, "height": H, "triangles": int(n_tris), "shadow_spp": 1, "ao_spp": ao,
+            "reflections": bool(refl), "svgf_atrous_iterations": 5,
+            "l2_policy": "no explicit flush: the per-frame working set (BVH + triangle records + G-buffer + SVGF images) exceeds the 126 MB L2",
+            "camera": "two poses alternating every frame (non-zero motion vectors), frame_index increments"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vulkanhybridrenderer_b200 import camera, capi
+    from vulkanhybridrenderer_b200 import hybrid_path as HP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = args.workload
+    W, H, _, ao_spp, refl = WORKLOADS[wl]
+    sc, poses = make_scene(wl, view=rank)
+    stream = torch.cuda.Stream()
+    K, Wm = args.steps, args.warmup
+    peak, peak_src = load_peaks()
+
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(W, H, device=local, stream=stream.cuda_stream)
+        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+        st = ctx.bvh_stats()
+        ctx.set_option(capi.OPT_TRACE_SHADOWS, 1)
+        ctx.set_option(capi.OPT_TRACE_AO, 1 if ao_spp else 0)
+        ctx.set_option(capi.OPT_AO_SPP, max(ao_spp, 1))
+        ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
+        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2)
+        seq = camera.FrameSequencer(W, H, sc.light)
+        cam = sc.camera
+
+        # ---- set-up (untimed): the G-buffer producer pass renders both poses into the two resident image sets -------
+        pfds, host_g = [None, None], [None, None]
+        for s in (1, 0, 1):           # pose 1 first so that pose 0's "previous camera" is pose 1 and vice versa
+            cam.set_pose(*poses[s])
+            pfd = seq.next(cam)
+            ctx.update_per_frame_ubo(pfd)
+            g = path.gsets[s]
+            ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
+            ctx.gbuffer_pass(W, H)
+            pfds[s] = pfd
+        nonsky = []
+        for s in (0, 1):
+            g = path.gsets[s]
+            hg = {}
+            for key in (HP.N_DEPTH, HP.N_NORMALS, HP.N_MOTION):
+                _, w, h, f = ctx.image_info(g[key])
+                tb = HP.T.FORMAT_TEXEL_BYTES[f]
+                t = torch.empty(h * w * tb, dtype=torch.uint8, pin_memory=True)
+                ctx.image_download_into(g[key], t)
+                hg[key] = t
+            ctx.synchronize()
+            host_g[s] = hg
+            nonsky.append(int((hg[HP.N_DEPTH].view(torch.float32) > 0).sum()))
+        rays_per_frame = [n * (1 + ao_spp + refl) for n in nonsky]
+
+        frame_no = [0]
+
+        def step(instrument=True):
+            k = frame_no[0]
+            s = k & 1
+            pfd = pfds[s]
+            pfd["frame_index"] = 3 + k
+            frame_no[0] += 1
+            path.frame(pfd, gset=s)
+            return rays_per_frame[s]
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- value: inputs resident in HBM ----------------------------------------------------------------------------
+        path.timestamps = None
+        for _ in range(Wm):
+            step()
+        path.enable_timestamps(K)
+        l0 = ctx.kernel_launches
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        rays = 0
+        for _ in range(K):
+            rays += step()
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = ctx.kernel_launches - l0
+        pass_ms = path.pass_times_ms(K)            # [K, passes]
+        path.timestamps = None
+
+        # ---- e2e: host G-buffer -> H2D -> frame -> D2H of the denoised + raw shadow/AO images, every step ---------------
+        out_den = torch.empty(W * H * 8, dtype=torch.uint8, pin_memory=True)
+        out_rt = torch.empty(W * H * 4, dtype=torch.uint8, pin_memory=True)
+        h2d = sum(t.numel() for t in host_g[0].values())
+        d2h = out_den.numel() + out_rt.numel()
+
+        def step_e2e():
+            k = frame_no[0]
+            s = k & 1
+            g = path.gsets[s]
+            for key, t in host_g[s].items():
+                capi._check(capi.lib().vhr_image_upload(ctx._h, g[key].encode(), t.data_ptr(), t.numel()))
+            r = step()
+            ctx.image_download_into(HP.N_DENOISED, out_den)
+            ctx.image_download_into(HP.N_RT, out_rt)
+            ctx.synchronize()
+            return r
+
+        for _ in range(max(2, Wm // 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record(stream)
+        rays_e = 0
+        for _ in range(K):
+            rays_e += step_e2e()
+        ee1.record(stream)
+        barrier()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(ee0.elapsed_time(ee1), 0.0)
+        checksum = float(out_den.view(torch.float16)[::4097].float().nan_to_num().sum())
+
+    # ---- reduce over ranks: max time, summed rays ------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms, e2e_wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms, e2e_wall_ms = (float(x) for x in t.cpu())
+        r = torch.tensor([rays, rays_e, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays, rays_e, launches = (float(x) for x in r.cpu())
+
+    if rank == 0:
+        px = W * H
+        mean_pass = pass_ms.mean(axis=0)
+        labels = path.PASS_LABELS
+        pm = dict(zip(labels, (float(x) for x in mean_pass)))
+        frame_ms = ms_total / K
+        svgf_ms = sum(pm[k] for k in labels if k != "raytrace")
+        # per-kernel roofline (HBM): algorithmic bytes / launch = per-pixel bytes x pixels
+        kernels = []
+        def add(name, ms, bytes_, note=None):
+            ach = bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            kernels.append({"kernel": name, "ms": ms, "share": ms / frame_ms, "algorithmic_bytes": bytes_,
+                            "achieved_gbs": ach, "frac": ach / peak, **({"note": note} if note else {})})
+        add("raygen_kernel", pm["raytrace"], px * (HP.BYTES_RAYGEN_IO + (8 if refl else 0)),
+            "traversal-bound (software BVH, no RT cores): compulsory G-buffer in + mask out bytes only; see Mrays/s")
+        add("svgf_temporal_kernel", pm["svgf_temporal"], px * HP.BYTES_TEMPORAL)
+        at_ms = float(np.mean([pm[f"atrous{i}"] for i in (1, 2, 3, 4)]))
+        add("atrous_tiled_kernel (mean of iterations 1-4)", at_ms, px * HP.BYTES_ATROUS)
+        add("atrous iteration 0 + history blit", pm["atrous0"], px * (HP.BYTES_ATROUS + HP.BYTES_BLIT))
+        add("blits (prev-normals, denoised)", pm["blits"], px * 2 * HP.BYTES_BLIT)
+        dom = max(kernels[:3], key=lambda k: k["ms"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom["kernel"].split(" ")[0])
+        roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "ms_per_launch": dom["ms"],
+                    "share_of_step": dom["share"]}
+        svgf_bytes = px * (HP.BYTES_TEMPORAL + 5 * HP.BYTES_ATROUS + 3 * HP.BYTES_BLIT)
+        svgf_min_bytes = px * 148
+        line = {
+            "metric": METRIC, "value": rays / (ms_total * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(wl, sc.num_triangles),
+            "e2e": {"value": rays_e / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kernels,
+            "rt_pass": {"ms": pm["raytrace"], "mrays_s": (rays / K / world) / (pm["raytrace"] * 1e-3) / 1e6, "rays_per_frame": rays / K / world},
+            "svgf": {"ms_per_frame": svgf_ms, "reference_dataflow_bytes": svgf_bytes, "achieved_gbs": svgf_bytes / (svgf_ms * 1e-3) / 1e9,
+                     "frac_of_peak": svgf_bytes / (svgf_ms * 1e-3) / 1e9 / peak,
+                     "fused_minimum_bytes": svgf_min_bytes, "frac_of_peak_vs_fused_minimum": svgf_min_bytes / (svgf_ms * 1e-3) / 1e9 / peak},
+            "bvh": {"triangles": st.n_triangles, "wide_nodes": st.n_wide_nodes, "build_ms": st.build_ms, "sah_cost": st.sah_cost},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            arm = CpuArm(wl, args.cpu_rows)
+            arm.prepare()
+            arm.step()
+            t_s, t_r, n = 0.0, 0, 0
+            svgf_s = 0.0
+            while n < 3 or (t_s < 8.0 and n < 10):
+                s_, r_, _, b_ = arm.step()
+                t_s += s_; t_r += r_; svgf_s += b_; n += 1
+            line["cpu_baseline"] = {"value": t_r / t_s / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
+                                    "sample": arm.sample_desc() + f", {n} samples",
+                                    "svgf_ms_per_full_frame_extrapolated": svgf_s / n * 1e3 * H / arm.rows}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hybrid_frame_1080p_3Mtri", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-rows", type=int, default=64, help="rows of the frame the CPU arm renders per sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

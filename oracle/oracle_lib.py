@@ -11,7 +11,7 @@ import numpy as np
 
 from vulkanhybridrenderer_b200 import types as T
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in oracle/)
 _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 _SO = os.path.join(_ORACLE_DIR, "_build", "libvhr_oracle.so")
 _SRCS = ["oracle_common.h", "oracle_svgf.cpp", "oracle_rt.cpp", "Makefile"]

@@ -1,0 +1,144 @@
+"""Python mirror of the hot-path nodes of HybridRenderPath::RegisterPath, issued call by call through the C-ABI.
+
+Reference: /root/reference/src/render_paths/hybrid_render_path.cpp
+    :101-136  "Raytrace Pass"      (TraceRays, bindings 0 normals, 1 depth, 2 shadow/AO, 3 reflections)
+    :138-200  "SSAO Pass" + "SSAO Blur Pass"
+    :245-331  "SVGF Denoise Pass"  (five persistent storage images, temporal + 5 a-trous dispatches, three blits,
+                                    ping-pong swaps; "Denoised" = iteration 3's output)
+The C++ twin of this file (host/hybrid_render_path.cpp -> libvhr_host.so) is what a maintainer of the reference links;
+this one exists so tests and bench.py can drive exactly the same call sequence from Python. No CPU fallback anywhere:
+every call lands in libvhr_b200.so.
+"""
+import numpy as np
+
+from . import capi
+from . import types as T
+
+F4, F2 = T.VK_FORMAT_R16G16B16A16_SFLOAT, T.VK_FORMAT_R16G16_SFLOAT
+
+N_ALBEDO = "Albedo"
+N_NORMALS = "World Space Normals and Object IDs"
+N_MOTION = "Motion Vectors and Metallic Roughness"
+N_DEPTH = "Depth"
+N_RT = "Raytraced Shadows and Ambient Occlusion"
+N_REFL = "Raytraced Reflections"
+N_DENOISED = "Denoised Raytraced Shadows and Ambient Occlusion"
+N_SSAO_RAW = "Screen Space Ambient Occlusion Raw"
+N_SSAO = "Screen Space Ambient Occlusion"
+
+GBUFFER_FORMATS = {N_ALBEDO: T.VK_FORMAT_B8G8R8A8_UNORM, N_NORMALS: F4, N_MOTION: F4, N_DEPTH: T.VK_FORMAT_D32_SFLOAT}
+
+SHADER_SVGF = "hybrid_render_path/svgf.comp"
+SHADER_ATROUS = "hybrid_render_path/svgf_atrous_filter.comp"
+SHADER_SSAO = "hybrid_render_path/ssao.comp"
+SHADER_SSAO_BLUR = "hybrid_render_path/ssao_blur.comp"
+
+# per-pixel algorithmic bytes (SURVEY §8d / DESIGN.md): each distinct texel once
+BYTES_TEMPORAL = 52
+BYTES_ATROUS = 24
+BYTES_BLIT = 16
+BYTES_RAYGEN_IO = 12 + 4          # depth + normals in, RG16F out (reflections add 8)
+BYTES_SSAO = 20
+BYTES_SSAO_BLUR = 16
+
+
+def groups(n):
+    return n // 8 + (n % 8 != 0)       # hybrid_render_path.cpp:291-294
+
+
+class HybridRenderPath:
+    """Owns the images of the hot-path passes on one context and replays the reference's per-frame call sequence."""
+
+    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False):
+        self.ctx, self.W, self.H = ctx, width, height
+        self.gsets = []
+        for s in range(gbuffer_sets):
+            sfx = "" if s == 0 else f" [{s}]"
+            names = {k: k + sfx for k in GBUFFER_FORMATS}
+            for k, n in names.items():
+                ctx.actualize_image(n, GBUFFER_FORMATS[k])
+            self.gsets.append(names)
+        ctx.actualize_image(N_RT, F2)
+        ctx.actualize_image(N_REFL, F4)
+        ctx.actualize_image(N_DENOISED, F4)
+        if ssao:
+            ctx.actualize_image(N_SSAO_RAW, F4)
+            ctx.actualize_image(N_SSAO, F4)
+        # hybrid_render_path.cpp:247-261
+        pc = np.zeros((), T.SVGFPushConstants)
+        pc["integrated_shadow_and_ao"] = (ctx.upload_new_storage_image(width, height, F4),
+                                          ctx.upload_new_storage_image(width, height, F4))
+        pc["prev_frame_normals_and_object_ids"] = ctx.upload_new_storage_image(width, height, F4)
+        pc["shadow_and_ao_history"] = ctx.upload_new_storage_image(width, height, F4)
+        pc["shadow_and_ao_moments_history"] = ctx.upload_new_storage_image(width, height, F2)
+        self.pc = pc
+        self.ssao_radius = np.array(0.75, np.float32)
+        self.timestamps = None
+
+    # ---- optional per-pass timestamps (render_graph.cpp:167-182) --------------------------------------------------
+    PASS_LABELS = ("raytrace", "svgf_temporal", "atrous0", "atrous1", "atrous2", "atrous3", "atrous4", "blits")
+
+    def enable_timestamps(self, frames):
+        """Query pool with len(PASS_LABELS)+1 timestamps per frame for `frames` frames."""
+        self._ts_per_frame = len(self.PASS_LABELS) + 1
+        capi._check(capi.lib().vhr_create_query_pool(self.ctx._h, self._ts_per_frame * frames))
+        self.timestamps = 0
+
+    def _stamp(self):
+        if self.timestamps is not None:
+            capi._check(capi.lib().vhr_write_timestamp(self.ctx._h, self.timestamps))
+            self.timestamps += 1
+
+    def pass_times_ms(self, frames):
+        """Per-pass device time (ms) of each recorded frame: array [frames, len(PASS_LABELS)]."""
+        import ctypes as C
+        out = np.zeros((frames, len(self.PASS_LABELS)))
+        ms = C.c_double()
+        for f in range(frames):
+            b = f * self._ts_per_frame
+            for k in range(len(self.PASS_LABELS)):
+                capi._check(capi.lib().vhr_get_query_elapsed_ms(self.ctx._h, b + k, b + k + 1, C.byref(ms)))
+                out[f, k] = ms.value
+        return out
+
+    # ---- passes ---------------------------------------------------------------------------------------------------
+    def raytrace_pass(self, gset=0):
+        g = self.gsets[gset]
+        self.ctx.bind_pass_images([g[N_NORMALS], g[N_DEPTH], N_RT, N_REFL])
+        self.ctx.trace_rays(self.W, self.H)
+
+    def ssao_passes(self, gset=0):
+        g = self.gsets[gset]
+        gx, gy = groups(self.W), groups(self.H)
+        self.ctx.bind_pass_images([g[N_NORMALS], g[N_DEPTH], N_SSAO_RAW])     # hybrid_render_path.cpp:143-150
+        # the reference dispatches ssao.comp WITHOUT push constants (Q15) => radius 0.75 unless the caller set one
+        self.ctx.dispatch(SHADER_SSAO, gx, gy, 1, self.ssao_radius)
+        self.ctx.bind_pass_images([N_SSAO_RAW, N_SSAO])
+        self.ctx.dispatch(SHADER_SSAO_BLUR, gx, gy, 1, self.ssao_radius)
+
+    def svgf_denoise_pass(self, gset=0):
+        """hybrid_render_path.cpp:288-330, statement by statement."""
+        ctx, pc, g = self.ctx, self.pc, self.gsets[gset]
+        gx, gy = groups(self.W), groups(self.H)
+        ctx.bind_pass_images([g[N_NORMALS], g[N_MOTION], g[N_DEPTH], N_RT, N_DENOISED])
+        ctx.dispatch(SHADER_SVGF, gx, gy, 1, pc)
+        self._stamp()
+        for i in range(5):
+            pc["atrous_step"] = 1 << i
+            ctx.dispatch(SHADER_ATROUS, gx, gy, 1, pc)
+            if i == 0:
+                ctx.blit_storage_to_storage(int(pc["integrated_shadow_and_ao"][1]), int(pc["shadow_and_ao_history"]))
+            pc["integrated_shadow_and_ao"] = pc["integrated_shadow_and_ao"][::-1].copy()
+            self._stamp()
+        ctx.blit_transient_to_storage(g[N_NORMALS], int(pc["prev_frame_normals_and_object_ids"]))
+        ctx.blit_storage_to_transient(int(pc["integrated_shadow_and_ao"][1]), N_DENOISED)
+        pc["integrated_shadow_and_ao"] = pc["integrated_shadow_and_ao"][::-1].copy()
+        self._stamp()
+
+    def frame(self, pfd, gset=0):
+        """Raytrace Pass -> SVGF Denoise Pass for one frame whose G-buffer already sits in image set `gset`."""
+        self.ctx.update_per_frame_ubo(pfd)
+        self._stamp()
+        self.raytrace_pass(gset)
+        self._stamp()
+        self.svgf_denoise_pass(gset)
