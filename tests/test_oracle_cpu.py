@@ -1,0 +1,325 @@
+"""CPU tests of the oracle (test infrastructure) — run with -m "not gpu".
+
+The reference ships no tests or golden vectors for this path (parity unpinned). What pins the C oracle
+here is (1) the known-answer vectors of SURVEY Appendix A.3, derived by hand from common.glsl:47-68; (2) a second,
+independent restatement of the GLSL written in numpy in THIS file, directly from the shader text
+(svgf_atrous_filter.comp:17-103, svgf.comp:16-145, ssao_blur.comp:11-26, common.glsl:29-93), evaluated on small
+images; (3) the committed fixtures under tests/golden/ (tools/make_golden.py) which freeze today's oracle outputs so a
+later edit of the oracle cannot drift silently.
+"""
+import numpy as np
+import pytest
+
+import helpers as Hh
+import oracle_lib as O
+from vulkanhybridrenderer_b200 import camera, scenes
+from vulkanhybridrenderer_b200 import types as T
+
+f32 = np.float32
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# common.glsl
+# ---------------------------------------------------------------------------------------------------------------
+def py_seed_thread(seed):          # common.glsl:47-56
+    seed &= 0xFFFFFFFF
+    seed = (seed ^ 61) ^ (seed >> 16)
+    seed = (seed * 9) & 0xFFFFFFFF
+    seed = seed ^ (seed >> 4)
+    seed = (seed * 0x27d4eb2d) & 0xFFFFFFFF
+    seed = seed ^ (seed >> 15)
+    return seed
+
+
+def py_random(state):              # common.glsl:58-64
+    state ^= (state << 13) & 0xFFFFFFFF
+    state ^= state >> 17
+    state ^= (state << 5) & 0xFFFFFFFF
+    return state
+
+
+def py_random01(state):            # common.glsl:66-68
+    state = py_random(state)
+    return state, np.array(0x3f800000 | (state >> 9), np.uint32).view(np.float32) - f32(1.0)
+
+
+KATS = {
+    0: (0xc0a9496a, [0.847836018, 0.639855146, 0.355129719, 0.101476431]),
+    1: (0x27922c9d, [0.133637309, 0.616365790, 0.992120028, 0.394519806]),
+    16221: (0x6fff9630, [0.226605177, 0.090955853, 0.430844665, 0.511248469]),
+}
+
+
+@pytest.mark.parametrize("seed", sorted(KATS))
+def test_rng_known_answers(seed):
+    import ctypes as C
+    want_state, want = KATS[seed]
+    assert py_seed_thread(seed) == want_state
+    assert O.lib().vo_seed_thread(seed) == want_state
+    st_py = want_state
+    st_c = C.c_uint32(want_state)
+    for w in want:
+        st_py, r = py_random01(st_py)
+        rc = O.lib().vo_random01(C.byref(st_c))
+        assert abs(float(r) - w) < 5e-9 and float(r) == rc
+        assert st_c.value == st_py
+
+
+def test_rng_pixel_seed_rule():
+    # raygen.rgen:17 (Q4): seed = (y * LaunchSize.y + x) * frame_index — x=7, y=5, H=1080, frame 3 => 16221
+    assert (5 * 1080 + 7) * 3 == 16221
+
+
+def test_half_conversion_matches_numpy_rte():
+    allh = np.arange(65536, dtype=np.uint16)
+    vals = allh.view(np.float16).astype(np.float32)
+    for h in allh[::97]:
+        got = O.lib().vo_h2f(int(h))
+        want = float(vals[h])
+        assert (np.isnan(got) and np.isnan(want)) or got == want
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.standard_normal(4000).astype(f32) * f32(10), rng.uniform(-7e4, 7e4, 500).astype(f32),
+                         np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e-8, 6e-8, 2.98e-8, 6.1e-5, np.inf, -np.inf], f32),
+                         (rng.uniform(1, 2, 500).astype(f32))])
+    for x in xs:
+        got = O.lib().vo_f2h(float(x))
+        want = int(np.array(x, f32).astype(np.float16).view(np.uint16))
+        assert got == want, (x, hex(got), hex(want))
+
+
+def test_sampling_helpers():
+    rng = np.random.default_rng(1)
+    out3 = np.zeros(3, f32)
+    out9 = np.zeros(9, f32)
+    for _ in range(200):
+        u0, u1 = f32(rng.uniform()), f32(rng.uniform())
+        # common.glsl:29-34
+        O.lib().vo_uniform_sample_cone(float(u0), float(u1), 0.999995, O._p(out3))
+        ct = (f32(1) - u0) + u0 * f32(0.999995)
+        st = np.sqrt(f32(1) - ct * ct)
+        phi = u1 * f32(2 * np.pi)
+        np.testing.assert_allclose(out3, [np.cos(phi) * st, np.sin(phi) * st, ct], rtol=0, atol=2e-7)
+        # common.glsl:37-42
+        O.lib().vo_cosine_hemisphere(float(u0), float(u1), O._p(out3))
+        r = np.sqrt(u0)
+        np.testing.assert_allclose(out3, [r * np.cos(f32(2 * np.pi) * u1), r * np.sin(f32(2 * np.pi) * u1), np.sqrt(f32(1) - u0)], atol=2e-7)
+        assert abs(np.linalg.norm(out3) - 1) < 1e-6
+        # common.glsl:80-93: columns (b1, b2, n) orthonormal
+        n = rng.standard_normal(3); n = (n / np.linalg.norm(n)).astype(f32)
+        O.lib().vo_onb(O._p(n), O._p(out9))
+        M = out9.reshape(3, 3)          # column-major: M[c] = column c
+        np.testing.assert_allclose(M[2], n, atol=0)
+        np.testing.assert_allclose(M @ M.T, np.eye(3), atol=5e-5)   # Frisvad amplifies rounding as n.z -> -1
+    n = np.array([0, 0, -1], f32)       # the z < -0.9999999 branch
+    O.lib().vo_onb(O._p(n), O._p(out9))
+    np.testing.assert_array_equal(out9.reshape(3, 3), [[0, -1, 0], [-1, 0, 0], [0, 0, -1]])
+
+
+def test_struct_sizes():
+    # glsl_common.h sizes measured with g++ on the reference header
+    want = {0: 584, 1: 56, 2: 44, 3: 120, 4: 112}   # PerFrameData, Vertex, Material, Primitive, DirectionalLight
+    for k, v in want.items():
+        assert O.lib().vo_sizeof(k) == v
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent numpy restatement of svgf_atrous_filter.comp (vectorised over the image, fp32)
+# ---------------------------------------------------------------------------------------------------------------
+def np_atrous(normals_h, integ_h, step):
+    H, W = normals_h.shape[:2]
+    n = normals_h.astype(f32)
+    I = integ_h.astype(f32)
+    ids = np.trunc(n[..., 3]).astype(np.int32)
+    yy, xx = np.mgrid[0:H, 0:W]
+
+    def shifted(a, dx, dy, fill=0):
+        out = np.full_like(a, fill)
+        ys, xs = yy + dy, xx + dx
+        ok = (ys >= 0) & (ys < H) & (xs >= 0) & (xs < W)
+        out[ok] = a[ys[ok], xs[ok]]
+        return out, ok
+
+    gauss = np.array([[1 / 16, 1 / 8, 1 / 16], [1 / 8, 1 / 4, 1 / 8], [1 / 16, 1 / 8, 1 / 16]], f32)
+    var = np.zeros((H, W, 2), f32)
+    for y in (-1, 0, 1):
+        for x in (-1, 0, 1):
+            q, ok = shifted(I[..., 2:4], x, y)
+            var = var + np.where(ok[..., None], gauss[y + 1, x + 1] * q, f32(0)).astype(f32)
+    aw = np.array([1 / 16, 1 / 4, 3 / 8, 1 / 4, 1 / 16], f32)
+    sum_w = np.ones((H, W, 2), f32)
+    acc = I.copy()
+    den = f32(4.0) * np.sqrt(var) + f32(1e-6)
+    for y in range(-2, 3):
+        for x in range(-2, 3):
+            if x == 0 and y == 0:
+                continue
+            q, ok = shifted(I, x * step, y * step)
+            nq, _ = shifted(n, x * step, y * step)
+            idq, _ = shifted(ids, x * step, y * step, fill=-12345)
+            kern = f32(aw[y + 2] * aw[x + 2])
+            d = (n[..., 0] * nq[..., 0] + n[..., 1] * nq[..., 1]) + n[..., 2] * nq[..., 2]
+            with np.errstate(all="ignore"):
+                wn = np.where(d > 0, np.power(np.maximum(d, f32(0)), f32(128.0)), f32(0)).astype(f32)   # Q10
+            wid = (ids == idq).astype(f32)
+            w0 = (kern * wn * wid).astype(f32)
+            e = np.abs(I[..., 0:2] - q[..., 0:2]) / den
+            w = (w0[..., None] * np.exp(-e)).astype(f32)
+            w = np.where(ok[..., None], w, f32(0))
+            sum_w = sum_w + w
+            acc = acc + np.concatenate([w, w * w], -1) * q
+    out = acc / np.concatenate([sum_w, sum_w * sum_w], -1)
+    return out.astype(np.float16)
+
+
+@pytest.mark.parametrize("step", [1, 2, 4, 16])
+def test_atrous_oracle_vs_numpy_restatement(step):
+    W, H = 96, 56
+    _, _, frames = Hh.scene_and_gbuffer(W, H, tris=6000)
+    pfd, g = frames[0]
+    integ = Hh.noise_integrated(H, W, seed=7)
+    ref = O.svgf_atrous(pfd, g["normals"], integ, step)
+    mine = np_atrous(g["normals"], integ, step)
+    s = Hh.compare(mine, ref)
+    # two fp32 evaluations with different summation order / libm: agreement to ~1 half ulp
+    assert s["nan_mismatch"] == 0 and s["max_abs"] <= 1e-3 and s["exact"] > 0.98, s
+
+
+def test_atrous_properties():
+    W, H = 64, 40
+    _, _, frames = Hh.scene_and_gbuffer(W, H, tris=6000)
+    pfd, g = frames[0]
+    # constant image with zero variance stays constant wherever a normal exists; sky pixels (n = 0) pass through (Q10)
+    integ = np.zeros((H, W, 4), np.float16)
+    integ[..., 0] = 0.5; integ[..., 1] = 0.25
+    out = O.svgf_atrous(pfd, g["normals"], integ, 2)
+    np.testing.assert_array_equal(out[..., :2], integ[..., :2])
+    # a pixel whose object id differs from every neighbour is returned unchanged (centre weight 1, others 0)
+    normals = g["normals"].copy()
+    normals[..., 3] = np.arange(W * H, dtype=np.float32).reshape(H, W) % 2048   # unique-ish ids within any 5x5 window
+    noisy = Hh.noise_integrated(H, W, seed=9)
+    out = O.svgf_atrous(pfd, normals, noisy, 1)
+    np.testing.assert_array_equal(out, noisy)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent restatement of svgf.comp for the zero-motion case + structural properties of the pass
+# ---------------------------------------------------------------------------------------------------------------
+def test_temporal_zero_history_passthrough_and_q2():
+    W, H = 48, 32
+    _, _, frames = Hh.scene_and_gbuffer(W, H, tris=6000)
+    pfd, g = frames[0]
+    rng = np.random.default_rng(3)
+    rt = np.stack([rng.integers(0, 2, (H, W)), rng.integers(0, 3, (H, W)) * 0.5], -1).astype(np.float16)
+    zero4 = np.zeros((H, W, 4), np.float16)
+    zero2 = np.zeros((H, W, 2), np.float16)
+    # frame 0: zero prev-normals reject every reprojection (Q14) => pass-through, variance 0, moments (l, l^2)
+    integ, mom = O.svgf_temporal(pfd, g["normals"], g["motion"], rt, zero4, zero4, zero2)
+    np.testing.assert_array_equal(integ[..., :2], rt)
+    assert not integ[..., 2:].any()
+    np.testing.assert_array_equal(mom[..., 0], rt[..., 0])
+    np.testing.assert_array_equal(mom[..., 1], (rt[..., 0].astype(f32) ** 2).astype(np.float16))
+    # frame 1, zero motion, history = constant c, prev normals = current: interior pixels of large flat regions get
+    # mix(c, cur, 0.2); AO variance follows Q2: moments (0.2a, 0.8 + 0.2 a^2)
+    motion = np.zeros((H, W, 4), np.float16)
+    hist = np.zeros((H, W, 4), np.float16); hist[..., 0] = 0.5; hist[..., 1] = 0.25
+    integ, mom = O.svgf_temporal(pfd, g["normals"], motion, rt, g["normals"], hist, mom)
+    n = g["normals"].astype(f32)
+    ids = n[..., 3]
+    same = np.ones((H, W), bool)
+    for dy in (0, 1):
+        for dx in (0, 1):
+            sh = np.roll(np.roll(ids, -dy, 0), -dx, 1)
+            nn = np.roll(np.roll(n[..., :3], -dy, 0), -dx, 1)
+            same &= (sh == ids) & (np.sum(nn * n[..., :3], -1) >= np.cos(np.pi / 4))
+    same[-1, :] = False; same[:, -1] = False
+    same &= np.linalg.norm(n[..., :3], axis=-1) > 0.5
+    assert same.sum() > 100
+    cur = rt.astype(f32)
+    want_s = (f32(0.5) * f32(0.8) + cur[..., 0] * f32(0.2)).astype(np.float16)
+    want_a = (f32(0.25) * f32(0.8) + cur[..., 1] * f32(0.2)).astype(np.float16)
+    assert np.max(np.abs(integ[..., 0][same].astype(f32) - want_s[same].astype(f32))) <= 5e-4
+    assert np.max(np.abs(integ[..., 1][same].astype(f32) - want_a[same].astype(f32))) <= 5e-4
+    a = cur[..., 1]
+    am0, am1 = f32(0.2) * a, f32(0.8) + f32(0.2) * a * a
+    want_var_a = np.maximum(0, am1 - am0 * am0)
+    assert np.max(np.abs(integ[..., 3][same].astype(f32) - want_var_a[same])) <= 1e-3
+
+
+def test_svgf_pass_bookkeeping_q1():
+    """Denoised == output of iteration index 3; history == iteration 0 output; prev normals == normals (hybrid_render_path.cpp:299-328)."""
+    W, H = 64, 40
+    _, _, frames = Hh.scene_and_gbuffer(W, H, tris=6000)
+    st = O.SvgfState(W, H)
+    rng = np.random.default_rng(4)
+    for f in range(2):
+        pfd, g = frames[f]
+        rt = np.stack([rng.integers(0, 2, (H, W)), rng.integers(0, 3, (H, W)) * 0.5], -1).astype(np.float16)
+        den, iters, temporal = st.run(pfd, g["normals"], g["motion"], rt)
+        np.testing.assert_array_equal(den, iters[3])
+        # the pass is the composition of the two kernels
+        it = temporal
+        for i in range(5):
+            it = O.svgf_atrous(pfd, g["normals"], it, 1 << i)
+            np.testing.assert_array_equal(it, iters[i])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SSAO blur restatement (ssao_blur.comp:11-26) and ray oracle vs brute force
+# ---------------------------------------------------------------------------------------------------------------
+def test_ssao_blur_vs_numpy():
+    W, H = 40, 30
+    rng = np.random.default_rng(5)
+    raw = np.repeat(rng.uniform(0, 1, (H, W, 1)).astype(np.float16), 4, -1)
+    pfd = np.zeros((), T.PerFrameData)
+    pfd["display_size"] = (W, H)
+    got = O.ssao_blur(pfd, raw).astype(f32)
+    x = raw[..., 0].astype(np.float64)
+    pad = np.zeros((H + 12, W + 12)); pad[6:-6, 6:-6] = x
+    want = sum(pad[6 + dy:6 + dy + H, 6 + dx:6 + dx + W] for dy in range(-6, 7) for dx in range(-6, 7)) / 169.0
+    assert np.max(np.abs(got[..., 0] - want)) <= 1e-3
+    for c in range(1, 4):
+        np.testing.assert_array_equal(got[..., c], got[..., 0])
+
+
+def test_ray_oracle_vs_brute_force():
+    sc = scenes.tiny_scene()
+    osc = O.OracleScene(sc)
+    tris = Hh.world_triangles(sc)
+    assert osc.num_triangles == len(tris) == sc.num_triangles
+    rng = np.random.default_rng(6)
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    n_hit = 0
+    for _ in range(300):
+        o = rng.uniform(lo - 0.5, hi + 0.5).astype(f32)
+        d = rng.standard_normal(3); d = (d / np.linalg.norm(d)).astype(f32)
+        tmax = float(rng.choice([5.0, 1e4]))
+        bf_any, bf_t, margin = Hh.brute_force_hits(tris, o, d, 0.01, tmax)
+        if margin < 1e-6:
+            continue    # grazing: either answer is legitimate
+        assert osc.trace_any(o, d, 0.01, tmax) == bf_any
+        cl = osc.trace_closest(o, d, 0.01, tmax)
+        assert (cl is not None) == bf_any
+        if cl is not None:
+            n_hit += 1
+            assert abs(cl[0][0] - bf_t) <= 1e-5 * max(1.0, bf_t)
+    assert n_hit > 30
+
+
+def test_raygen_sky_and_band_consistency():
+    W, H = 64, 48
+    sc = scenes.tiny_scene(width=W, height=H)
+    osc = O.OracleScene(sc)
+    seq = camera.FrameSequencer(W, H, sc.light)
+    pfd = seq.next(sc.camera)
+    g = osc.gbuffer(pfd, W, H)
+    full = osc.raygen(pfd, g["depth"], g["normals"])
+    sky = g["depth"] == 0
+    assert sky.any() and (~sky).any()
+    assert np.all(full["shadow_ao"][sky].astype(f32) == 1.0)          # raygen.rgen:20-24
+    assert not full["reflections"][sky].any()
+    assert full["rays"] == int((~sky).sum()) * 4                        # 1 shadow + 2 AO + 1 reflection (Q3)
+    # row bands stitch to the full frame (the multi-GPU split relies on this)
+    top = osc.raygen(pfd, g["depth"], g["normals"], rows=(0, 20))
+    bot = osc.raygen(pfd, g["depth"], g["normals"], rows=(20, H))
+    np.testing.assert_array_equal(np.concatenate([top["shadow_ao"][:20], bot["shadow_ao"][20:]]), full["shadow_ao"])
+    np.testing.assert_array_equal(np.concatenate([top["reflections"][:20], bot["reflections"][20:]]), full["reflections"])

@@ -36,6 +36,13 @@ struct RayPre {
     uint32_t neg;         // bit a set: d[a] < 0
 };
 
+// MUFU.RCP (1 ulp): traversal set-up and hit distances are compared with an exact oracle under a tolerance, so the
+// IEEE division's slow path (a CALL per use) buys nothing here.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float comp(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 __device__ __forceinline__ float comp4(float4 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 
@@ -47,7 +54,7 @@ __device__ __forceinline__ RayPre prepare(const Ray &r) {
     float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
     float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
     float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
-    p.idir = make_float3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+    p.idir = make_float3(rcp_fast(dx), rcp_fast(dy), rcp_fast(dz));
     // sign of the *adjusted* component: -0.0 becomes -tiny, so near/far must swap for it too
     p.neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
@@ -56,9 +63,9 @@ __device__ __forceinline__ RayPre prepare(const Ray &r) {
     p.ky = p.kx + 1; if (p.ky == 3) p.ky = 0;
     float dkz = comp(d, p.kz);
     if (dkz < 0.0f) { int t = p.kx; p.kx = p.ky; p.ky = t; }
-    p.Sx = comp(d, p.kx) / dkz;
-    p.Sy = comp(d, p.ky) / dkz;
-    p.Sz = 1.0f / dkz;
+    p.Sz = rcp_fast(dkz);
+    p.Sx = comp(d, p.kx) * p.Sz;
+    p.Sy = comp(d, p.ky) * p.Sz;
     return p;
 }
 
@@ -88,7 +95,7 @@ __device__ __forceinline__ bool intersect_tri(const RayPre &r, float tmin, float
     if (det == 0.0f) return false;
     const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
     const float T = U * Az + V * Bz + W * Cz;
-    const float rdet = 1.0f / det;
+    const float rdet = rcp_fast(det);
     const float t = T * rdet;
     if (!(t > tmin && t < tmax)) return false;
     t_out = t;
@@ -97,7 +104,12 @@ __device__ __forceinline__ bool intersect_tri(const RayPre &r, float tmin, float
     return true;
 }
 
-__device__ __forceinline__ float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+// Byte -> float without the quarter-rate conversion unit: PRMT drops byte i of `w` into mantissa bits 8..15 of
+// 0x47000000 (= 32768.0f), giving exactly 32768 + q on the integer pipe; the bias is folded into the slab offset.
+// (I2F.U8 runs on the XU pipe at 16 lanes/clk/SM and was 73 % busy in the first profile — profiles/r01_*.)
+__device__ __forceinline__ float byte_biased(uint32_t w, int i) {
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7604u | ((uint32_t)i << 4)));
+}
 
 struct Hit {
     float t, u, v;
@@ -114,9 +126,14 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
     const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                 sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
     const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
-    const float bx = (__uint_as_float(n0.x) - r.o.x) * r.idir.x;
-    const float by = (__uint_as_float(n0.y) - r.o.y) * r.idir.y;
-    const float bz = (__uint_as_float(n0.z) - r.o.z) * r.idir.z;
+    // plane distance t(q) = q*a + b with b = (origin - o) * idir, evaluated as fma(32768 + q, a, b - 32768 a). The
+    // rounding of the folded offset is < |a|/512 (1/512 of a quantisation step); the near offset is lowered and the
+    // far offset raised by |a|/256 so the test only ever grows the box (conservative, like the builder's rounding).
+    const float bx = fmaf(-32768.0f, ax, (__uint_as_float(n0.x) - r.o.x) * r.idir.x);
+    const float by = fmaf(-32768.0f, ay, (__uint_as_float(n0.y) - r.o.y) * r.idir.y);
+    const float bz = fmaf(-32768.0f, az, (__uint_as_float(n0.z) - r.o.z) * r.idir.z);
+    const float ex = fabsf(ax) * 0.00390625f, ey = fabsf(ay) * 0.00390625f, ez = fabsf(az) * 0.00390625f;
+    const float bnx = bx - ex, bfx = bx + ex, bny = by - ey, bfy = by + ey, bnz = bz - ez, bfz = bz + ez;
     // qlo: x = n2.xy, y = n2.zw, z = n3.xy ; qhi: x = n3.zw, y = n4.xy, z = n4.zw
     const bool nx = r.neg & 1u, ny = r.neg & 2u, nz = r.neg & 4u;
     const uint32_t nearx[2] = {nx ? n3.z : n2.x, nx ? n3.w : n2.y}, farx[2] = {nx ? n2.x : n3.z, nx ? n2.y : n3.w};
@@ -130,9 +147,9 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const int w = s >> 2, b = s & 3;
-        const float tnx = fmaf(byte_f(nearx[w], b), ax, bx), tfx = fmaf(byte_f(farx[w], b), ax, bx);
-        const float tny = fmaf(byte_f(neary[w], b), ay, by), tfy = fmaf(byte_f(fary[w], b), ay, by);
-        const float tnz = fmaf(byte_f(nearz[w], b), az, bz), tfz = fmaf(byte_f(farz[w], b), az, bz);
+        const float tnx = fmaf(byte_biased(nearx[w], b), ax, bnx), tfx = fmaf(byte_biased(farx[w], b), ax, bfx);
+        const float tny = fmaf(byte_biased(neary[w], b), ay, bny), tfy = fmaf(byte_biased(fary[w], b), ay, bfy);
+        const float tnz = fmaf(byte_biased(nearz[w], b), az, bnz), tfz = fmaf(byte_biased(farz[w], b), az, bfz);
         const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
         // Ize 2013: inflate the exit distance by a few ulps so rounding never culls a box the exact test would enter
         const float tf = fminf(fminf(tfx, tfy), tfz) * 1.0000004f;
@@ -144,6 +161,10 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
     }
 }
 
+// while-while traversal (Aila & Laine 2009) over the 8-wide nodes: phase 1 walks internal nodes until THIS lane holds
+// a batch of candidate triangles (or runs out of nodes); phase 2 tests the batch. Because every lane leaves phase 1
+// with work for phase 2, the warp runs the (long) triangle test with most lanes active instead of serialising it
+// behind each node step — the first profile showed the triangle test issuing at 5-14 % lane utilisation.
 template <bool ANY>
 __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
                                       const Ray &ray, Hit &hit) {
@@ -154,18 +175,24 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
     uint2 stack[kStackSize];
     int sp = 0;
     uint2 group = make_uint2(0u, 1u);   // (child_base, hit mask over child ordinals): the root
+    uint32_t tri_base = 0u, tri_hits = 0u;
     while (true) {
-        if (group.y == 0u) {
-            if (sp == 0) break;
-            group = stack[--sp];
+        // ---- phase 1: internal nodes ---------------------------------------------------------------------------
+        while (tri_hits == 0u) {
+            if (group.y == 0u) {
+                if (sp == 0) break;
+                group = stack[--sp];
+            }
+            const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
+            group.y &= group.y - 1u;
+            if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
+            uint32_t child_base, child_hits;
+            intersect_node(nodes, group.x + k, r, ray.tmin, tmax, child_base, child_hits, tri_base, tri_hits);
+            group = make_uint2(child_base, child_hits);
         }
-        const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
-        group.y &= group.y - 1u;
-        if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
-        uint32_t child_base, child_hits, tri_base, tri_hits;
-        intersect_node(nodes, group.x + k, r, ray.tmin, tmax, child_base, child_hits, tri_base, tri_hits);
-        group = make_uint2(child_base, child_hits);
-        while (tri_hits) {
+        if (tri_hits == 0u) break;      // no nodes left
+        // ---- phase 2: the pending triangle batch ---------------------------------------------------------------
+        do {
             const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
             tri_hits &= tri_hits - 1u;
             const float4 *tp = tris + (size_t)(tri_base + j) * 3;
@@ -177,7 +204,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
                 hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
                 found = true;
             }
-        }
+        } while (tri_hits);
     }
     return found;
 }
