@@ -42,6 +42,11 @@ enum {
     VHR_FORMAT_D32_SFLOAT = 126
 };
 
+/* device index for a validation-only context: image/slot tables and pass bookkeeping work (so a host can build and
+ * sanity-check its render graph on a machine without a GPU); every entry point that needs the GPU fails with
+ * VHR_ERR_CUDA. This is not a CPU fallback: nothing is ever computed on the host. */
+#define VHR_DEVICE_NONE (-1)
+
 #define VHR_MAX_GLOBAL_RESOURCES 2048   /* src/rendering_backend/resource_manager.h:13 */
 #define VHR_MAX_PASS_BINDINGS 16
 

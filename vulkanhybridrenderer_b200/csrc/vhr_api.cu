@@ -26,8 +26,10 @@ static int alloc_image(vhr_context *ctx, Image &im, uint32_t w, uint32_t h, int 
     if (w == 0 || h == 0) return fail(VHR_ERR_INVALID, "image size %ux%u", w, h);
     im.width = w; im.height = h; im.format = fmt;
     im.bytes = (size_t)w * h * tb;
-    VHR_CUDA_CHECK(cudaMalloc(&im.ptr, im.bytes));
-    VHR_CUDA_CHECK(cudaMemsetAsync(im.ptr, 0, im.bytes, ctx->stream));
+    if (ctx->device >= 0) {    // a VHR_DEVICE_NONE context only keeps the image table (graph building / validation)
+        VHR_CUDA_CHECK(cudaMalloc(&im.ptr, im.bytes));
+        VHR_CUDA_CHECK(cudaMemsetAsync(im.ptr, 0, im.bytes, ctx->stream));
+    }
     im.twin = nullptr;
     im.used = true;
     return VHR_OK;
@@ -68,6 +70,11 @@ static int blit(vhr_context *ctx, Image *src, Image *dst, const char *what) {
 
 using namespace vhr;
 
+#define VHR_NEED_DEVICE(ctx)                                                                                     \
+    do {                                                                                                         \
+        if ((ctx)->device < 0) return fail(VHR_ERR_CUDA, "%s: context was created with VHR_DEVICE_NONE (no GPU work possible, no CPU fallback)", __func__); \
+    } while (0)
+
 extern "C" {
 
 const char *vhr_last_error(void) { return g_error; }
@@ -76,6 +83,16 @@ int vhr_context_create(int device, void *cuda_stream, uint32_t width, uint32_t h
     if (!out) return fail(VHR_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (width == 0 || height == 0) return fail(VHR_ERR_INVALID, "display size %ux%u", width, height);
+    if (device == VHR_DEVICE_NONE) {
+        // validation-only context: image / storage-slot tables and pass bookkeeping work, every entry point that would
+        // touch the GPU fails with VHR_ERR_CUDA. Lets hosts build and check a render graph on a machine without a GPU.
+        vhr_context *ctx = new vhr_context();
+        ctx->device = VHR_DEVICE_NONE;
+        ctx->width = width; ctx->height = height;
+        ctx->storage.resize(VHR_MAX_GLOBAL_RESOURCES);
+        *out = ctx;
+        return VHR_OK;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -102,6 +119,7 @@ int vhr_context_create(int device, void *cuda_stream, uint32_t width, uint32_t h
 
 void vhr_context_destroy(vhr_context *ctx) {
     if (!ctx) return;
+    if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->transient) free_image(kv.second);
@@ -119,6 +137,7 @@ void vhr_context_destroy(vhr_context *ctx) {
 
 int vhr_context_synchronize(vhr_context *ctx) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (ctx->device < 0) return VHR_OK;
     VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return VHR_OK;
 }
@@ -134,6 +153,7 @@ uint64_t vhr_kernel_launch_count(vhr_context *ctx) { return ctx ? ctx->launches 
 int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_vertices, const uint32_t *indices,
                         uint32_t n_indices, const void *primitives, uint32_t n_primitives) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     if ((n_vertices && !vertices) || (n_indices && !indices) || (n_primitives && !primitives))
         return fail(VHR_ERR_INVALID, "NULL geometry array");
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -203,7 +223,7 @@ int vhr_update_per_frame_ubo(vhr_context *ctx, const void *per_frame_data, size_
 
 int vhr_upload_new_storage_image(vhr_context *ctx, uint32_t width, uint32_t height, int vk_format) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
-    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (ctx->device >= 0) VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     for (int i = 0; i < VHR_MAX_GLOBAL_RESOURCES; ++i) {
         if (!ctx->storage[i].used) {
             int rc = alloc_image(ctx, ctx->storage[i], width, height, vk_format);
@@ -217,14 +237,14 @@ int vhr_destroy_storage_image(vhr_context *ctx, int slot) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     Image *im = storage_slot(ctx, slot);
     if (!im) return fail(VHR_ERR_INVALID, "storage image %d does not exist", slot);
-    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->device >= 0) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     free_image(*im);
     return VHR_OK;
 }
 
 int vhr_actualize_image(vhr_context *ctx, const char *name, uint32_t width, uint32_t height, int vk_format) {
     if (!ctx || !name) return fail(VHR_ERR_INVALID, "NULL argument");
-    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (ctx->device >= 0) VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (width == 0 && height == 0) { width = ctx->width; height = ctx->height; }
     Image *im = find_transient(ctx, name);
     if (im) {
@@ -242,7 +262,7 @@ int vhr_actualize_image(vhr_context *ctx, const char *name, uint32_t width, uint
 
 int vhr_destroy_transient_resources(vhr_context *ctx) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
-    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->device >= 0) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (auto &kv : ctx->transient) free_image(kv.second);
     ctx->transient.clear();
     ctx->n_bound = 0;
@@ -251,18 +271,22 @@ int vhr_destroy_transient_resources(vhr_context *ctx) {
 
 int vhr_image_upload(vhr_context *ctx, const char *name, const void *host, size_t bytes) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return copy_in(ctx, find_transient(ctx, name), host, bytes, name ? name : "(null)");
 }
 int vhr_image_download(vhr_context *ctx, const char *name, void *host, size_t bytes) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return copy_out(ctx, find_transient(ctx, name), host, bytes, name ? name : "(null)");
 }
 int vhr_storage_image_upload(vhr_context *ctx, int slot, const void *host, size_t bytes) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return copy_in(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
 }
 int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t bytes) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return copy_out(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
 }
 void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format) {
@@ -297,6 +321,7 @@ int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, 
 int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
                  const void *push_constants, size_t push_constants_size) {
     if (!ctx || !shader_path) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
     if (z_groups != 1) return fail(VHR_ERR_INVALID, "z_groups = %u (the hot-path kernels are 2D)", z_groups);
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -331,6 +356,7 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
 
 int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height) {
     if (!ctx || !pipeline_name) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_NEED_DEVICE(ctx);
     if (strcmp(pipeline_name, "Raytrace Pipeline")) return fail(VHR_ERR_INVALID, "unknown ray-tracing pipeline '%s'", pipeline_name);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -339,6 +365,7 @@ int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, 
 
 int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     return launch_gbuffer(ctx, width, height);
@@ -347,25 +374,30 @@ int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height) {
 int vhr_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
                        float *out_uv) {
     if (!ctx || (n && (!rays || !out_t))) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_NEED_DEVICE(ctx);
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     return launch_trace_explicit(ctx, rays, n, any_hit, out_t, out_ids, out_uv);
 }
 
 int vhr_blit_storage_to_transient(vhr_context *ctx, int src_slot, const char *dst_name) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return blit(ctx, storage_slot(ctx, src_slot), find_transient(ctx, dst_name), "BlitImageStorageToTransient");
 }
 int vhr_blit_transient_to_storage(vhr_context *ctx, const char *src_name, int dst_slot) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return blit(ctx, find_transient(ctx, src_name), storage_slot(ctx, dst_slot), "BlitImageTransientToStorage");
 }
 int vhr_blit_storage_to_storage(vhr_context *ctx, int src_slot, int dst_slot) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
     return blit(ctx, storage_slot(ctx, src_slot), storage_slot(ctx, dst_slot), "BlitImageStorageToStorage");
 }
 
 int vhr_create_query_pool(vhr_context *ctx, uint32_t count) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (ctx->device < 0) return VHR_OK;
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
     ctx->queries.assign(count, nullptr);
@@ -374,11 +406,13 @@ int vhr_create_query_pool(vhr_context *ctx, uint32_t count) {
 }
 int vhr_write_timestamp(vhr_context *ctx, uint32_t query) {
     if (!ctx || query >= ctx->queries.size()) return fail(VHR_ERR_INVALID, "timestamp query %u out of range", query);
+    VHR_NEED_DEVICE(ctx);
     VHR_CUDA_CHECK(cudaEventRecord(ctx->queries[query], ctx->stream));
     return VHR_OK;
 }
 int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms) {
     if (!ctx || !out_ms || first >= ctx->queries.size() || last >= ctx->queries.size())
+    VHR_NEED_DEVICE(ctx);
         return fail(VHR_ERR_INVALID, "timestamp query range [%u, %u] invalid", first, last);
     VHR_CUDA_CHECK(cudaEventSynchronize(ctx->queries[last]));
     float ms = 0.0f;
@@ -404,6 +438,7 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
         case VHR_OPT_DEBUG_REFLECTION_T:
             ctx->opt.debug_refl_t = value != 0;
+            if (ctx->device < 0) return VHR_OK;
             if (ctx->opt.debug_refl_t && !ctx->d_refl_t) {
                 VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
                 VHR_CUDA_CHECK(cudaMalloc(&ctx->d_refl_t, (size_t)ctx->width * ctx->height * sizeof(float)));
@@ -435,6 +470,7 @@ int64_t vhr_get_option(vhr_context *ctx, int option) {
 
 int vhr_debug_download_reflection_t(vhr_context *ctx, float *host, size_t bytes) {
     if (!ctx || !host) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_NEED_DEVICE(ctx);
     if (!ctx->d_refl_t) return fail(VHR_ERR_STATE, "VHR_OPT_DEBUG_REFLECTION_T is not enabled");
     size_t need = (size_t)ctx->width * ctx->height * sizeof(float);
     if (bytes != need) return fail(VHR_ERR_INVALID, "reflection-t image is %zu bytes, got %zu", need, bytes);

@@ -1,0 +1,118 @@
+"""ctypes binding of the C++ host (vulkanhybridrenderer_b200/libvhr_host.so): RenderGraph + HybridRenderPath mirrors.
+
+`Renderer` is the headless stand-in for the reference's `Renderer` (src/rendering_backend/renderer.cpp): it owns a
+ResourceManager (one vhr_context), a RenderGraph and a HybridRenderPath, loads a scene, switches modes (the ImGui radio
+buttons of hybrid_render_path.cpp:394-441) and renders frames. Images are read back through the underlying C-ABI context.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from . import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvhr_host.so")
+SYMBOLS = ["vhrh_last_error", "vhrh_renderer_create", "vhrh_renderer_destroy", "vhrh_context", "vhrh_load_scene", "vhrh_set_modes",
+           "vhrh_set_gbuffer_producer", "vhrh_render", "vhrh_execution_order", "vhrh_pass_time_ms", "vhrh_svgf_push_constants"]
+
+SHADOW_MODE_RAYTRACED, SHADOW_MODE_RASTERIZED, SHADOW_MODE_OFF = 0, 1, 2
+AO_MODE_RAYTRACED, AO_MODE_SSAO, AO_MODE_OFF = 0, 1, 2
+REFLECTION_MODE_RAYTRACED, REFLECTION_MODE_SSR, REFLECTION_MODE_OFF = 0, 1, 2
+DEVICE_NONE = -1
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        capi.lib()     # libvhr_b200.so first (the host library links against it by rpath=$ORIGIN)
+        if not os.path.exists(LIB_PATH):
+            raise capi.VhrError(f"{LIB_PATH} is missing: run `python -m vulkanhybridrenderer_b200.build`")
+        L = C.CDLL(LIB_PATH)
+        vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+        L.vhrh_last_error.restype = C.c_char_p
+        L.vhrh_renderer_create.argtypes = [i32, vp, u32, u32, C.POINTER(vp)]
+        L.vhrh_renderer_destroy.argtypes = [vp]
+        L.vhrh_renderer_destroy.restype = None
+        L.vhrh_context.argtypes = [vp]
+        L.vhrh_context.restype = vp
+        L.vhrh_load_scene.argtypes = [vp, vp, u32, vp, u32, vp, u32, u32]
+        L.vhrh_set_modes.argtypes = [vp, i32, i32, i32, i32, i32]
+        L.vhrh_set_gbuffer_producer.argtypes = [vp, i32]
+        L.vhrh_render.argtypes = [vp, vp, C.c_size_t, i32]
+        L.vhrh_execution_order.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.vhrh_execution_order.restype = u32
+        L.vhrh_pass_time_ms.argtypes = [vp, C.c_char_p, i32]
+        L.vhrh_pass_time_ms.restype = C.c_double
+        L.vhrh_svgf_push_constants.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise capi.VhrError(f"vhr host status {rc}: {lib().vhrh_last_error().decode()}")
+    return rc
+
+
+class _BorrowedContext(capi.Context):
+    """capi.Context view of the renderer's vhr_context (not owned: never destroyed from here)."""
+
+    def __init__(self, handle, width, height):
+        self._h = C.c_void_p(handle)
+        self.width, self.height = width, height
+
+    def close(self):
+        self._h = None
+
+
+class Renderer:
+    def __init__(self, width, height, device=0, stream=None):
+        self._r = C.c_void_p()
+        _check(lib().vhrh_renderer_create(int(device), C.c_void_p(stream) if stream else None, width, height, C.byref(self._r)))
+        self.width, self.height = width, height
+        self.ctx = _BorrowedContext(lib().vhrh_context(self._r), width, height)
+
+    def close(self):
+        if getattr(self, "_r", None):
+            lib().vhrh_renderer_destroy(self._r)
+            self._r = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def load_scene(self, scene, prims_per_mesh=0):
+        v = np.ascontiguousarray(scene.vertices); i = np.ascontiguousarray(scene.indices, np.uint32); p = np.ascontiguousarray(scene.primitives)
+        assert v.dtype == T.Vertex and p.dtype == T.Primitive
+        _check(lib().vhrh_load_scene(self._r, capi._ptr(v), len(v), capi._ptr(i), len(i), capi._ptr(p), len(p), prims_per_mesh))
+
+    def set_modes(self, shadow=SHADOW_MODE_RAYTRACED, ao=AO_MODE_OFF, reflection=REFLECTION_MODE_OFF, denoise=False, svgf_fused=False):
+        _check(lib().vhrh_set_modes(self._r, shadow, ao, reflection, int(denoise), int(svgf_fused)))
+
+    def set_gbuffer_producer(self, cuda_primary_rays):
+        _check(lib().vhrh_set_gbuffer_producer(self._r, 1 if cuda_primary_rays else 0))
+
+    def render(self, pfd, gather_statistics=False):
+        pfd = np.ascontiguousarray(pfd)
+        _check(lib().vhrh_render(self._r, capi._ptr(pfd), pfd.nbytes, int(gather_statistics)))
+
+    def execution_order(self):
+        buf = C.create_string_buffer(4096)
+        n = lib().vhrh_execution_order(self._r, buf, len(buf))
+        return buf.value.decode().split("\n") if n else []
+
+    def pass_time_ms(self, name, last=True):
+        return lib().vhrh_pass_time_ms(self._r, name.encode(), int(last))
+
+    def svgf_push_constants(self):
+        pc = np.zeros((), T.SVGFPushConstants)
+        _check(lib().vhrh_svgf_push_constants(self._r, capi._ptr(pc)))
+        return pc
