@@ -414,6 +414,105 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm, row-band partition of ONE frame (BASELINE config 4): strong scaling, NCCL halo exchange per a-trous iteration
+# ---------------------------------------------------------------------------------------------------------------------
+def run_rowband(args):
+    import torch
+    import torch.distributed as dist
+    from vulkanhybridrenderer_b200 import camera, capi
+    from vulkanhybridrenderer_b200 import hybrid_path as HP
+    from vulkanhybridrenderer_b200 import multi_gpu as MG
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = args.workload
+    W, H, _, ao_spp, refl = WORKLOADS[wl]
+    sc, poses = make_scene(wl, view=0)          # every rank renders the SAME view; the scene and BVH are replicated
+    stream = torch.cuda.Stream()
+    K, Wm = args.steps, args.warmup
+    y0, y1 = MG.band_rows(H, world, rank)
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(W, H, device=local, stream=stream.cuda_stream)
+        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+        ctx.set_option(capi.OPT_TRACE_AO, 1 if ao_spp else 0)
+        ctx.set_option(capi.OPT_AO_SPP, max(ao_spp, 1))
+        ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
+        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2)
+        seq = camera.FrameSequencer(W, H, sc.light)
+        cam = sc.camera
+        pfds = [None, None]
+        g0, g1 = max(0, y0 - MG.GBUFFER_HALO), min(H, y1 + MG.GBUFFER_HALO)
+        ctx.set_option(capi.OPT_ROW_BEGIN, g0); ctx.set_option(capi.OPT_ROW_END, g1)     # G-buffer input: band + halo rows only
+        for s_ in (1, 0, 1):
+            cam.set_pose(*poses[s_])
+            pfd = seq.next(cam)
+            ctx.update_per_frame_ubo(pfd)
+            g = path.gsets[s_]
+            ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
+            ctx.gbuffer_pass(W, H)
+            pfds[s_] = pfd
+        nonsky = [int((ctx.image_download(path.gsets[s_][HP.N_DEPTH])[y0:y1] > 0).sum()) for s_ in (0, 1)]
+        backends = [MG.CabiBandBackend(ctx, path, gset=s_) for s_ in (0, 1)]
+        drivers = [MG.RowBandSvgf(b, H, world, rank, motion_halo=args.motion_halo) for b in backends]
+        frame_no = [0]
+
+        def step():
+            k = frame_no[0]; s_ = k & 1
+            pfd = pfds[s_]; pfd["frame_index"] = 3 + k
+            frame_no[0] += 1
+            ctx.update_per_frame_ubo(pfd)
+            backends[s_].trace((y0, y1))
+            drivers[s_].run()
+            return nonsky[s_] * (1 + ao_spp + refl)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(Wm):
+            step()
+        l0 = ctx.kernel_launches
+        sampler = ClockSampler(local)
+        barrier(); sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        rays = 0
+        for _ in range(K):
+            rays += step()
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = ctx.kernel_launches - l0
+        sent = sum(d.x.bytes_sent for d in drivers) / max(1, frame_no[0])
+        # stitched result for the checksum / parity (outside the timed region)
+        den = torch.as_tensor(MG._DeviceRows(ctx.image_info(HP.N_DENOISED)[0], H, W * 4), device="cuda")
+        band_sum = den[y0:y1].float().nan_to_num().sum().double()
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_total = float(t)
+        r = torch.tensor([rays, launches, float(band_sum), sent], device="cuda", dtype=torch.float64); dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays, launches, band_sum, sent = (float(x) for x in r.cpu())
+    if rank == 0:
+        cfg = config_dict(wl, sc.num_triangles)
+        cfg.update({"partition": f"row bands x{world}, BVH replicated, NCCL halo exchange (6 grouped send/recv per frame)", "motion_halo_rows": args.motion_halo})
+        print(json.dumps({
+            "metric": METRIC, "value": rays / (ms_total * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "gpu_launches": int(launches), "clocks": clocks, "halo_bytes_per_frame_all_ranks": sent,
+            "denoised_checksum": float(band_sum)}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -423,11 +522,16 @@ def main():
     ap.add_argument("--workload", default="hybrid_frame_1080p_3Mtri", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-rows", type=int, default=64, help="rows of the frame the CPU arm renders per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="views", choices=["views", "rows"],
+                    help="N>1: independent views per rank (weak scaling, default) or row bands of one frame (strong scaling, NCCL halos)")
+    ap.add_argument("--motion-halo", type=int, default=8, help="rows of history/moments exchanged for the temporal pass (row-band mode)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.partition == "rows":
+        run_rowband(args)
     else:
         run_gpu(args)
 
