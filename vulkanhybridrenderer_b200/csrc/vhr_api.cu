@@ -411,8 +411,9 @@ int vhr_write_timestamp(vhr_context *ctx, uint32_t query) {
     return VHR_OK;
 }
 int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms) {
-    if (!ctx || !out_ms || first >= ctx->queries.size() || last >= ctx->queries.size())
+    if (!ctx || !out_ms) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
+    if (first >= ctx->queries.size() || last >= ctx->queries.size())
         return fail(VHR_ERR_INVALID, "timestamp query range [%u, %u] invalid", first, last);
     VHR_CUDA_CHECK(cudaEventSynchronize(ctx->queries[last]));
     float ms = 0.0f;
