@@ -1,0 +1,66 @@
+"""Generates tests/golden/*.npz — small frozen input/output vectors of the CPU oracle for every hot-path kernel.
+
+The reference ships no fixtures and cannot run here, so these are NOT reference outputs: they freeze the
+oracle (so an edit cannot drift silently) and give the CUDA path committed vectors to match. Regenerate only when the
+oracle is deliberately changed:  python tools/make_golden.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+import numpy as np
+
+import helpers as Hh
+import oracle_lib as O
+from vulkanhybridrenderer_b200 import camera, scenes
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    W, H = 96, 64
+    sc = scenes.sponza_like(6000, seed=21, width=W, height=H, n_clutter=12)
+    osc = O.OracleScene(sc)
+    seq = camera.FrameSequencer(W, H, sc.light)
+    cam = sc.camera
+    st = O.SvgfState(W, H)
+    frames = []
+    for f in range(3):
+        if f:
+            cam.set_pose(cam.position + np.array([0.06, 0.0, 0.02]), cam.yaw + 0.004, cam.pitch)
+        pfd = seq.next(cam)
+        g = osc.gbuffer(pfd, W, H)
+        rg = osc.raygen(pfd, g["depth"], g["normals"], want_t=True)
+        den, iters, temporal = st.run(pfd, g["normals"], g["motion"], rg["shadow_ao"])
+        ssao_raw = O.ssao(pfd, g["depth"], g["normals"], 0.75)
+        frames.append(dict(pfd=pfd, depth=g["depth"], normals=g["normals"], motion=g["motion"], albedo=g["albedo"],
+                           shadow_ao=rg["shadow_ao"], reflections=rg["reflections"], refl_t=rg["refl_t"], temporal=temporal,
+                           atrous=iters, denoised=den, ssao_raw=ssao_raw, ssao=O.ssao_blur(pfd, ssao_raw)))
+    flat = {}
+    for i, fr in enumerate(frames):
+        for k, v in fr.items():
+            flat[f"f{i}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "hybrid_frames_96x64.npz"), vertices=sc.vertices, indices=sc.indices, primitives=sc.primitives, **flat)
+    # stand-alone a-trous vectors on worst-case noise, every step
+    pfd, normals = frames[0]["pfd"], frames[0]["normals"]
+    integ = Hh.noise_integrated(H, W, seed=2)
+    np.savez_compressed(os.path.join(OUT, "atrous_noise_96x64.npz"), pfd=pfd, normals=normals, integ=integ,
+                        **{f"step{s}": O.svgf_atrous(pfd, normals, integ, s) for s in (1, 2, 3, 4, 8, 16)})
+    # RNG / sampling KATs
+    import ctypes as C
+    seeds = np.array([0, 1, 16221, 0xdeadbeef, 12345678], np.uint32)
+    states = np.array([O.lib().vo_seed_thread(int(s)) for s in seeds], np.uint32)
+    r01 = np.zeros((len(seeds), 8), np.float32)
+    for i, s in enumerate(states):
+        st_ = C.c_uint32(int(s))
+        for k in range(8):
+            r01[i, k] = O.lib().vo_random01(C.byref(st_))
+    np.savez_compressed(os.path.join(OUT, "rng_kat.npz"), seeds=seeds, states=states, random01=r01)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
