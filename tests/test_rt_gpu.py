@@ -224,3 +224,27 @@ def test_gbuffer_pass_matches_oracle_encodings():
     dm = np.abs(got["motion"].astype(np.float32) - g["motion"].astype(np.float32))[m]
     assert np.quantile(dm.max(axis=-1), 0.999) <= 1e-3
     assert np.mean(np.all(got["albedo"][m] == g["albedo"][m], axis=-1)) > 0.999
+
+
+def test_persistent_raygen_variant_matches_per_pixel_kernel():
+    """VHR_OPT_RAYGEN_VARIANT 1 (persistent warps, pixel queue) must produce the same images as variant 0."""
+    W, H = 203, 117
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, tris=20_000, moving=True)
+    pfd, g = frames[1]
+    outs = []
+    with capi.Context(W, H) as ctx:
+        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+        ctx.update_per_frame_ubo(pfd)
+        ctx.actualize_image(Hh.N_NORMALS, F4); ctx.actualize_image(Hh.N_DEPTH, T.VK_FORMAT_D32_SFLOAT)
+        ctx.actualize_image(Hh.N_RT, F2); ctx.actualize_image(Hh.N_REFL, F4)
+        ctx.image_upload(Hh.N_NORMALS, g["normals"]); ctx.image_upload(Hh.N_DEPTH, g["depth"])
+        ctx.bind_pass_images([Hh.N_NORMALS, Hh.N_DEPTH, Hh.N_RT, Hh.N_REFL])
+        for variant in (0, 1):
+            ctx.set_option(capi.OPT_RAYGEN_VARIANT, variant)
+            ctx.set_option(capi.OPT_ROW_BEGIN, 9); ctx.set_option(capi.OPT_ROW_END, 101)     # ragged band
+            ctx.image_upload(Hh.N_RT, np.zeros((H, W, 2), np.float16)); ctx.image_upload(Hh.N_REFL, np.zeros((H, W, 4), np.float16))
+            ctx.trace_rays(W, H)
+            outs.append((ctx.image_download(Hh.N_RT), ctx.image_download(Hh.N_REFL)))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1].view(np.uint16), outs[1][1].view(np.uint16))
+    assert outs[0][0][:9].astype(np.float32).sum() == 0 and outs[0][0][101:].astype(np.float32).sum() == 0   # rows outside the band untouched

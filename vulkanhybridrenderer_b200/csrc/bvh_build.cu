@@ -130,6 +130,7 @@ struct Tree2 {
     float4 *bmax;            // [2n-1] xyz = box max, w = triangle count (as uint bits)
     uint8_t *cluster;        // [n-1] 1: subtree is emitted as one leaf (<= kMaxLeafTris triangles)
     int *visit;              // [n-1]
+    uint32_t *lcount;        // [2n-1] number of leaf clusters (future leaf slots) in the subtree
 };
 
 __device__ __forceinline__ int delta(const uint64_t *keys, int n, int i, int j) {
@@ -185,6 +186,7 @@ __global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__
     uint32_t id = t.n - 1 + j;
     t.bmin[id] = make_float4(mn.x, mn.y, mn.z, box_half_area(mn, mx));      // leaf cost = area * 1 triangle
     t.bmax[id] = make_float4(mx.x, mx.y, mx.z, __uint_as_float(1u));
+    t.lcount[id] = 1u;
     if (t.n == 1) return;
     __threadfence();
     uint32_t p = t.parent[id];
@@ -202,6 +204,7 @@ __global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__
         float cost_leaf = area * (float)cnt;
         bool cl = cnt <= (uint32_t)kMaxLeafTris && cost_leaf <= cost_inner;
         t.cluster[p] = cl ? 1 : 0;
+        t.lcount[p] = cl ? 1u : __ldcg(&t.lcount[l]) + __ldcg(&t.lcount[rr]);
         t.bmin[p] = make_float4(mn.x, mn.y, mn.z, cl ? cost_leaf : cost_inner);
         t.bmax[p] = make_float4(mx.x, mx.y, mx.z, __uint_as_float(cnt));
         __threadfence();
@@ -305,19 +308,38 @@ __global__ void widen_kernel(const __grid_constant__ WidenArgs a) {
     int nk = 2;
     kids[0] = t.child_l[item.x];
     kids[1] = t.child_r[item.x];
+    // Collapse rule. Every slot of a wide node is slab-tested whether it is used or not, so filling slots is free:
+    //   1. an internal child whose whole subtree fits into the free slots (lcount - 1 <= free) is absorbed first, best
+    //      area-per-slot first — this removes the small, mostly empty nodes an LBVH leaves at the bottom;
+    //   2. otherwise the child with the largest surface area is opened one level (the usual SAH-greedy rule).
     while (nk < 8) {
-        int best = -1;
-        float best_area = -1.0f;
+        const int free_slots = 8 - nk;
+        int best = -1, best_abs = -1;
+        float best_area = -1.0f, best_ratio = -1.0f;
         for (int c = 0; c < nk; ++c) {
             if (leaf_like(t, kids[c])) continue;
             float4 mn = t.bmin[kids[c]], mx = t.bmax[kids[c]];
             float ar = box_half_area(make_float3(mn.x, mn.y, mn.z), make_float3(mx.x, mx.y, mx.z));
             if (ar > best_area) { best_area = ar; best = c; }
+            const int need = (int)t.lcount[kids[c]] - 1;
+            if (need <= free_slots) {
+                float ratio = ar / (float)max(need, 1);
+                if (ratio > best_ratio) { best_ratio = ratio; best_abs = c; }
+            }
         }
         if (best < 0) break;
+        if (best_abs >= 0) best = best_abs;
         uint32_t id = kids[best];
         kids[best] = t.child_l[id];
         kids[nk++] = t.child_r[id];
+    }
+    // internal children first: slot index == child ordinal, and the internal-child mask is a run of low bits
+    {
+        uint32_t tmp[8];
+        int k = 0;
+        for (int c = 0; c < nk; ++c) if (!leaf_like(t, kids[c])) tmp[k++] = kids[c];
+        for (int c = 0; c < nk; ++c) if (leaf_like(t, kids[c])) tmp[k++] = kids[c];
+        for (int c = 0; c < nk; ++c) kids[c] = tmp[c];
     }
     float4 nmn = t.bmin[item.x], nmx = t.bmax[item.x];
     emit_wide_node(a, item.y, kids, nk, make_float3(nmn.x, nmn.y, nmn.z), make_float3(nmx.x, nmx.y, nmx.z));
@@ -428,6 +450,7 @@ int build_bvh(vhr_context *ctx) {
         TRY(dmalloc(&t.bmax, 2 * (size_t)n)); track(t.bmax);
         TRY(dmalloc(&t.cluster, n_inner)); track(t.cluster);
         TRY(dmalloc(&t.visit, n_inner)); track(t.visit);
+        TRY(dmalloc(&t.lcount, 2 * (size_t)n)); track(t.lcount);
         TRYCUDA(cudaMemsetAsync(t.visit, 0, std::max<size_t>(n_inner, 1) * sizeof(int), st));
         TRYCUDA(cudaMemsetAsync(t.cluster, 0, std::max<size_t>(n_inner, 1), st));
         if (n_inner) {

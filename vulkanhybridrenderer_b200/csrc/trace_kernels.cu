@@ -11,6 +11,8 @@
 // opaque triangles, no culling (TLAS instance flag TRIANGLE_FACING_CULL_DISABLE, resource_manager.cpp:704-718),
 // a triangle counts when tMin < t < tMax, shared edges are watertight (Woop/Benthin/Wald 2013 with the double
 // fallback for zero edge functions).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -116,13 +118,14 @@ struct Hit {
     uint32_t tri;
 };
 
-// Intersects the ray with the 8 quantised child boxes of node `idx`. Returns the hit internal children as an 8-bit
-// mask over child ordinals and the triangles of the hit leaf children as a 24-bit mask over [tri_base, tri_base+24).
+// Intersects the ray with the 8 quantised child boxes of node `idx`. The builder stores internal children in the low
+// slots, so the hit bits split into (internal children, by ordinal) and (leaf slots) with two ANDs; the leaf slots'
+// triangle ranges are only decoded when the triangles are actually tested (expand_leaves).
 __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ nodes, uint32_t idx, const RayPre &r, float tmin,
-                                               float tmax, uint32_t &child_base, uint32_t &child_hits, uint32_t &tri_base,
-                                               uint32_t &tri_hits) {
+                                               float tmax, uint32_t &child_base, uint32_t &child_hits, uint32_t &leaf_hits) {
     const uint4 *np = reinterpret_cast<const uint4 *>(nodes + idx);
-    const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    const uint4 n0 = __ldg(np + 0), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    child_base = __ldg(reinterpret_cast<const uint32_t *>(np + 1));
     const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                 sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
     const float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
@@ -133,78 +136,88 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
     const float by = fmaf(-32768.0f, ay, (__uint_as_float(n0.y) - r.o.y) * r.idir.y);
     const float bz = fmaf(-32768.0f, az, (__uint_as_float(n0.z) - r.o.z) * r.idir.z);
     const float ex = fabsf(ax) * 0.00390625f, ey = fabsf(ay) * 0.00390625f, ez = fabsf(az) * 0.00390625f;
-    const float bnx = bx - ex, bfx = bx + ex, bny = by - ey, bfy = by + ey, bnz = bz - ez, bfz = bz + ez;
+    const float bnx = bx - ex, bny = by - ey, bnz = bz - ez;
+    // Ize 2013: the exit distance is inflated by a few ulps so rounding never culls a box the exact test would enter;
+    // the factor is folded into the far slope and offset (t_far * k = q * (a k) + (b k))
+    const float kInfl = 1.0000004f;
+    const float afx = ax * kInfl, afy = ay * kInfl, afz = az * kInfl;
+    const float bfx = (bx + ex) * kInfl, bfy = (by + ey) * kInfl, bfz = (bz + ez) * kInfl;
     // qlo: x = n2.xy, y = n2.zw, z = n3.xy ; qhi: x = n3.zw, y = n4.xy, z = n4.zw
     const bool nx = r.neg & 1u, ny = r.neg & 2u, nz = r.neg & 4u;
     const uint32_t nearx[2] = {nx ? n3.z : n2.x, nx ? n3.w : n2.y}, farx[2] = {nx ? n2.x : n3.z, nx ? n2.y : n3.w};
     const uint32_t neary[2] = {ny ? n4.x : n2.z, ny ? n4.y : n2.w}, fary[2] = {ny ? n2.z : n4.x, ny ? n2.w : n4.y};
     const uint32_t nearz[2] = {nz ? n4.z : n3.x, nz ? n4.w : n3.y}, farz[2] = {nz ? n3.x : n4.z, nz ? n3.y : n4.w};
-    const uint32_t meta[2] = {n1.z, n1.w};
-    child_base = n1.x;
-    tri_base = n1.y;
-    child_hits = 0;
-    tri_hits = 0;
+    uint32_t hits = 0u;
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const int w = s >> 2, b = s & 3;
-        const float tnx = fmaf(byte_biased(nearx[w], b), ax, bnx), tfx = fmaf(byte_biased(farx[w], b), ax, bfx);
-        const float tny = fmaf(byte_biased(neary[w], b), ay, bny), tfy = fmaf(byte_biased(fary[w], b), ay, bfy);
-        const float tnz = fmaf(byte_biased(nearz[w], b), az, bnz), tfz = fmaf(byte_biased(farz[w], b), az, bfz);
+        const float tnx = fmaf(byte_biased(nearx[w], b), ax, bnx), tfx = fmaf(byte_biased(farx[w], b), afx, bfx);
+        const float tny = fmaf(byte_biased(neary[w], b), ay, bny), tfy = fmaf(byte_biased(fary[w], b), afy, bfy);
+        const float tnz = fmaf(byte_biased(nearz[w], b), az, bnz), tfz = fmaf(byte_biased(farz[w], b), afz, bfz);
         const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-        // Ize 2013: inflate the exit distance by a few ulps so rounding never culls a box the exact test would enter
-        const float tf = fminf(fminf(tfx, tfy), tfz) * 1.0000004f;
-        const uint32_t m = (meta[w] >> (8 * b)) & 0xffu;
-        if (tn <= fminf(tf, tmax) && m != 0u) {
-            if (m & 0x80u) child_hits |= 1u << (m & 7u);
-            else tri_hits |= ((1u << (m >> 5)) - 1u) << (m & 31u);
-        }
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+        // empty slots carry an inverted box (qlo = 255, qhi = 0) and can never pass this test
+        if (tn <= tf) hits |= 1u << s;
+    }
+    const uint32_t imask = n0.w >> 24;
+    child_hits = hits & imask;
+    leaf_hits = hits & ~imask;
+}
+
+// Decodes the triangle ranges of the hit leaf slots of a node into a 24-bit mask over [tri_base, tri_base + 24).
+__device__ __forceinline__ void expand_leaves(const WideNode *__restrict__ nodes, uint32_t idx, uint32_t leaf_hits, uint32_t &tri_base,
+                                              uint32_t &tri_hits) {
+    const uint4 n1 = __ldg(reinterpret_cast<const uint4 *>(nodes + idx) + 1);
+    tri_base = n1.y;
+    tri_hits = 0u;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const uint32_t m = ((s < 4 ? n1.z : n1.w) >> (8 * (s & 3))) & 0xffu;
+        if ((leaf_hits >> s) & 1u) tri_hits |= ((1u << (m >> 5)) - 1u) << (m & 31u);
     }
 }
 
-// while-while traversal (Aila & Laine 2009) over the 8-wide nodes: phase 1 walks internal nodes until THIS lane holds
-// a batch of candidate triangles (or runs out of nodes); phase 2 tests the batch. Because every lane leaves phase 1
-// with work for phase 2, the warp runs the (long) triangle test with most lanes active instead of serialising it
-// behind each node step — the first profile showed the triangle test issuing at 5-14 % lane utilisation.
+// while-while traversal (Aila & Laine 2009) over the 8-wide nodes, one ray per lane; every lane of the warp calls
+// trace() together (`alive` = this lane really has a ray) so callers never diverge before the loop.
 template <bool ANY>
 __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
-                                      const Ray &ray, Hit &hit) {
-    if (n_wide == 0) return false;
+                                      const Ray &ray, bool alive, Hit &hit) {
+    if (!alive || n_wide == 0) return false;
     const RayPre r = prepare(ray);
     float tmax = ray.tmax;
     bool found = false;
     uint2 stack[kStackSize];
     int sp = 0;
     uint2 group = make_uint2(0u, 1u);   // (child_base, hit mask over child ordinals): the root
-    uint32_t tri_base = 0u, tri_hits = 0u;
     while (true) {
-        // ---- phase 1: internal nodes ---------------------------------------------------------------------------
-        while (tri_hits == 0u) {
-            if (group.y == 0u) {
-                if (sp == 0) break;
-                group = stack[--sp];
-            }
-            const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
-            group.y &= group.y - 1u;
-            if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
-            uint32_t child_base, child_hits;
-            intersect_node(nodes, group.x + k, r, ray.tmin, tmax, child_base, child_hits, tri_base, tri_hits);
-            group = make_uint2(child_base, child_hits);
+        if (group.y == 0u) {
+            if (sp == 0) break;
+            group = stack[--sp];
         }
-        if (tri_hits == 0u) break;      // no nodes left
-        // ---- phase 2: the pending triangle batch ---------------------------------------------------------------
-        do {
-            const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
-            tri_hits &= tri_hits - 1u;
-            const float4 *tp = tris + (size_t)(tri_base + j) * 3;
-            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-            float t, u, v;
-            if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v)) {
-                if (ANY) return true;
-                tmax = t;
-                hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
-                found = true;
-            }
-        } while (tri_hits);
+        const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
+        group.y &= group.y - 1u;
+        if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
+        const uint32_t node = group.x + k;
+        uint32_t child_base, child_hits, leaf_hits;
+        intersect_node(nodes, node, r, ray.tmin, tmax, child_base, child_hits, leaf_hits);
+        group = make_uint2(child_base, child_hits);
+        if (leaf_hits) {
+            uint32_t tri_base, tri_hits;
+            expand_leaves(nodes, node, leaf_hits, tri_base, tri_hits);
+            do {
+                const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
+                tri_hits &= tri_hits - 1u;
+                const float4 *tp = tris + (size_t)(tri_base + j) * 3;
+                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                float t, u, v;
+                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v)) {
+                    if (ANY) return true;
+                    tmax = t;
+                    hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
+                    found = true;
+                }
+            } while (tri_hits);
+        }
     }
     return found;
 }
@@ -313,20 +326,21 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
     int x, y;
     tile_coords(x, y);
     y += p.y_begin;
-    if (x >= p.W || y >= p.y_end) return;
-    const size_t pix = (size_t)y * p.W + x;
+    // every lane stays in the kernel: trace() is warp-synchronous, lanes without a ray just pass alive = false
+    const bool in_range = x < p.W && y < p.y_end;
+    const size_t pix = in_range ? (size_t)y * p.W + x : 0;
     const float u = __fdiv_rn(add_rn((float)x, 0.5f), (float)p.W), v = __fdiv_rn(add_rn((float)y, 0.5f), (float)p.H);
     uint32_t rng = seed_thread(((uint32_t)y * (uint32_t)p.H + (uint32_t)x) * pfd.frame_index);   // raygen.rgen:17 (Q4)
-    const float depth = __ldg(&p.depth[pix]);                                                    // texel centre: exact texel (Q17)
-    if (depth == 0.0f) {
+    const float depth = in_range ? __ldg(&p.depth[pix]) : 0.0f;                                  // texel centre: exact texel (Q17)
+    const bool lit = in_range && depth != 0.0f;
+    if (in_range && !lit) {                                                                      // raygen.rgen:20-24
         p.shadow_ao[pix] = pack_rg16f(1.0f, 1.0f);
         p.reflections[pix] = make_uint2(0u, 0u);
         if (p.refl_t) p.refl_t[pix] = -1.0f;
-        return;
     }
-    const float3 P = unproject_rn(pfd.camera_viewproj_inverse, depth, u, v);
+    const float3 P = unproject_rn(pfd.camera_viewproj_inverse, lit ? depth : 1.0f, u, v);
     const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
-    const float4 n4 = unpack_rgba16f(__ldg(&p.normals[pix]));
+    const float4 n4 = lit ? unpack_rgba16f(__ldg(&p.normals[pix])) : make_float4(0.0f, 0.0f, 1.0f, 0.0f);
     const float3 N = make_float3(n4.x, n4.y, n4.z);
     Ray ray;
     ray.o = make_float3(add_rn(P.x, mul_rn(N.x, 0.1f)), add_rn(P.y, mul_rn(N.y, 0.1f)), add_rn(P.z, mul_rn(N.z, 0.1f)));
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
         const float3 cone = normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f));
         ray.d = onb_apply(L, cone);
         ray.tmax = 10000.0f;
-        shadow = trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, hit) ? 0.0f : 1.0f;
+        shadow = trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, lit, hit) ? 0.0f : 1.0f;
     }
     // ambient occlusion (raygen.rgen:44-55)
     float ao = 0.0f;
@@ -350,30 +364,243 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
         if (p.flags & 2) {
             ray.d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
             ray.tmax = 5.0f;
-            ao = add_rn(ao, trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, hit) ? 0.0f : 1.0f);
+            ao = add_rn(ao, trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, lit, hit) ? 0.0f : 1.0f);
         } else {
             ao = add_rn(ao, 1.0f);
         }
     }
     ao = __fdiv_rn(ao, (float)p.ao_spp);
-    p.shadow_ao[pix] = pack_rg16f(shadow, ao);
+    if (lit) p.shadow_ao[pix] = pack_rg16f(shadow, ao);
 
     // mirror reflection (raygen.rgen:59-65)
-    float4 payload = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float rt = -1.0f;
     if (p.flags & 4) {
+        float4 payload = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float rt = -1.0f;
         const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
         const float3 I = normalize_rn(make_float3(sub_rn(P.x, cam.x), sub_rn(P.y, cam.y), sub_rn(P.z, cam.z)));
         const float k2 = mul_rn(2.0f, dot3_rn(N, I));
         ray.d = make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2)));
         ray.tmax = 10000.0f;
-        if (trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, hit)) {
+        if (trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, lit, hit) && lit) {
             payload = reflection_hit(p.scene, pfd, hit);
             rt = hit.t;
         }
+        if (lit) {
+            p.reflections[pix] = pack_rgba16f(payload);
+            if (p.refl_t) p.refl_t[pix] = rt;
+        }
+    } else if (lit) {
+        p.reflections[pix] = make_uint2(0u, 0u);
+        if (p.refl_t) p.refl_t[pix] = -1.0f;
     }
-    p.reflections[pix] = pack_rgba16f(payload);
-    if (p.refl_t) p.refl_t[pix] = rt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// raygen, persistent variant: warps pull pixels from a global queue and every lane runs its pixel's rays back to back
+// ---------------------------------------------------------------------------------------------------------------
+// The per-pixel kernel above synchronises the warp after every ray kind: all 32 shadow rays finish before the first AO
+// ray starts, so a lane whose any-hit ray ended early idles until the slowest ray of the warp is done (the first
+// profile shows the AO node test at 45 % lane utilisation). Here a lane owns a small state machine
+//     pixel -> shadow ray -> AO ray x spp -> reflection ray -> write results -> next pixel
+// and the warp alternates between two phases (Aila & Laine 2009, persistent threads with dynamic fetch):
+//     refill   when at least kRefillIdle lanes have no ray in flight: finished pixels are written, new pixels are
+//              handed out from the warp's chunk of the tile-ordered pixel queue (one atomicAdd per chunk), the next
+//              ray of every idle lane is generated;
+//     traverse node step + triangle tests for every lane with a ray, repeated until too many lanes have gone idle.
+// Ray generation is the same arithmetic in the same RNG order as raygen_kernel, so both variants produce identical images.
+constexpr int kChunkPixels = 64;      // pixels a warp takes from the queue per atomicAdd (two 8x4 tiles)
+
+__global__ void __launch_bounds__(128) raygen_persistent_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd,
+                                                                uint32_t *__restrict__ queue_head, const int kRefillIdle, const int kBurst) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (p.W + 7) >> 3;
+    const int rows = p.y_end - p.y_begin;
+    const uint32_t n_items = (uint32_t)tiles_x * (uint32_t)((rows + 3) >> 2) * 32u;
+    const int last_stage = p.ao_spp + ((p.flags & 4) ? 1 : 0);     // stage 0 shadow, 1..spp AO, spp+1 reflection
+    const WideNode *__restrict__ nodes = p.scene.nodes;
+    const float4 *__restrict__ tris = p.scene.tris;
+
+    // warp-uniform chunk of the pixel queue
+    uint32_t chunk_next = 0u, chunk_end = 0u;
+    bool queue_empty = p.scene.n_wide == 0 && false;
+    // per-lane pixel state
+    bool have_pixel = false;
+    int stage = 0;
+    size_t pix = 0;
+    uint32_t rng = 0u;
+    float3 P = make_float3(0.f, 0.f, 0.f), N = make_float3(0.f, 0.f, 1.f);
+    float shadow = 1.0f, ao = 0.0f;
+    // per-lane ray state
+    bool ray_active = false, closest = false, found = false;
+    RayPre r;
+    r.o = P; r.idir = P; r.kx = 0; r.ky = 1; r.kz = 2; r.Sx = r.Sy = r.Sz = 0.f; r.neg = 0u;
+    float tmin = 0.01f, tmax = 0.0f;
+    Hit hit;
+    hit.t = -1.f; hit.u = hit.v = 0.f; hit.tri = 0u;
+    uint2 stack[kStackSize];
+    int sp = 0;
+    uint2 group = make_uint2(0u, 0u);
+
+    while (true) {
+        // ================================ refill ==================================================================
+        const uint32_t idle_mask = __ballot_sync(FULL, !ray_active);
+        if (__popc(idle_mask) >= kRefillIdle) {
+            // 1. idle lanes whose pixel has no rays left write it out and give it up
+            if (!ray_active && have_pixel && stage > last_stage) {
+                p.shadow_ao[pix] = pack_rg16f(shadow, __fdiv_rn(ao, (float)p.ao_spp));
+                if (p.flags & 4) {
+                    float4 payload = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float rt = -1.0f;
+                    if (found) { payload = reflection_hit(p.scene, pfd, hit); rt = hit.t; }
+                    p.reflections[pix] = pack_rgba16f(payload);
+                    if (p.refl_t) p.refl_t[pix] = rt;
+                } else {
+                    p.reflections[pix] = make_uint2(0u, 0u);
+                    if (p.refl_t) p.refl_t[pix] = -1.0f;
+                }
+                have_pixel = false;
+            }
+            // 2. hand out new pixels (warp-uniform control flow)
+            bool want = !ray_active && !have_pixel;
+            uint32_t item = 0xffffffffu;
+            while (true) {
+                const uint32_t wm = __ballot_sync(FULL, want);
+                if (wm == 0u || queue_empty) break;
+                if (chunk_next >= chunk_end) {
+                    uint32_t base = 0u;
+                    if (lane == 0) base = atomicAdd(queue_head, (uint32_t)kChunkPixels);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base >= n_items) { queue_empty = true; break; }
+                    chunk_next = base;
+                    chunk_end = min(base + (uint32_t)kChunkPixels, n_items);
+                }
+                const uint32_t rank = __popc(wm & ((1u << lane) - 1u));
+                const uint32_t avail = chunk_end - chunk_next;
+                if (want && rank < avail) { item = chunk_next + rank; want = false; }
+                chunk_next += min((uint32_t)__popc(wm), avail);
+            }
+            // 3. set up the new pixel (raygen.rgen:15-29)
+            if (item != 0xffffffffu) {
+                const uint32_t tile = item >> 5, within = item & 31u;
+                const int x = (int)(tile % (uint32_t)tiles_x) * 8 + (int)(within & 7u);
+                const int y = p.y_begin + (int)(tile / (uint32_t)tiles_x) * 4 + (int)(within >> 3);
+                if (x < p.W && y < p.y_end) {
+                    pix = (size_t)y * p.W + x;
+                    const float depth = __ldg(&p.depth[pix]);
+                    if (depth == 0.0f) {                                   // sky: raygen.rgen:20-24
+                        p.shadow_ao[pix] = pack_rg16f(1.0f, 1.0f);
+                        p.reflections[pix] = make_uint2(0u, 0u);
+                        if (p.refl_t) p.refl_t[pix] = -1.0f;
+                    } else {
+                        const float u = __fdiv_rn(add_rn((float)x, 0.5f), (float)p.W), v = __fdiv_rn(add_rn((float)y, 0.5f), (float)p.H);
+                        rng = seed_thread(((uint32_t)y * (uint32_t)p.H + (uint32_t)x) * pfd.frame_index);
+                        P = unproject_rn(pfd.camera_viewproj_inverse, depth, u, v);
+                        const float4 n4 = unpack_rgba16f(__ldg(&p.normals[pix]));
+                        N = make_float3(n4.x, n4.y, n4.z);
+                        have_pixel = true;
+                        stage = 0;
+                        shadow = 1.0f; ao = 0.0f; found = false;
+                    }
+                }
+            }
+            // 4. generate the next ray of every idle lane that owns a pixel
+            if (!ray_active && have_pixel) {
+                Ray ray;
+                ray.o = make_float3(add_rn(P.x, mul_rn(N.x, 0.1f)), add_rn(P.y, mul_rn(N.y, 0.1f)), add_rn(P.z, mul_rn(N.z, 0.1f)));
+                ray.tmin = 0.01f;
+                bool launch = false;
+                while (!launch && stage <= last_stage) {
+                    if (stage == 0) {                                      // shadow (raygen.rgen:32-41)
+                        const float rnd1 = random01(rng), rnd2 = random01(rng);
+                        if (p.flags & 1) {
+                            const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+                            ray.d = onb_apply(L, normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f)));
+                            ray.tmax = 10000.0f;
+                            closest = false; launch = true;
+                        } else {
+                            ++stage;
+                        }
+                    } else if (stage <= p.ao_spp) {                        // ambient occlusion (raygen.rgen:44-55)
+                        const float rnd1 = random01(rng), rnd2 = random01(rng);
+                        if (p.flags & 2) {
+                            ray.d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
+                            ray.tmax = 5.0f;
+                            closest = false; launch = true;
+                        } else {
+                            ao = add_rn(ao, 1.0f);
+                            ++stage;
+                        }
+                    } else {                                               // mirror reflection (raygen.rgen:59-65)
+                        const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
+                        const float3 I = normalize_rn(make_float3(sub_rn(P.x, cam.x), sub_rn(P.y, cam.y), sub_rn(P.z, cam.z)));
+                        const float k2 = mul_rn(2.0f, dot3_rn(N, I));
+                        ray.d = make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2)));
+                        ray.tmax = 10000.0f;
+                        closest = true; launch = true;
+                    }
+                }
+                if (launch) {
+                    r = prepare(ray);
+                    tmin = ray.tmin; tmax = ray.tmax;
+                    found = false;
+                    sp = 0;
+                    group = make_uint2(0u, p.scene.n_wide ? 1u : 0u);
+                    ray_active = true;
+                }
+            }
+            if (__ballot_sync(FULL, ray_active) == 0u) {
+                // nothing in flight: either pixels are still being finalised (loop again) or the queue is drained
+                if (queue_empty && __ballot_sync(FULL, have_pixel) == 0u) break;
+                continue;
+            }
+        }
+        // ================================ traverse ================================================================
+        // A burst of up to kBurst node steps per lane with no warp-level synchronisation in between (lanes in the
+        // triangle test and lanes already in their next node test interleave under independent thread scheduling);
+        // the warp only re-votes on refilling after the burst.
+#pragma unroll 1
+        for (int it = 0; it < kBurst && ray_active; ++it) {
+            bool done = false, occluded = false;
+            if (group.y == 0u) {
+                if (sp == 0) done = true;
+                else group = stack[--sp];
+            }
+            if (!done) {
+                const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
+                group.y &= group.y - 1u;
+                if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
+                const uint32_t node = group.x + k;
+                uint32_t child_base, child_hits, leaf_hits;
+                intersect_node(nodes, node, r, tmin, tmax, child_base, child_hits, leaf_hits);
+                group = make_uint2(child_base, child_hits);
+                if (leaf_hits) {
+                    uint32_t tri_base, tri_hits;
+                    expand_leaves(nodes, node, leaf_hits, tri_base, tri_hits);
+                    do {
+                        const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
+                        tri_hits &= tri_hits - 1u;
+                        const float4 *tp = tris + (size_t)(tri_base + j) * 3;
+                        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                        float t, u, v;
+                        if (intersect_tri(r, tmin, tmax, v0, v1, v2, t, u, v)) {
+                            if (!closest) { occluded = true; done = true; break; }
+                            tmax = t;
+                            hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
+                            found = true;
+                        }
+                    } while (tri_hits);
+                }
+            }
+            if (done) {
+                // miss.rmiss: payload 1 (visible); any hit leaves it 0
+                if (stage == 0) shadow = occluded ? 0.0f : 1.0f;
+                else if (stage <= p.ao_spp) ao = add_rn(ao, occluded ? 0.0f : 1.0f);
+                ++stage;
+                ray_active = false;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -398,8 +625,8 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
     int x, y;
     tile_coords(x, y);
     y += p.y_begin;
-    if (x >= p.W || y >= p.y_end) return;
-    const size_t pix = (size_t)y * p.W + x;
+    const bool in_range = x < p.W && y < p.y_end;       // trace() is warp-synchronous: no early return
+    const size_t pix = in_range ? (size_t)y * p.W + x : 0;
     const float u = mul_rn(add_rn((float)x, 0.5f), pfd.display_size_inverse[0]);
     const float v = mul_rn(add_rn((float)y, 0.5f), pfd.display_size_inverse[1]);
     const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
@@ -410,7 +637,9 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
     ray.tmin = 1.0f;
     ray.tmax = 3.0e38f;
     Hit h;
-    if (!trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, h)) {
+    const bool found = trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, in_range, h);
+    if (!in_range) return;
+    if (!found) {
         // clear values of hybrid_render_path.cpp:16-19
         if (p.albedo) p.albedo[pix] = 0u;
         p.normals[pix] = make_uint2(0u, 0u);
@@ -453,19 +682,22 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
 __global__ void trace_explicit_kernel(const float *__restrict__ rays, uint32_t n, int any_hit, SceneRefs s, float *out_t,
                                       uint32_t *out_ids, float *out_uv) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool in_range = i < n;                         // trace() is warp-synchronous: no early return
+    const uint32_t ii = in_range ? i : 0u;
     Ray r;
-    r.o = make_float3(rays[8 * i + 0], rays[8 * i + 1], rays[8 * i + 2]);
-    r.tmin = rays[8 * i + 3];
-    r.d = make_float3(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6]);
-    r.tmax = rays[8 * i + 7];
+    r.o = make_float3(rays[8 * ii + 0], rays[8 * ii + 1], rays[8 * ii + 2]);
+    r.tmin = rays[8 * ii + 3];
+    r.d = make_float3(rays[8 * ii + 4], rays[8 * ii + 5], rays[8 * ii + 6]);
+    r.tmax = rays[8 * ii + 7];
     Hit h;
     h.t = -1.0f; h.u = 0.0f; h.v = 0.0f; h.tri = 0xffffffffu;
-    if (any_hit) {
-        out_t[i] = trace<true>(s.nodes, s.tris, s.n_wide, r, h) ? 1.0f : 0.0f;
+    if (any_hit) {      // uniform across the launch
+        const bool occluded = trace<true>(s.nodes, s.tris, s.n_wide, r, in_range, h);
+        if (in_range) out_t[i] = occluded ? 1.0f : 0.0f;
         return;
     }
-    bool found = trace<false>(s.nodes, s.tris, s.n_wide, r, h);
+    bool found = trace<false>(s.nodes, s.tris, s.n_wide, r, in_range, h);
+    if (!in_range) return;
     out_t[i] = found ? h.t : -1.0f;
     if (out_ids) {
         out_ids[2 * i] = found ? __float_as_uint(s.tris[(size_t)h.tri * 3].w) : 0xffffffffu;
@@ -510,6 +742,20 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
     p.shadow_ao = (uint32_t *)sa->ptr; p.reflections = (uint2 *)refl->ptr;
     p.refl_t = ctx->opt.debug_refl_t ? ctx->d_refl_t : nullptr;
     p.scene = scene_refs(ctx);
+    if (ctx->opt.raygen_variant == 1 && p.ao_spp >= 1) {
+        if (!ctx->d_ray_queue) VHR_CUDA_CHECK(cudaMalloc(&ctx->d_ray_queue, sizeof(uint32_t)));
+        if (ctx->raygen_blocks == 0) {
+            int per_sm = 0, sms = 0;
+            VHR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raygen_persistent_kernel, 128, 0));
+            VHR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->raygen_blocks = std::max(1, per_sm) * std::max(1, sms);     // one resident wave: 148 SMs x blocks/SM
+        }
+        VHR_CUDA_CHECK(cudaMemsetAsync(ctx->d_ray_queue, 0, sizeof(uint32_t), ctx->stream));
+        raygen_persistent_kernel<<<ctx->raygen_blocks, 128, 0, ctx->stream>>>(p, ctx->pfd, ctx->d_ray_queue, getenv("VHR_REFILL_IDLE") ? atoi(getenv("VHR_REFILL_IDLE")) : 16, getenv("VHR_BURST") ? atoi(getenv("VHR_BURST")) : 4);
+        VHR_CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        return VHR_OK;
+    }
     dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
     raygen_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());

@@ -130,6 +130,7 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->d_primitives) cudaFree(ctx->d_primitives);
     if (ctx->d_normal_mats) cudaFree(ctx->d_normal_mats);
     if (ctx->d_refl_t) cudaFree(ctx->d_refl_t);
+    if (ctx->d_ray_queue) cudaFree(ctx->d_ray_queue);
     for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -437,6 +438,9 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
         case VHR_OPT_ATROUS_VARIANT:
             if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
+        case VHR_OPT_RAYGEN_VARIANT:
+            if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);
+            ctx->opt.raygen_variant = (int)value; return VHR_OK;
         case VHR_OPT_DEBUG_REFLECTION_T:
             ctx->opt.debug_refl_t = value != 0;
             if (ctx->device < 0) return VHR_OK;
@@ -465,6 +469,7 @@ int64_t vhr_get_option(vhr_context *ctx, int option) {
         case VHR_OPT_SVGF_FUSED: return ctx->opt.svgf_fused;
         case VHR_OPT_ATROUS_VARIANT: return ctx->opt.atrous_variant;
         case VHR_OPT_DEBUG_REFLECTION_T: return ctx->opt.debug_refl_t;
+        case VHR_OPT_RAYGEN_VARIANT: return ctx->opt.raygen_variant;
     }
     return -1;
 }

@@ -52,6 +52,7 @@ struct Options {
     int svgf_fused = 0;
     int atrous_variant = 1;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel
     int debug_refl_t = 0;        // 1: the ray pass also writes the reflection ray's hit distance (tests)
+    int raygen_variant = 0;      // 0 (default, faster as measured): one thread per pixel, ray kinds in lock step; 1: persistent warps + pixel queue
 };
 
 }  // namespace vhr
@@ -74,6 +75,8 @@ struct vhr_context {
     uint32_t n_vertices = 0, n_indices = 0, n_primitives = 0;
     float *d_normal_mats = nullptr;                // 9 floats per primitive: inverseTranspose(mat3(transform)), column-major
     float *d_refl_t = nullptr;                     // optional debug image: reflection-ray hit distance per pixel
+    uint32_t *d_ray_queue = nullptr;               // head of the persistent ray kernel's pixel queue
+    int raygen_blocks = 0;                         // resident grid of the persistent ray kernel (SMs x blocks/SM)
     vhr::Bvh bvh;
     vhr::Options opt;
     uint64_t launches = 0;
