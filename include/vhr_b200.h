@@ -104,6 +104,18 @@ int vhr_image_upload(vhr_context *ctx, const char *name, const void *host, size_
 int vhr_image_download(vhr_context *ctx, const char *name, void *host, size_t bytes);
 int vhr_storage_image_upload(vhr_context *ctx, int slot, const void *host, size_t bytes);
 int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t bytes);
+/* Transfer queues: the same copies on dedicated upload / download streams, overlapping the passes on the compute
+ * stream (the reference keeps up to three frames in flight behind fences, src/rendering_backend/renderer.cpp:103-108,157).
+ *   upload_async    starts after every pass enqueued so far (the image's last readers); the first later call that
+ *                   binds / blits / copies the image makes the compute stream wait for the upload.
+ *   download_async  snapshots the image on the compute stream (device-to-device) and reads the snapshot back on the
+ *                   download stream, so later passes may overwrite the image immediately; `*ticket` identifies the
+ *                   read-back for vhr_wait_download (reference: vkWaitForFences on the frame's fence). A ticket older
+ *                   than the 64 most recent ones counts as complete.
+ * Host memory must be pinned for the copies to overlap. vhr_context_synchronize also drains both queues. */
+int vhr_image_upload_async(vhr_context *ctx, const char *name, const void *host, size_t bytes);
+int vhr_image_download_async(vhr_context *ctx, const char *name, void *host, size_t bytes, uint32_t *ticket);
+int vhr_wait_download(vhr_context *ctx, uint32_t ticket);
 /* Device pointer of a named image (zero-copy interop, e.g. NCCL halo exchange); NULL if unknown. */
 void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format);
 void *vhr_storage_image_device_ptr(vhr_context *ctx, int slot, uint32_t *width, uint32_t *height, int *vk_format);

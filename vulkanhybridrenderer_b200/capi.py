@@ -23,6 +23,7 @@ SYMBOLS = [
     "vhr_blit_storage_to_transient", "vhr_blit_transient_to_storage", "vhr_blit_storage_to_storage", "vhr_set_option",
     "vhr_get_option", "vhr_get_bvh_stats", "vhr_trace_explicit", "vhr_gbuffer_pass", "vhr_create_query_pool",
     "vhr_write_timestamp", "vhr_get_query_elapsed_ms", "vhr_debug_download_reflection_t",
+    "vhr_image_upload_async", "vhr_image_download_async", "vhr_wait_download",
 ]
 
 OPT_AO_SPP, OPT_TRACE_SHADOWS, OPT_TRACE_AO, OPT_TRACE_REFLECTIONS = 1, 2, 3, 4
@@ -66,6 +67,9 @@ def lib():
         L.vhr_destroy_transient_resources.argtypes = [vp]
         L.vhr_image_upload.argtypes = [vp, C.c_char_p, vp, sz]
         L.vhr_image_download.argtypes = [vp, C.c_char_p, vp, sz]
+        L.vhr_image_upload_async.argtypes = [vp, C.c_char_p, vp, sz]
+        L.vhr_image_download_async.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(u32)]
+        L.vhr_wait_download.argtypes = [vp, u32]
         L.vhr_storage_image_upload.argtypes = [vp, i32, vp, sz]
         L.vhr_storage_image_download.argtypes = [vp, i32, vp, sz]
         L.vhr_image_device_ptr.argtypes = [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(i32)]
@@ -169,6 +173,21 @@ class Context:
     def image_download_into(self, name, host):
         a, n = _addr(host)
         _check(lib().vhr_image_download(self._h, name.encode(), a, n))
+
+    def image_upload_async(self, name, host):
+        """Upload from pinned host memory on the transfer queue; the next pass that binds `name` waits for it."""
+        a, n = _addr(host)
+        _check(lib().vhr_image_upload_async(self._h, name.encode(), a, n))
+
+    def image_download_async(self, name, host):
+        """Read-back on the download queue; returns the ticket for wait_download()."""
+        a, n = _addr(host)
+        t = C.c_uint32()
+        _check(lib().vhr_image_download_async(self._h, name.encode(), a, n, C.byref(t)))
+        return t.value
+
+    def wait_download(self, ticket):
+        _check(lib().vhr_wait_download(self._h, int(ticket)))
 
     def image_info(self, name):
         w, h, f = C.c_uint32(), C.c_uint32(), C.c_int()

@@ -37,7 +37,25 @@ static int alloc_image(vhr_context *ctx, Image &im, uint32_t w, uint32_t h, int 
 static void free_image(Image &im) {
     if (im.ptr) cudaFree(im.ptr);
     if (im.twin) cudaFree(im.twin);
+    if (im.staging) cudaFree(im.staging);
+    if (im.upload_done) cudaEventDestroy(im.upload_done);
+    if (im.staged) cudaEventDestroy(im.staged);
+    if (im.staging_free) cudaEventDestroy(im.staging_free);
     im = Image();
+}
+// Orders the compute stream after an asynchronous upload into `im` that it has not consumed yet.
+static int consume_upload(vhr_context *ctx, Image *im) {
+    if (im && im->upload_pending) {
+        VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, im->upload_done, 0));
+        im->upload_pending = false;
+    }
+    return VHR_OK;
+}
+static int ensure_transfer_queues(vhr_context *ctx) {
+    if (!ctx->upload_stream) VHR_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+    if (!ctx->download_stream) VHR_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->download_stream, cudaStreamNonBlocking));
+    if (!ctx->compute_tail) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->compute_tail, cudaEventDisableTiming));
+    return VHR_OK;
 }
 static Image *find_transient(vhr_context *ctx, const char *name) {
     if (!name) return nullptr;
@@ -47,12 +65,14 @@ static Image *find_transient(vhr_context *ctx, const char *name) {
 static int copy_in(vhr_context *ctx, Image *im, const void *host, size_t bytes, const char *what) {
     if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
     if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", what, bytes, im->bytes);
+    if (int rc = consume_upload(ctx, im)) return rc;
     VHR_CUDA_CHECK(cudaMemcpyAsync(im->ptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return VHR_OK;
 }
 static int copy_out(vhr_context *ctx, Image *im, void *host, size_t bytes, const char *what) {
     if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
     if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", what, bytes, im->bytes);
+    if (int rc = consume_upload(ctx, im)) return rc;
     VHR_CUDA_CHECK(cudaMemcpyAsync(host, im->ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return VHR_OK;
 }
@@ -62,6 +82,8 @@ static int blit(vhr_context *ctx, Image *src, Image *dst, const char *what) {
     if (src->width != dst->width || src->height != dst->height || src->bytes != dst->bytes)
         return fail(VHR_ERR_INVALID, "%s: extents/formats differ (%ux%u fmt %d -> %ux%u fmt %d)", what, src->width,
                     src->height, src->format, dst->width, dst->height, dst->format);
+    if (int rc = consume_upload(ctx, src)) return rc;
+    if (int rc = consume_upload(ctx, dst)) return rc;
     VHR_CUDA_CHECK(cudaMemcpyAsync(dst->ptr, src->ptr, src->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return VHR_OK;
 }
@@ -122,6 +144,8 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
+    if (ctx->download_stream) cudaStreamSynchronize(ctx->download_stream);
     for (auto &kv : ctx->transient) free_image(kv.second);
     for (auto &im : ctx->storage) if (im.used) free_image(im);
     free_bvh(ctx);
@@ -132,6 +156,10 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->d_refl_t) cudaFree(ctx->d_refl_t);
     if (ctx->d_ray_queue) cudaFree(ctx->d_ray_queue);
     for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
+    if (ctx->upload_stream) { cudaStreamSynchronize(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream); }
+    if (ctx->download_stream) { cudaStreamSynchronize(ctx->download_stream); cudaStreamDestroy(ctx->download_stream); }
+    if (ctx->compute_tail) cudaEventDestroy(ctx->compute_tail);
+    for (cudaEvent_t e : ctx->tickets) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -140,6 +168,8 @@ int vhr_context_synchronize(vhr_context *ctx) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     if (ctx->device < 0) return VHR_OK;
     VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->upload_stream) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->upload_stream));
+    if (ctx->download_stream) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->download_stream));
     return VHR_OK;
 }
 
@@ -290,6 +320,66 @@ int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t by
     VHR_NEED_DEVICE(ctx);
     return copy_out(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
 }
+int vhr_image_upload_async(vhr_context *ctx, const char *name, const void *host, size_t bytes) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
+    Image *im = find_transient(ctx, name);
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", name ? name : "(null)");
+    if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", name, bytes, im->bytes);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_transfer_queues(ctx)) return rc;
+    if (!im->upload_done) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->upload_done, cudaEventDisableTiming));
+    // the copy may only start once every pass enqueued so far (the image's last readers) has finished
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->compute_tail, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->upload_stream, ctx->compute_tail, 0));
+    VHR_CUDA_CHECK(cudaMemcpyAsync(im->ptr, host, bytes, cudaMemcpyHostToDevice, ctx->upload_stream));
+    VHR_CUDA_CHECK(cudaEventRecord(im->upload_done, ctx->upload_stream));
+    im->upload_pending = true;
+    return VHR_OK;
+}
+
+int vhr_image_download_async(vhr_context *ctx, const char *name, void *host, size_t bytes, uint32_t *ticket) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
+    Image *im = find_transient(ctx, name);
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", name ? name : "(null)");
+    if (!host || !ticket || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", name, bytes, im->bytes);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_transfer_queues(ctx)) return rc;
+    if (int rc = consume_upload(ctx, im)) return rc;
+    if (!im->staging) {
+        VHR_CUDA_CHECK(cudaMalloc(&im->staging, im->bytes));
+        VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->staged, cudaEventDisableTiming));
+        VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->staging_free, cudaEventDisableTiming));
+    }
+    // snapshot on the compute stream (a device-to-device copy at HBM speed), so later passes may overwrite the image
+    // while the PCIe copy is still in flight; the snapshot itself is reused only after its previous read-back
+    if (im->staging_busy) VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, im->staging_free, 0));
+    VHR_CUDA_CHECK(cudaMemcpyAsync(im->staging, im->ptr, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    VHR_CUDA_CHECK(cudaEventRecord(im->staged, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->download_stream, im->staged, 0));
+    VHR_CUDA_CHECK(cudaMemcpyAsync(host, im->staging, bytes, cudaMemcpyDeviceToHost, ctx->download_stream));
+    VHR_CUDA_CHECK(cudaEventRecord(im->staging_free, ctx->download_stream));
+    im->staging_busy = true;
+    if (ctx->tickets.empty()) {
+        ctx->tickets.resize(64);
+        for (auto &e : ctx->tickets) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint32_t t = ctx->next_ticket++;
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->tickets[t % ctx->tickets.size()], ctx->download_stream));
+    *ticket = t;
+    return VHR_OK;
+}
+
+int vhr_wait_download(vhr_context *ctx, uint32_t ticket) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
+    if (ticket >= ctx->next_ticket) return fail(VHR_ERR_INVALID, "download ticket %u was never issued", ticket);
+    if (ctx->next_ticket - ticket > ctx->tickets.size()) return VHR_OK;   // recycled: that download finished long ago
+    VHR_CUDA_CHECK(cudaEventSynchronize(ctx->tickets[ticket % ctx->tickets.size()]));
+    return VHR_OK;
+}
+
 void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format) {
     Image *im = ctx ? find_transient(ctx, name) : nullptr;
     if (!im) return nullptr;
@@ -313,6 +403,8 @@ int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, 
     for (uint32_t i = 0; i < count; ++i) {
         Image *im = names_by_binding ? find_transient(ctx, names_by_binding[i]) : nullptr;
         if (!im) return fail(VHR_ERR_INVALID, "binding %u: unknown image '%s'", i, (names_by_binding && names_by_binding[i]) ? names_by_binding[i] : "(null)");
+        if (ctx->device >= 0)
+            if (int rc = consume_upload(ctx, im)) return rc;
         ctx->bound[i] = im;
     }
     ctx->n_bound = count;

@@ -19,6 +19,13 @@ struct Image {
     int format = 0;
     size_t bytes = 0;
     bool used = false;
+    // transfer-queue state (vhr_image_upload_async / vhr_image_download_async)
+    cudaEvent_t upload_done = nullptr;   // recorded on the upload stream after the last asynchronous upload
+    bool upload_pending = false;         // the compute stream has not yet waited on upload_done
+    void *staging = nullptr;             // device-side snapshot the download stream reads (the image itself may be rewritten)
+    cudaEvent_t staged = nullptr;        // snapshot written (compute stream)
+    cudaEvent_t staging_free = nullptr;  // snapshot read back (download stream)
+    bool staging_busy = false;
 };
 
 inline int format_texel_bytes(int fmt) {
@@ -81,6 +88,11 @@ struct vhr_context {
     vhr::Options opt;
     uint64_t launches = 0;
     std::vector<cudaEvent_t> queries;              // timestamp query pool
+    // transfer queues: copies that overlap the compute stream (the reference's frames in flight, renderer.cpp:103-108)
+    cudaStream_t upload_stream = nullptr, download_stream = nullptr;
+    cudaEvent_t compute_tail = nullptr;            // scratch event: "everything enqueued on the compute stream so far"
+    std::vector<cudaEvent_t> tickets;              // ring of download-completion events
+    uint32_t next_ticket = 0;
 };
 
 namespace vhr {
