@@ -408,7 +408,7 @@ def run_gpu(args):
             "traversal-bound (software BVH, no RT cores): compulsory G-buffer in + mask out bytes only; see Mrays/s")
         add("svgf_temporal_kernel", pm["svgf_temporal"], px * HP.BYTES_TEMPORAL)
         at_ms = float(np.mean([pm[f"atrous{i}"] for i in (1, 2, 3, 4)]))
-        add("atrous_tiled_kernel (mean of iterations 1-4)", at_ms, px * HP.BYTES_ATROUS)
+        add("atrous_pair_kernel (mean of iterations 1-4)", at_ms, px * HP.BYTES_ATROUS)
         add("atrous iteration 0 + history blit", pm["atrous0"], px * (HP.BYTES_ATROUS + HP.BYTES_BLIT))
         add("blits (prev-normals, denoised)", pm["blits"], px * 2 * HP.BYTES_BLIT)
         dom = max(kernels[:3], key=lambda k: k["ms"])

@@ -1,24 +1,17 @@
-"""Quick device timing of the SVGF / SSAO kernels through the C-ABI (development aid, not the bench)."""
-import sys, os
+"""Profiling target: a few launches of the a-trous kernel (variant / steps from argv) on 1080p synthetic input."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import ctypes as C
 import numpy as np
 from vulkanhybridrenderer_b200 import capi, types as T
+import tools.time_svgf as TS  # noqa: F401  (same inputs)
 
-F4, F2 = T.VK_FORMAT_R16G16B16A16_SFLOAT, T.VK_FORMAT_R16G16_SFLOAT
-
-
-def elapsed(ctx, a, b):
-    ms = C.c_double()
-    capi._check(capi.lib().vhr_get_query_elapsed_ms(ctx._h, a, b, C.byref(ms)))
-    return ms.value
+F4 = T.VK_FORMAT_R16G16B16A16_SFLOAT
 
 
-def main(W=1920, H=1080, reps=20):
+def main(variant=2, W=1920, H=1080):
     rng = np.random.default_rng(0)
     pfd = np.zeros((), T.PerFrameData)
     pfd["display_size"] = (W, H); pfd["display_size_inverse"] = (1.0 / W, 1.0 / H); pfd["frame_index"] = 3
-    pfd["camera_proj_inverse"] = np.eye(4); pfd["camera_view"] = np.eye(4)
     normals = np.zeros((H, W, 4), np.float16)
     n = rng.standard_normal((H // 40 + 1, W // 40 + 1, 3)); n /= np.linalg.norm(n, axis=-1, keepdims=True)
     normals[..., :3] = np.kron(n, np.ones((40, 40, 1)))[:H, :W]
@@ -32,20 +25,13 @@ def main(W=1920, H=1080, reps=20):
         a, b = ctx.upload_new_storage_image(W, H, F4), ctx.upload_new_storage_image(W, H, F4)
         ctx.storage_image_upload(a, integ)
         ctx.bind_pass_images(["n"])
-        capi._check(capi.lib().vhr_create_query_pool(ctx._h, 2))
+        ctx.set_option(capi.OPT_ATROUS_VARIANT, variant)
         gx, gy = (W + 7) // 8, (H + 7) // 8
-        for variant in (0, 1, 2):
-            ctx.set_option(capi.OPT_ATROUS_VARIANT, variant)
+        for rep in range(2):
             for step in (1, 2, 4, 8, 16):
                 pc = np.zeros((), T.SVGFPushConstants); pc["integrated_shadow_and_ao"] = (a, b); pc["atrous_step"] = step
-                for _ in range(3):
-                    ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", gx, gy, 1, pc)
-                capi.lib().vhr_write_timestamp(ctx._h, 0)
-                for _ in range(reps):
-                    ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", gx, gy, 1, pc)
-                capi.lib().vhr_write_timestamp(ctx._h, 1)
-                us = elapsed(ctx, 0, 1) / reps * 1e3
-                print(f"atrous variant {variant} step {step:2d}: {us:8.1f} us  {W*H*24/us/1e3:8.1f} GB/s algorithmic")
+                ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", gx, gy, 1, pc)
+        ctx.synchronize()
 
 
 if __name__ == "__main__":

@@ -9,6 +9,8 @@
 //                                fp32x2 instructions (FADD2/FMUL2/FFMA2).
 //
 // Images: dense row-major; RGBA16F texel = uint2, RG16F texel = uint32. fp32 math, fp16 RTE stores.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "vhr_internal.h"
@@ -354,6 +356,232 @@ static int launch_tiled(vhr_context *ctx, const AtrousParams &p, int x_pixels, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// À-trous, variant 2 (default): pixel pairs on packed fp32x2 + register-level tap reuse
+// ---------------------------------------------------------------------------------------------------------------
+// The first profile of variant 1 (profiles/r01_ncu_full_summary.md) shows the filter bound by instruction issue (70 %)
+// and shared-memory bandwidth (2 x LDS.128 per tap and pixel = 63 % of the LSU's wavefront rate), not by HBM (5 %).
+// This variant attacks both:
+//   * a thread owns a PAIR of pixels PD columns apart and every shared-memory plane stores the two pixels' values side
+//     by side, so one LDS.128 delivers two aligned register pairs and the WHOLE tap pipeline — normal dot product, id
+//     edge stop, the seven squarings of d^128, luminance weights, all accumulations — runs on FMUL2/FFMA2/FADD2
+//     (two pixels per issue slot instead of two channels of one pixel);
+//   * a thread owns RY lattice-adjacent rows of that pair, so a loaded tap is used by up to RY outputs
+//     ((RY+4)*5 loads for RY*25 taps) — shared-memory traffic per tap drops by 5*RY/(RY+4);
+//   * FFMA2 halves the issue slots but not the FP32 lane-cycles (measured: the first packed version, 28.75 FP32 ops per
+//     tap and pixel, ran no faster than variant 1), so the arithmetic itself is cut: kernel weight, d^128 (a cubic in
+//     d - 1 for 128 log2 d) and both luminance stops fold into the argument of ONE ex2 per channel, the id stop is an
+//     integer compare + select on the ALU pipe. 18 FP32 ops + 2 MUFU.EX2 + 2 ALU ops per tap and pixel.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 pmul(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 padd(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 pfma(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 pclamp0(u64 v) { float a, b; upk(v, a, b); return pk(fmaxf(a, 0.0f), fmaxf(b, 0.0f)); }
+__device__ __forceinline__ u64 pex2_negabs(u64 v) { float a, b; upk(v, a, b); return pk(ex2_approx(-fabsf(a)), ex2_approx(-fabsf(b))); }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int S, int PD, int RY, int TR>
+struct PairCfg {
+    static constexpr int PC = PD + 4 * S;        // staged pair-columns per row
+    static constexpr int LR = TR * RY;           // lattice rows (S apart) per CTA
+    static constexpr int SR = LR + 4;            // staged rows
+    static constexpr int THREADS = PD * TR;
+    static constexpr size_t SMEM = (size_t)4 * SR * PC * sizeof(ulonglong2);
+};
+
+template <int S, int PD, int RY, int TR>
+__global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair_kernel(const __grid_constant__ AtrousParams p) {
+    typedef PairCfg<S, PD, RY, TR> C;
+    constexpr int PC = C::PC, SR = C::SR, LR = C::LR;
+    extern __shared__ ulonglong2 psm[];
+    ulonglong2 *sN0 = psm;                 // (nx_a, nx_b), (ny_a, ny_b)
+    ulonglong2 *sN1 = psm + SR * PC;       // (nz_a, nz_b), (id_a, id_b)
+    ulonglong2 *sL = psm + 2 * SR * PC;    // (shadow_a, shadow_b), (ao_a, ao_b)
+    ulonglong2 *sV = psm + 3 * SR * PC;    // (var_shadow_a, var_shadow_b), (var_ao_a, var_ao_b)
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * PD + tx;
+    const int x0 = blockIdx.x * (2 * PD);
+    const int k = blockIdx.y / S, r = blockIdx.y % S;       // (super-tile, residue): rows y = yb + S*j
+    const int yb = p.y_begin + k * (S * LR) + r;
+
+    // ---- stage: every texel converted to fp32 once, pixel a = column j, pixel b = column j + PD ------------------
+    // Two sweeps (all loads, then convert + store) so that every global load of the tile is in flight at once: the
+    // first profile of this kernel had its warps parked on long-scoreboard stalls, one round trip per loop iteration.
+    constexpr int NIT = (SR * PC + C::THREADS - 1) / C::THREADS;
+    uint2 rna[NIT], rnb[NIT], rva[NIT], rvb[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * C::THREADS;
+        const int row = idx / PC, j = idx - row * PC;
+        const int gy = yb + (row - 2) * S;
+        const int gxa = x0 - 2 * S + j, gxb = gxa + PD;
+        rna[it] = rnb[it] = rva[it] = rvb[it] = make_uint2(0u, 0u);     // out of bounds: zero normal => weight 0 ("skipped")
+        if (idx < SR * PC && gy >= 0 && gy < p.H) {
+            const size_t rowp = (size_t)gy * p.W;
+            if (gxa >= 0 && gxa < p.W) { rna[it] = __ldg(&p.normals[rowp + gxa]); rva[it] = __ldg(&p.integ_in[rowp + gxa]); }
+            if (gxb >= 0 && gxb < p.W) { rnb[it] = __ldg(&p.normals[rowp + gxb]); rvb[it] = __ldg(&p.integ_in[rowp + gxb]); }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * C::THREADS;
+        if (idx < SR * PC) {
+            const float4 na = unpack_rgba16f(rna[it]), nb = unpack_rgba16f(rnb[it]);
+            const float4 va = unpack_rgba16f(rva[it]), vb = unpack_rgba16f(rvb[it]);
+            const int ia = f2i_rz(na.w), ib = f2i_rz(nb.w);
+            sN0[idx] = make_ulonglong2(pk(na.x, nb.x), pk(na.y, nb.y));
+            sN1[idx] = make_ulonglong2(pk(na.z, nb.z), (u64)(uint32_t)ia | ((u64)(uint32_t)ib << 32));
+            sL[idx] = make_ulonglong2(pk(va.x, vb.x), pk(va.y, vb.y));
+            sV[idx] = make_ulonglong2(pk(va.z, vb.z), pk(va.w, vb.w));
+        }
+    }
+    __syncthreads();
+
+    const int ca = x0 + tx, cb = ca + PD;
+    const int lr0 = ty * RY;
+    if (ca >= p.x_end || yb + lr0 * S >= p.y_end) return;
+    const int jc = tx + 2 * S;
+
+    // ---- per-output set-up ----------------------------------------------------------------------------------------
+    u64 pnx[RY], pny[RY], pnz[RY], nls[RY], nla[RY];
+    uint32_t ida[RY], idb[RY];
+    float ksa[RY], ksb[RY], kaa[RY], kab[RY];
+    u64 sws[RY], swa[RY], scs[RY], sca[RY], svs[RY], sva[RY];
+    const u64 ONE = pk(1.0f, 1.0f);
+#pragma unroll
+    for (int i = 0; i < RY; ++i) {
+        const int oc = (lr0 + i + 2) * PC + jc;
+        const ulonglong2 n0 = sN0[oc], n1 = sN1[oc], l = sL[oc], v = sV[oc];
+        pnx[i] = n0.x; pny[i] = n0.y; pnz[i] = n1.x;
+        ida[i] = (uint32_t)n1.y; idb[i] = (uint32_t)(n1.y >> 32);
+        float a, b;
+        upk(l.x, a, b); nls[i] = pk(-a, -b);
+        upk(l.y, a, b); nla[i] = pk(-a, -b);
+        sws[i] = ONE; swa[i] = ONE; scs[i] = l.x; sca[i] = l.y; svs[i] = v.x; sva[i] = v.y;
+
+        // 3x3 gaussian of the variance, reference accumulation order; weights are powers of two, so the fused
+        // multiply-adds round exactly like the reference's separate multiply and add
+        u64 gs = pk(0.0f, 0.0f), ga = gs;
+        const int cy = yb + (lr0 + i) * S;
+#pragma unroll
+        for (int y = -1; y <= 1; ++y)
+#pragma unroll
+            for (int x = -1; x <= 1; ++x) {
+                const float w = (x == 0 ? 0.5f : 0.25f) * (y == 0 ? 0.5f : 0.25f);
+                u64 qs, qa;
+                if (S == 1 || y == 0) {
+                    const ulonglong2 t = sV[oc + y * PC + x];          // OOB texels staged as 0
+                    qs = t.x; qa = t.y;
+                } else {
+                    const int sy = cy + y;
+                    float2 ta = make_float2(0.0f, 0.0f), tb = ta;
+                    if (sy >= 0 && sy < p.H) {
+                        const uint32_t *rowp = reinterpret_cast<const uint32_t *>(p.integ_in + (size_t)sy * p.W);
+                        const int xa = ca + x, xb = cb + x;
+                        if (xa >= 0 && xa < p.W) ta = unpack_rg16f(__ldg(rowp + 2 * xa + 1));
+                        if (xb >= 0 && xb < p.W) tb = unpack_rg16f(__ldg(rowp + 2 * xb + 1));
+                    }
+                    qs = pk(ta.x, tb.x); qa = pk(ta.y, tb.y);
+                }
+                gs = pfma(pk(w, w), qs, gs);
+                ga = pfma(pk(w, w), qa, ga);
+            }
+        // exp(-|dl| / (4 sqrt(var) + 1e-6)) = exp2(-|dl| * k), k = log2(e) / (4 sqrt(var) + 1e-6)
+        const float LOG2E = 1.4426950408889634f;
+        float gsa, gsb, gaa, gab;
+        upk(gs, gsa, gsb); upk(ga, gaa, gab);
+        ksa[i] = LOG2E * rcp_approx(fmaf(4.0f, sqrt_approx(gsa), 1e-6f));
+        ksb[i] = LOG2E * rcp_approx(fmaf(4.0f, sqrt_approx(gsb), 1e-6f));
+        kaa[i] = LOG2E * rcp_approx(fmaf(4.0f, sqrt_approx(gaa), 1e-6f));
+        kab[i] = LOG2E * rcp_approx(fmaf(4.0f, sqrt_approx(gab), 1e-6f));
+    }
+
+    // ---- taps: each staged texel pair is loaded once and used by every output row it is a tap of ------------------
+    // All three edge stops and the kernel weight go through ONE exponential per channel:
+    //     w = h * max(d,0)^128 * [id_q == id_p] * exp(-|dl|/sigma) = exp2(g - |dl| * k)
+    //     g = log2(h) + 128 log2(d),  128 log2(1+e) ~ C1 e + C2 e^2 + C3 e^3   (e = d - 1, from the dot product started at -1)
+    // The cubic's error in g is 46 e^4: below 1e-6 in the weight for every d (where |e| is large the weight itself is
+    // < 1e-5), i.e. less than the rounding of the seven fp32 squarings it replaces; d <= 0 gives g <= -338 => w = 0
+    // (pow()'s negative-base rule); a different object id replaces g by -1e30 => w = 0.
+    const u64 M1 = pk(-1.0f, -1.0f);
+    const u64 C1 = pk(184.66496523378731f, 184.66496523378731f);
+    const u64 C2 = pk(-92.33248261689366f, -92.33248261689366f);
+    const u64 C3 = pk(61.55498841126244f, 61.55498841126244f);
+#pragma unroll
+    for (int tr = 0; tr < RY + 4; ++tr) {
+#pragma unroll
+        for (int x = -2; x <= 2; ++x) {
+            const int o = (lr0 + tr) * PC + jc + x * S;
+            const ulonglong2 n0 = sN0[o], n1 = sN1[o], l = sL[o], v = sV[o];
+            const uint32_t qa = (uint32_t)n1.y, qb = (uint32_t)(n1.y >> 32);
+#pragma unroll
+            for (int i = 0; i < RY; ++i) {
+                const int y = tr - 2 - i;                       // this texel is tap (x, y) of output row i
+                if (y < -2 || y > 2 || (x == 0 && y == 0)) continue;
+                // log2 of the kernel weight h(y) h(x), h = (1/16, 1/4, 3/8, 1/4, 1/16)
+                const float lgh = ((y == 0) ? -1.4150374992788437f : ((y == 1 || y == -1) ? -2.0f : -4.0f)) +
+                                  ((x == 0) ? -1.4150374992788437f : ((x == 1 || x == -1) ? -2.0f : -4.0f));
+                u64 e = pfma(pnx[i], n0.x, M1);
+                e = pfma(pny[i], n0.y, e);
+                e = pfma(pnz[i], n1.x, e);
+                u64 u = pfma(C3, e, C2);
+                u = pfma(u, e, C1);
+                const u64 g = pfma(u, e, pk(lgh, lgh));
+                float ga, gb, da, db;
+                upk(g, ga, gb);
+                ga = (qa == ida[i]) ? ga : -1.0e30f;
+                gb = (qb == idb[i]) ? gb : -1.0e30f;
+                upk(padd(l.x, nls[i]), da, db);
+                const u64 wsh = pk(ex2_approx(fmaf(-fabsf(da), ksa[i], ga)), ex2_approx(fmaf(-fabsf(db), ksb[i], gb)));
+                upk(padd(l.y, nla[i]), da, db);
+                const u64 wao = pk(ex2_approx(fmaf(-fabsf(da), kaa[i], ga)), ex2_approx(fmaf(-fabsf(db), kab[i], gb)));
+                sws[i] = padd(sws[i], wsh);
+                swa[i] = padd(swa[i], wao);
+                scs[i] = pfma(wsh, l.x, scs[i]);
+                sca[i] = pfma(wao, l.y, sca[i]);
+                svs[i] = pfma(pmul(wsh, wsh), v.x, svs[i]);
+                sva[i] = pfma(pmul(wao, wao), v.y, sva[i]);
+            }
+        }
+    }
+
+    // ---- normalise, fp16 RTE store -----------------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < RY; ++i) {
+        const int cy = yb + (lr0 + i) * S;
+        if (cy >= p.y_end) break;
+        float wsa, wsb, waa, wab, csa, csb, caa, cab, vsa, vsb, vaa, vab;
+        upk(sws[i], wsa, wsb); upk(swa[i], waa, wab);
+        upk(scs[i], csa, csb); upk(sca[i], caa, cab);
+        upk(svs[i], vsa, vsb); upk(sva[i], vaa, vab);
+        const float rsa = rcp_approx(wsa), rsb = rcp_approx(wsb), raa = rcp_approx(waa), rab = rcp_approx(wab);
+        uint2 *orow = p.integ_out + (size_t)cy * p.W;
+        orow[ca] = pack_rgba16f(make_float4(csa * rsa, caa * raa, vsa * (rsa * rsa), vaa * (raa * raa)));
+        if (cb < p.x_end) orow[cb] = pack_rgba16f(make_float4(csb * rsb, cab * rab, vsb * (rsb * rsb), vab * (rab * rab)));
+    }
+}
+
+template <int S, int PD, int RY, int TR>
+static int launch_pair(vhr_context *ctx, const AtrousParams &p, int x_pixels, int y_pixels) {
+    typedef PairCfg<S, PD, RY, TR> C;
+    static_assert(C::SMEM <= 110 * 1024, "two CTAs per SM must fit in shared memory");
+    static bool configured = false;     // per (kernel instantiation, process); the attribute is per function, not per device context
+    if (!configured) {
+        VHR_CUDA_CHECK(cudaFuncSetAttribute(atrous_pair_kernel<S, PD, RY, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    dim3 block(PD, TR);
+    dim3 grid((x_pixels + 2 * PD - 1) / (2 * PD), ((y_pixels + S * C::LR - 1) / (S * C::LR)) * S);
+    atrous_pair_kernel<S, PD, RY, TR><<<grid, block, C::SMEM, ctx->stream>>>(p);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------------------------
 static bool dispatch_range(vhr_context *ctx, const Image *ref, uint32_t xg, uint32_t yg, int &x_end, int &y0, int &y1) {
@@ -426,8 +654,30 @@ int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPus
     p.normals = (const uint2 *)normals->ptr; p.integ_in = (const uint2 *)in->ptr; p.integ_out = (uint2 *)out->ptr;
     // The tiled kernel bounds-checks against the image size; the reference checks against pfd.display_size. They are
     // the same thing whenever the UBO matches the images, which the tiled path requires.
-    bool tiled_ok = ctx->opt.atrous_variant == 1 && p.dsx == (float)p.W && p.dsy == (float)p.H;
-    if (tiled_ok) {
+    bool tiled_ok = ctx->opt.atrous_variant >= 1 && p.dsx == (float)p.W && p.dsy == (float)p.H;
+    static const int dev_tr = getenv("VHR_ATROUS_TR") ? atoi(getenv("VHR_ATROUS_TR")) : 4;     // development A/B switch
+    if (tiled_ok && ctx->opt.atrous_variant == 2 && dev_tr == 2) {
+        int xp = p.x_end, yp = p.y_end - p.y_begin;
+        switch (p.step) {
+            case 1: return launch_pair<1, 64, 2, 2>(ctx, p, xp, yp);
+            case 2: return launch_pair<2, 64, 2, 2>(ctx, p, xp, yp);
+            case 4: return launch_pair<4, 64, 2, 2>(ctx, p, xp, yp);
+            case 8: return launch_pair<8, 64, 2, 2>(ctx, p, xp, yp);
+            case 16: return launch_pair<16, 64, 2, 2>(ctx, p, xp, yp);
+            default: break;
+        }
+    }
+    if (tiled_ok && ctx->opt.atrous_variant == 2) {
+        int xp = p.x_end, yp = p.y_end - p.y_begin;
+        switch (p.step) {
+            case 1: return launch_pair<1, 64, 2, 4>(ctx, p, xp, yp);
+            case 2: return launch_pair<2, 64, 2, 4>(ctx, p, xp, yp);
+            case 4: return launch_pair<4, 64, 2, 4>(ctx, p, xp, yp);
+            case 8: return launch_pair<8, 64, 2, 4>(ctx, p, xp, yp);
+            case 16: return launch_pair<16, 64, 2, 4>(ctx, p, xp, yp);
+            default: break;   // other steps: direct kernel
+        }
+    } else if (tiled_ok) {
         int xp = p.x_end, yp = p.y_end - p.y_begin;
         switch (p.step) {
             case 1: return launch_tiled<1>(ctx, p, xp, yp);

@@ -528,7 +528,7 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
         case VHR_OPT_ROW_END: ctx->opt.row_end = (int)value; return VHR_OK;
         case VHR_OPT_SVGF_FUSED: ctx->opt.svgf_fused = value != 0; return VHR_OK;
         case VHR_OPT_ATROUS_VARIANT:
-            if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
+            if (value < 0 || value > 2) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
         case VHR_OPT_RAYGEN_VARIANT:
             if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);

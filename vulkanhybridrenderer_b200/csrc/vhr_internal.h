@@ -57,7 +57,7 @@ struct Options {
     int row_begin = 0;
     int row_end = -1;            // -1 = image height
     int svgf_fused = 0;
-    int atrous_variant = 1;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel
+    int atrous_variant = 2;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel, 2 = pixel-pair packed kernel
     int debug_refl_t = 0;        // 1: the ray pass also writes the reflection ray's hit distance (tests)
     int raygen_variant = 0;      // 0 (default, faster as measured): one thread per pixel, ray kinds in lock step; 1: persistent warps + pixel queue
 };
