@@ -109,8 +109,17 @@ __device__ __forceinline__ bool intersect_tri(const RayPre &r, float tmin, float
 // Byte -> float without the quarter-rate conversion unit: PRMT drops byte i of `w` into mantissa bits 8..15 of
 // 0x47000000 (= 32768.0f), giving exactly 32768 + q on the integer pipe; the bias is folded into the slab offset.
 // (I2F.U8 runs on the XU pipe at 16 lanes/clk/SM and was 73 % busy in the first profile — profiles/r01_*.)
-__device__ __forceinline__ float byte_biased(uint32_t w, int i) {
-    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7604u | ((uint32_t)i << 4)));
+// `bias` is 0x47000000 passed in through the kernel parameters (SceneRefs::bias) so that ptxas cannot fold it: PRMT takes one immediate, and
+// with both the bias and the selector known it kept the four selectors in registers and re-materialised them around
+// every use (~40 MOV / IMAD.U32 per node test in the second profile); now the selector is the immediate.
+__device__ __forceinline__ float byte_biased(uint32_t w, int i, uint32_t bias) {
+    return __uint_as_float(__byte_perm(w, bias, 0x7604u | ((uint32_t)i << 4)));
+}
+// (a <= b) ? 0xffffffff : 0 in one instruction (FSET.BF), so a hit bit costs FSET + LOP3 instead of FSETP + SEL + IADD3
+__device__ __forceinline__ uint32_t set_le(float a, float b) {
+    uint32_t r;
+    asm("set.le.u32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
 }
 
 struct Hit {
@@ -122,7 +131,7 @@ struct Hit {
 // slots, so the hit bits split into (internal children, by ordinal) and (leaf slots) with two ANDs; the leaf slots'
 // triangle ranges are only decoded when the triangles are actually tested (expand_leaves).
 __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ nodes, uint32_t idx, const RayPre &r, float tmin,
-                                               float tmax, uint32_t &child_base, uint32_t &child_hits, uint32_t &leaf_hits) {
+                                               float tmax, uint32_t bias, uint32_t &child_base, uint32_t &child_hits, uint32_t &leaf_hits) {
     const uint4 *np = reinterpret_cast<const uint4 *>(nodes + idx);
     const uint4 n0 = __ldg(np + 0), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     child_base = __ldg(reinterpret_cast<const uint32_t *>(np + 1));
@@ -151,13 +160,13 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const int w = s >> 2, b = s & 3;
-        const float tnx = fmaf(byte_biased(nearx[w], b), ax, bnx), tfx = fmaf(byte_biased(farx[w], b), afx, bfx);
-        const float tny = fmaf(byte_biased(neary[w], b), ay, bny), tfy = fmaf(byte_biased(fary[w], b), afy, bfy);
-        const float tnz = fmaf(byte_biased(nearz[w], b), az, bnz), tfz = fmaf(byte_biased(farz[w], b), afz, bfz);
+        const float tnx = fmaf(byte_biased(nearx[w], b, bias), ax, bnx), tfx = fmaf(byte_biased(farx[w], b, bias), afx, bfx);
+        const float tny = fmaf(byte_biased(neary[w], b, bias), ay, bny), tfy = fmaf(byte_biased(fary[w], b, bias), afy, bfy);
+        const float tnz = fmaf(byte_biased(nearz[w], b, bias), az, bnz), tfz = fmaf(byte_biased(farz[w], b, bias), afz, bfz);
         const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
         const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
         // empty slots carry an inverted box (qlo = 255, qhi = 0) and can never pass this test
-        if (tn <= tf) hits |= 1u << s;
+        hits |= set_le(tn, tf) & (1u << s);
     }
     const uint32_t imask = n0.w >> 24;
     child_hits = hits & imask;
@@ -166,22 +175,24 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
 
 // Decodes the triangle ranges of the hit leaf slots of a node into a 24-bit mask over [tri_base, tri_base + 24).
 __device__ __forceinline__ void expand_leaves(const WideNode *__restrict__ nodes, uint32_t idx, uint32_t leaf_hits, uint32_t &tri_base,
-                                              uint32_t &tri_hits) {
+                                              uint32_t &tri_hits) {   // leaf_hits != 0
     const uint4 n1 = __ldg(reinterpret_cast<const uint4 *>(nodes + idx) + 1);
     tri_base = n1.y;
     tri_hits = 0u;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        const uint32_t m = ((s < 4 ? n1.z : n1.w) >> (8 * (s & 3))) & 0xffu;
-        if ((leaf_hits >> s) & 1u) tri_hits |= ((1u << (m >> 5)) - 1u) << (m & 31u);
-    }
+    // one short iteration per hit slot (usually one or two) instead of decoding all eight
+    do {
+        const uint32_t s = (uint32_t)__ffs((int)leaf_hits) - 1u;
+        leaf_hits &= leaf_hits - 1u;
+        const uint32_t m = __byte_perm(n1.z, n1.w, s) & 0xffu;
+        tri_hits |= ((1u << (m >> 5)) - 1u) << (m & 31u);
+    } while (leaf_hits);
 }
 
 // while-while traversal (Aila & Laine 2009) over the 8-wide nodes, one ray per lane; every lane of the warp calls
 // trace() together (`alive` = this lane really has a ray) so callers never diverge before the loop.
 template <bool ANY>
 __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
-                                      const Ray &ray, bool alive, Hit &hit) {
+                                      uint32_t bias, const Ray &ray, bool alive, Hit &hit) {
     if (!alive || n_wide == 0) return false;
     const RayPre r = prepare(ray);
     float tmax = ray.tmax;
@@ -199,7 +210,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
         if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
         const uint32_t node = group.x + k;
         uint32_t child_base, child_hits, leaf_hits;
-        intersect_node(nodes, node, r, ray.tmin, tmax, child_base, child_hits, leaf_hits);
+        intersect_node(nodes, node, r, ray.tmin, tmax, bias, child_base, child_hits, leaf_hits);
         group = make_uint2(child_base, child_hits);
         if (leaf_hits) {
             uint32_t tri_base, tri_hits;
@@ -233,6 +244,7 @@ struct SceneRefs {
     const WideNode *nodes;
     const float4 *tris;
     uint32_t n_wide;
+    uint32_t bias;                // 0x47000000 (see byte_biased)
 };
 
 __device__ __forceinline__ float3 f3(const float *p) { return make_float3(p[0], p[1], p[2]); }
@@ -354,7 +366,7 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
         const float3 cone = normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f));
         ray.d = onb_apply(L, cone);
         ray.tmax = 10000.0f;
-        shadow = trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, lit, hit) ? 0.0f : 1.0f;
+        shadow = trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit) ? 0.0f : 1.0f;
     }
     // ambient occlusion (raygen.rgen:44-55)
     float ao = 0.0f;
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
         if (p.flags & 2) {
             ray.d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
             ray.tmax = 5.0f;
-            ao = add_rn(ao, trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, lit, hit) ? 0.0f : 1.0f);
+            ao = add_rn(ao, trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit) ? 0.0f : 1.0f);
         } else {
             ao = add_rn(ao, 1.0f);
         }
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
         const float k2 = mul_rn(2.0f, dot3_rn(N, I));
         ray.d = make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2)));
         ray.tmax = 10000.0f;
-        if (trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, lit, hit) && lit) {
+        if (trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit) && lit) {
             payload = reflection_hit(p.scene, pfd, hit);
             rt = hit.t;
         }
@@ -441,6 +453,7 @@ __global__ void __launch_bounds__(128) raygen_persistent_kernel(const __grid_con
     uint2 stack[kStackSize];
     int sp = 0;
     uint2 group = make_uint2(0u, 0u);
+    const uint32_t bias = p.scene.bias;
 
     while (true) {
         // ================================ refill ==================================================================
@@ -572,7 +585,7 @@ __global__ void __launch_bounds__(128) raygen_persistent_kernel(const __grid_con
                 if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
                 const uint32_t node = group.x + k;
                 uint32_t child_base, child_hits, leaf_hits;
-                intersect_node(nodes, node, r, tmin, tmax, child_base, child_hits, leaf_hits);
+                intersect_node(nodes, node, r, tmin, tmax, bias, child_base, child_hits, leaf_hits);
                 group = make_uint2(child_base, child_hits);
                 if (leaf_hits) {
                     uint32_t tri_base, tri_hits;
@@ -637,7 +650,7 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
     ray.tmin = 1.0f;
     ray.tmax = 3.0e38f;
     Hit h;
-    const bool found = trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, ray, in_range, h);
+    const bool found = trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, in_range, h);
     if (!in_range) return;
     if (!found) {
         // clear values of hybrid_render_path.cpp:16-19
@@ -692,11 +705,11 @@ __global__ void trace_explicit_kernel(const float *__restrict__ rays, uint32_t n
     Hit h;
     h.t = -1.0f; h.u = 0.0f; h.v = 0.0f; h.tri = 0xffffffffu;
     if (any_hit) {      // uniform across the launch
-        const bool occluded = trace<true>(s.nodes, s.tris, s.n_wide, r, in_range, h);
+        const bool occluded = trace<true>(s.nodes, s.tris, s.n_wide, s.bias, r, in_range, h);
         if (in_range) out_t[i] = occluded ? 1.0f : 0.0f;
         return;
     }
-    bool found = trace<false>(s.nodes, s.tris, s.n_wide, r, in_range, h);
+    bool found = trace<false>(s.nodes, s.tris, s.n_wide, s.bias, r, in_range, h);
     if (!in_range) return;
     out_t[i] = found ? h.t : -1.0f;
     if (out_ids) {
@@ -711,6 +724,7 @@ SceneRefs scene_refs(vhr_context *ctx) {
     s.verts = ctx->d_vertices; s.indices = ctx->d_indices; s.prims = ctx->d_primitives;
     s.normal_mats = ctx->d_normal_mats;
     s.nodes = (const WideNode *)ctx->bvh.wide_nodes; s.tris = ctx->bvh.tri_verts; s.n_wide = ctx->bvh.n_wide;
+    s.bias = 0x47000000u;
     return s;
 }
 
