@@ -37,6 +37,7 @@ typedef enum vhr_status {
 /* VkFormat values accepted for images (src/render_paths/hybrid_render_path.cpp:16-19,109-110,247-261). */
 enum {
     VHR_FORMAT_B8G8R8A8_UNORM = 44,
+    VHR_FORMAT_B8G8R8A8_SRGB = 50,   /* the swapchain format RENDER_OUTPUT has in the reference (vulkan_context.cpp:331) */
     VHR_FORMAT_R16G16_SFLOAT = 83,
     VHR_FORMAT_R16G16B16A16_SFLOAT = 97,
     VHR_FORMAT_D32_SFLOAT = 126
@@ -139,6 +140,19 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
  * raygen.rgen + miss.rmiss + reflection_miss.rmiss + reflection_hit.rchit (hybrid_render_path.cpp:111-123).
  * Bound images: 0 normals/object ids, 1 depth, 2 shadow+AO (RG16F), 3 reflections (RGBA16F). */
 int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height);
+
+/* GraphicsExecutionContext::Draw (src/render_graph/graphics_execution_context.cpp:38-41) inside
+ * execute_pipeline(<graphics pipeline>) (render_graph.cpp:722-796). The one graphics pipeline on the hot path's
+ * consumer side is "Composition Pipeline" (hybrid_render_path.cpp:333-379): composition.vert + composition.frag drawn
+ * as one full-screen triangle, Draw(3, 1, 0, 0). `fragment_shader` selects the kernel ("hybrid_render_path/
+ * composition.frag"), `specialization_constants` are the pipeline's (shadow_mode, ambient_occlusion_mode,
+ * reflection_mode), common.glsl:12-25. Bound images: the nine sampled inputs by binding (0 albedo, 1 normals/ids,
+ * 2 motion/metallic-roughness, 3 depth, 4 shadow map, 5 SSAO, 6 SSR, 7 shadow+AO — denoised RGBA16F or raw RG16F —,
+ * 8 reflections) followed by colour attachment 0 (RENDER_OUTPUT) at index 9. The attachment may be B8G8R8A8_SRGB (the
+ * reference's swapchain: sRGB-encoded on store), B8G8R8A8_UNORM, or R16G16B16A16_SFLOAT (linear HDR radiance, for
+ * parity measurements). Any other shader or draw shape fails with VHR_ERR_INVALID (there is no rasteriser). */
+int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *specialization_constants, uint32_t n_constants,
+             uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance);
 
 /* ComputeExecutionContext::Blit* (compute_execution_context.cpp:31-211): same-size, same-format image copies. */
 int vhr_blit_storage_to_transient(vhr_context *ctx, int src_slot, const char *dst_name);

@@ -14,7 +14,7 @@ from vulkanhybridrenderer_b200 import types as T
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in oracle/)
 _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 _SO = os.path.join(_ORACLE_DIR, "_build", "libvhr_oracle.so")
-_SRCS = ["oracle_common.h", "oracle_svgf.cpp", "oracle_rt.cpp", "Makefile"]
+_SRCS = ["oracle_common.h", "oracle_svgf.cpp", "oracle_rt.cpp", "oracle_composition.cpp", "Makefile"]
 
 
 def build(force=False):
@@ -56,6 +56,7 @@ def _declare(L):
     L.vo_svgf_pass.argtypes = [vp] * 8
     L.vo_ssao.argtypes = [vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]
     L.vo_ssao_blur.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.vo_composition.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]
     L.vo_seed_thread.restype = C.c_uint32
     L.vo_seed_thread.argtypes = [C.c_uint32]
     L.vo_random01.restype = C.c_float
@@ -143,6 +144,26 @@ def ssao_blur(pfd, raw):
     H, W = raw.shape[:2]
     out = np.empty((H, W, 4), np.float16)
     lib().vo_ssao_blur(_p(pfd), W, H, _p(_h(raw)), _p(out))
+    return out
+
+
+def composition(pfd, albedo, normals, motion, depth, rt, shadow_mode=0, ao_mode=0, reflection_mode=2, ssao_img=None, ssr_img=None,
+                refl=None, shadow_map=None, out_format=T.VK_FORMAT_R16G16B16A16_SFLOAT):
+    """composition.frag over a whole frame. `rt` is the raw RG16F or the denoised RGBA16F shadow/AO image (binding 7)."""
+    H, W = depth.shape[:2]
+    zero4 = np.zeros((H, W, 4), np.float16)
+    ssao_img = zero4 if ssao_img is None else _h(ssao_img)
+    ssr_img = zero4 if ssr_img is None else _h(ssr_img)
+    refl = zero4 if refl is None else _h(refl)
+    if shadow_map is None:
+        shadow_map = np.zeros((4, 4), np.float32)
+    sm = np.ascontiguousarray(shadow_map, np.float32)
+    rt = _h(rt)
+    out = np.empty((H, W, 4), np.float16 if out_format == T.VK_FORMAT_R16G16B16A16_SFLOAT else np.uint8)
+    a8 = np.ascontiguousarray(albedo, np.uint8)
+    d = np.ascontiguousarray(depth, np.float32)
+    lib().vo_composition(_p(pfd), W, H, int(shadow_mode), int(ao_mode), int(reflection_mode), _p(a8), _p(_h(normals)), _p(_h(motion)), _p(d),
+                         _p(sm), sm.shape[1], sm.shape[0], _p(ssao_img), _p(ssr_img), _p(rt), rt.shape[-1], _p(refl), int(out_format), _p(out))
     return out
 
 

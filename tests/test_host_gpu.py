@@ -45,6 +45,15 @@ def test_hybrid_path_frames_vs_oracle():
             ref_den, _, _ = state.run(pfd, normals, motion, rt, want_iters=False)
             Hh.assert_parity(den, ref_den, f"host frame {f} denoised")
             assert r.pass_time_ms("Raytrace Pass") > 0 and r.pass_time_ms("SVGF Denoise Pass", last=False) > 0
+            # Composition Pass (the graph's last node, a CUDA kernel behind GraphicsExecutionContext::Draw): RENDER_OUTPUT is
+            # the reference's B8G8R8A8_SRGB swapchain image
+            out = ctx.image_download(HP.N_RENDER_OUTPUT)
+            want = O.composition(pfd, ctx.image_download(HP.N_ALBEDO), normals, motion, depth, den, 0, 0, 0, refl=refl,
+                                 out_format=HP.T.VK_FORMAT_B8G8R8A8_SRGB)
+            code = np.abs(out.astype(np.int32) - want.astype(np.int32))
+            print(f"[host] frame {f}: RENDER_OUTPUT exact {np.mean(code == 0)*100:.3f}% max code diff {code.max()}  composition {r.pass_time_ms('Composition Pass'):.3f} ms")
+            assert code.max() <= 1 and np.mean(code == 0) >= 0.995
+            assert out[..., :3].max() > 0 and r.pass_time_ms("Composition Pass") > 0
 
 
 def test_mode_switch_and_ssao_nodes():

@@ -23,7 +23,7 @@ SYMBOLS = [
     "vhr_blit_storage_to_transient", "vhr_blit_transient_to_storage", "vhr_blit_storage_to_storage", "vhr_set_option",
     "vhr_get_option", "vhr_get_bvh_stats", "vhr_trace_explicit", "vhr_gbuffer_pass", "vhr_create_query_pool",
     "vhr_write_timestamp", "vhr_get_query_elapsed_ms", "vhr_debug_download_reflection_t",
-    "vhr_image_upload_async", "vhr_image_download_async", "vhr_wait_download",
+    "vhr_image_upload_async", "vhr_image_download_async", "vhr_wait_download", "vhr_draw",
 ]
 
 OPT_AO_SPP, OPT_TRACE_SHADOWS, OPT_TRACE_AO, OPT_TRACE_REFLECTIONS = 1, 2, 3, 4
@@ -88,6 +88,7 @@ def lib():
         L.vhr_get_bvh_stats.argtypes = [vp, C.POINTER(BvhStats)]
         L.vhr_trace_explicit.argtypes = [vp, vp, u32, i32, vp, vp, vp]
         L.vhr_gbuffer_pass.argtypes = [vp, u32, u32]
+        L.vhr_draw.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32), u32, u32, u32, u32, u32]
         L.vhr_debug_download_reflection_t.argtypes = [vp, vp, sz]
         L.vhr_create_query_pool.argtypes = [vp, u32]
         L.vhr_write_timestamp.argtypes = [vp, u32]
@@ -241,6 +242,12 @@ class Context:
 
     def trace_rays(self, width, height, pipeline="Raytrace Pipeline"):
         _check(lib().vhr_trace_rays(self._h, pipeline.encode(), width, height))
+
+    def draw(self, fragment_shader, specialization_constants, vertex_count=3, instance_count=1, first_vertex=0, first_instance=0):
+        """GraphicsExecutionContext::Draw for the composition pipeline (see vhr_draw)."""
+        sc = (C.c_int32 * len(specialization_constants))(*[int(v) for v in specialization_constants])
+        _check(lib().vhr_draw(self._h, fragment_shader.encode(), sc, len(specialization_constants), vertex_count, instance_count,
+                              first_vertex, first_instance))
 
     def gbuffer_pass(self, width, height):
         _check(lib().vhr_gbuffer_pass(self._h, width, height))

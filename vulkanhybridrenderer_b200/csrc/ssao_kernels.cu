@@ -21,27 +21,6 @@ struct SsaoParams {
     uint2 *out;               // binding 2 (RGBA16F)
 };
 
-__device__ __forceinline__ int wrap_repeat(int i, int n) {
-    int m = i % n;
-    return m < 0 ? m + n : m;
-}
-__device__ __forceinline__ void bilinear_setup(float u, int n, int &i0, int &i1, float &a) {
-    float uu = sub_rn(mul_rn(u, (float)n), 0.5f);
-    float fl = floorf(uu);
-    a = sub_rn(uu, fl);
-    int i = (fl == fl && fabsf(fl) < 1e9f) ? (int)fl : 0;
-    i0 = wrap_repeat(i, n);
-    i1 = wrap_repeat(i + 1, n);
-}
-// (1-a)(1-b) t00 + a(1-b) t10 + (1-a) b t01 + a b t11, accumulated left to right like the oracle
-__device__ __forceinline__ float bilerp_rn(float a, float b, float t00, float t10, float t01, float t11) {
-    float oma = sub_rn(1.0f, a), omb = sub_rn(1.0f, b);
-    float r = mul_rn(mul_rn(oma, omb), t00);
-    r = add_rn(r, mul_rn(mul_rn(a, omb), t10));
-    r = add_rn(r, mul_rn(mul_rn(oma, b), t01));
-    r = add_rn(r, mul_rn(mul_rn(a, b), t11));
-    return r;
-}
 __device__ __forceinline__ float sample_depth(const SsaoParams &p, float u, float v) {
     int x0, x1, y0, y1;
     float a, b;

@@ -456,6 +456,21 @@ int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, 
     return launch_trace_rays(ctx, width, height);
 }
 
+int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *specialization_constants, uint32_t n_constants,
+             uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance) {
+    if (!ctx || !fragment_shader) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_NEED_DEVICE(ctx);
+    if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
+    if (strcmp(fragment_shader, "hybrid_render_path/composition.frag"))
+        return fail(VHR_ERR_INVALID, "vhr_draw: no kernel for fragment shader '%s' (only the composition pass is a CUDA kernel)", fragment_shader);
+    if (vertex_count != 3 || instance_count != 1 || first_vertex != 0 || first_instance != 0)
+        return fail(VHR_ERR_INVALID, "vhr_draw: composition is Draw(3, 1, 0, 0), got (%u, %u, %u, %u)", vertex_count, instance_count, first_vertex, first_instance);
+    if (!specialization_constants || n_constants != 3)
+        return fail(VHR_ERR_INVALID, "vhr_draw: composition.frag takes 3 specialization constants, got %u", n_constants);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_composition(ctx, specialization_constants[0], specialization_constants[1], specialization_constants[2]);
+}
+
 int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);

@@ -31,6 +31,7 @@ struct Image {
 inline int format_texel_bytes(int fmt) {
     switch (fmt) {
         case VHR_FORMAT_B8G8R8A8_UNORM: return 4;
+        case VHR_FORMAT_B8G8R8A8_SRGB: return 4;
         case VHR_FORMAT_R16G16_SFLOAT: return 4;
         case VHR_FORMAT_R16G16B16A16_SFLOAT: return 8;
         case VHR_FORMAT_D32_SFLOAT: return 4;
@@ -113,6 +114,7 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius);
 int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg);
 int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height);
 int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height);
+int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int reflection_mode);
 int launch_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
                           float *out_uv);
 int build_bvh(vhr_context *ctx);

@@ -21,6 +21,7 @@
 enum VkFormat : int {
     VK_FORMAT_UNDEFINED = 0,
     VK_FORMAT_B8G8R8A8_UNORM = VHR_FORMAT_B8G8R8A8_UNORM,
+    VK_FORMAT_B8G8R8A8_SRGB = VHR_FORMAT_B8G8R8A8_SRGB,
     VK_FORMAT_R16G16_SFLOAT = VHR_FORMAT_R16G16_SFLOAT,
     VK_FORMAT_R16G16B16A16_SFLOAT = VHR_FORMAT_R16G16B16A16_SFLOAT,
     VK_FORMAT_D32_SFLOAT = VHR_FORMAT_D32_SFLOAT,
@@ -151,9 +152,10 @@ inline TransientResource CreateTransientSampledImage(const char *name, uint32_t 
 inline TransientResource CreateTransientStorageImage(const char *name, VkFormat format, uint32_t binding) {
     return MakeImage(TransientImageType::StorageImage, name, 0, 0, format, binding);
 }
-// vulkan_utils.h:444-453: the swapchain image; in the headless build a BGRA8 image named RENDER_OUTPUT
+// vulkan_utils.h:444-453: the swapchain image; in the headless build an image named RENDER_OUTPUT in the swapchain's
+// format, B8G8R8A8_SRGB (vulkan_context.cpp:331)
 inline TransientResource CreateTransientRenderOutput(uint32_t binding) {
-    return MakeImage(TransientImageType::AttachmentImage, "RENDER_OUTPUT", 0, 0, VK_FORMAT_B8G8R8A8_UNORM, binding);
+    return MakeImage(TransientImageType::AttachmentImage, "RENDER_OUTPUT", 0, 0, VK_FORMAT_B8G8R8A8_SRGB, binding);
 }
 }  // namespace VkUtils
 

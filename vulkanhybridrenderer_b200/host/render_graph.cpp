@@ -180,6 +180,18 @@ void RenderGraph::BindPassImages(const RenderPassDescription &pass) {
     VHR_CHECK(vhr_bind_pass_images(resource_manager.ctx, names, count));
 }
 
+bool GraphicsExecutionContext::HasKernel(const GraphicsPipelineDescription &pipeline) {
+    return pipeline.fragment_shader && std::string(pipeline.fragment_shader) == "hybrid_render_path/composition.frag";
+}
+void GraphicsExecutionContext::Draw(uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance) {
+    ++draws;
+    if (!pipeline || !HasKernel(*pipeline)) return;
+    const std::vector<int> &sc = pipeline->specialization_constants;
+    std::vector<int32_t> constants(sc.begin(), sc.end());
+    VHR_CHECK(vhr_draw(resource_manager.ctx, pipeline->fragment_shader, constants.data(), (uint32_t)constants.size(), vertex_count, instance_count,
+                       first_vertex, first_instance));
+}
+
 void RenderGraph::SetGraphicsPassHook(const std::string &pass_name, std::function<void(vhr_context *)> hook) { graphics_hooks[pass_name] = std::move(hook); }
 
 void RenderGraph::Execute(uint32_t resource_idx) {
@@ -198,9 +210,38 @@ void RenderGraph::Execute(uint32_t resource_idx) {
                 VHR_CHECK(vhr_bind_pass_images(ctx, names, count));
                 hook->second(ctx);
             } else {
-                // no rasteriser in this build: run the draw-call recording against a counting context so the path's
-                // lambdas execute exactly as in the reference, then drop the result
-                g->callback([&](std::string, GraphicsExecutionCallback cb) { GraphicsExecutionContext ec(resource_manager); cb(ec); });
+                // Pipelines whose fragment shader exists as a CUDA kernel (the composition pass) execute for real: sampled
+                // inputs by binding, colour attachments after them. For the rest there is no rasteriser in this build:
+                // the draw-call recording runs against a counting context so the path's lambdas execute exactly as in the
+                // reference, and the result is dropped.
+                bool bound = false;
+                g->callback([&](std::string pipeline_name, GraphicsExecutionCallback cb) {
+                    const GraphicsPipelineDescription *pipeline = nullptr;
+                    for (const GraphicsPipelineDescription &d : g->pipeline_descriptions)
+                        if (pipeline_name == d.name) pipeline = &d;
+                    VHR_ASSERT(pipeline != nullptr, "unknown graphics pipeline: " + pipeline_name);      // render_graph.cpp:738
+                    if (GraphicsExecutionContext::HasKernel(*pipeline)) {
+                        if (!bound) {
+                            const char *names[VHR_MAX_PASS_BINDINGS] = {};
+                            uint32_t count = 0, n_sampled = 0;
+                            for (const TransientResource &r : pass.dependencies) { names[r.image.binding] = r.name; n_sampled = std::max(n_sampled, r.image.binding + 1); }
+                            count = n_sampled;
+                            for (const TransientResource &r : pass.outputs) {
+                                VHR_ASSERT(n_sampled + r.image.binding < VHR_MAX_PASS_BINDINGS, "too many graphics-pass images");
+                                names[n_sampled + r.image.binding] = r.name;
+                                count = std::max(count, n_sampled + r.image.binding + 1);
+                            }
+                            for (uint32_t k = 0; k < count; ++k) VHR_ASSERT(names[k] != nullptr, std::string("pass '") + pass.name + "' leaves a binding gap");
+                            VHR_CHECK(vhr_bind_pass_images(ctx, names, count));
+                            bound = true;
+                        }
+                        GraphicsExecutionContext ec(resource_manager, pipeline);
+                        cb(ec);
+                    } else {
+                        GraphicsExecutionContext ec(resource_manager);
+                        cb(ec);
+                    }
+                });
             }
         } else if (auto *r = std::get_if<RaytracingPassDescription>(&pass.description)) {
             BindPassImages(pass);

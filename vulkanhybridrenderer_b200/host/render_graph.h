@@ -68,14 +68,21 @@ private:
 
 class GraphicsExecutionContext {
 public:
-    explicit GraphicsExecutionContext(ResourceManager &resource_manager) : resource_manager(resource_manager) {}
-    // Draw-call recording has no CUDA counterpart; the calls are accepted and counted so RegisterPath runs unchanged.
+    // `pipeline` is the graphics pipeline being executed (graphics_execution_context.h:6-10); nullptr for the counting
+    // context used when a rasterised pass has no CUDA counterpart.
+    explicit GraphicsExecutionContext(ResourceManager &resource_manager, const GraphicsPipelineDescription *pipeline = nullptr)
+        : resource_manager(resource_manager), pipeline(pipeline) {}
+    // Geometry draw calls have no CUDA counterpart; they are accepted and counted so RegisterPath runs unchanged.
     void BindGlobalVertexAndIndexBuffers() {}
     template <typename T> void PushConstants(T &) {}
     void DrawIndexed(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) { ++draws; }
-    void Draw(uint32_t, uint32_t, uint32_t, uint32_t) { ++draws; }
+    // graphics_execution_context.cpp:38-41. For a pipeline whose fragment shader has a CUDA kernel (the composition
+    // pass) this launches it through vhr_draw; otherwise the call only counts.
+    void Draw(uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance);
+    static bool HasKernel(const GraphicsPipelineDescription &pipeline);
     uint32_t draws = 0;
     ResourceManager &resource_manager;
+    const GraphicsPipelineDescription *pipeline;
 };
 
 class RenderGraph {

@@ -25,6 +25,9 @@ N_REFL = "Raytraced Reflections"
 N_DENOISED = "Denoised Raytraced Shadows and Ambient Occlusion"
 N_SSAO_RAW = "Screen Space Ambient Occlusion Raw"
 N_SSAO = "Screen Space Ambient Occlusion"
+N_SSR = "Screen Space Reflections"
+N_SHADOW_MAP = "Shadow Map"
+N_RENDER_OUTPUT = "RENDER_OUTPUT"
 
 GBUFFER_FORMATS = {N_ALBEDO: T.VK_FORMAT_B8G8R8A8_UNORM, N_NORMALS: F4, N_MOTION: F4, N_DEPTH: T.VK_FORMAT_D32_SFLOAT}
 
@@ -32,6 +35,12 @@ SHADER_SVGF = "hybrid_render_path/svgf.comp"
 SHADER_ATROUS = "hybrid_render_path/svgf_atrous_filter.comp"
 SHADER_SSAO = "hybrid_render_path/ssao.comp"
 SHADER_SSAO_BLUR = "hybrid_render_path/ssao_blur.comp"
+SHADER_COMPOSITION = "hybrid_render_path/composition.frag"
+
+# common.glsl:12-25 / hybrid_render_path.h:4-20
+SHADOW_MODE_RAYTRACED, SHADOW_MODE_RASTERIZED, SHADOW_MODE_OFF = 0, 1, 2
+AO_MODE_RAYTRACED, AO_MODE_SSAO, AO_MODE_OFF = 0, 1, 2
+REFLECTION_MODE_RAYTRACED, REFLECTION_MODE_SSR, REFLECTION_MODE_OFF = 0, 1, 2
 
 # per-pixel algorithmic bytes (SURVEY §8d / DESIGN.md): each distinct texel once
 BYTES_TEMPORAL = 52
@@ -40,6 +49,7 @@ BYTES_BLIT = 16
 BYTES_RAYGEN_IO = 12 + 4          # depth + normals in, RG16F out (reflections add 8)
 BYTES_SSAO = 20
 BYTES_SSAO_BLUR = 16
+BYTES_COMPOSITION = 4 + 8 + 8 + 4 + 8 + 4   # albedo, normals, motion texel, depth, denoised shadow/AO in; BGRA8 out (+8 reflections)
 
 
 def groups(n):
@@ -49,7 +59,9 @@ def groups(n):
 class HybridRenderPath:
     """Owns the images of the hot-path passes on one context and replays the reference's per-frame call sequence."""
 
-    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False):
+    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False, composition=None, shadow_map_size=(4096, 4096)):
+        """composition: None (no composition pass) or the VkFormat of RENDER_OUTPUT (B8G8R8A8_SRGB = the reference's
+        swapchain; R16G16B16A16_SFLOAT = linear HDR radiance for parity measurements)."""
         self.ctx, self.W, self.H = ctx, width, height
         self.gsets = []
         for s in range(gbuffer_sets):
@@ -61,9 +73,13 @@ class HybridRenderPath:
         ctx.actualize_image(N_RT, F2)
         ctx.actualize_image(N_REFL, F4)
         ctx.actualize_image(N_DENOISED, F4)
-        if ssao:
+        if ssao or composition is not None:
             ctx.actualize_image(N_SSAO_RAW, F4)
             ctx.actualize_image(N_SSAO, F4)
+        if composition is not None:      # hybrid_render_path.cpp:335-349: every sampled input exists even when its mode is off
+            ctx.actualize_image(N_SSR, F4)
+            ctx.actualize_image(N_SHADOW_MAP, T.VK_FORMAT_D32_SFLOAT, *shadow_map_size)
+            ctx.actualize_image(N_RENDER_OUTPUT, composition)
         # hybrid_render_path.cpp:247-261
         pc = np.zeros((), T.SVGFPushConstants)
         pc["integrated_shadow_and_ao"] = (ctx.upload_new_storage_image(width, height, F4),
@@ -134,6 +150,14 @@ class HybridRenderPath:
         ctx.blit_storage_to_transient(int(pc["integrated_shadow_and_ao"][1]), N_DENOISED)
         pc["integrated_shadow_and_ao"] = pc["integrated_shadow_and_ao"][::-1].copy()
         self._stamp()
+
+    def composition_pass(self, shadow_mode=SHADOW_MODE_RAYTRACED, ao_mode=AO_MODE_RAYTRACED, reflection_mode=REFLECTION_MODE_OFF,
+                         denoised=True, gset=0):
+        """hybrid_render_path.cpp:333-379: nine sampled inputs by binding, RENDER_OUTPUT as colour attachment 0, Draw(3,1,0,0)."""
+        g = self.gsets[gset]
+        self.ctx.bind_pass_images([g[N_ALBEDO], g[N_NORMALS], g[N_MOTION], g[N_DEPTH], N_SHADOW_MAP, N_SSAO, N_SSR,
+                                   N_DENOISED if denoised else N_RT, N_REFL, N_RENDER_OUTPUT])
+        self.ctx.draw(SHADER_COMPOSITION, (shadow_mode, ao_mode, reflection_mode))
 
     def frame(self, pfd, gset=0):
         """Raytrace Pass -> SVGF Denoise Pass for one frame whose G-buffer already sits in image set `gset`."""

@@ -76,12 +76,14 @@ assert SVGFPushConstants.itemsize == 24
 
 # VkFormat values used on the hot path (hybrid_render_path.cpp:16-19,109-110,247-261)
 VK_FORMAT_B8G8R8A8_UNORM = 44
+VK_FORMAT_B8G8R8A8_SRGB = 50
 VK_FORMAT_R16G16_SFLOAT = 83
 VK_FORMAT_R16G16B16A16_SFLOAT = 97
 VK_FORMAT_D32_SFLOAT = 126
 
 FORMAT_TEXEL_BYTES = {
     VK_FORMAT_B8G8R8A8_UNORM: 4,
+    VK_FORMAT_B8G8R8A8_SRGB: 4,
     VK_FORMAT_R16G16_SFLOAT: 4,
     VK_FORMAT_R16G16B16A16_SFLOAT: 8,
     VK_FORMAT_D32_SFLOAT: 4,
@@ -89,6 +91,7 @@ FORMAT_TEXEL_BYTES = {
 # (numpy dtype, channels) of the host-side view of each format
 FORMAT_NUMPY = {
     VK_FORMAT_B8G8R8A8_UNORM: (np.uint8, 4),
+    VK_FORMAT_B8G8R8A8_SRGB: (np.uint8, 4),
     VK_FORMAT_R16G16_SFLOAT: (np.float16, 2),
     VK_FORMAT_R16G16B16A16_SFLOAT: (np.float16, 4),
     VK_FORMAT_D32_SFLOAT: (np.float32, 1),
