@@ -307,6 +307,28 @@ def run_gpu(args):
         pass_ms = path.pass_times_ms(K)            # [K, passes]
         path.timestamps = None
 
+        # ---- next row, timed on its own and NOT part of the step: the composition pass that consumes
+        # the denoised image (composition.frag as a CUDA kernel, B8G8R8A8_SRGB output like the reference's swapchain)
+        comp_ms = None
+        try:
+            path_c = HP.HybridRenderPath.__new__(HP.HybridRenderPath)
+            path_c.ctx, path_c.W, path_c.H, path_c.gsets = ctx, W, H, path.gsets
+            for n, f in ((HP.N_SSAO, HP.F4), (HP.N_SSR, HP.F4)):
+                ctx.actualize_image(n, f)
+            ctx.actualize_image(HP.N_SHADOW_MAP, HP.T.VK_FORMAT_D32_SFLOAT, 4096, 4096)
+            ctx.actualize_image(HP.N_RENDER_OUTPUT, HP.T.VK_FORMAT_B8G8R8A8_SRGB)
+            for _ in range(3):
+                path_c.composition_pass(0, 0, 0 if refl else 2, denoised=True, gset=0)
+            ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ec0.record(stream)
+            for i in range(20):
+                path_c.composition_pass(0, 0, 0 if refl else 2, denoised=True, gset=i & 1)
+            ec1.record(stream)
+            torch.cuda.synchronize()
+            comp_ms = ec0.elapsed_time(ec1) / 20
+        except capi.VhrError as e:      # never let the extra row break the headline measurement
+            sys.stderr.write(f"bench.py: composition row skipped: {e}\n")
+
         # ---- e2e: host G-buffer -> H2D -> frame -> D2H of the denoised + raw shadow/AO images, every step ---------------
         out_den = torch.empty(W * H * 8, dtype=torch.uint8, pin_memory=True)
         out_rt = torch.empty(W * H * 4, dtype=torch.uint8, pin_memory=True)
@@ -442,6 +464,11 @@ def run_gpu(args):
                      "fused_minimum_bytes": svgf_min_bytes, "frac_of_peak_vs_fused_minimum": svgf_min_bytes / (svgf_ms * 1e-3) / 1e9 / peak},
             "bvh": {"triangles": st.n_triangles, "wide_nodes": st.n_wide_nodes, "build_ms": st.build_ms, "sah_cost": st.sah_cost},
         }
+        if comp_ms:
+            cb = px * (HP.BYTES_COMPOSITION + (8 if refl else 0))
+            line["next_rows"] = {"composition": {"kernel": "composition_kernel", "ms": comp_ms, "algorithmic_bytes": cb,
+                                                 "achieved_gbs": cb / (comp_ms * 1e-3) / 1e9, "frac": cb / (comp_ms * 1e-3) / 1e9 / peak,
+                                                 "note": "timed on its own after the frames, not part of the step"}}
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuArm(wl, args.cpu_rows)
             arm.prepare()

@@ -36,10 +36,19 @@ struct CompositionParams {
     void *out;                     // attachment 0
 };
 
+// Divisions, square roots and the sRGB power run on the MUFU unit (rcp / rsq / lg2 / ex2, <= 2 ulp) instead of the IEEE
+// sequences: the first version of this kernel spent ~85 us at 1080p on ~25 exact divisions and three powf() per pixel
+// (14 % of the HBM rate it is bound by). The results stay inside the parity bar (1e-3 on linear radiance, one code on
+// the 8-bit outputs); products and sums keep the oracle's evaluation order.
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float3 normalize_fast(float3 a) {
+    const float r = rsqrtf(dot3_rn(a, a));
+    return make_float3(mul_rn(a.x, r), mul_rn(a.y, r), mul_rn(a.z, r));
+}
 __device__ __forceinline__ float srgb_encode(float c) {
     // NaN -> 0, clamp to [0, 1] (Vulkan float -> UNORM conversion), then the sRGB OETF
     c = (c == c) ? fminf(fmaxf(c, 0.0f), 1.0f) : 0.0f;
-    return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+    return c <= 0.0031308f ? 12.92f * c : fmaf(1.055f, exp2f(__log2f(c) * (1.0f / 2.4f)), -0.055f);
 }
 __device__ __forceinline__ uint32_t unorm8_rn(float c) {
     c = (c == c) ? fminf(fmaxf(c, 0.0f), 1.0f) : 0.0f;
@@ -57,41 +66,50 @@ __device__ __forceinline__ float sample_shadow_map(const CompositionParams &p, f
     return bilerp_rn(a, b, __ldg(&d[y0 * W + x0]), __ldg(&d[y0 * W + x1]), __ldg(&d[y1 * W + x0]), __ldg(&d[y1 * W + x1]));
 }
 
+// The three modes are template parameters, the CUDA counterpart of the reference's specialisation constants
+// (composition.frag:6-8, hybrid_render_path.cpp:361-369): each of the 27 pipelines carries only the loads and the
+// arithmetic of its own mode.
+template <int SHADOW_MODE, int AO_MODE, int REFLECTION_MODE>
 __global__ void __launch_bounds__(256) composition_kernel(const __grid_constant__ CompositionParams p, const __grid_constant__ PerFrameData pfd) {
     const int x = blockIdx.x * 64 + threadIdx.x;        // blockDim = (64, 4): 512-byte rows of 8-byte texels per warp pair
     const int y = p.y_begin + blockIdx.y * 4 + threadIdx.y;
     if (x >= p.W || y >= p.y_end) return;
     const size_t pix = (size_t)y * p.W + x;
     // in_uv of the full-screen triangle at the pixel centre
-    const float u = __fdiv_rn(add_rn((float)x, 0.5f), (float)p.W), v = __fdiv_rn(add_rn((float)y, 0.5f), (float)p.H);
+    const float u = fdiv(add_rn((float)x, 0.5f), (float)p.W), v = fdiv(add_rn((float)y, 0.5f), (float)p.H);
 
     const uint32_t a8 = __ldg(&p.albedo[pix]);          // B8G8R8A8: byte 0 = B
-    const float3 albedo = make_float3(__fdiv_rn((float)((a8 >> 16) & 0xffu), 255.0f), __fdiv_rn((float)((a8 >> 8) & 0xffu), 255.0f),
-                                      __fdiv_rn((float)(a8 & 0xffu), 255.0f));
+    const float3 albedo = make_float3(fdiv((float)((a8 >> 16) & 0xffu), 255.0f), fdiv((float)((a8 >> 8) & 0xffu), 255.0f),
+                                      fdiv((float)(a8 & 0xffu), 255.0f));
     const float depth = __ldg(&p.depth[pix]);
-    const float3 P = unproject_rn(pfd.camera_viewproj_inverse, depth, u, v);
+    float3 P;
+    {
+        const float4 q = mul44_rn(pfd.camera_viewproj_inverse, make_float4(sub_rn(mul_rn(u, 2.0f), 1.0f), sub_rn(mul_rn(v, 2.0f), 1.0f), depth, 1.0f));
+        const float rw = fdiv(1.0f, q.w);
+        P = make_float3(mul_rn(q.x, rw), mul_rn(q.y, rw), mul_rn(q.z, rw));
+    }
     const float4 n4 = unpack_rgba16f(__ldg(&p.normals[pix]));
     const float3 N = make_float3(n4.x, n4.y, n4.z);
     const float2 mr = unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(&p.motion[pix]) + 1));   // .zw
 
     float2 rt = make_float2(1.0f, 1.0f);
-    if (p.shadow_mode == 0 || p.ao_mode == 0)
+    if (SHADOW_MODE == 0 || AO_MODE == 0)
         rt = p.rt_is_rg16 ? unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(p.rt) + pix))
                           : unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint2 *>(p.rt) + pix)));
 
     const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
-    const float3 V = normalize_rn(make_float3(sub_rn(cam.x, P.x), sub_rn(cam.y, P.y), sub_rn(cam.z, P.z)));
+    const float3 V = normalize_fast(make_float3(sub_rn(cam.x, P.x), sub_rn(cam.y, P.y), sub_rn(cam.z, P.z)));
     const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
-    const float3 H = normalize_rn(make_float3(add_rn(L.x, V.x), add_rn(L.y, V.y), add_rn(L.z, V.z)));
+    const float3 H = normalize_fast(make_float3(add_rn(L.x, V.x), add_rn(L.y, V.y), add_rn(L.z, V.z)));
 
     float shadow = 1.0f;
-    if (p.shadow_mode == 0) {
+    if (SHADOW_MODE == 0) {
         shadow = rt.x;
-    } else if (p.shadow_mode == 1) {
+    } else if (SHADOW_MODE == 1) {
         // composition.frag:81-104: SHADOW_BIAS_MATRIX * projview * P, 4x4 PCF on the 4096^2 shadow map
         const float4 lp = mul44_rn(pfd.directional_light.projview, make_float4(P.x, P.y, P.z, 1.0f));
         const float4 ls = make_float4(add_rn(mul_rn(0.5f, lp.x), mul_rn(0.5f, lp.w)), add_rn(mul_rn(0.5f, lp.y), mul_rn(0.5f, lp.w)), lp.z, lp.w);
-        const float sx = __fdiv_rn(ls.x, ls.w), sy = __fdiv_rn(ls.y, ls.w), sz = __fdiv_rn(ls.z, ls.w);
+        const float sx = fdiv(ls.x, ls.w), sy = fdiv(ls.y, ls.w), sz = fdiv(ls.z, ls.w);
         const float scale = 1.0f / 4096.0f;
         float acc = 0.0f;
 #pragma unroll
@@ -100,11 +118,11 @@ __global__ void __launch_bounds__(256) composition_kernel(const __grid_constant_
             const float ds = sample_shadow_map(p, add_rn(sx, mul_rn(ox, scale)), add_rn(sy, mul_rn(oy, scale)));
             acc = add_rn(acc, (sz < sub_rn(ds, 1e-4f)) ? 0.0f : 1.0f);
         }
-        shadow = __fdiv_rn(acc, 16.0f);
+        shadow = fdiv(acc, 16.0f);
     }
     float ao = 1.0f;
-    if (p.ao_mode == 0) ao = rt.y;
-    else if (p.ao_mode == 1) ao = unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(&p.ssao[pix]))).x;
+    if (AO_MODE == 0) ao = rt.y;
+    else if (AO_MODE == 1) ao = unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(&p.ssao[pix]))).x;
 
     const float metallic = fminf(fmaxf(mr.x, 0.0f), 1.0f);
     const float roughness = fminf(fmaxf(mr.y, 0.04f), 1.0f);
@@ -120,21 +138,21 @@ __global__ void __launch_bounds__(256) composition_kernel(const __grid_constant_
 
     // diffuse_brdf (common.glsl:146-150)
     const float sdm = sub_rn(1.0f, metallic);
-    const float3 dbrdf = make_float3(__fdiv_rn(mul_rn(mul_rn(sub_rn(1.0f, F.x), sdm), albedo.x), VHR_PI),
-                                     __fdiv_rn(mul_rn(mul_rn(sub_rn(1.0f, F.y), sdm), albedo.y), VHR_PI),
-                                     __fdiv_rn(mul_rn(mul_rn(sub_rn(1.0f, F.z), sdm), albedo.z), VHR_PI));
+    const float3 dbrdf = make_float3(fdiv(mul_rn(mul_rn(sub_rn(1.0f, F.x), sdm), albedo.x), VHR_PI),
+                                     fdiv(mul_rn(mul_rn(sub_rn(1.0f, F.y), sdm), albedo.y), VHR_PI),
+                                     fdiv(mul_rn(mul_rn(sub_rn(1.0f, F.z), sdm), albedo.z), VHR_PI));
     // specular_brdf (common.glsl:121-144)
     const float a2 = mul_rn(roughness, roughness);
     const float nh = fmaxf(dot3_rn(N, H), 0.0f);
     const float ff = add_rn(mul_rn(mul_rn(nh, nh), sub_rn(a2, 1.0f)), 1.0f);
-    const float D = __fdiv_rn(a2, mul_rn(mul_rn(VHR_PI, ff), ff));
+    const float D = fdiv(a2, mul_rn(mul_rn(VHR_PI, ff), ff));
     const float kk = mul_rn(mul_rn(add_rn(roughness, 1.0f), add_rn(roughness, 1.0f)), 0.125f);
     const float nv = fmaxf(dot3_rn(N, V), 0.0f);
-    const float g_nvk = __fdiv_rn(nv, add_rn(mul_rn(nv, sub_rn(1.0f, kk)), kk));
-    const float g_nlk = __fdiv_rn(ndl, add_rn(mul_rn(ndl, sub_rn(1.0f, kk)), kk));
+    const float g_nvk = fdiv(nv, add_rn(mul_rn(nv, sub_rn(1.0f, kk)), kk));
+    const float g_nlk = fdiv(ndl, add_rn(mul_rn(ndl, sub_rn(1.0f, kk)), kk));
     const float dg = mul_rn(D, mul_rn(g_nvk, g_nlk));
     const float denom = fmaxf(mul_rn(mul_rn(4.0f, nv), ndl), 1e-6f);
-    const float3 sbrdf = make_float3(__fdiv_rn(mul_rn(dg, F.x), denom), __fdiv_rn(mul_rn(dg, F.y), denom), __fdiv_rn(mul_rn(dg, F.z), denom));
+    const float3 sbrdf = make_float3(fdiv(mul_rn(dg, F.x), denom), fdiv(mul_rn(dg, F.y), denom), fdiv(mul_rn(dg, F.z), denom));
 
     // brdf * N_dot_L * light_intensity * light_color * shadow, left to right (composition.frag:136-137)
     auto lit = [&](float brdf, int c) { return mul_rn(mul_rn(mul_rn(mul_rn(brdf, ndl), li[c]), lc[c]), shadow); };
@@ -143,8 +161,8 @@ __global__ void __launch_bounds__(256) composition_kernel(const __grid_constant_
     const float3 diffuse = make_float3(lit(dbrdf.x, 0), lit(dbrdf.y, 1), lit(dbrdf.z, 2));
     float3 specular = make_float3(lit(sbrdf.x, 0), lit(sbrdf.y, 1), lit(sbrdf.z, 2));
 
-    if (p.reflection_mode == 0 || p.reflection_mode == 1) {     // composition.frag:139-156 (ray traced / SSR: same blend)
-        const float4 r4 = unpack_rgba16f(__ldg(p.reflection_mode == 0 ? &p.refl[pix] : &p.ssr[pix]));
+    if (REFLECTION_MODE == 0 || REFLECTION_MODE == 1) {     // composition.frag:139-156 (ray traced / SSR: same blend)
+        const float4 r4 = unpack_rgba16f(__ldg(REFLECTION_MODE == 0 ? &p.refl[pix] : &p.ssr[pix]));
         const float3 refl = make_float3(mul_rn(r4.x, shadow), mul_rn(r4.y, shadow), mul_rn(r4.z, shadow));
         if (metallic == 1.0f) specular = refl;
         else specular = make_float3(mixc_rn(specular.x, refl.x, roughness), mixc_rn(specular.y, refl.y, roughness), mixc_rn(specular.z, refl.z, roughness));
@@ -199,7 +217,13 @@ int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int refle
     p.depth = (const float *)b[3]->ptr; p.shadow_map = (const float *)b[4]->ptr; p.ssao = (const uint2 *)b[5]->ptr;
     p.ssr = (const uint2 *)b[6]->ptr; p.rt = b[7]->ptr; p.refl = (const uint2 *)b[8]->ptr; p.out = out->ptr;
     dim3 block(64, 4), grid((p.W + 63) / 64, (p.y_end - p.y_begin + 3) / 4);
-    composition_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    typedef void (*Kernel)(const CompositionParams, const PerFrameData);
+#define VHR_COMP_ROW(S, A) {composition_kernel<S, A, 0>, composition_kernel<S, A, 1>, composition_kernel<S, A, 2>}
+    static const Kernel table[3][3][3] = {{VHR_COMP_ROW(0, 0), VHR_COMP_ROW(0, 1), VHR_COMP_ROW(0, 2)},
+                                          {VHR_COMP_ROW(1, 0), VHR_COMP_ROW(1, 1), VHR_COMP_ROW(1, 2)},
+                                          {VHR_COMP_ROW(2, 0), VHR_COMP_ROW(2, 1), VHR_COMP_ROW(2, 2)}};
+#undef VHR_COMP_ROW
+    table[shadow_mode][ao_mode][reflection_mode]<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return VHR_OK;
