@@ -50,6 +50,8 @@ enum {
 
 #define VHR_MAX_GLOBAL_RESOURCES 2048   /* src/rendering_backend/resource_manager.h:13 */
 #define VHR_MAX_PASS_BINDINGS 16
+#define VHR_MAX_RANKS 8                 /* GPUs of one NVSwitch box a frame can be partitioned over */
+#define VHR_IPC_HANDLE_BYTES 64         /* sizeof(cudaIpcMemHandle_t) */
 
 /* ---- context (replaces VulkanContext device/queue creation, src/rendering_backend/vulkan_context.cpp:44) -------- */
 
@@ -165,6 +167,39 @@ int vhr_create_query_pool(vhr_context *ctx, uint32_t count);
 int vhr_write_timestamp(vhr_context *ctx, uint32_t query);
 /* Blocks until query `last` has been reached, then writes the elapsed milliseconds between `first` and `last`. */
 int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms);
+
+/* ---- one frame over several GPUs (no counterpart in the reference) ------------------------------------
+ * One process per GPU, scene + BVH replicated, every image full-size on every rank. The frame is split by rows:
+ *   - SVGF / SSAO / composition work on contiguous row bands: rank r owns rows [band_begin[r], band_begin[r+1]);
+ *   - the ray pass deals blocks of `ray_block_rows` rows round-robin over the ranks (traversal cost varies strongly
+ *     over the screen, contiguous bands are badly balanced) and every thread stores its result straight into the
+ *     OWNER's image over NVLink — compute and the all-to-all that would follow it are one kernel;
+ *   - the temporal and a-trous kernels store the boundary rows of their output a second time into the neighbours' copy
+ *     of the image (the halo the next kernel there reads): compute and halo exchange are one kernel.
+ * Ordering between GPUs is stream-ordered: after such a kernel the library writes a sequence number into the other
+ * ranks' flag words (cuStreamWriteValue32 on peer memory) and makes its own stream wait for theirs
+ * (cuStreamWaitValue32). No host synchronisation, no NCCL call, no extra copy kernel in the frame. The host keeps
+ * issuing the reference's call sequence (vhr_trace_rays, vhr_dispatch, vhr_blit_*) unchanged on every rank.
+ * Set-up, once: every rank exports its images (vhr_*_export_ipc), the handles travel between the processes by any
+ * means (torch.distributed all_gather_object in multi_gpu.py), every rank attaches the others' (vhr_*_attach_peer),
+ * then vhr_set_partition. Requires every band to be at least 64 rows (halos never skip a rank). */
+typedef struct vhr_partition {
+    uint32_t world, rank;
+    uint32_t band_begin[VHR_MAX_RANKS + 1]; /* rows; band_begin[0] = 0, band_begin[world] = image height */
+    uint32_t ray_block_rows;                /* 8 = interleaved ray pass (the kernel's tile height); 0 = each rank traces its own band */
+    uint32_t motion_halo;                   /* rows of history / moments / previous normals the temporal pass may reach outside the band */
+    uint32_t no_exchange_step;              /* a-trous dispatches with this step do not push halos: 16, the reference never reads that output (Q1) */
+} vhr_partition;
+int vhr_set_partition(vhr_context *ctx, const vhr_partition *partition);       /* NULL: back to single-GPU behaviour */
+/* cudaIpcGetMemHandle of the image's buffer; `twin_handle` (may be NULL) exports the second buffer of the
+ * double-buffered moments image (allocated on demand). */
+int vhr_image_export_ipc(vhr_context *ctx, const char *name, void *handle);
+int vhr_storage_image_export_ipc(vhr_context *ctx, int slot, void *handle, void *twin_handle);
+int vhr_image_attach_peer(vhr_context *ctx, const char *name, uint32_t rank, const void *handle);
+int vhr_storage_image_attach_peer(vhr_context *ctx, int slot, uint32_t rank, const void *handle, const void *twin_handle);
+/* The context's flag words (allocated on first use) for the stream-ordered synchronisation. */
+int vhr_sync_export_ipc(vhr_context *ctx, void *handle);
+int vhr_sync_attach_peer(vhr_context *ctx, uint32_t rank, const void *handle);
 
 /* ---- options that have no counterpart in the reference (documented in DESIGN.md) -------------------------------- */
 

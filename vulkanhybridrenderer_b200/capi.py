@@ -24,7 +24,17 @@ SYMBOLS = [
     "vhr_get_option", "vhr_get_bvh_stats", "vhr_trace_explicit", "vhr_gbuffer_pass", "vhr_create_query_pool",
     "vhr_write_timestamp", "vhr_get_query_elapsed_ms", "vhr_debug_download_reflection_t",
     "vhr_image_upload_async", "vhr_image_download_async", "vhr_wait_download", "vhr_draw",
+    "vhr_set_partition", "vhr_image_export_ipc", "vhr_storage_image_export_ipc", "vhr_image_attach_peer",
+    "vhr_storage_image_attach_peer", "vhr_sync_export_ipc", "vhr_sync_attach_peer",
 ]
+MAX_RANKS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class Partition(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("band_begin", C.c_uint32 * (MAX_RANKS + 1)),
+                ("ray_block_rows", C.c_uint32), ("motion_halo", C.c_uint32), ("no_exchange_step", C.c_uint32)]
+
 
 OPT_AO_SPP, OPT_TRACE_SHADOWS, OPT_TRACE_AO, OPT_TRACE_REFLECTIONS = 1, 2, 3, 4
 OPT_ROW_BEGIN, OPT_ROW_END, OPT_SVGF_FUSED, OPT_ATROUS_VARIANT, OPT_DEBUG_REFLECTION_T, OPT_RAYGEN_VARIANT = 5, 6, 7, 8, 9, 10
@@ -89,6 +99,13 @@ def lib():
         L.vhr_trace_explicit.argtypes = [vp, vp, u32, i32, vp, vp, vp]
         L.vhr_gbuffer_pass.argtypes = [vp, u32, u32]
         L.vhr_draw.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32), u32, u32, u32, u32, u32]
+        L.vhr_set_partition.argtypes = [vp, C.POINTER(Partition)]
+        L.vhr_image_export_ipc.argtypes = [vp, C.c_char_p, vp]
+        L.vhr_storage_image_export_ipc.argtypes = [vp, i32, vp, vp]
+        L.vhr_image_attach_peer.argtypes = [vp, C.c_char_p, u32, vp]
+        L.vhr_storage_image_attach_peer.argtypes = [vp, i32, u32, vp, vp]
+        L.vhr_sync_export_ipc.argtypes = [vp, vp]
+        L.vhr_sync_attach_peer.argtypes = [vp, u32, vp]
         L.vhr_debug_download_reflection_t.argtypes = [vp, vp, sz]
         L.vhr_create_query_pool.argtypes = [vp, u32]
         L.vhr_write_timestamp.argtypes = [vp, u32]
@@ -248,6 +265,43 @@ class Context:
         sc = (C.c_int32 * len(specialization_constants))(*[int(v) for v in specialization_constants])
         _check(lib().vhr_draw(self._h, fragment_shader.encode(), sc, len(specialization_constants), vertex_count, instance_count,
                               first_vertex, first_instance))
+
+    # -- one frame over several GPUs (include/vhr_b200.h) --
+    def set_partition(self, world, rank, band_begin, ray_block_rows=8, motion_halo=8, no_exchange_step=16):
+        p = Partition()
+        p.world, p.rank = world, rank
+        for i, b in enumerate(band_begin):
+            p.band_begin[i] = int(b)
+        p.ray_block_rows, p.motion_halo, p.no_exchange_step = ray_block_rows, motion_halo, no_exchange_step
+        _check(lib().vhr_set_partition(self._h, C.byref(p)))
+
+    def clear_partition(self):
+        _check(lib().vhr_set_partition(self._h, None))
+
+    def image_export_ipc(self, name):
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().vhr_image_export_ipc(self._h, name.encode(), h))
+        return h.raw
+
+    def storage_image_export_ipc(self, slot, twin=False):
+        h, t = C.create_string_buffer(IPC_HANDLE_BYTES), C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().vhr_storage_image_export_ipc(self._h, int(slot), h, t if twin else None))
+        return (h.raw, t.raw) if twin else (h.raw, None)
+
+    def image_attach_peer(self, name, rank, handle):
+        _check(lib().vhr_image_attach_peer(self._h, name.encode(), rank, C.create_string_buffer(handle, IPC_HANDLE_BYTES)))
+
+    def storage_image_attach_peer(self, slot, rank, handle, twin_handle=None):
+        t = C.create_string_buffer(twin_handle, IPC_HANDLE_BYTES) if twin_handle else None
+        _check(lib().vhr_storage_image_attach_peer(self._h, int(slot), rank, C.create_string_buffer(handle, IPC_HANDLE_BYTES), t))
+
+    def sync_export_ipc(self):
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().vhr_sync_export_ipc(self._h, h))
+        return h.raw
+
+    def sync_attach_peer(self, rank, handle):
+        _check(lib().vhr_sync_attach_peer(self._h, rank, C.create_string_buffer(handle, IPC_HANDLE_BYTES)))
 
     def gbuffer_pass(self, width, height):
         _check(lib().vhr_gbuffer_pass(self._h, width, height))

@@ -32,6 +32,7 @@ struct TemporalParams {
     const uint32_t *moments_in;    // storage_images[pc.shadow_and_ao_moments_history] (previous frame, Q11 snapshot)
     uint2 *integrated_out;         // storage_images[pc.integrated_shadow_and_ao[0]]
     uint32_t *moments_out;
+    HaloPush push_integ, push_mom; // multi-GPU: boundary rows also go to the neighbours' copies (NVLink peer stores)
 };
 
 // svgf.comp:16-39
@@ -121,8 +122,16 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
         float av = fmaxf(0.0f, sub_rn(am1, mul_rn(am0, am0)));
         out = make_float4(cur.x, cur.y, sv, av);
     }
-    p.integrated_out[pix] = pack_rgba16f(out);
-    p.moments_out[pix] = pack_rg16f(sm0, sm1);   // RG16F keeps the shadow moments only (Q2)
+    const uint2 o = pack_rgba16f(out);
+    const uint32_t m = pack_rg16f(sm0, sm1);      // RG16F keeps the shadow moments only (Q2)
+    p.integrated_out[pix] = o;
+    p.moments_out[pix] = m;
+    if (p.push_integ.rows | p.push_mom.rows) {    // halo exchange fused into the kernel: the next pass on the neighbour reads these rows
+        if (p.push_integ.up && cy < p.y_begin + p.push_integ.rows) reinterpret_cast<uint2 *>(p.push_integ.up)[pix] = o;
+        if (p.push_integ.down && cy >= p.y_end - p.push_integ.rows) reinterpret_cast<uint2 *>(p.push_integ.down)[pix] = o;
+        if (p.push_mom.up && cy < p.y_begin + p.push_mom.rows) reinterpret_cast<uint32_t *>(p.push_mom.up)[pix] = m;
+        if (p.push_mom.down && cy >= p.y_end - p.push_mom.rows) reinterpret_cast<uint32_t *>(p.push_mom.down)[pix] = m;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -136,7 +145,16 @@ struct AtrousParams {
     const uint2 *normals;      // binding 0
     const uint2 *integ_in;     // storage_images[pc.integrated_shadow_and_ao[0]]
     uint2 *integ_out;          // storage_images[pc.integrated_shadow_and_ao[1]]
+    HaloPush push;             // multi-GPU: boundary rows of the output also go to the neighbours' copies
 };
+
+__device__ __forceinline__ void store_out(const AtrousParams &p, int cy, size_t pix, uint2 v) {
+    p.integ_out[pix] = v;
+    if (p.push.rows) {
+        if (p.push.up && cy < p.y_begin + p.push.rows) reinterpret_cast<uint2 *>(p.push.up)[pix] = v;
+        if (p.push.down && cy >= p.y_end - p.push.rows) reinterpret_cast<uint2 *>(p.push.down)[pix] = v;
+    }
+}
 
 __constant__ float c_atrous_h[5] = {1.0f / 16, 1.0f / 4, 3.0f / 8, 1.0f / 4, 1.0f / 16};
 
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(256) atrous_direct_kernel(const __grid_constan
         }
     float4 out = make_float4(__fdiv_rn(sum.x, swx), __fdiv_rn(sum.y, swy), __fdiv_rn(sum.z, mul_rn(swx, swx)),
                              __fdiv_rn(sum.w, mul_rn(swy, swy)));
-    p.integ_out[pix] = pack_rgba16f(out);
+    store_out(p, cy, pix, pack_rgba16f(out));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(AT_TX * AT_TY, 2) atrous_tiled_kernel(const __
     }
     float4 out = make_float4(__fdiv_rn(sc.x, sw.x), __fdiv_rn(sc.y, sw.y), __fdiv_rn(sv.x, mul_rn(sw.x, sw.x)),
                              __fdiv_rn(sv.y, mul_rn(sw.y, sw.y)));
-    p.integ_out[(size_t)cy * p.W + cx] = pack_rgba16f(out);
+    store_out(p, cy, (size_t)cy * p.W + cx, pack_rgba16f(out));
 }
 
 template <int S>
@@ -558,9 +576,9 @@ __global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair
         upk(scs[i], csa, csb); upk(sca[i], caa, cab);
         upk(svs[i], vsa, vsb); upk(sva[i], vaa, vab);
         const float rsa = rcp_approx(wsa), rsb = rcp_approx(wsb), raa = rcp_approx(waa), rab = rcp_approx(wab);
-        uint2 *orow = p.integ_out + (size_t)cy * p.W;
-        orow[ca] = pack_rgba16f(make_float4(csa * rsa, caa * raa, vsa * (rsa * rsa), vaa * (raa * raa)));
-        if (cb < p.x_end) orow[cb] = pack_rgba16f(make_float4(csb * rsb, cab * rab, vsb * (rsb * rsb), vab * (rab * rab)));
+        const size_t orow = (size_t)cy * p.W;
+        store_out(p, cy, orow + ca, pack_rgba16f(make_float4(csa * rsa, caa * raa, vsa * (rsa * rsa), vaa * (raa * raa))));
+        if (cb < p.x_end) store_out(p, cy, orow + cb, pack_rgba16f(make_float4(csb * rsb, cab * rab, vsb * (rsb * rsb), vab * (rab * rab))));
     }
 }
 
@@ -627,15 +645,20 @@ int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFP
     p.normals = (const uint2 *)normals->ptr; p.motion = (const uint2 *)motion->ptr; p.rt = (const uint32_t *)rt->ptr;
     p.prev_normals = (const uint2 *)prevn->ptr; p.history = (const uint2 *)hist->ptr;
     p.moments_in = (const uint32_t *)mom->ptr; p.integrated_out = (uint2 *)integ0->ptr; p.moments_out = (uint32_t *)mom->twin;
+    // multi-GPU: iteration 0 on the neighbours reads 2 rows of this output beyond their band, their next temporal pass
+    // reads `motion_halo` rows of these moments
+    p.push_integ = halo_push_for(ctx, integ0, false, 2);
+    p.push_mom = halo_push_for(ctx, mom, true, ctx->part.motion_halo);
     dim3 block(32, 8), grid((p.x_end + 31) / 32, (p.y_end - p.y_begin + 7) / 8);
     svgf_temporal_kernel<<<grid, block, 0, ctx->stream>>>(p);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     std::swap(mom->ptr, mom->twin);   // this frame's moments become "the" moments image
-    return VHR_OK;
+    for (int r = 0; r < VHR_MAX_RANKS; ++r) std::swap(mom->peer[r], mom->peer_twin[r]);
+    return peer_sync_neighbours(ctx);
 }
 
-int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc) {
+static int atrous_launch_only(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc, bool &pushed) {
     if (ctx->n_bound < 1) return fail(VHR_ERR_STATE, "svgf_atrous_filter.comp: pass images not bound");
     Image *normals = ctx->bound[0];
     Image *in = storage_slot(ctx, pc.integrated_shadow_and_ao[0]);
@@ -652,6 +675,11 @@ int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPus
     p.step = pc.atrous_step;
     p.dsx = ctx->pfd.display_size[0]; p.dsy = ctx->pfd.display_size[1];
     p.normals = (const uint2 *)normals->ptr; p.integ_in = (const uint2 *)in->ptr; p.integ_out = (uint2 *)out->ptr;
+    // multi-GPU: the next iteration (step 2s) reads 4s rows beyond a band; iteration 0's output is also next frame's
+    // history (motion halo); the reference never reads the last iteration's output, so it is not exchanged
+    if (ctx->part.enabled && p.step != ctx->part.no_exchange_step)
+        p.push = halo_push_for(ctx, out, false, p.step == 1 ? std::max(4, ctx->part.motion_halo) : 4 * p.step);
+    pushed = p.push.rows > 0;
     // The tiled kernel bounds-checks against the image size; the reference checks against pfd.display_size. They are
     // the same thing whenever the UBO matches the images, which the tiled path requires.
     bool tiled_ok = ctx->opt.atrous_variant >= 1 && p.dsx == (float)p.W && p.dsy == (float)p.H;
@@ -693,6 +721,12 @@ int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPus
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return VHR_OK;
+}
+
+int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc) {
+    bool pushed = false;
+    if (int rc = atrous_launch_only(ctx, xg, yg, pc, pushed)) return rc;
+    return pushed ? peer_sync_neighbours(ctx) : VHR_OK;
 }
 
 }  // namespace vhr

@@ -325,6 +325,13 @@ struct RaygenParams {
     uint2 *reflections;       // binding 3 (RGBA16F)
     float *refl_t;            // optional debug output: closest-hit distance of the reflection ray (-1 = miss/sky)
     SceneRefs scene;
+    // multi-GPU (vhr_set_partition with ray_block_rows = 8): this rank traces the 8-row blocks b with b % world == rank and
+    // stores every pixel into the image of the rank that OWNS the row (its SVGF band) over NVLink — the all-to-all that
+    // would follow the pass is fused into it. world == 0: single-GPU addressing.
+    int world, rank;
+    int band_begin[VHR_MAX_RANKS + 1];
+    uint32_t *shadow_ao_of[VHR_MAX_RANKS];
+    uint2 *reflections_of[VHR_MAX_RANKS];
 };
 
 // 8x4-pixel warp tiles inside a 16x8 block: neighbouring lanes trace neighbouring pixels.
@@ -337,7 +344,20 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
 __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     int x, y;
     tile_coords(x, y);
-    y += p.y_begin;
+    uint32_t *__restrict__ out_sa = p.shadow_ao;
+    uint2 *__restrict__ out_refl = p.reflections;
+    if (p.world > 0) {
+        // blockIdx.y counts this rank's 8-row blocks; the block's rows belong to one or two SVGF bands
+        y = (y - blockIdx.y * 8) + (blockIdx.y * p.world + p.rank) * 8;
+        int owner = 0;
+#pragma unroll
+        for (int r = 1; r < VHR_MAX_RANKS; ++r)
+            if (r < p.world && y >= p.band_begin[r]) owner = r;
+        out_sa = p.shadow_ao_of[owner];
+        out_refl = p.reflections_of[owner];
+    } else {
+        y += p.y_begin;
+    }
     // every lane stays in the kernel: trace() is warp-synchronous, lanes without a ray just pass alive = false
     const bool in_range = x < p.W && y < p.y_end;
     const size_t pix = in_range ? (size_t)y * p.W + x : 0;
@@ -346,8 +366,8 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
     const float depth = in_range ? __ldg(&p.depth[pix]) : 0.0f;                                  // texel centre: exact texel (Q17)
     const bool lit = in_range && depth != 0.0f;
     if (in_range && !lit) {                                                                      // raygen.rgen:20-24
-        p.shadow_ao[pix] = pack_rg16f(1.0f, 1.0f);
-        p.reflections[pix] = make_uint2(0u, 0u);
+        out_sa[pix] = pack_rg16f(1.0f, 1.0f);
+        out_refl[pix] = make_uint2(0u, 0u);
         if (p.refl_t) p.refl_t[pix] = -1.0f;
     }
     const float3 P = unproject_rn(pfd.camera_viewproj_inverse, lit ? depth : 1.0f, u, v);
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
         }
     }
     ao = __fdiv_rn(ao, (float)p.ao_spp);
-    if (lit) p.shadow_ao[pix] = pack_rg16f(shadow, ao);
+    if (lit) out_sa[pix] = pack_rg16f(shadow, ao);
 
     // mirror reflection (raygen.rgen:59-65)
     if (p.flags & 4) {
@@ -398,11 +418,11 @@ __global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ Ray
             rt = hit.t;
         }
         if (lit) {
-            p.reflections[pix] = pack_rgba16f(payload);
+            out_refl[pix] = pack_rgba16f(payload);
             if (p.refl_t) p.refl_t[pix] = rt;
         }
     } else if (lit) {
-        p.reflections[pix] = make_uint2(0u, 0u);
+        out_refl[pix] = make_uint2(0u, 0u);
         if (p.refl_t) p.refl_t[pix] = -1.0f;
     }
 }
@@ -756,6 +776,28 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
     p.shadow_ao = (uint32_t *)sa->ptr; p.reflections = (uint2 *)refl->ptr;
     p.refl_t = ctx->opt.debug_refl_t ? ctx->d_refl_t : nullptr;
     p.scene = scene_refs(ctx);
+    p.world = 0; p.rank = 0;
+    const Partition &pt = ctx->part;
+    if (pt.enabled && pt.world > 1 && pt.ray_block_rows == 8) {
+        p.world = pt.world; p.rank = pt.rank;
+        p.y_begin = 0; p.y_end = (int)height;
+        for (int r = 0; r <= pt.world; ++r) p.band_begin[r] = pt.band_begin[r];
+        for (int r = 0; r < pt.world; ++r) {
+            p.shadow_ao_of[r] = (uint32_t *)(r == pt.rank ? sa->ptr : sa->peer[r]);
+            p.reflections_of[r] = (uint2 *)(r == pt.rank ? refl->ptr : refl->peer[r]);
+            if (!p.shadow_ao_of[r] || !p.reflections_of[r])
+                return fail(VHR_ERR_STATE, "TraceRays: rank %d's output images are not attached (vhr_image_attach_peer)", r);
+        }
+        const int n_blocks = ((int)height + 7) / 8;
+        const int mine = (n_blocks - pt.rank + pt.world - 1) / pt.world;          // blocks b = rank, rank + world, ...
+        dim3 block(128), grid((width + 15) / 16, mine);
+        if (mine > 0) {
+            raygen_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+            VHR_CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+        }
+        return peer_sync_all(ctx);      // every rank's rows have landed in their owners' images before anyone reads them
+    }
     if (ctx->opt.raygen_variant == 1 && p.ao_spp >= 1) {
         if (!ctx->d_ray_queue) VHR_CUDA_CHECK(cudaMalloc(&ctx->d_ray_queue, sizeof(uint32_t)));
         if (ctx->raygen_blocks == 0) {

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "vhr_internal.h"
@@ -84,6 +85,15 @@ static int blit(vhr_context *ctx, Image *src, Image *dst, const char *what) {
                     src->height, src->format, dst->width, dst->height, dst->format);
     if (int rc = consume_upload(ctx, src)) return rc;
     if (int rc = consume_upload(ctx, dst)) return rc;
+    if (ctx->part.enabled && ctx->part.world > 1 && src->height == ctx->height) {
+        // a rank only ever reads its band and the halo rows around it: copy those (band +- 64 rows)
+        const int y0 = std::max(0, ctx->part.band_begin[ctx->part.rank] - 64);
+        const int y1 = std::min((int)src->height, ctx->part.band_begin[ctx->part.rank + 1] + 64);
+        const size_t row = src->bytes / src->height;
+        VHR_CUDA_CHECK(cudaMemcpyAsync((char *)dst->ptr + y0 * row, (const char *)src->ptr + y0 * row, (size_t)(y1 - y0) * row,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        return VHR_OK;
+    }
     VHR_CUDA_CHECK(cudaMemcpyAsync(dst->ptr, src->ptr, src->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return VHR_OK;
 }
@@ -146,6 +156,7 @@ void vhr_context_destroy(vhr_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
     if (ctx->download_stream) cudaStreamSynchronize(ctx->download_stream);
+    peer_close_all(ctx);
     for (auto &kv : ctx->transient) free_image(kv.second);
     for (auto &im : ctx->storage) if (im.used) free_image(im);
     free_bvh(ctx);

@@ -26,6 +26,9 @@ struct Image {
     cudaEvent_t staged = nullptr;        // snapshot written (compute stream)
     cudaEvent_t staging_free = nullptr;  // snapshot read back (download stream)
     bool staging_busy = false;
+    // multi-GPU: the same image in the other ranks' HBM, mapped through CUDA IPC (NVLink peer memory); index = rank
+    void *peer[VHR_MAX_RANKS] = {};
+    void *peer_twin[VHR_MAX_RANKS] = {};
 };
 
 inline int format_texel_bytes(int fmt) {
@@ -63,6 +66,22 @@ struct Options {
     int raygen_variant = 0;      // 0 (default, faster as measured): one thread per pixel, ray kinds in lock step; 1: persistent warps + pixel queue
 };
 
+// Row partition of one frame over the GPUs of a box (vhr_set_partition)
+struct Partition {
+    bool enabled = false;
+    int world = 1, rank = 0;
+    int band_begin[VHR_MAX_RANKS + 1] = {};
+    int ray_block_rows = 0;
+    int motion_halo = 8;
+    int no_exchange_step = 16;
+};
+// What a kernel needs to push its boundary rows into the neighbours' copies of the image it writes
+struct HaloPush {
+    void *up = nullptr;       // same image on rank-1 (nullptr: no neighbour / no push)
+    void *down = nullptr;     // same image on rank+1
+    int rows = 0;             // output rows [y_begin, y_begin+rows) go up, [y_end-rows, y_end) go down
+};
+
 }  // namespace vhr
 
 struct vhr_context {
@@ -94,6 +113,12 @@ struct vhr_context {
     cudaEvent_t compute_tail = nullptr;            // scratch event: "everything enqueued on the compute stream so far"
     std::vector<cudaEvent_t> tickets;              // ring of download-completion events
     uint32_t next_ticket = 0;
+    // multi-GPU partition + peer synchronisation (peer.cu)
+    vhr::Partition part;
+    uint32_t *sync_flags = nullptr;                       // device: [0, MAX) ray-pass arrivals, [MAX, 2 MAX) halo arrivals, by source rank
+    uint32_t *peer_flags[VHR_MAX_RANKS] = {};             // the other ranks' sync_flags (IPC mapped)
+    uint32_t seq_ray = 0, seq_halo = 0;
+    std::vector<void *> ipc_opened;                       // everything cudaIpcOpenMemHandle returned (closed with the context)
 };
 
 namespace vhr {
@@ -117,6 +142,11 @@ int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height);
 int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int reflection_mode);
 int launch_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
                           float *out_uv);
+// peer.cu: stream-ordered flag exchange with the other ranks (cuStreamWriteValue32 / cuStreamWaitValue32)
+int peer_sync_neighbours(vhr_context *ctx);   // after a kernel that pushed halo rows: tell both neighbours, wait for theirs
+int peer_sync_all(vhr_context *ctx);          // after the ray pass scattered its rows to their owners: all ranks <-> all ranks
+HaloPush halo_push_for(vhr_context *ctx, Image *out, bool twin, int rows);
+void peer_close_all(vhr_context *ctx);
 int build_bvh(vhr_context *ctx);
 void free_bvh(vhr_context *ctx);
 

@@ -59,7 +59,7 @@ def groups(n):
 class HybridRenderPath:
     """Owns the images of the hot-path passes on one context and replays the reference's per-frame call sequence."""
 
-    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False, composition=None, shadow_map_size=(4096, 4096)):
+    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False, composition=None, shadow_map_size=(4096, 4096), rt_sets=1):
         """composition: None (no composition pass) or the VkFormat of RENDER_OUTPUT (B8G8R8A8_SRGB = the reference's
         swapchain; R16G16B16A16_SFLOAT = linear HDR radiance for parity measurements)."""
         self.ctx, self.W, self.H = ctx, width, height
@@ -70,8 +70,14 @@ class HybridRenderPath:
             for k, n in names.items():
                 ctx.actualize_image(n, GBUFFER_FORMATS[k])
             self.gsets.append(names)
-        ctx.actualize_image(N_RT, F2)
-        ctx.actualize_image(N_REFL, F4)
+        # rt_sets = 2 (multi-GPU fused partition): the ray pass of frame k+1 stores into OTHER ranks' images while those may
+        # still be reading frame k's, so consecutive frames alternate between two output sets
+        self.rt_sets = []
+        for s in range(rt_sets):
+            sfx = "" if s == 0 else f" [{s}]"
+            ctx.actualize_image(N_RT + sfx, F2)
+            ctx.actualize_image(N_REFL + sfx, F4)
+            self.rt_sets.append((N_RT + sfx, N_REFL + sfx))
         ctx.actualize_image(N_DENOISED, F4)
         if ssao or composition is not None:
             ctx.actualize_image(N_SSAO_RAW, F4)
@@ -118,9 +124,9 @@ class HybridRenderPath:
         return out
 
     # ---- passes ---------------------------------------------------------------------------------------------------
-    def raytrace_pass(self, gset=0):
+    def raytrace_pass(self, gset=0, rtset=0):
         g = self.gsets[gset]
-        self.ctx.bind_pass_images([g[N_NORMALS], g[N_DEPTH], N_RT, N_REFL])
+        self.ctx.bind_pass_images([g[N_NORMALS], g[N_DEPTH], *self.rt_sets[rtset]])
         self.ctx.trace_rays(self.W, self.H)
 
     def ssao_passes(self, gset=0):
@@ -132,11 +138,11 @@ class HybridRenderPath:
         self.ctx.bind_pass_images([N_SSAO_RAW, N_SSAO])
         self.ctx.dispatch(SHADER_SSAO_BLUR, gx, gy, 1, self.ssao_radius)
 
-    def svgf_denoise_pass(self, gset=0):
+    def svgf_denoise_pass(self, gset=0, rtset=0):
         """hybrid_render_path.cpp:288-330, statement by statement."""
         ctx, pc, g = self.ctx, self.pc, self.gsets[gset]
         gx, gy = groups(self.W), groups(self.H)
-        ctx.bind_pass_images([g[N_NORMALS], g[N_MOTION], g[N_DEPTH], N_RT, N_DENOISED])
+        ctx.bind_pass_images([g[N_NORMALS], g[N_MOTION], g[N_DEPTH], self.rt_sets[rtset][0], N_DENOISED])
         ctx.dispatch(SHADER_SVGF, gx, gy, 1, pc)
         self._stamp()
         for i in range(5):
@@ -159,10 +165,10 @@ class HybridRenderPath:
                                    N_DENOISED if denoised else N_RT, N_REFL, N_RENDER_OUTPUT])
         self.ctx.draw(SHADER_COMPOSITION, (shadow_mode, ao_mode, reflection_mode))
 
-    def frame(self, pfd, gset=0):
+    def frame(self, pfd, gset=0, rtset=0):
         """Raytrace Pass -> SVGF Denoise Pass for one frame whose G-buffer already sits in image set `gset`."""
         self.ctx.update_per_frame_ubo(pfd)
         self._stamp()
-        self.raytrace_pass(gset)
+        self.raytrace_pass(gset, rtset)
         self._stamp()
-        self.svgf_denoise_pass(gset)
+        self.svgf_denoise_pass(gset, rtset)

@@ -147,6 +147,46 @@ class RowBandSvgf:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Fused partition: no collective in the frame. Kernels store into the other ranks' images over NVLink (CUDA IPC peer
+# memory) and the library orders the streams with flag words (include/vhr_b200.h, "one frame over several GPUs").
+# torch.distributed only carries the IPC handles at set-up.
+# ---------------------------------------------------------------------------------------------------------------------
+def setup_fused_partition(ctx, path, world, rank, group=None, motion_halo=8, ray_block_rows=8):
+    """Exports this rank's exchanged images, attaches everybody else's, installs the row partition on `ctx`.
+
+    Exchanged images: the ray pass outputs (every rank stores into every owner's), the two integrated ping-pong images and
+    the moments image with its twin (boundary rows pushed to the two neighbours). After this the plain single-GPU call
+    sequence (`HybridRenderPath.frame`) runs the partitioned frame."""
+    import torch.distributed as dist
+    pc = path.pc
+    mine = {"sync": ctx.sync_export_ipc(), "rt": [], "integ": [], "moments": None}
+    for rt_name, refl_name in path.rt_sets:
+        mine["rt"].append((ctx.image_export_ipc(rt_name), ctx.image_export_ipc(refl_name)))
+    for slot in pc["integrated_shadow_and_ao"]:
+        mine["integ"].append((int(slot), ctx.storage_image_export_ipc(int(slot))[0]))
+    mslot = int(pc["shadow_and_ao_moments_history"])
+    mine["moments"] = (mslot,) + ctx.storage_image_export_ipc(mslot, twin=True)
+    ctx.synchronize()
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    for r, other in enumerate(everyone):
+        if r == rank:
+            continue
+        ctx.sync_attach_peer(r, other["sync"])
+        for (rt_name, refl_name), (h_rt, h_refl) in zip(path.rt_sets, other["rt"]):
+            ctx.image_attach_peer(rt_name, r, h_rt)
+            ctx.image_attach_peer(refl_name, r, h_refl)
+        if abs(r - rank) == 1:                       # halos only ever go to the two neighbours
+            for (slot, _), (_, h) in zip(mine["integ"], other["integ"]):
+                ctx.storage_image_attach_peer(slot, r, h)
+            ctx.storage_image_attach_peer(mslot, r, other["moments"][1], other["moments"][2])
+    bands = [band_rows(path.H, world, r)[0] for r in range(world)] + [path.H]
+    ctx.set_partition(world, rank, bands, ray_block_rows=ray_block_rows, motion_halo=motion_halo)
+    dist.barrier(group=group)                        # nobody starts storing into a peer that has not attached yet
+    return bands
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # GPU backend over the C-ABI
 # ---------------------------------------------------------------------------------------------------------------------
 class _DeviceRows:
