@@ -517,12 +517,15 @@ def run_rowband(args):
         ctx.set_option(capi.OPT_TRACE_AO, 1 if ao_spp else 0)
         ctx.set_option(capi.OPT_AO_SPP, max(ao_spp, 1))
         ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
-        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2)
+        fused = args.halo == "fused" and world > 1
+        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=2 if fused else 1)
         seq = camera.FrameSequencer(W, H, sc.light)
         cam = sc.camera
         pfds = [None, None]
-        g0, g1 = max(0, y0 - MG.GBUFFER_HALO), min(H, y1 + MG.GBUFFER_HALO)
-        ctx.set_option(capi.OPT_ROW_BEGIN, g0); ctx.set_option(capi.OPT_ROW_END, g1)     # G-buffer input: band + halo rows only
+        # G-buffer input (untimed set-up). NCCL mode: band + halo rows. Fused mode: the ray pass is interleaved over the
+        # whole frame, so every rank is given the full G-buffer.
+        g0, g1 = (0, H) if fused else (max(0, y0 - MG.GBUFFER_HALO), min(H, y1 + MG.GBUFFER_HALO))
+        ctx.set_option(capi.OPT_ROW_BEGIN, g0); ctx.set_option(capi.OPT_ROW_END, g1)
         for s_ in (1, 0, 1):
             cam.set_pose(*poses[s_])
             pfd = seq.next(cam)
@@ -532,18 +535,35 @@ def run_rowband(args):
             ctx.gbuffer_pass(W, H)
             pfds[s_] = pfd
         nonsky = [int((ctx.image_download(path.gsets[s_][HP.N_DEPTH])[y0:y1] > 0).sum()) for s_ in (0, 1)]
-        backends = [MG.CabiBandBackend(ctx, path, gset=s_) for s_ in (0, 1)]
-        drivers = [MG.RowBandSvgf(b, H, world, rank, motion_halo=args.motion_halo) for b in backends]
         frame_no = [0]
+        if args.motion_halo <= 0:       # auto: what this camera motion needs (every rank sees the same G-buffer rows it compares)
+            mv = max(float(np.abs(ctx.image_download(path.gsets[s_][HP.N_MOTION])[g0:g1, :, 1].astype(np.float32)).max()) for s_ in (0, 1))
+            t = torch.tensor([mv], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            args.motion_halo = min(64, MG.required_motion_halo(float(t), H))
+        if fused:
+            MG.setup_fused_partition(ctx, path, world, rank, motion_halo=args.motion_halo)
+            drivers = []
 
-        def step():
-            k = frame_no[0]; s_ = k & 1
-            pfd = pfds[s_]; pfd["frame_index"] = 3 + k
-            frame_no[0] += 1
-            ctx.update_per_frame_ubo(pfd)
-            backends[s_].trace((y0, y1))
-            drivers[s_].run()
-            return nonsky[s_] * (1 + ao_spp + refl)
+            def step():
+                k = frame_no[0]; s_ = k & 1
+                pfd = pfds[s_]; pfd["frame_index"] = 3 + k
+                frame_no[0] += 1
+                path.frame(pfd, gset=s_, rtset=k & 1)          # the plain single-GPU call sequence
+                return nonsky[s_] * (1 + ao_spp + refl)
+        else:
+            backends = [MG.CabiBandBackend(ctx, path, gset=s_) for s_ in (0, 1)]
+            drivers = [MG.RowBandSvgf(b, H, world, rank, motion_halo=args.motion_halo) for b in backends]
+
+            def step():
+                k = frame_no[0]; s_ = k & 1
+                pfd = pfds[s_]; pfd["frame_index"] = 3 + k
+                frame_no[0] += 1
+                ctx.update_per_frame_ubo(pfd)
+                backends[s_].trace((y0, y1))
+                drivers[s_].run()
+                return nonsky[s_] * (1 + ao_spp + refl)
 
         def barrier():
             if world > 1:
@@ -575,7 +595,10 @@ def run_rowband(args):
         rays, launches, band_sum, sent = (float(x) for x in r.cpu())
     if rank == 0:
         cfg = config_dict(wl, sc.num_triangles)
-        cfg.update({"partition": f"row bands x{world}, BVH replicated, NCCL halo exchange (6 grouped send/recv per frame)", "motion_halo_rows": args.motion_halo})
+        how = ("ray pass in 8-row blocks dealt round-robin with results stored into the owners' images over NVLink peer memory, SVGF on row bands "
+               "with halo rows pushed by the kernels, stream-ordered flag words; no collective in the frame") if args.halo == "fused" and world > 1 else \
+              "NCCL halo exchange (6 grouped send/recv per frame), ray pass on the contiguous band"
+        cfg.update({"partition": f"row bands x{world}, BVH replicated, {how}", "motion_halo_rows": args.motion_halo})
         print(json.dumps({
             "metric": METRIC, "value": rays / (ms_total * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -597,7 +620,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partition", default="views", choices=["views", "rows"],
                     help="N>1: independent views per rank (weak scaling, default) or row bands of one frame (strong scaling, NCCL halos)")
-    ap.add_argument("--motion-halo", type=int, default=8, help="rows of history/moments exchanged for the temporal pass (row-band mode)")
+    ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],
+                    help="row-band mode: halo rows pushed by the kernels over NVLink peer memory (default) or NCCL send/recv between passes")
+    ap.add_argument("--motion-halo", type=int, default=0,
+                    help="rows of history/moments exchanged for the temporal pass (row-band mode); 0 = derive from the G-buffer's motion vectors")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -117,3 +117,33 @@ def test_rebuild_recreates_svgf_storage_images():
         # rendering needs the GPU: fails loudly on the validation context, never falls back
         with pytest.raises(capi.VhrError):
             r.render(np.zeros((), T.PerFrameData))
+
+
+# ---- multi-GPU partition (include/vhr_b200.h, "one frame over several GPUs"): argument validation needs no GPU -------------
+def test_partition_arguments_are_validated():
+    from vulkanhybridrenderer_b200 import multi_gpu as MG
+    H = 1080
+    with capi.Context(1920, H, device=host_api.DEVICE_NONE) as ctx:
+        bands = [MG.band_rows(H, 4, r)[0] for r in range(4)] + [H]
+        ctx.set_partition(4, 1, bands)                                     # well formed
+        assert ctx.get_option(capi.OPT_ROW_BEGIN) == bands[1] and ctx.get_option(capi.OPT_ROW_END) == bands[2]
+        ctx.clear_partition()
+        with pytest.raises(capi.VhrError):
+            ctx.set_partition(4, 4, bands)                                 # rank out of range
+        with pytest.raises(capi.VhrError):
+            ctx.set_partition(9, 0, list(range(0, 1081, 120)))             # more ranks than VHR_MAX_RANKS
+        with pytest.raises(capi.VhrError):
+            ctx.set_partition(4, 0, bands[:-1] + [H - 8])                  # bands do not cover the image
+        with pytest.raises(capi.VhrError):
+            ctx.set_partition(4, 0, [0, 30, 540, 810, H])                  # a band thinner than the widest halo
+        with pytest.raises(capi.VhrError):
+            ctx.set_partition(4, 0, bands, ray_block_rows=4)               # the ray kernel deals 8-row blocks
+        with pytest.raises(capi.VhrError):
+            ctx.set_partition(4, 0, bands, motion_halo=200)
+        # exporting / attaching peer memory needs the device: loud failure, no fallback
+        ctx.actualize_image("Depth", T.VK_FORMAT_D32_SFLOAT)
+        for call in (lambda: ctx.image_export_ipc("Depth"), lambda: ctx.sync_export_ipc(),
+                     lambda: ctx.image_attach_peer("Depth", 1, b"\0" * 64)):
+            with pytest.raises(capi.VhrError) as e:
+                call()
+            assert "VHR_DEVICE_NONE" in str(e.value)

@@ -33,7 +33,22 @@ def main():
             ctx.set_option(capi.OPT_TRACE_REFLECTIONS, 1)
             return ctx, HP.HybridRenderPath(ctx, W, H, rt_sets=rt_sets)
         ctx, path = make(2)
-        MG.setup_fused_partition(ctx, path, world, rank, motion_halo=8)
+        # Dry run over the camera path: the halo of history / moments rows a frame's temporal pass needs was pushed during
+        # the PREVIOUS frame, so the partition carries the maximum over the whole path (same G-buffer on every rank).
+        seq0 = camera.FrameSequencer(W, H, sc.light)
+        pos0, yaw0, pitch0 = sc.camera.position.copy(), sc.camera.yaw, sc.camera.pitch
+        halo = 4
+        for f in range(n_frames):
+            if f:
+                sc.camera.set_pose(sc.camera.position + np.array([0.05, 0.0, 0.01]), sc.camera.yaw + 0.002, sc.camera.pitch)
+            ctx.update_per_frame_ubo(seq0.next(sc.camera))
+            g = path.gsets[0]
+            ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
+            ctx.gbuffer_pass(W, H)
+            halo = max(halo, MG.required_motion_halo(float(np.abs(ctx.image_download(g[HP.N_MOTION])[..., 1].astype(np.float32)).max()), H))
+        assert halo <= 64, f"camera motion needs {halo} halo rows (max 64)"
+        sc.camera.set_pose(pos0, yaw0, pitch0)
+        MG.setup_fused_partition(ctx, path, world, rank, motion_halo=halo)
         ref = make(1) if rank == 0 else None
         seq = camera.FrameSequencer(W, H, sc.light)
         cam = sc.camera
@@ -55,7 +70,7 @@ def main():
                 c.gbuffer_pass(W, H)
                 if c is ctx:
                     bands = [MG.band_rows(H, world, r)[0] for r in range(world)] + [H]
-                    c.set_partition(world, rank, bands, ray_block_rows=8, motion_halo=8)
+                    c.set_partition(world, rank, bands, ray_block_rows=8, motion_halo=halo)
             path.frame(pfd, gset=0, rtset=f & 1)
             if ref:
                 ref[1].frame(pfd)
@@ -74,6 +89,10 @@ def main():
                     want = rc.image_download(name).reshape(H, -1)
                     bad = int((outs[key].view(np.uint16) != want.view(np.uint16)).sum())
                     msg.append(f"{key} {bad}")
+                    if bad:
+                        rows_bad = np.nonzero((outs[key].view(np.uint16) != want.view(np.uint16)).any(axis=1))[0]
+                        runs = np.split(rows_bad, np.nonzero(np.diff(rows_bad) > 1)[0] + 1)
+                        msg.append("rows " + " ".join(f"{r[0]}-{r[-1]}" for r in runs[:12]))
                     ok &= bad == 0
                 print(f"[fused x{world}] frame {f}: mismatching halfs: " + ", ".join(msg) + f" (of {outs['den'].size} denoised)")
         if rank == 0:

@@ -270,6 +270,8 @@ class Context:
     def set_partition(self, world, rank, band_begin, ray_block_rows=8, motion_halo=8, no_exchange_step=16):
         p = Partition()
         p.world, p.rank = world, rank
+        if len(band_begin) > MAX_RANKS + 1:
+            raise VhrError(f"partition over {len(band_begin) - 1} ranks (max {MAX_RANKS})")
         for i, b in enumerate(band_begin):
             p.band_begin[i] = int(b)
         p.ray_block_rows, p.motion_halo, p.no_exchange_step = ray_block_rows, motion_halo, no_exchange_step

@@ -33,6 +33,13 @@ def band_rows(height, world, rank):
     return y0, y0 + base + (1 if rank < rem else 0)
 
 
+def required_motion_halo(motion_y_max_uv, height):
+    """Rows of last frame's history / moments / normals the temporal pass can reach outside a band: svgf.comp:52 reprojects to
+    coords - motion * size + 0.5 and the 3x3 retry (:81-97) looks one more texel around it. `motion_y_max_uv` is max |motion.y|
+    over the frame (in UV units, as stored in the G-buffer)."""
+    return int(np.ceil(float(motion_y_max_uv) * height)) + 2
+
+
 def views_for_rank(n_views, world, rank):
     """Batch-of-views partition (config 5): round-robin."""
     return list(range(rank, n_views, world))
