@@ -212,7 +212,8 @@ typedef enum vhr_option {
     VHR_OPT_ROW_END = 6,           /* default = image height */
     VHR_OPT_SVGF_FUSED = 7,        /* 1: temporal pass also produces a-trous iteration 0 (fused kernel) */
     VHR_OPT_ATROUS_VARIANT = 8,    /* 0: direct-load kernel (the reference's dataflow); 1: tiled kernel; 2 (default): pixel-pair
-                                      packed fp32x2 kernel with register-level tap reuse */
+                                      packed fp32x2 kernel with register-level tap reuse; 3: variant 2's arithmetic in a persistent
+                                      CTA with TMA-staged tiles (measured 4-8 % slower than 2 on B200: kept for study) */
     VHR_OPT_DEBUG_REFLECTION_T = 9,/* 1: the ray pass also records the reflection ray's closest-hit distance */
     VHR_OPT_RAYGEN_VARIANT = 10    /* 0 (default): one thread per pixel, ray kinds in lock step; 1: persistent warps pulling pixels from a
                                       queue, every lane running its pixel's rays back to back. Same images either way; measured

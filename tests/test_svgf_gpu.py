@@ -16,7 +16,7 @@ def _groups(n):
     return n // 8 + (n % 8 != 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("size", [(320, 184), (333, 171)])   # second one is ragged (not a multiple of 8 / 64)
 def test_atrous_all_steps_noise(variant, size):
     W, H = size

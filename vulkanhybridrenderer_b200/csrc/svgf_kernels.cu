@@ -9,6 +9,7 @@
 //                                fp32x2 instructions (FADD2/FMUL2/FFMA2).
 //
 // Images: dense row-major; RGBA16F texel = uint2, RG16F texel = uint32. fp32 math, fp16 RTE stores.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -68,13 +69,28 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
 
     float prev_s = 0.0f, prev_a = 0.0f, sum = 0.0f;
     float psm0 = 0.0f, psm1 = 0.0f, pam0 = 0.0f, pam1 = 0.0f;
+    // All twelve tap loads (previous normals, history, moments of the 2x2 footprint) are issued before any of them is
+    // examined: the reference's order (test the normal, then fetch history) costs a second dependent memory round trip
+    // per pixel, and this kernel is bound by exactly that latency (profiles/: DRAM 23 %, long-scoreboard stalls).
+    uint2 tpn[4];
+    uint32_t th[4], tm[4];
+    bool inb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int sx = ax + (i & 1), sy = ay + (i >> 1);
-        if (is_valid_reprojection(p, sx, sy, cur_id, cur_n)) {
-            size_t sp = (size_t)sy * p.W + sx;
-            float2 h = unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(&p.history[sp])));
-            float2 m = unpack_rg16f(__ldg(&p.moments_in[sp]));
+        const int sx = ax + (i & 1), sy = ay + (i >> 1);
+        inb[i] = !(sx < 0 || sy < 0 || (float)sx >= p.dsx || (float)sy >= p.dsy);
+        const size_t sp = inb[i] ? (size_t)sy * p.W + sx : pix;
+        tpn[i] = __ldg(&p.prev_normals[sp]);
+        th[i] = __ldg(reinterpret_cast<const uint32_t *>(&p.history[sp]));
+        tm[i] = __ldg(&p.moments_in[sp]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 pn = unpack_rgba16f(tpn[i]);
+        // is_valid_reprojection (svgf.comp:16-39) on the prefetched texel
+        if (inb[i] && cur_id == f2i_rz(pn.w) && !(dot3_rn(cur_n, make_float3(pn.x, pn.y, pn.z)) < VHR_COS_PI_4)) {
+            float2 h = unpack_rg16f(th[i]);
+            float2 m = unpack_rg16f(tm[i]);
             prev_s = add_rn(prev_s, mul_rn(bw[i], h.x));
             prev_a = add_rn(prev_a, mul_rn(bw[i], h.y));
             psm0 = add_rn(psm0, mul_rn(bw[i], m.x));
@@ -409,55 +425,13 @@ struct PairCfg {
     static constexpr size_t SMEM = (size_t)4 * SR * PC * sizeof(ulonglong2);
 };
 
+// Taps + normalisation + store for one staged tile (shared by the direct-staging and the TMA-staged kernels): thread
+// (tx, ty) owns pixel columns x0 + tx and x0 + tx + PD on the RY lattice rows ty*RY.. of the tile whose first row is yb.
 template <int S, int PD, int RY, int TR>
-__global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair_kernel(const __grid_constant__ AtrousParams p) {
+__device__ __forceinline__ void pair_compute(const AtrousParams &p, const ulonglong2 *__restrict__ sN0, const ulonglong2 *__restrict__ sN1,
+                                             const ulonglong2 *__restrict__ sL, const ulonglong2 *__restrict__ sV, int x0, int yb, int tx, int ty) {
     typedef PairCfg<S, PD, RY, TR> C;
-    constexpr int PC = C::PC, SR = C::SR, LR = C::LR;
-    extern __shared__ ulonglong2 psm[];
-    ulonglong2 *sN0 = psm;                 // (nx_a, nx_b), (ny_a, ny_b)
-    ulonglong2 *sN1 = psm + SR * PC;       // (nz_a, nz_b), (id_a, id_b)
-    ulonglong2 *sL = psm + 2 * SR * PC;    // (shadow_a, shadow_b), (ao_a, ao_b)
-    ulonglong2 *sV = psm + 3 * SR * PC;    // (var_shadow_a, var_shadow_b), (var_ao_a, var_ao_b)
-
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * PD + tx;
-    const int x0 = blockIdx.x * (2 * PD);
-    const int k = blockIdx.y / S, r = blockIdx.y % S;       // (super-tile, residue): rows y = yb + S*j
-    const int yb = p.y_begin + k * (S * LR) + r;
-
-    // ---- stage: every texel converted to fp32 once, pixel a = column j, pixel b = column j + PD ------------------
-    // Two sweeps (all loads, then convert + store) so that every global load of the tile is in flight at once: the
-    // first profile of this kernel had its warps parked on long-scoreboard stalls, one round trip per loop iteration.
-    constexpr int NIT = (SR * PC + C::THREADS - 1) / C::THREADS;
-    uint2 rna[NIT], rnb[NIT], rva[NIT], rvb[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const int idx = tid + it * C::THREADS;
-        const int row = idx / PC, j = idx - row * PC;
-        const int gy = yb + (row - 2) * S;
-        const int gxa = x0 - 2 * S + j, gxb = gxa + PD;
-        rna[it] = rnb[it] = rva[it] = rvb[it] = make_uint2(0u, 0u);     // out of bounds: zero normal => weight 0 ("skipped")
-        if (idx < SR * PC && gy >= 0 && gy < p.H) {
-            const size_t rowp = (size_t)gy * p.W;
-            if (gxa >= 0 && gxa < p.W) { rna[it] = __ldg(&p.normals[rowp + gxa]); rva[it] = __ldg(&p.integ_in[rowp + gxa]); }
-            if (gxb >= 0 && gxb < p.W) { rnb[it] = __ldg(&p.normals[rowp + gxb]); rvb[it] = __ldg(&p.integ_in[rowp + gxb]); }
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const int idx = tid + it * C::THREADS;
-        if (idx < SR * PC) {
-            const float4 na = unpack_rgba16f(rna[it]), nb = unpack_rgba16f(rnb[it]);
-            const float4 va = unpack_rgba16f(rva[it]), vb = unpack_rgba16f(rvb[it]);
-            const int ia = f2i_rz(na.w), ib = f2i_rz(nb.w);
-            sN0[idx] = make_ulonglong2(pk(na.x, nb.x), pk(na.y, nb.y));
-            sN1[idx] = make_ulonglong2(pk(na.z, nb.z), (u64)(uint32_t)ia | ((u64)(uint32_t)ib << 32));
-            sL[idx] = make_ulonglong2(pk(va.x, vb.x), pk(va.y, vb.y));
-            sV[idx] = make_ulonglong2(pk(va.z, vb.z), pk(va.w, vb.w));
-        }
-    }
-    __syncthreads();
-
+    constexpr int PC = C::PC;
     const int ca = x0 + tx, cb = ca + PD;
     const int lr0 = ty * RY;
     if (ca >= p.x_end || yb + lr0 * S >= p.y_end) return;
@@ -583,6 +557,174 @@ __global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair
 }
 
 template <int S, int PD, int RY, int TR>
+__global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair_kernel(const __grid_constant__ AtrousParams p) {
+    typedef PairCfg<S, PD, RY, TR> C;
+    constexpr int PC = C::PC, SR = C::SR, LR = C::LR;
+    extern __shared__ ulonglong2 psm[];
+    ulonglong2 *sN0 = psm;                 // (nx_a, nx_b), (ny_a, ny_b)
+    ulonglong2 *sN1 = psm + SR * PC;       // (nz_a, nz_b), (id_a, id_b)
+    ulonglong2 *sL = psm + 2 * SR * PC;    // (shadow_a, shadow_b), (ao_a, ao_b)
+    ulonglong2 *sV = psm + 3 * SR * PC;    // (var_shadow_a, var_shadow_b), (var_ao_a, var_ao_b)
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * PD + tx;
+    const int x0 = blockIdx.x * (2 * PD);
+    const int k = blockIdx.y / S, r = blockIdx.y % S;       // (super-tile, residue): rows y = yb + S*j
+    const int yb = p.y_begin + k * (S * LR) + r;
+
+    // ---- stage: every texel converted to fp32 once, pixel a = column j, pixel b = column j + PD ------------------
+    // Two sweeps (all loads, then convert + store) so that every global load of the tile is in flight at once: the
+    // first profile of this kernel had its warps parked on long-scoreboard stalls, one round trip per loop iteration.
+    constexpr int NIT = (SR * PC + C::THREADS - 1) / C::THREADS;
+    uint2 rna[NIT], rnb[NIT], rva[NIT], rvb[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * C::THREADS;
+        const int row = idx / PC, j = idx - row * PC;
+        const int gy = yb + (row - 2) * S;
+        const int gxa = x0 - 2 * S + j, gxb = gxa + PD;
+        rna[it] = rnb[it] = rva[it] = rvb[it] = make_uint2(0u, 0u);     // out of bounds: zero normal => weight 0 ("skipped")
+        if (idx < SR * PC && gy >= 0 && gy < p.H) {
+            const size_t rowp = (size_t)gy * p.W;
+            if (gxa >= 0 && gxa < p.W) { rna[it] = __ldg(&p.normals[rowp + gxa]); rva[it] = __ldg(&p.integ_in[rowp + gxa]); }
+            if (gxb >= 0 && gxb < p.W) { rnb[it] = __ldg(&p.normals[rowp + gxb]); rvb[it] = __ldg(&p.integ_in[rowp + gxb]); }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * C::THREADS;
+        if (idx < SR * PC) {
+            const float4 na = unpack_rgba16f(rna[it]), nb = unpack_rgba16f(rnb[it]);
+            const float4 va = unpack_rgba16f(rva[it]), vb = unpack_rgba16f(rvb[it]);
+            const int ia = f2i_rz(na.w), ib = f2i_rz(nb.w);
+            sN0[idx] = make_ulonglong2(pk(na.x, nb.x), pk(na.y, nb.y));
+            sN1[idx] = make_ulonglong2(pk(na.z, nb.z), (u64)(uint32_t)ia | ((u64)(uint32_t)ib << 32));
+            sL[idx] = make_ulonglong2(pk(va.x, vb.x), pk(va.y, vb.y));
+            sV[idx] = make_ulonglong2(pk(va.z, vb.z), pk(va.w, vb.w));
+        }
+    }
+    __syncthreads();
+
+    pair_compute<S, PD, RY, TR>(p, sN0, sN1, sL, sV, x0, yb, tx, ty);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// À-trous, variant 3 (default for steps 1..8): variant 2's arithmetic in a persistent CTA with TMA-staged tiles
+// ---------------------------------------------------------------------------------------------------------------
+// The profile of variant 2 (profiles/r01_ncu_atrous_pair.md) attributes a third of its warp-time to staging: address
+// arithmetic, bounds predicates, and above all the global-load round trip in front of every tile, with only two CTAs per
+// SM to hide it. Here one elected thread hands the whole tile + halo to the TMA unit:
+//   * the images are described to TMA as 3-D tensors (x, row mod S, row div S) of 8-byte texels, so one
+//     cp.async.bulk.tensor box {2 PD + 4 S texels, 1, LR + 4} fetches rows S apart; out-of-image coordinates arrive as
+//     zeros (= taps the reference skips), no bounds code anywhere;
+//   * the CTA is persistent over tiles: the raw fp16 box of tile t+1 lands in shared memory (mbarrier complete_tx)
+//     while the taps of tile t run; a short convert sweep (LDS raw -> fp32 pair planes) replaces the staging loop.
+struct AtrousTmaParams {
+    AtrousParams a;
+    int n_tx, n_tiles;         // tiles per row of tiles, total (n_tx * tile rows * S)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int S, int PD, int RY, int TR>
+struct TmaCfg {
+    typedef PairCfg<S, PD, RY, TR> C;
+    static constexpr int PCT = 2 * PD + 4 * S;                                 // staged texels per row (the TMA box width)
+    static constexpr size_t PLANES = (size_t)4 * C::SR * C::PC * sizeof(ulonglong2);
+    static constexpr size_t RAW = (size_t)C::SR * PCT * sizeof(uint2);         // one raw image box
+    static constexpr size_t SMEM = PLANES + 2 * RAW + 16;
+};
+
+template <int S, int PD, int RY, int TR>
+__global__ void __launch_bounds__(PD * TR, 2) atrous_tma_kernel(const __grid_constant__ AtrousTmaParams q, const __grid_constant__ CUtensorMap map_normals,
+                                                                const __grid_constant__ CUtensorMap map_integ) {
+    typedef PairCfg<S, PD, RY, TR> C;
+    typedef TmaCfg<S, PD, RY, TR> T;
+    constexpr int PC = C::PC, SR = C::SR, LR = C::LR, PCT = T::PCT;
+    const AtrousParams &p = q.a;
+    extern __shared__ __align__(128) unsigned char tsm[];
+    ulonglong2 *sN0 = reinterpret_cast<ulonglong2 *>(tsm);
+    ulonglong2 *sN1 = sN0 + SR * PC, *sL = sN0 + 2 * SR * PC, *sV = sN0 + 3 * SR * PC;
+    uint2 *raw_n = reinterpret_cast<uint2 *>(tsm + T::PLANES);
+    uint2 *raw_i = reinterpret_cast<uint2 *>(tsm + T::PLANES + T::RAW);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tsm + T::PLANES + 2 * T::RAW);
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * PD + tx;
+
+    // tile -> (x0, first row yb); the TMA box starts 2 S texels left of / 2 lattice rows above it
+    auto tile_origin = [&](int tile, int &x0, int &yb) {
+        const int bx = tile % q.n_tx, by = tile / q.n_tx;
+        x0 = bx * (2 * PD);
+        yb = p.y_begin + (by / S) * (S * LR) + (by % S);
+    };
+    auto issue = [&](int tile) {
+        int x0, yb;
+        tile_origin(tile, x0, yb);
+        const int base = yb - 2 * S;                       // first staged row (may be negative)
+        const int qrow = (base >= 0) ? base / S : -((-base + S - 1) / S);
+        const int rrow = base - qrow * S;                  // 0 <= rrow < S: rows base + j S = (rrow, qrow + j)
+        mbar_expect_tx(bar, (uint32_t)(2 * T::RAW));
+        tma_load_3d(raw_n, &map_normals, x0 - 2 * S, rrow, qrow, bar);
+        tma_load_3d(raw_i, &map_integ, x0 - 2 * S, rrow, qrow, bar);
+    };
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        if ((int)blockIdx.x < q.n_tiles) issue(blockIdx.x);
+    }
+    __syncthreads();
+
+    uint32_t parity = 0;
+    for (int tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // ---- convert the raw fp16 boxes into the fp32 pair planes (pixel a = texel j, pixel b = texel j + PD) ------
+        for (int idx = tid; idx < SR * PC; idx += C::THREADS) {
+            const int row = idx / PC, j = idx - row * PC;
+            const uint2 *rn = raw_n + row * PCT + j, *ri = raw_i + row * PCT + j;
+            const float4 na = unpack_rgba16f(rn[0]), nb = unpack_rgba16f(rn[PD]);
+            const float4 va = unpack_rgba16f(ri[0]), vb = unpack_rgba16f(ri[PD]);
+            const int ia = f2i_rz(na.w), ib = f2i_rz(nb.w);
+            sN0[idx] = make_ulonglong2(pk(na.x, nb.x), pk(na.y, nb.y));
+            sN1[idx] = make_ulonglong2(pk(na.z, nb.z), (u64)(uint32_t)ia | ((u64)(uint32_t)ib << 32));
+            sL[idx] = make_ulonglong2(pk(va.x, vb.x), pk(va.y, vb.y));
+            sV[idx] = make_ulonglong2(pk(va.z, vb.z), pk(va.w, vb.w));
+        }
+        __syncthreads();                                   // planes complete, raw boxes free
+        if (tid == 0 && tile + (int)gridDim.x < q.n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of raw before the async-proxy overwrite
+            issue(tile + gridDim.x);
+        }
+        int x0, yb;
+        tile_origin(tile, x0, yb);
+        pair_compute<S, PD, RY, TR>(p, sN0, sN1, sL, sV, x0, yb, tx, ty);
+        __syncthreads();                                   // every tap read done before the next convert overwrites the planes
+    }
+}
+
+template <int S, int PD, int RY, int TR>
 static int launch_pair(vhr_context *ctx, const AtrousParams &p, int x_pixels, int y_pixels) {
     typedef PairCfg<S, PD, RY, TR> C;
     static_assert(C::SMEM <= 110 * 1024, "two CTAs per SM must fit in shared memory");
@@ -594,6 +736,59 @@ static int launch_pair(vhr_context *ctx, const AtrousParams &p, int x_pixels, in
     dim3 block(PD, TR);
     dim3 grid((x_pixels + 2 * PD - 1) / (2 * PD), ((y_pixels + S * C::LR - 1) / (S * C::LR)) * S);
     atrous_pair_kernel<S, PD, RY, TR><<<grid, block, C::SMEM, ctx->stream>>>(p);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+// (x, row mod S, row div S) view of a dense RGBA16F image, box = {box_w texels, 1, box_rows}. The image allocation is
+// padded by 16 rows of zeros (alloc_image), which is what the last partial slab (rows H .. ceil(H/S) S) reads.
+static int make_tensor_map(CUtensorMap *map, const Image *im, int S, int box_w, int box_rows) {
+    if (!g_encode_tiled) {
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        VHR_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(VHR_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        g_encode_tiled = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t W = im->width, H = im->height;
+    const cuuint64_t dims[3] = {W, (cuuint64_t)S, (H + S - 1) / S};
+    const cuuint64_t strides[2] = {W * 8, W * 8 * (cuuint64_t)S};     // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, 1u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64 /* 8-byte elements: one texel */, 3, im->ptr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VHR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %ux%u image, step %d", (int)r, im->width, im->height, S);
+    return VHR_OK;
+}
+
+template <int S, int PD, int RY, int TR>
+static int launch_tma(vhr_context *ctx, const AtrousParams &p, const Image *normals, const Image *in, int x_pixels, int y_pixels) {
+    typedef PairCfg<S, PD, RY, TR> C;
+    typedef TmaCfg<S, PD, RY, TR> T;
+    static_assert(T::SMEM <= 112 * 1024, "two CTAs per SM must fit in shared memory");
+    static bool configured = false;
+    static int sms = 0;
+    if (!configured) {
+        VHR_CUDA_CHECK(cudaFuncSetAttribute(atrous_tma_kernel<S, PD, RY, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        VHR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        configured = true;
+    }
+    CUtensorMap map_n, map_i;
+    if (int rc = make_tensor_map(&map_n, normals, S, T::PCT, C::SR)) return rc;
+    if (int rc = make_tensor_map(&map_i, in, S, T::PCT, C::SR)) return rc;
+    AtrousTmaParams q;
+    q.a = p;
+    q.n_tx = (x_pixels + 2 * PD - 1) / (2 * PD);
+    q.n_tiles = q.n_tx * ((y_pixels + S * C::LR - 1) / (S * C::LR)) * S;
+    const int grid = std::min(q.n_tiles, 2 * sms);          // persistent: two resident CTAs per SM, tiles dealt round-robin
+    atrous_tma_kernel<S, PD, RY, TR><<<grid, dim3(PD, TR), T::SMEM, ctx->stream>>>(q, map_n, map_i);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return VHR_OK;
@@ -684,7 +879,7 @@ static int atrous_launch_only(vhr_context *ctx, uint32_t xg, uint32_t yg, const 
     // the same thing whenever the UBO matches the images, which the tiled path requires.
     bool tiled_ok = ctx->opt.atrous_variant >= 1 && p.dsx == (float)p.W && p.dsy == (float)p.H;
     static const int dev_tr = getenv("VHR_ATROUS_TR") ? atoi(getenv("VHR_ATROUS_TR")) : 4;     // development A/B switch
-    if (tiled_ok && ctx->opt.atrous_variant == 2 && dev_tr == 2) {
+    if (tiled_ok && ctx->opt.atrous_variant >= 2 && dev_tr == 2) {
         int xp = p.x_end, yp = p.y_end - p.y_begin;
         switch (p.step) {
             case 1: return launch_pair<1, 64, 2, 2>(ctx, p, xp, yp);
@@ -695,7 +890,17 @@ static int atrous_launch_only(vhr_context *ctx, uint32_t xg, uint32_t yg, const 
             default: break;
         }
     }
-    if (tiled_ok && ctx->opt.atrous_variant == 2) {
+    if (tiled_ok && ctx->opt.atrous_variant == 3 && (p.W % 2) == 0) {        // TMA needs 16-byte row strides
+        int xp = p.x_end, yp = p.y_end - p.y_begin;
+        switch (p.step) {
+            case 1: return launch_tma<1, 64, 2, 4>(ctx, p, normals, in, xp, yp);
+            case 2: return launch_tma<2, 64, 2, 4>(ctx, p, normals, in, xp, yp);
+            case 4: return launch_tma<4, 64, 2, 4>(ctx, p, normals, in, xp, yp);
+            case 8: return launch_tma<8, 64, 2, 4>(ctx, p, normals, in, xp, yp);
+            default: break;   // step 16: the raw boxes no longer fit beside the planes twice per SM -> variant 2
+        }
+    }
+    if (tiled_ok && ctx->opt.atrous_variant >= 2) {
         int xp = p.x_end, yp = p.y_end - p.y_begin;
         switch (p.step) {
             case 1: return launch_pair<1, 64, 2, 4>(ctx, p, xp, yp);

@@ -28,8 +28,11 @@ static int alloc_image(vhr_context *ctx, Image &im, uint32_t w, uint32_t h, int 
     im.width = w; im.height = h; im.format = fmt;
     im.bytes = (size_t)w * h * tb;
     if (ctx->device >= 0) {    // a VHR_DEVICE_NONE context only keeps the image table (graph building / validation)
-        VHR_CUDA_CHECK(cudaMalloc(&im.ptr, im.bytes));
-        VHR_CUDA_CHECK(cudaMemsetAsync(im.ptr, 0, im.bytes, ctx->stream));
+        // 16 rows of zero padding behind the image: the TMA view (x, row mod S, row div S) of the a-trous kernel reads the
+        // whole last slab, i.e. up to S - 1 <= 15 rows past the image, and those must read as "no texel"
+        const size_t padded = im.bytes + (size_t)16 * w * tb;
+        VHR_CUDA_CHECK(cudaMalloc(&im.ptr, padded));
+        VHR_CUDA_CHECK(cudaMemsetAsync(im.ptr, 0, padded, ctx->stream));
     }
     im.twin = nullptr;
     im.used = true;
@@ -554,7 +557,7 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
         case VHR_OPT_ROW_END: ctx->opt.row_end = (int)value; return VHR_OK;
         case VHR_OPT_SVGF_FUSED: ctx->opt.svgf_fused = value != 0; return VHR_OK;
         case VHR_OPT_ATROUS_VARIANT:
-            if (value < 0 || value > 2) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
+            if (value < 0 || value > 3) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
         case VHR_OPT_RAYGEN_VARIANT:
             if (value < 0 || value > 1) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);
