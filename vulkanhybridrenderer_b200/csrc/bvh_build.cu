@@ -9,6 +9,7 @@
 //   5. refit     bottom-up AABBs + SAH cost; subtrees of <= 3 triangles collapse into leaves when SAH prefers it
 //   6. widen     level-synchronous collapse of the binary tree into 8-wide nodes (largest-area child opened first),
 //                child boxes quantised to 8 bits (conservative), leaf triangles rewritten contiguously per node
+#include <stdlib.h>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -177,14 +178,14 @@ __device__ __forceinline__ float box_half_area(float3 mn, float3 mx) {
     return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__restrict__ order, Tree2 t) {
+__global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__restrict__ order, Tree2 t, float tri_cost) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= t.n) return;
     const TriRef r = tris[order[j]];
     float3 mn = make_float3(fminf(r.v0.x, fminf(r.v1.x, r.v2.x)), fminf(r.v0.y, fminf(r.v1.y, r.v2.y)), fminf(r.v0.z, fminf(r.v1.z, r.v2.z)));
     float3 mx = make_float3(fmaxf(r.v0.x, fmaxf(r.v1.x, r.v2.x)), fmaxf(r.v0.y, fmaxf(r.v1.y, r.v2.y)), fmaxf(r.v0.z, fmaxf(r.v1.z, r.v2.z)));
     uint32_t id = t.n - 1 + j;
-    t.bmin[id] = make_float4(mn.x, mn.y, mn.z, box_half_area(mn, mx));      // leaf cost = area * 1 triangle
+    t.bmin[id] = make_float4(mn.x, mn.y, mn.z, box_half_area(mn, mx) * tri_cost);      // leaf cost = area * 1 triangle
     t.bmax[id] = make_float4(mx.x, mx.y, mx.z, __uint_as_float(1u));
     t.lcount[id] = 1u;
     if (t.n == 1) return;
@@ -201,7 +202,7 @@ __global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__
         uint32_t cnt = __float_as_uint(lmx.w) + __float_as_uint(rmx.w);
         float area = box_half_area(mn, mx);
         float cost_inner = area * 1.0f + lmn.w + rmn.w;       // node cost 1, triangle cost 1
-        float cost_leaf = area * (float)cnt;
+        float cost_leaf = area * (float)cnt * tri_cost;
         bool cl = cnt <= (uint32_t)kMaxLeafTris && cost_leaf <= cost_inner;
         t.cluster[p] = cl ? 1 : 0;
         t.lcount[p] = cl ? 1u : __ldcg(&t.lcount[l]) + __ldcg(&t.lcount[rr]);
@@ -457,7 +458,7 @@ int build_bvh(vhr_context *ctx) {
             karras_kernel<<<(n_inner + B - 1) / B, B, 0, st>>>(d_keys2, t);
             TRYCUDA(cudaGetLastError()); ctx->launches++;
         }
-        refit_kernel<<<G, B, 0, st>>>(d_tris, d_vals2, t);
+        refit_kernel<<<G, B, 0, st>>>(d_tris, d_vals2, t, getenv("VHR_BVH_CT") ? (float)atof(getenv("VHR_BVH_CT")) : 1.0f);
         TRYCUDA(cudaGetLastError()); ctx->launches++;
 
         // widen
