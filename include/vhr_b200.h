@@ -200,6 +200,13 @@ int vhr_storage_image_attach_peer(vhr_context *ctx, int slot, uint32_t rank, con
 /* The context's flag words (allocated on first use) for the stream-ordered synchronisation. */
 int vhr_sync_export_ipc(vhr_context *ctx, void *handle);
 int vhr_sync_attach_peer(vhr_context *ctx, uint32_t rank, const void *handle);
+/* The same attachments by plain device pointer, for ranks that live in ONE process (several contexts driven by one host
+ * thread, on one or several GPUs with peer access enabled): `twin` / flag pointers come from the two getters below. */
+int vhr_image_attach_peer_pointer(vhr_context *ctx, const char *name, uint32_t rank, void *device_ptr);
+int vhr_storage_image_attach_peer_pointer(vhr_context *ctx, int slot, uint32_t rank, void *device_ptr, void *twin_device_ptr);
+int vhr_sync_attach_peer_pointer(vhr_context *ctx, uint32_t rank, void *flag_words);
+void *vhr_storage_image_twin_device_ptr(vhr_context *ctx, int slot);     /* second buffer of the moments image (allocated on demand) */
+void *vhr_sync_device_ptr(vhr_context *ctx);
 
 /* ---- options that have no counterpart in the reference (documented in DESIGN.md) -------------------------------- */
 

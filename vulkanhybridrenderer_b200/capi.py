@@ -26,6 +26,8 @@ SYMBOLS = [
     "vhr_image_upload_async", "vhr_image_download_async", "vhr_wait_download", "vhr_draw",
     "vhr_set_partition", "vhr_image_export_ipc", "vhr_storage_image_export_ipc", "vhr_image_attach_peer",
     "vhr_storage_image_attach_peer", "vhr_sync_export_ipc", "vhr_sync_attach_peer",
+    "vhr_image_attach_peer_pointer", "vhr_storage_image_attach_peer_pointer", "vhr_sync_attach_peer_pointer",
+    "vhr_storage_image_twin_device_ptr", "vhr_sync_device_ptr",
 ]
 MAX_RANKS = 8
 IPC_HANDLE_BYTES = 64
@@ -106,6 +108,13 @@ def lib():
         L.vhr_storage_image_attach_peer.argtypes = [vp, i32, u32, vp, vp]
         L.vhr_sync_export_ipc.argtypes = [vp, vp]
         L.vhr_sync_attach_peer.argtypes = [vp, u32, vp]
+        L.vhr_image_attach_peer_pointer.argtypes = [vp, C.c_char_p, u32, vp]
+        L.vhr_storage_image_attach_peer_pointer.argtypes = [vp, i32, u32, vp, vp]
+        L.vhr_sync_attach_peer_pointer.argtypes = [vp, u32, vp]
+        L.vhr_storage_image_twin_device_ptr.argtypes = [vp, i32]
+        L.vhr_storage_image_twin_device_ptr.restype = vp
+        L.vhr_sync_device_ptr.argtypes = [vp]
+        L.vhr_sync_device_ptr.restype = vp
         L.vhr_debug_download_reflection_t.argtypes = [vp, vp, sz]
         L.vhr_create_query_pool.argtypes = [vp, u32]
         L.vhr_write_timestamp.argtypes = [vp, u32]

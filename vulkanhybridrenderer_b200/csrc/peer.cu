@@ -193,4 +193,42 @@ int vhr_sync_attach_peer(vhr_context *ctx, uint32_t rank, const void *handle) {
     return VHR_OK;
 }
 
+int vhr_image_attach_peer_pointer(vhr_context *ctx, const char *name, uint32_t rank, void *device_ptr) {
+    VHR_NEED_DEVICE(ctx);
+    Image *im = transient(ctx, name);
+    if (!im || !device_ptr || rank >= VHR_MAX_RANKS) return fail(VHR_ERR_INVALID, "attach: unknown image '%s' or rank %u", name ? name : "(null)", rank);
+    im->peer[rank] = device_ptr;
+    return VHR_OK;
+}
+int vhr_storage_image_attach_peer_pointer(vhr_context *ctx, int slot, uint32_t rank, void *device_ptr, void *twin_device_ptr) {
+    VHR_NEED_DEVICE(ctx);
+    Image *im = storage_slot(ctx, slot);
+    if (!im || !device_ptr || rank >= VHR_MAX_RANKS) return fail(VHR_ERR_INVALID, "attach: storage image %d does not exist or rank %u", slot, rank);
+    im->peer[rank] = device_ptr;
+    im->peer_twin[rank] = twin_device_ptr;
+    return VHR_OK;
+}
+int vhr_sync_attach_peer_pointer(vhr_context *ctx, uint32_t rank, void *flag_words) {
+    VHR_NEED_DEVICE(ctx);
+    if (!flag_words || rank >= VHR_MAX_RANKS) return fail(VHR_ERR_INVALID, "attach: rank %u", rank);
+    if (int rc = ensure_flags(ctx)) return rc;
+    ctx->peer_flags[rank] = (uint32_t *)flag_words;
+    return VHR_OK;
+}
+void *vhr_storage_image_twin_device_ptr(vhr_context *ctx, int slot) {
+    if (!ctx || ctx->device < 0) return nullptr;
+    Image *im = storage_slot(ctx, slot);
+    if (!im) return nullptr;
+    if (!im->twin) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&im->twin, im->bytes) != cudaSuccess) return nullptr;
+        cudaMemsetAsync(im->twin, 0, im->bytes, ctx->stream);
+    }
+    return im->twin;
+}
+void *vhr_sync_device_ptr(vhr_context *ctx) {
+    if (!ctx || ctx->device < 0) return nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || ensure_flags(ctx) != VHR_OK) return nullptr;
+    return ctx->sync_flags;
+}
+
 }  // extern "C"

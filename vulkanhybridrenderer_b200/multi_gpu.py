@@ -193,6 +193,35 @@ def setup_fused_partition(ctx, path, world, rank, group=None, motion_halo=8, ray
     return bands
 
 
+def setup_fused_partition_inprocess(ctxs, paths, motion_halo=8, ray_block_rows=8):
+    """The same partition for ranks that live in ONE process (one context per rank, all driven by this thread): peers are
+    attached by plain device pointer. With all contexts on one GPU this exercises the whole fused path — interleaved ray
+    blocks, halo pushes, flag-word ordering between the streams — on a single-GPU box (tests/test_partition_gpu.py)."""
+    from . import capi
+    L = capi.lib()
+    world = len(ctxs)
+    H = paths[0].H
+    for r, (ctx, path) in enumerate(zip(ctxs, paths)):
+        for q, (octx, opath) in enumerate(zip(ctxs, paths)):
+            if q == r:
+                continue
+            capi._check(L.vhr_sync_attach_peer_pointer(ctx._h, q, L.vhr_sync_device_ptr(octx._h)))
+            for (rt_name, refl_name), (ort, orefl) in zip(path.rt_sets, opath.rt_sets):
+                capi._check(L.vhr_image_attach_peer_pointer(ctx._h, rt_name.encode(), q, octx.image_info(ort)[0]))
+                capi._check(L.vhr_image_attach_peer_pointer(ctx._h, refl_name.encode(), q, octx.image_info(orefl)[0]))
+            if abs(q - r) == 1:
+                for slot, oslot in zip(path.pc["integrated_shadow_and_ao"], opath.pc["integrated_shadow_and_ao"]):
+                    capi._check(L.vhr_storage_image_attach_peer_pointer(ctx._h, int(slot), q, octx.storage_image_info(int(oslot))[0], None))
+                ms, oms = int(path.pc["shadow_and_ao_moments_history"]), int(opath.pc["shadow_and_ao_moments_history"])
+                L.vhr_storage_image_twin_device_ptr(ctx._h, ms)          # allocate my own twin before anybody swaps
+                capi._check(L.vhr_storage_image_attach_peer_pointer(ctx._h, ms, q, octx.storage_image_info(oms)[0],
+                                                                    L.vhr_storage_image_twin_device_ptr(octx._h, oms)))
+    bands = [band_rows(H, world, r)[0] for r in range(world)] + [H]
+    for r, ctx in enumerate(ctxs):
+        ctx.set_partition(world, r, bands, ray_block_rows=ray_block_rows, motion_halo=motion_halo)
+    return bands
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU backend over the C-ABI
 # ---------------------------------------------------------------------------------------------------------------------
