@@ -25,7 +25,7 @@ def test_fused_partition_matches_single_context(world):
         ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
         ctx.set_option(capi.OPT_AO_SPP, 2)
         ctx.set_option(capi.OPT_TRACE_REFLECTIONS, 1)
-        return ctx, HP.HybridRenderPath(ctx, W, H, rt_sets=rt_sets)
+        return ctx, HP.HybridRenderPath(ctx, W, H, rt_sets=rt_sets, ssao=True, composition=HP.T.VK_FORMAT_B8G8R8A8_SRGB, shadow_map_size=(8, 8))
 
     ref_ctx, ref_path = make(1)
     ranks = [make(2) for _ in range(world)]
@@ -45,24 +45,35 @@ def test_fused_partition_matches_single_context(world):
             g = ref_path.gsets[0]
             ref_ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
             ref_ctx.gbuffer_pass(W, H)
-            gb = {k: ref_ctx.image_download(g[k]) for k in (HP.N_NORMALS, HP.N_MOTION, HP.N_DEPTH)}
+            gb = {k: ref_ctx.image_download(g[k]) for k in (HP.N_ALBEDO, HP.N_NORMALS, HP.N_MOTION, HP.N_DEPTH)}
             assert MG.required_motion_halo(float(np.abs(gb[HP.N_MOTION][..., 1].astype(np.float32)).max()), H) <= halo
             for ctx, path in zip(ctxs, paths):
                 for k, v in gb.items():
                     ctx.image_upload(path.gsets[0][k], v)
             ref_path.frame(pfd)
+            ref_path.ssao_passes()
+            ref_path.composition_pass(0, 1, 0, denoised=True)        # ray-traced shadows, SSAO, ray-traced reflections
             # every rank issues the plain single-GPU call sequence; nothing blocks on the host in between, the streams order
             # themselves through the flag words
             for path in paths:
                 path.frame(pfd, rtset=f & 1)
-            want = {k: ref_ctx.image_download(n) for k, n in (("rt", HP.N_RT), ("refl", HP.N_REFL), ("den", HP.N_DENOISED))}
+            # SSAO (6-row halo of the raw image pushed by ssao.comp's kernel) and the composition pass on the same bands
+            for path in paths:
+                path.ssao_passes()
+            for ctx, path in zip(ctxs, paths):
+                g0 = path.gsets[0]
+                ctx.bind_pass_images([g0[HP.N_ALBEDO], g0[HP.N_NORMALS], g0[HP.N_MOTION], g0[HP.N_DEPTH], HP.N_SHADOW_MAP, HP.N_SSAO, HP.N_SSR,
+                                      HP.N_DENOISED, path.rt_sets[f & 1][1], HP.N_RENDER_OUTPUT])
+                ctx.draw(HP.SHADER_COMPOSITION, (0, 1, 0))
+            want = {k: ref_ctx.image_download(n) for k, n in (("rt", HP.N_RT), ("refl", HP.N_REFL), ("den", HP.N_DENOISED), ("ssao", HP.N_SSAO),
+                                                              ("out", HP.N_RENDER_OUTPUT))}
             for r, (ctx, path) in enumerate(zip(ctxs, paths)):
                 y0, y1 = bands[r]
                 got = {"rt": ctx.image_download(path.rt_sets[f & 1][0]), "refl": ctx.image_download(path.rt_sets[f & 1][1]),
-                       "den": ctx.image_download(HP.N_DENOISED)}
+                       "den": ctx.image_download(HP.N_DENOISED), "ssao": ctx.image_download(HP.N_SSAO), "out": ctx.image_download(HP.N_RENDER_OUTPUT)}
                 for k in want:
-                    bad = int((got[k][y0:y1].view(np.uint16) != want[k][y0:y1].view(np.uint16)).sum())
-                    assert bad == 0, f"frame {f} rank {r}/{world} image {k}: {bad} mismatching halfs in rows [{y0},{y1})"
+                    bad = int((got[k][y0:y1].view(np.uint8) != want[k][y0:y1].view(np.uint8)).sum())
+                    assert bad == 0, f"frame {f} rank {r}/{world} image {k}: {bad} mismatching bytes in rows [{y0},{y1})"
     finally:
         for c in ctxs + [ref_ctx]:
             c.close()

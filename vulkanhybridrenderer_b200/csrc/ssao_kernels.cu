@@ -19,7 +19,16 @@ struct SsaoParams {
     const uint2 *normals;     // binding 0 (RGBA16F, sampled)
     const float *depth;       // binding 1 (D32F, sampled)
     uint2 *out;               // binding 2 (RGBA16F)
+    HaloPush push;            // multi-GPU: the blur on the neighbours reads 6 rows of this output beyond their band
 };
+
+__device__ __forceinline__ void ssao_store(const SsaoParams &p, int gy, size_t pix, uint2 v) {
+    p.out[pix] = v;
+    if (p.push.rows) {
+        if (p.push.up && gy < p.y_begin + p.push.rows) reinterpret_cast<uint2 *>(p.push.up)[pix] = v;
+        if (p.push.down && gy >= p.y_end - p.push.rows) reinterpret_cast<uint2 *>(p.push.down)[pix] = v;
+    }
+}
 
 __device__ __forceinline__ float sample_depth(const SsaoParams &p, float u, float v) {
     int x0, x1, y0, y1;
@@ -40,7 +49,7 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
     const float cv = mul_rn((float)gy, pfd.display_size_inverse[1]);
     float current_depth = sample_depth(p, cu, cv);
     if (current_depth == 0.0f) {
-        p.out[pix] = make_uint2(0u, 0u);
+        ssao_store(p, gy, pix, make_uint2(0u, 0u));
         return;
     }
     float3 P = unproject_rn(pfd.camera_proj_inverse, current_depth, cu, cv);
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
         sum = add_rn(sum, __fdiv_rn(num, add_rn(dot3_rn(V, V), 1e-4f)));
     }
     float ao = fmaxf(sub_rn(1.0f, mul_rn(0.125f, sum)), 0.0f);
-    p.out[pix] = pack_rgba16f(make_float4(ao, ao, ao, ao));
+    ssao_store(p, gy, pix, pack_rgba16f(make_float4(ao, ao, ao, ao)));
 }
 
 // 13x13 box sum of .x, OOB skipped, always divided by 169. Tile 32x8 outputs; raw values staged in shared memory
@@ -142,11 +151,16 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     if (!dispatch_range(ctx, normals, xg, yg, p.x_end, p.y_begin, p.y_end)) return VHR_OK;
     p.radius = radius;
     p.normals = (const uint2 *)normals->ptr; p.depth = (const float *)depth->ptr; p.out = (uint2 *)out->ptr;
+    // multi-GPU (row bands; every rank holds the full depth / normal G-buffer the samples reach into): the 13x13 blur on the
+    // neighbours reads 6 rows of this output beyond their band -> pushed by this kernel, then the flag-word round trip
+    p.push = halo_push_for(ctx, out, false, 6);
+    if (p.push.rows && ((p.push.up == nullptr && ctx->part.rank > 0) || (p.push.down == nullptr && ctx->part.rank + 1 < ctx->part.world)))
+        return fail(VHR_ERR_STATE, "ssao.comp: the neighbours' '%s' image is not attached (vhr_image_attach_peer)", "Screen Space Ambient Occlusion Raw");
     dim3 block(32, 8), grid((p.x_end + 31) / 32, (p.y_end - p.y_begin + 7) / 8);
     ssao_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
-    return VHR_OK;
+    return p.push.rows ? peer_sync_neighbours(ctx) : VHR_OK;
 }
 
 int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg) {

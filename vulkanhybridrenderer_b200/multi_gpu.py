@@ -158,6 +158,15 @@ class RowBandSvgf:
 # memory) and the library orders the streams with flag words (include/vhr_b200.h, "one frame over several GPUs").
 # torch.distributed only carries the IPC handles at set-up.
 # ---------------------------------------------------------------------------------------------------------------------
+def _has_image(ctx, name):
+    from . import capi
+    try:
+        ctx.image_info(name)
+        return True
+    except capi.VhrError:
+        return False
+
+
 def setup_fused_partition(ctx, path, world, rank, group=None, motion_halo=8, ray_block_rows=8):
     """Exports this rank's exchanged images, attaches everybody else's, installs the row partition on `ctx`.
 
@@ -173,6 +182,8 @@ def setup_fused_partition(ctx, path, world, rank, group=None, motion_halo=8, ray
         mine["integ"].append((int(slot), ctx.storage_image_export_ipc(int(slot))[0]))
     mslot = int(pc["shadow_and_ao_moments_history"])
     mine["moments"] = (mslot,) + ctx.storage_image_export_ipc(mslot, twin=True)
+    has_ssao = _has_image(ctx, "Screen Space Ambient Occlusion Raw")
+    mine["ssao_raw"] = ctx.image_export_ipc("Screen Space Ambient Occlusion Raw") if has_ssao else None
     ctx.synchronize()
     everyone = [None] * world
     dist.all_gather_object(everyone, mine, group=group)
@@ -187,6 +198,8 @@ def setup_fused_partition(ctx, path, world, rank, group=None, motion_halo=8, ray
             for (slot, _), (_, h) in zip(mine["integ"], other["integ"]):
                 ctx.storage_image_attach_peer(slot, r, h)
             ctx.storage_image_attach_peer(mslot, r, other["moments"][1], other["moments"][2])
+            if has_ssao and other["ssao_raw"]:
+                ctx.image_attach_peer("Screen Space Ambient Occlusion Raw", r, other["ssao_raw"])
     bands = [band_rows(path.H, world, r)[0] for r in range(world)] + [path.H]
     ctx.set_partition(world, rank, bands, ray_block_rows=ray_block_rows, motion_halo=motion_halo)
     dist.barrier(group=group)                        # nobody starts storing into a peer that has not attached yet
@@ -216,6 +229,9 @@ def setup_fused_partition_inprocess(ctxs, paths, motion_halo=8, ray_block_rows=8
                 L.vhr_storage_image_twin_device_ptr(ctx._h, ms)          # allocate my own twin before anybody swaps
                 capi._check(L.vhr_storage_image_attach_peer_pointer(ctx._h, ms, q, octx.storage_image_info(oms)[0],
                                                                     L.vhr_storage_image_twin_device_ptr(octx._h, oms)))
+                if _has_image(ctx, "Screen Space Ambient Occlusion Raw") and _has_image(octx, "Screen Space Ambient Occlusion Raw"):
+                    capi._check(L.vhr_image_attach_peer_pointer(ctx._h, b"Screen Space Ambient Occlusion Raw", q,
+                                                                octx.image_info("Screen Space Ambient Occlusion Raw")[0]))
     bands = [band_rows(H, world, r)[0] for r in range(world)] + [H]
     for r, ctx in enumerate(ctxs):
         ctx.set_partition(world, r, bands, ray_block_rows=ray_block_rows, motion_halo=motion_halo)
