@@ -131,9 +131,10 @@ int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, 
 
 /* ComputeExecutionContext::Dispatch (src/render_graph/compute_execution_context.cpp:12-29, .h:20-27). Kernels are
  * looked up by the reference's shader path: "hybrid_render_path/svgf.comp", ".../svgf_atrous_filter.comp",
- * ".../ssao.comp", ".../ssao_blur.comp". Group size is the shaders' 8x8 (svgf.comp:6): the launcher covers
+ * ".../ssao.comp", ".../ssao_blur.comp", ".../ssr.comp". Group size is the shaders' 8x8 (svgf.comp:6): the launcher covers
  * x_groups*8 by y_groups*8 pixels clipped to the image. `push_constants` is SVGFPushConstants (24 B,
- * glsl_common.h:31-39) for the two SVGF kernels and SSAOPushConstants (4 B, :48-50) or NULL (radius 0.75) for SSAO;
+ * glsl_common.h:31-39) for the two SVGF kernels, SSAOPushConstants (4 B, :48-50) or NULL (radius 0.75) for SSAO and
+ * SSRPushConstants (16 B, :41-46; bound images 0 albedo, 1 normals, 2 motion/metallic-roughness, 3 depth, 4 output) for SSR;
  * a size that does not match fails like the reference's assert (compute_execution_context.h:23). */
 int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
                  const void *push_constants, size_t push_constants_size);

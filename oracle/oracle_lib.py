@@ -14,7 +14,7 @@ from vulkanhybridrenderer_b200 import types as T
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in oracle/)
 _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 _SO = os.path.join(_ORACLE_DIR, "_build", "libvhr_oracle.so")
-_SRCS = ["oracle_common.h", "oracle_svgf.cpp", "oracle_rt.cpp", "oracle_composition.cpp", "Makefile"]
+_SRCS = ["oracle_common.h", "oracle_svgf.cpp", "oracle_rt.cpp", "oracle_composition.cpp", "oracle_ssr.cpp", "Makefile"]
 
 
 def build(force=False):
@@ -57,6 +57,7 @@ def _declare(L):
     L.vo_ssao.argtypes = [vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]
     L.vo_ssao_blur.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.vo_composition.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]
+    L.vo_ssr.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp, vp, vp]
     L.vo_seed_thread.restype = C.c_uint32
     L.vo_seed_thread.argtypes = [C.c_uint32]
     L.vo_random01.restype = C.c_float
@@ -144,6 +145,18 @@ def ssao_blur(pfd, raw):
     H, W = raw.shape[:2]
     out = np.empty((H, W, 4), np.float16)
     lib().vo_ssao_blur(_p(pfd), W, H, _p(_h(raw)), _p(out))
+    return out
+
+
+def ssr(pfd, albedo, normals, motion, depth, ray_distance=25.0, step_size=0.1, thickness=0.5, bsearch_steps=10, rows=None):
+    """ssr.comp over rows [y0, y1) (default: the whole frame); defaults = hybrid_render_path.cpp:203-208."""
+    H, W = depth.shape[:2]
+    y0, y1 = (0, H) if rows is None else rows
+    out = np.zeros((H, W, 4), np.float16)
+    a8 = np.ascontiguousarray(albedo, np.uint8)
+    d = np.ascontiguousarray(depth, np.float32)
+    lib().vo_ssr(_p(pfd), W, H, y0, y1, float(ray_distance), float(step_size), float(thickness), int(bsearch_steps), _p(a8), _p(_h(normals)),
+                 _p(_h(motion)), _p(d), _p(out))
     return out
 
 

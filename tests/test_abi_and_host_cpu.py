@@ -92,6 +92,8 @@ G, RT, SVGF, COMP = "G-Buffer Pass", "Raytrace Pass", "SVGF Denoise Pass", "Comp
     (dict(shadow=0, ao=1, reflection=2, denoise=True), [G, "SSAO Pass", "SSAO Blur Pass", RT, SVGF, COMP]),
     (dict(shadow=1, ao=0, reflection=2, denoise=True), [G, "Shadow Map Pass", SVGF, COMP]),   # Q21: the else-if drops the ray pass but SVGF still runs (on an unwritten image)
     (dict(shadow=2, ao=2, reflection=2, denoise=True), [G, COMP]),
+    (dict(shadow=0, ao=0, reflection=1, denoise=True), [G, "SSR Pass", RT, SVGF, COMP]),      # hybrid_render_path.cpp:202-243
+    (dict(shadow=2, ao=2, reflection=1, denoise=False), [G, "SSR Pass", COMP]),
 ])
 def test_execution_order_matches_reference_algorithm(modes, want):
     with host_api.Renderer(128, 72, device=host_api.DEVICE_NONE) as r:

@@ -1,0 +1,208 @@
+// ssr_kernels.cu — screen-space reflections of the hybrid path (sm_100a).
+//
+//   ssr_kernel <- /root/reference/data/shaders/hybrid_render_path/ssr.comp:61-137 (march + binary search) and
+//                 :29-59 (compute_lighting), dispatched by the "SSR Pass" node
+//                 (/root/reference/src/render_paths/hybrid_render_path.cpp:202-243) with SSRPushConstants
+//                 (/root/reference/src/rendering_backend/glsl_common.h:41-46)
+//
+// One thread per pixel in 8x4-pixel warp tiles (neighbouring pixels march almost the same ray, so the warp leaves the
+// loop together and the depth taps of a step share cache lines). Every step re-projects the ray point, takes one
+// bilinear depth tap through the reference's default sampler (LINEAR / REPEAT, evaluated in software with the Vulkan
+// float weights, like ssao_kernels.cu) and compares two camera distances against 0.3 / thickness — threshold tests on
+// nearly equal numbers, so all of it is written with explicitly rounded operations in the oracle's order: one ulp of
+// difference would pick another march step and change the whole pixel. The matrix product camera_proj * camera_view
+// of world_space_to_uv (ssr.comp:22-26, GLSL evaluates it left to right) is formed once per dispatch.
+#include <algorithm>
+#include <cmath>
+
+#include "vhr_internal.h"
+
+namespace vhr {
+
+struct SsrParams {
+    int W, H;
+    int x_end, y_begin, y_end;
+    float step_size, thickness;
+    int n_steps;               // int(ray_distance / step_size), ssr.comp:89
+    int bsearch_steps;
+    const uint32_t *albedo;    // binding 0 (BGRA8, sampled)
+    const uint2 *normals;      // binding 1
+    const uint2 *motion;       // binding 2 (.zw = metallic, roughness)
+    const float *depth;        // binding 3
+    uint2 *out;                // binding 4 (RGBA16F)
+    float pv[16];              // camera_proj * camera_view, column-major
+};
+
+namespace {
+
+struct Taps {
+    size_t i00, i10, i01, i11;
+    float a, b;
+};
+__device__ __forceinline__ Taps taps_for(const SsrParams &p, float u, float v) {
+    int x0, x1, y0, y1;
+    Taps t;
+    bilinear_setup(u, p.W, x0, x1, t.a);
+    bilinear_setup(v, p.H, y0, y1, t.b);
+    t.i00 = (size_t)y0 * p.W + x0; t.i10 = (size_t)y0 * p.W + x1;
+    t.i01 = (size_t)y1 * p.W + x0; t.i11 = (size_t)y1 * p.W + x1;
+    return t;
+}
+__device__ __forceinline__ float sample_depth(const SsrParams &p, float u, float v) {
+    const Taps t = taps_for(p, u, v);
+    return bilerp_rn(t.a, t.b, __ldg(&p.depth[t.i00]), __ldg(&p.depth[t.i10]), __ldg(&p.depth[t.i01]), __ldg(&p.depth[t.i11]));
+}
+__device__ __forceinline__ float3 sample_xyz16(const uint2 *img, const Taps &t) {
+    const float4 t00 = unpack_rgba16f(__ldg(&img[t.i00])), t10 = unpack_rgba16f(__ldg(&img[t.i10]));
+    const float4 t01 = unpack_rgba16f(__ldg(&img[t.i01])), t11 = unpack_rgba16f(__ldg(&img[t.i11]));
+    return make_float3(bilerp_rn(t.a, t.b, t00.x, t10.x, t01.x, t11.x), bilerp_rn(t.a, t.b, t00.y, t10.y, t01.y, t11.y),
+                       bilerp_rn(t.a, t.b, t00.z, t10.z, t01.z, t11.z));
+}
+__device__ __forceinline__ float2 sample_zw16(const uint2 *img, const Taps &t) {
+    const float2 t00 = unpack_rg16f(__ldg(&img[t.i00].y)), t10 = unpack_rg16f(__ldg(&img[t.i10].y));
+    const float2 t01 = unpack_rg16f(__ldg(&img[t.i01].y)), t11 = unpack_rg16f(__ldg(&img[t.i11].y));
+    return make_float2(bilerp_rn(t.a, t.b, t00.x, t10.x, t01.x, t11.x), bilerp_rn(t.a, t.b, t00.y, t10.y, t01.y, t11.y));
+}
+// B8G8R8A8_UNORM: byte 0 = B; UNORM -> float is c / 255
+__device__ __forceinline__ float3 bgra8_rgb(uint32_t c) {
+    return make_float3(__fdiv_rn((float)((c >> 16) & 0xffu), 255.0f), __fdiv_rn((float)((c >> 8) & 0xffu), 255.0f),
+                       __fdiv_rn((float)(c & 0xffu), 255.0f));
+}
+__device__ __forceinline__ float3 sample_albedo(const uint32_t *img, const Taps &t) {
+    const float3 t00 = bgra8_rgb(__ldg(&img[t.i00])), t10 = bgra8_rgb(__ldg(&img[t.i10]));
+    const float3 t01 = bgra8_rgb(__ldg(&img[t.i01])), t11 = bgra8_rgb(__ldg(&img[t.i11]));
+    return make_float3(bilerp_rn(t.a, t.b, t00.x, t10.x, t01.x, t11.x), bilerp_rn(t.a, t.b, t00.y, t10.y, t01.y, t11.y),
+                       bilerp_rn(t.a, t.b, t00.z, t10.z, t01.z, t11.z));
+}
+__device__ __forceinline__ float distance_rn(float3 a, float3 b) {
+    const float3 d = make_float3(sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z));
+    return sqrtf(dot3_rn(d, d));
+}
+
+// One probe of the march / the binary search (ssr.comp:90-99, 115-123): delta_distance at `offset` along the ray and
+// the uv the ray point projects to.
+__device__ __forceinline__ float probe(const SsrParams &p, const PerFrameData &pfd, float3 P, float3 dir, float3 cam, float offset,
+                                       float &su, float &sv) {
+    const float3 rp = make_float3(add_rn(P.x, mul_rn(dir.x, offset)), add_rn(P.y, mul_rn(dir.y, offset)), add_rn(P.z, mul_rn(dir.z, offset)));
+    const float distance_to_ray = distance_rn(cam, rp);
+    const float4 clip = mul44_rn(p.pv, make_float4(rp.x, rp.y, rp.z, 1.0f));
+    su = add_rn(mul_rn(__fdiv_rn(clip.x, clip.w), 0.5f), 0.5f);
+    sv = add_rn(mul_rn(__fdiv_rn(clip.y, clip.w), 0.5f), 0.5f);
+    const float3 sp = unproject_rn(pfd.camera_viewproj_inverse, sample_depth(p, su, sv), su, sv);
+    return sub_rn(distance_to_ray, distance_rn(cam, sp));
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrParams p, const __grid_constant__ PerFrameData pfd) {
+    // 16x8 block of four 8x4 warp tiles
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = p.y_begin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (gx >= p.x_end || gy >= p.y_end) return;
+    const size_t pix = (size_t)gy * p.W + gx;
+    const uint2 zero = make_uint2(0u, 0u);                                           // ssr.comp:62-66
+    const float cu = mul_rn((float)gx, pfd.display_size_inverse[0]);                 // texel corner (ssr.comp:68)
+    const float cv = mul_rn((float)gy, pfd.display_size_inverse[1]);
+    const Taps t0 = taps_for(p, cu, cv);
+    const float fragment_depth = bilerp_rn(t0.a, t0.b, __ldg(&p.depth[t0.i00]), __ldg(&p.depth[t0.i10]), __ldg(&p.depth[t0.i01]), __ldg(&p.depth[t0.i11]));
+    const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
+    const float3 P = unproject_rn(pfd.camera_viewproj_inverse, fragment_depth, cu, cv);
+    const float3 N = sample_xyz16(p.normals, t0);
+    const float3 I = normalize_rn(make_float3(sub_rn(P.x, cam.x), sub_rn(P.y, cam.y), sub_rn(P.z, cam.z)));
+    const float k2 = mul_rn(2.0f, dot3_rn(N, I));
+    const float3 dir = normalize_rn(make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2))));
+
+    bool found = false;
+    float prev_step = 0.0f, final_step = 0.0f;
+    float su, sv;
+    for (int i = 0; i < p.n_steps; ++i) {                                            // ssr.comp:89-108
+        const float offset = mul_rn(p.step_size, (float)i);
+        const float delta = probe(p, pfd, P, dir, cam, offset, su, sv);
+        if (delta > 0.3f && delta < p.thickness) {
+            final_step = offset;
+            found = true;
+            break;
+        }
+        prev_step = offset;
+    }
+    if (!found) {                                                                    // ssr.comp:110-112
+        p.out[pix] = zero;
+        return;
+    }
+    float mid_step = mul_rn(add_rn(prev_step, final_step), 0.5f);                    // ssr.comp:115-135
+    float fu = 0.0f, fv = 0.0f;
+    for (int i = 0; i < p.bsearch_steps; ++i) {
+        const float delta = probe(p, pfd, P, dir, cam, mid_step, fu, fv);
+        if (delta > 0.3f && delta < p.thickness) {
+            mid_step = mul_rn(add_rn(prev_step, mid_step), 0.5f);
+        } else {
+            const float tmp = mid_step;
+            mid_step = add_rn(mid_step, sub_rn(mid_step, prev_step));
+            prev_step = tmp;
+        }
+    }
+    // compute_lighting(final_uv), ssr.comp:29-59
+    const Taps t = taps_for(p, fu, fv);
+    const float3 albedo = sample_albedo(p.albedo, t);
+    const float d = bilerp_rn(t.a, t.b, __ldg(&p.depth[t.i00]), __ldg(&p.depth[t.i10]), __ldg(&p.depth[t.i01]), __ldg(&p.depth[t.i11]));
+    const float3 position = unproject_rn(pfd.camera_viewproj_inverse, d, fu, fv);
+    const float2 mr = sample_zw16(p.motion, t);
+    const float3 V = normalize_rn(make_float3(sub_rn(cam.x, position.x), sub_rn(cam.y, position.y), sub_rn(cam.z, position.z)));
+    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+    const float3 Nh = sample_xyz16(p.normals, t);
+    const float3 H = normalize_rn(make_float3(add_rn(L.x, V.x), add_rn(L.y, V.y), add_rn(L.z, V.z)));
+    const float3 c = shade_direct_rn(albedo, mr.x, mr.y, Nh, V, L, H, pfd.directional_light.intensity, pfd.directional_light.color);
+    p.out[pix] = pack_rgba16f(make_float4(c.x, c.y, c.z, 1.0f));
+}
+
+int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc) {
+    // descriptor set 3 of the "SSR Pass" (hybrid_render_path.cpp:211-219): 0 albedo, 1 normals, 2 motion, 3 depth, 4 output
+    if (ctx->n_bound < 5) return fail(VHR_ERR_STATE, "ssr.comp: pass images not bound (need bindings 0..4)");
+    Image **b = ctx->bound;
+    for (int i = 0; i < 5; ++i)
+        if (!b[i]) return fail(VHR_ERR_STATE, "ssr.comp: unbound image");
+    const int want[5] = {VHR_FORMAT_B8G8R8A8_UNORM, VHR_FORMAT_R16G16B16A16_SFLOAT, VHR_FORMAT_R16G16B16A16_SFLOAT, VHR_FORMAT_D32_SFLOAT,
+                         VHR_FORMAT_R16G16B16A16_SFLOAT};
+    for (int i = 0; i < 5; ++i) {
+        if (b[i]->format != want[i]) return fail(VHR_ERR_INVALID, "ssr.comp: binding %d has format %d, expected %d", i, b[i]->format, want[i]);
+        if (b[i]->width != b[4]->width || b[i]->height != b[4]->height) return fail(VHR_ERR_INVALID, "ssr.comp: image sizes differ");
+    }
+    if (ctx->pfd.display_size[0] != (float)b[4]->width || ctx->pfd.display_size[1] != (float)b[4]->height)
+        return fail(VHR_ERR_INVALID, "ssr.comp: PerFrameData.display_size does not match the images");
+    // int(pc.ray_distance / pc.step_size), ssr.comp:89; a non-finite or huge quotient (step_size = 0) has no defined value in GLSL
+    const float q = pc.ray_distance / pc.step_size;
+    if (!(q == q) || q > 1048576.0f) return fail(VHR_ERR_INVALID, "ssr.comp: ray_distance / step_size = %g", (double)q);
+    if (pc.bsearch_steps < 0 || pc.bsearch_steps > 4096) return fail(VHR_ERR_INVALID, "ssr.comp: bsearch_steps = %d", pc.bsearch_steps);
+    SsrParams p;
+    p.W = (int)b[4]->width; p.H = (int)b[4]->height;
+    p.x_end = (int)std::min<uint64_t>(b[4]->width, (uint64_t)xg * 8);
+    const int y_cov = (int)std::min<uint64_t>(b[4]->height, (uint64_t)yg * 8);
+    p.y_begin = std::max(0, ctx->opt.row_begin);
+    p.y_end = ctx->opt.row_end < 0 ? y_cov : std::min(y_cov, ctx->opt.row_end);
+    if (p.x_end <= 0 || p.y_end <= p.y_begin) return VHR_OK;
+    p.step_size = pc.step_size; p.thickness = pc.thickness;
+    p.n_steps = q < 0.0f ? 0 : (int)q;
+    p.bsearch_steps = pc.bsearch_steps;
+    p.albedo = (const uint32_t *)b[0]->ptr; p.normals = (const uint2 *)b[1]->ptr; p.motion = (const uint2 *)b[2]->ptr;
+    p.depth = (const float *)b[3]->ptr; p.out = (uint2 *)b[4]->ptr;
+    // camera_proj * camera_view, each element a left-to-right sum of rounded products (volatile keeps the host compiler from
+    // contracting or reassociating; the oracle forms the same product)
+    const float *A = ctx->pfd.camera_proj, *B = ctx->pfd.camera_view;
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            volatile float acc = A[0 * 4 + r] * B[c * 4 + 0];
+            for (int k = 1; k < 4; ++k) {
+                volatile float prod = A[k * 4 + r] * B[c * 4 + k];
+                acc = acc + prod;
+            }
+            p.pv[c * 4 + r] = acc;
+        }
+    dim3 block(128), grid((p.x_end + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
+    ssr_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
+}  // namespace vhr

@@ -458,6 +458,13 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
             return fail(VHR_ERR_INVALID, "%s: push constants are %zu bytes, got %zu", shader_path, sizeof(SSAOPushConstants), push_constants_size);
         return launch_ssao_blur(ctx, x_groups, y_groups);
     }
+    if (!strcmp(shader_path, "hybrid_render_path/ssr.comp")) {
+        if (!push_constants || push_constants_size != sizeof(SSRPushConstants))
+            return fail(VHR_ERR_INVALID, "%s: push constants are %zu bytes, got %zu", shader_path, sizeof(SSRPushConstants), push_constants_size);
+        SSRPushConstants pc;
+        memcpy(&pc, push_constants, sizeof(pc));
+        return launch_ssr(ctx, x_groups, y_groups, pc);
+    }
     return fail(VHR_ERR_INVALID, "unknown compute kernel '%s'", shader_path);
 }
 

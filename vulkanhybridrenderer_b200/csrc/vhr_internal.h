@@ -137,6 +137,7 @@ int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFP
 int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
 int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius);
 int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg);
+int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc);
 int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height);
 int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height);
 int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int reflection_mode);

@@ -104,8 +104,19 @@ void HybridRenderPath::RegisterPath(RenderGraph &rg, ResourceManager &rm) {
                           });
     }
 
-    // SSR (:202-243) is outside the hot path: the node is not registered; composition then sees an
-    // unwritten "Screen Space Reflections" image exactly as with reflection_mode != SSR in the reference.
+    if (reflection_mode == REFLECTION_MODE_SSR) {
+        // ---- SSR Pass (:202-243) ----------------------------------------------------------------------------------------
+        ssr_push_constants = SSRPushConstants{25.0f, 0.1f, 0.5f, 10};
+        rg.AddComputePass("SSR Pass",
+                          {CreateTransientSampledImage(kAlbedo, BGRA8, 0), CreateTransientSampledImage(kNormals, F4, 1),
+                           CreateTransientSampledImage(kMotion, F4, 2), CreateTransientSampledImage(kDepth, D32, 3)},
+                          {CreateTransientStorageImage(kSsr, F4, 4)},
+                          ComputePipelineDescription{{ComputeKernel{"hybrid_render_path/ssr.comp"}}, PushConstantDescription{sizeof(SSRPushConstants), 0}},
+                          [this](ComputeExecutionContext &ec) {
+                              glmlite::uvec2 s = ec.GetDisplaySize();
+                              ec.Dispatch("hybrid_render_path/ssr.comp", groups(s.x), groups(s.y), 1, ssr_push_constants);
+                          });
+    }
 
     if (denoise_shadow_and_ao && any_rt) {
         // ---- SVGF Denoise Pass (:245-331) -----------------------------------------------------------------------------

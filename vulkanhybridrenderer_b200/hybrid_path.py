@@ -35,6 +35,7 @@ SHADER_SVGF = "hybrid_render_path/svgf.comp"
 SHADER_ATROUS = "hybrid_render_path/svgf_atrous_filter.comp"
 SHADER_SSAO = "hybrid_render_path/ssao.comp"
 SHADER_SSAO_BLUR = "hybrid_render_path/ssao_blur.comp"
+SHADER_SSR = "hybrid_render_path/ssr.comp"
 SHADER_COMPOSITION = "hybrid_render_path/composition.frag"
 
 # common.glsl:12-25 / hybrid_render_path.h:4-20
@@ -49,6 +50,7 @@ BYTES_BLIT = 16
 BYTES_RAYGEN_IO = 12 + 4          # depth + normals in, RG16F out (reflections add 8)
 BYTES_SSAO = 20
 BYTES_SSAO_BLUR = 16
+BYTES_SSR = 4 + 8 + 4 + 8 + 8     # compulsory G-buffer in (depth 4, normals 8, albedo 4, motion 8) + RGBA16F out 8
 BYTES_COMPOSITION = 4 + 8 + 8 + 4 + 8 + 4   # albedo, normals, motion texel, depth, denoised shadow/AO in; BGRA8 out (+8 reflections)
 
 
@@ -95,6 +97,8 @@ class HybridRenderPath:
         pc["shadow_and_ao_moments_history"] = ctx.upload_new_storage_image(width, height, F2)
         self.pc = pc
         self.ssao_radius = np.array(0.75, np.float32)
+        # hybrid_render_path.cpp:203-208
+        self.ssr_pc = np.array((25.0, 0.1, 0.5, 10), T.SSRPushConstants)
         self.timestamps = None
 
     # ---- optional per-pass timestamps (render_graph.cpp:167-182) --------------------------------------------------
@@ -137,6 +141,12 @@ class HybridRenderPath:
         self.ctx.dispatch(SHADER_SSAO, gx, gy, 1, self.ssao_radius)
         self.ctx.bind_pass_images([N_SSAO_RAW, N_SSAO])
         self.ctx.dispatch(SHADER_SSAO_BLUR, gx, gy, 1, self.ssao_radius)
+
+    def ssr_pass(self, gset=0):
+        """"SSR Pass", hybrid_render_path.cpp:202-243: 0 albedo, 1 normals, 2 motion / metallic-roughness, 3 depth, 4 output."""
+        g = self.gsets[gset]
+        self.ctx.bind_pass_images([g[N_ALBEDO], g[N_NORMALS], g[N_MOTION], g[N_DEPTH], N_SSR])
+        self.ctx.dispatch(SHADER_SSR, groups(self.W), groups(self.H), 1, self.ssr_pc)
 
     def svgf_denoise_pass(self, gset=0, rtset=0):
         """hybrid_render_path.cpp:288-330, statement by statement."""

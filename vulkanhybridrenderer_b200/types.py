@@ -67,12 +67,20 @@ SVGFPushConstants = np.dtype([
 
 SSAOPushConstants = np.dtype([("radius", np.float32)])
 
+SSRPushConstants = np.dtype([      # glsl_common.h:41-46
+    ("ray_distance", np.float32),
+    ("step_size", np.float32),
+    ("thickness", np.float32),
+    ("bsearch_steps", np.int32),
+])
+
 assert PerFrameData.itemsize == 584
 assert DirectionalLight.itemsize == 112
 assert Vertex.itemsize == 56
 assert Material.itemsize == 44
 assert Primitive.itemsize == 120
 assert SVGFPushConstants.itemsize == 24
+assert SSRPushConstants.itemsize == 16
 
 # VkFormat values used on the hot path (hybrid_render_path.cpp:16-19,109-110,247-261)
 VK_FORMAT_B8G8R8A8_UNORM = 44
