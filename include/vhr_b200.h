@@ -36,6 +36,8 @@ typedef enum vhr_status {
 
 /* VkFormat values accepted for images (src/render_paths/hybrid_render_path.cpp:16-19,109-110,247-261). */
 enum {
+    VHR_FORMAT_R8G8B8A8_UNORM = 37,  /* material textures: metallic-roughness, normal maps (scene_loader.cpp:258-272) */
+    VHR_FORMAT_R8G8B8A8_SRGB = 43,   /* material textures: base colour (scene_loader.cpp:249-252) */
     VHR_FORMAT_B8G8R8A8_UNORM = 44,
     VHR_FORMAT_B8G8R8A8_SRGB = 50,   /* the swapchain format RENDER_OUTPUT has in the reference (vulkan_context.cpp:331) */
     VHR_FORMAT_R16G16_SFLOAT = 83,
@@ -79,6 +81,26 @@ uint64_t vhr_kernel_launch_count(vhr_context *ctx);
  * into `primitives`. Host pointers; returns after the build has been enqueued. */
 int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_vertices, const uint32_t *indices,
                         uint32_t n_indices, const void *primitives, uint32_t n_primitives);
+
+/* ResourceManager::UploadTextureFromData + GetSampler (resource_manager.cpp:152-193, 821-849, 880-910): uploads one
+ * material texture — tightly packed R8G8B8A8 rows, host memory — into the first free slot of textures[2048]
+ * (descriptor set 0 binding 4, glsl_common.h:104) and returns that slot (>= 0), the index Material::base_color_texture /
+ * metallic_roughness_texture / normal_map name (glsl_common.h:82-91). `sampler_info` = the glTF sampler mapped by the scene
+ * loader (scene_loader.cpp:9-38,296-301; values are VkFilter / VkSamplerAddressMode); NULL = the default sampler
+ * (LINEAR, REPEAT; resource_manager.cpp:58-69). Border colour is opaque black, one mip level; the ray-traced stages
+ * sample LOD 0 (mag filter), anisotropy has no effect without derivatives. VK_FORMAT_R8G8B8A8_SRGB texels are decoded
+ * to linear before filtering. Upload textures BEFORE vhr_update_geometry (like the loader does): geometry whose
+ * materials name a missing texture is rejected. */
+typedef struct vhr_sampler_info {
+    int32_t mag_filter, min_filter;            /* VHR_FILTER_* */
+    int32_t address_mode_u, address_mode_v;    /* VHR_ADDRESS_MODE_* */
+} vhr_sampler_info;
+enum { VHR_FILTER_NEAREST = 0, VHR_FILTER_LINEAR = 1 };
+enum { VHR_ADDRESS_MODE_REPEAT = 0, VHR_ADDRESS_MODE_MIRRORED_REPEAT = 1, VHR_ADDRESS_MODE_CLAMP_TO_EDGE = 2, VHR_ADDRESS_MODE_CLAMP_TO_BORDER = 3 };
+int vhr_upload_texture_from_data(vhr_context *ctx, uint32_t width, uint32_t height, const uint8_t *data, int vk_format,
+                                 const vhr_sampler_info *sampler_info);
+/* ResourceManager::DestroyResources, texture part (resource_manager.cpp:79-84): frees every texture slot. */
+int vhr_destroy_textures(vhr_context *ctx);
 
 /* ResourceManager::UpdatePerFrameUBO (resource_manager.cpp:362-364): `per_frame_data` is the 584-byte PerFrameData
  * of glsl_common.h:59-72. Copied by value; used by every later dispatch until the next call. */

@@ -74,6 +74,9 @@ def _declare(L):
     L.vo_scene_create.restype = vp
     L.vo_scene_create.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
     L.vo_scene_destroy.argtypes = [vp]
+    L.vo_scene_add_texture.restype = C.c_int
+    L.vo_scene_add_texture.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.vo_sample_texture.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]
     L.vo_scene_num_triangles.restype = C.c_uint32
     L.vo_scene_num_triangles.argtypes = [vp]
     L.vo_trace_any.restype = C.c_int
@@ -187,6 +190,19 @@ class OracleScene:
         p = np.ascontiguousarray(scene.primitives)
         assert v.dtype == T.Vertex and p.dtype == T.Primitive
         self._s = lib().vo_scene_create(_p(v), len(v), _p(i), len(i), _p(p), len(p))
+        for t in getattr(scene, "textures", []):
+            self.add_texture(t.rgba, t.format, t.sampler)
+
+    def add_texture(self, rgba8, fmt=T.VK_FORMAT_R8G8B8A8_UNORM, sampler=None):
+        """ResourceManager::UploadTextureFromData: returns the texture index. sampler = (mag, min, wrap_u, wrap_v); None = default."""
+        a = np.ascontiguousarray(rgba8, np.uint8)
+        mag, mn, wu, wv = (1, 1, 0, 0) if sampler is None else [int(x) for x in sampler]
+        return lib().vo_scene_add_texture(self._s, a.shape[1], a.shape[0], _p(a), int(fmt), mag, mn, wu, wv)
+
+    def sample_texture(self, idx, u, v):
+        out = np.zeros(4, np.float32)
+        lib().vo_sample_texture(self._s, int(idx), float(u), float(v), _p(out))
+        return out
 
     def __del__(self):
         if getattr(self, "_s", None):

@@ -41,7 +41,62 @@ struct Scene {
     std::vector<uint32_t> tri_prim;  // triangle index inside the primitive (gl_PrimitiveID)
     std::vector<Node> nodes;
     uint32_t n_tris = 0;
+    // textures[] (glsl_common.h:104): ResourceManager::UploadTextureFromData (resource_manager.cpp:152-193) with the
+    // glTF sampler (GetSampler :880-910); index = slot the materials name (glsl_common.h:82-91)
+    struct Texture {
+        uint32_t w = 0, h = 0;
+        std::vector<uint8_t> rgba;
+        bool srgb = false;            // VK_FORMAT_R8G8B8A8_SRGB (base colour, scene_loader.cpp:249-252)
+        int mag = 1, min = 1;         // VkFilter: 0 NEAREST, 1 LINEAR
+        int wrap_u = 0, wrap_v = 0;   // VkSamplerAddressMode: 0 REPEAT, 1 MIRRORED_REPEAT, 2 CLAMP_TO_EDGE, 3 CLAMP_TO_BORDER
+    };
+    std::vector<Texture> textures;
 };
+
+// ---- texture(textures[i], uv) -------------------------------------------------------------------------------------
+// Vulkan spec, "Texel Coordinate Systems": ray-tracing stages have no implicit derivatives and the images have one mip
+// level, so the lookup is LOD 0 with the mag filter; unnormalised coordinate u * size, LINEAR taps floor(u - 0.5) and
+// +1 with weight fract(u - 0.5), NEAREST tap floor(u); wrapping per address mode; border = opaque black
+// (resource_manager.cpp:67,902). sRGB texels are decoded to linear BEFORE filtering (Khronos Data Format spec 13.3.1).
+inline int wrap_texel(int i, int n, int mode) {
+    auto mod = [](int a, int b) { int m = a % b; return m < 0 ? m + b : m; };
+    switch (mode) {
+        case 0: return mod(i, n);
+        case 1: { int m = mod(i, 2 * n) - n; m = m >= 0 ? m : -(1 + m); return (n - 1) - m; }
+        case 2: return std::min(std::max(i, 0), n - 1);
+        default: return (i < 0 || i >= n) ? -1 : i;
+    }
+}
+inline float srgb_to_linear(uint8_t c) {
+    double e = (double)c / 255.0;
+    return (float)(e <= 0.04045 ? e / 12.92 : std::pow((e + 0.055) / 1.055, 2.4));
+}
+inline vec4 fetch_texel(const Scene::Texture &t, int x, int y) {
+    if (x < 0 || y < 0) return vec4{0.0f, 0.0f, 0.0f, 1.0f};
+    const uint8_t *c = &t.rgba[((size_t)y * t.w + x) * 4];
+    if (t.srgb) return vec4{srgb_to_linear(c[0]), srgb_to_linear(c[1]), srgb_to_linear(c[2]), (float)c[3] / 255.0f};
+    return vec4{(float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f};
+}
+inline int texel_index(float f) { return (f == f && std::fabs(f) < 1e9f) ? (int)f : 0; }   // non-finite coordinate: texel 0
+inline vec4 sample_texture(const Scene &s, int idx, vec2 uv) {
+    const Scene::Texture &t = s.textures[(size_t)idx];
+    int W = (int)t.w, H = (int)t.h;
+    if (t.mag == 0) {
+        int i = texel_index(std::floor(uv.x * (float)W)), j = texel_index(std::floor(uv.y * (float)H));
+        return fetch_texel(t, wrap_texel(i, W, t.wrap_u), wrap_texel(j, H, t.wrap_v));
+    }
+    float uu = uv.x * (float)W - 0.5f, vv = uv.y * (float)H - 0.5f;
+    float fu = std::floor(uu), fv = std::floor(vv);
+    float a = uu - fu, b = vv - fv;
+    int i = texel_index(fu), j = texel_index(fv);
+    int x0 = wrap_texel(i, W, t.wrap_u), x1 = wrap_texel(i + 1, W, t.wrap_u), y0 = wrap_texel(j, H, t.wrap_v), y1 = wrap_texel(j + 1, H, t.wrap_v);
+    vec4 t00 = fetch_texel(t, x0, y0), t10 = fetch_texel(t, x1, y0), t01 = fetch_texel(t, x0, y1), t11 = fetch_texel(t, x1, y1);
+    auto lerp = [&](float c00, float c10, float c01, float c11) {
+        return (1 - a) * (1 - b) * c00 + a * (1 - b) * c10 + (1 - a) * b * c01 + a * b * c11;
+    };
+    return vec4{lerp(t00.x, t10.x, t01.x, t11.x), lerp(t00.y, t10.y, t01.y, t11.y), lerp(t00.z, t10.z, t01.z, t11.z), lerp(t00.w, t10.w, t01.w, t11.w)};
+}
+inline bool has_texture(const Scene &s, int idx) { return idx >= 0 && (size_t)idx < s.textures.size() && s.textures[(size_t)idx].w != 0; }
 
 struct Hit { double t, u, v; uint32_t tri; };   // u,v = barycentrics of vertex 1 and 2 (hitAttributeEXT)
 
@@ -237,7 +292,10 @@ bool trace_any(const Scene &s, vec3 o, vec3 d, float tmin, float tmax) {
     return false;
 }
 
-bool trace_closest(const Scene &s, vec3 o, vec3 d, float tmin, float tmax, Hit &hit) {
+// `accept` = the any-hit stage (NULL: opaque geometry, every candidate counts): a rejected candidate is ignored and the
+// traversal goes on — the G-buffer producer's alpha test (gbuf.frag:27-32).
+template <class Accept>
+bool trace_closest_filtered(const Scene &s, vec3 o, vec3 d, float tmin, float tmax, Hit &hit, const Accept &accept) {
     if (s.nodes.empty()) return false;
     RayD r; ray_setup(r, o, d, tmin, tmax);
     bool found = false;
@@ -250,7 +308,7 @@ bool trace_closest(const Scene &s, vec3 o, vec3 d, float tmin, float tmax, Hit &
         if (n.count) {
             for (uint32_t i = 0; i < n.count; ++i) {
                 double t, u, v;
-                if (tri_hit(r, &s.tri[(size_t)(n.left_first + i) * 9], t, u, v)) {
+                if (tri_hit(r, &s.tri[(size_t)(n.left_first + i) * 9], t, u, v) && accept(n.left_first + i, u, v)) {
                     r.tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = n.left_first + i; found = true;
                 }
             }
@@ -268,7 +326,11 @@ bool trace_closest(const Scene &s, vec3 o, vec3 d, float tmin, float tmax, Hit &
     return found;
 }
 
-// reflection_hit.rchit:10-72 (constant materials; texture indices are treated as -1 — no textures offline)
+bool trace_closest(const Scene &s, vec3 o, vec3 d, float tmin, float tmax, Hit &hit) {
+    return trace_closest_filtered(s, o, d, tmin, tmax, hit, [](uint32_t, double, double) { return true; });
+}
+
+// reflection_hit.rchit:10-72
 vec4 reflection_hit(const Scene &s, const PerFrameData &pfd, const Hit &hit) {
     uint32_t g = s.tri_geom[hit.tri], pid = s.tri_prim[hit.tri];
     const Primitive &prim = s.primitives[g];
@@ -287,9 +349,19 @@ vec4 reflection_hit(const Scene &s, const PerFrameData &pfd, const Hit &hit) {
     vec4 pw = mul44(prim.transform, vec4{pobj.x, pobj.y, pobj.z, 1.0f});
     vec3 position = v3(pw.x, pw.y, pw.z);
 
+    vec2 uv = {v0.uv0[0] * b0 + v1.uv0[0] * b1 + v2.uv0[0] * b2, v0.uv0[1] * b0 + v1.uv0[1] * b1 + v2.uv0[1] * b2};   // :22
     vec3 albedo = v3(prim.material.base_color[0], prim.material.base_color[1], prim.material.base_color[2]);
+    if (has_texture(s, prim.material.base_color_texture)) {                                                       // :26-32
+        vec4 c = sample_texture(s, prim.material.base_color_texture, uv);
+        albedo = v3(c.x, c.y, c.z);
+    }
     float metallic = prim.material.metallic_factor;
     float roughness = prim.material.roughness_factor;
+    if (has_texture(s, prim.material.metallic_roughness_texture)) {                                               // :35-39
+        vec4 mr = sample_texture(s, prim.material.metallic_roughness_texture, uv);
+        metallic *= mr.y;
+        roughness *= mr.z;
+    }
 
     vec3 camera_position = v3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
     vec3 V = normalize(camera_position - position);
@@ -370,6 +442,24 @@ vo_scene *vo_scene_create(const Vertex *vertices, uint32_t n_vertices, const uin
         s->tri_geom[i] = geom[src]; s->tri_prim[i] = pid[src];
     }
     return reinterpret_cast<vo_scene *>(s);
+}
+
+// ResourceManager::UploadTextureFromData: appends to textures[] and returns the index. format 43 = R8G8B8A8_SRGB, 37 = UNORM.
+int vo_scene_add_texture(vo_scene *s_, uint32_t w, uint32_t h, const uint8_t *rgba, int vk_format, int mag_filter, int min_filter,
+                         int address_mode_u, int address_mode_v) {
+    Scene &s = *reinterpret_cast<Scene *>(s_);
+    Scene::Texture t;
+    t.w = w; t.h = h;
+    t.rgba.assign(rgba, rgba + (size_t)w * h * 4);
+    t.srgb = vk_format == 43;
+    t.mag = mag_filter; t.min = min_filter; t.wrap_u = address_mode_u; t.wrap_v = address_mode_v;
+    s.textures.push_back(std::move(t));
+    return (int)s.textures.size() - 1;
+}
+// texture(textures[idx], uv) for unit tests
+void vo_sample_texture(const vo_scene *s_, int idx, float u, float v, float *out4) {
+    vec4 c = sample_texture(*reinterpret_cast<const Scene *>(s_), idx, vec2{u, v});
+    out4[0] = c.x; out4[1] = c.y; out4[2] = c.z; out4[3] = c.w;
 }
 
 void vo_scene_destroy(vo_scene *s) { delete reinterpret_cast<Scene *>(s); }
@@ -480,7 +570,23 @@ void vo_gbuffer(const vo_scene *s_, const PerFrameData *pfd_, int W, int H, uint
             vec3 pn = get_world_space_position(pfd, 1.0f, uv);   // point on the near plane (reverse-Z: depth 1)
             vec3 dir = pn - cam;
             Hit h;
-            bool hit = trace_closest(s, cam, dir, 1.0f, FLT_MAX, h);
+            // gbuf.frag:19-32: fragments failing the alpha-mask test, or with alpha exactly 0, are discarded
+            auto alpha_test = [&](uint32_t tri, double hu, double hv) {
+                const Primitive &pr = s.primitives[s.tri_geom[tri]];
+                float alpha = pr.material.base_color[3];
+                if (has_texture(s, pr.material.base_color_texture)) {
+                    uint32_t k = s.tri_prim[tri];
+                    const Vertex &a0 = s.vertices[pr.vertex_offset + s.indices[pr.index_offset + 3 * k + 0]];
+                    const Vertex &a1 = s.vertices[pr.vertex_offset + s.indices[pr.index_offset + 3 * k + 1]];
+                    const Vertex &a2 = s.vertices[pr.vertex_offset + s.indices[pr.index_offset + 3 * k + 2]];
+                    float c1 = (float)hu, c2 = (float)hv, c0 = 1.0f - c1 - c2;
+                    vec2 uvt = {a0.uv0[0] * c0 + a1.uv0[0] * c1 + a2.uv0[0] * c2, a0.uv0[1] * c0 + a1.uv0[1] * c1 + a2.uv0[1] * c2};
+                    alpha = sample_texture(s, pr.material.base_color_texture, uvt).w;
+                }
+                if (pr.material.alpha_mask == 1 && alpha < pr.material.alpha_cutoff) return false;
+                return alpha != 0.0f;
+            };
+            bool hit = trace_closest_filtered(s, cam, dir, 1.0f, FLT_MAX, h, alpha_test);
             if (hit_ids) { hit_ids[2 * pix] = hit ? (int32_t)s.tri_geom[h.tri] : -1; hit_ids[2 * pix + 1] = hit ? (int32_t)s.tri_prim[h.tri] : -1; }
             if (!hit) {
                 if (albedo_bgra8) std::memset(albedo_bgra8 + pix * 4, 0, 4);
@@ -499,6 +605,26 @@ void vo_gbuffer(const vo_scene *s_, const PerFrameData *pfd_, int W, int H, uint
                         v3(v2.normal[0], v2.normal[1], v2.normal[2]) * b2;
             vec3 pobj = v3(v0.pos[0], v0.pos[1], v0.pos[2]) * b0 + v3(v1.pos[0], v1.pos[1], v1.pos[2]) * b1 +
                         v3(v2.pos[0], v2.pos[1], v2.pos[2]) * b2;
+            const Material &mat = prim.material;
+            vec2 tuv = {v0.uv0[0] * b0 + v1.uv0[0] * b1 + v2.uv0[0] * b2, v0.uv0[1] * b0 + v1.uv0[1] * b1 + v2.uv0[1] * b2};
+            vec4 albedo4 = {mat.base_color[0], mat.base_color[1], mat.base_color[2], mat.base_color[3]};
+            if (has_texture(s, mat.base_color_texture)) albedo4 = sample_texture(s, mat.base_color_texture, tuv);       // gbuf.frag:20-26
+            if (has_texture(s, mat.normal_map)) {                                                                     // gbuf.frag:35-41
+                vec4 c = sample_texture(s, mat.normal_map, tuv);
+                vec3 tsn = normalize(v3(c.x * 2.0f - 1.0f, c.y * 2.0f - 1.0f, c.z * 2.0f - 1.0f));
+                vec3 tan3 = v3(v0.tangent[0], v0.tangent[1], v0.tangent[2]) * b0 + v3(v1.tangent[0], v1.tangent[1], v1.tangent[2]) * b1 +
+                            v3(v2.tangent[0], v2.tangent[1], v2.tangent[2]) * b2;
+                float tw = v0.tangent[3] * b0 + v1.tangent[3] * b1 + v2.tangent[3] * b2;
+                vec3 bitangent = cross(tsn, tan3) * tw;
+                vec3 tangent = normalize(tan3 - nobj * dot(tan3, nobj));
+                nobj = tangent * tsn.x + bitangent * tsn.y + nobj * tsn.z;
+            }
+            float metallic = mat.metallic_factor, roughness = mat.roughness_factor;
+            if (has_texture(s, mat.metallic_roughness_texture)) {                                                     // gbuf.frag:52-56
+                vec4 c = sample_texture(s, mat.metallic_roughness_texture, tuv);
+                metallic *= c.y;
+                roughness *= c.z;
+            }
             // normal_matrix = inverseTranspose(mat3(transform)) (hybrid_render_path.cpp:45) = cofactor(M) / det(M)
             const float *m = prim.transform;
             double a00 = m[0], a10 = m[1], a20 = m[2], a01 = m[4], a11 = m[5], a21 = m[6], a02 = m[8], a12 = m[9], a22 = m[10];
@@ -520,14 +646,13 @@ void vo_gbuffer(const vo_scene *s_, const PerFrameData *pfd_, int W, int H, uint
             vec2 cur_ndc = uv;   // gl_FragCoord.xy * display_size_inverse
             vec2 prev_ndc = {(pclip.x / pclip.w) * 0.5f + 0.5f, (pclip.y / pclip.w) * 0.5f + 0.5f};
             if (albedo_bgra8) {
-                const float *bc = prim.material.base_color;
                 auto q = [](float f) { f = std::min(std::max(f, 0.0f), 1.0f); return (uint8_t)std::lrintf(f * 255.0f); };
-                albedo_bgra8[pix * 4 + 0] = q(bc[2]); albedo_bgra8[pix * 4 + 1] = q(bc[1]);
-                albedo_bgra8[pix * 4 + 2] = q(bc[0]); albedo_bgra8[pix * 4 + 3] = q(bc[3]);
+                albedo_bgra8[pix * 4 + 0] = q(albedo4.z); albedo_bgra8[pix * 4 + 1] = q(albedo4.y);
+                albedo_bgra8[pix * 4 + 2] = q(albedo4.x); albedo_bgra8[pix * 4 + 3] = q(albedo4.w);
             }
             store_rgba16f(normals, W, x, y, vec4{nw.x, nw.y, nw.z, (float)g});
             store_rgba16f(motion, W, x, y, vec4{cur_ndc.x - prev_ndc.x, cur_ndc.y - prev_ndc.y,
-                                                prim.material.metallic_factor, prim.material.roughness_factor});
+                                                metallic, roughness});
             depth[pix] = clip.z / clip.w;
         }
     }

@@ -28,6 +28,7 @@ SYMBOLS = [
     "vhr_storage_image_attach_peer", "vhr_sync_export_ipc", "vhr_sync_attach_peer",
     "vhr_image_attach_peer_pointer", "vhr_storage_image_attach_peer_pointer", "vhr_sync_attach_peer_pointer",
     "vhr_storage_image_twin_device_ptr", "vhr_sync_device_ptr",
+    "vhr_upload_texture_from_data", "vhr_destroy_textures",
 ]
 MAX_RANKS = 8
 IPC_HANDLE_BYTES = 64
@@ -40,6 +41,15 @@ class Partition(C.Structure):
 
 OPT_AO_SPP, OPT_TRACE_SHADOWS, OPT_TRACE_AO, OPT_TRACE_REFLECTIONS = 1, 2, 3, 4
 OPT_ROW_BEGIN, OPT_ROW_END, OPT_SVGF_FUSED, OPT_ATROUS_VARIANT, OPT_DEBUG_REFLECTION_T, OPT_RAYGEN_VARIANT = 5, 6, 7, 8, 9, 10
+
+
+class SamplerInfo(C.Structure):
+    """SamplerInfo of vulkan_common.h:21-26 (VkFilter / VkSamplerAddressMode values)."""
+    _fields_ = [("mag_filter", C.c_int32), ("min_filter", C.c_int32), ("address_mode_u", C.c_int32), ("address_mode_v", C.c_int32)]
+
+
+FILTER_NEAREST, FILTER_LINEAR = 0, 1
+ADDRESS_MODE_REPEAT, ADDRESS_MODE_MIRRORED_REPEAT, ADDRESS_MODE_CLAMP_TO_EDGE, ADDRESS_MODE_CLAMP_TO_BORDER = 0, 1, 2, 3
 
 
 class BvhStats(C.Structure):
@@ -73,6 +83,8 @@ def lib():
         L.vhr_kernel_launch_count.restype = C.c_uint64
         L.vhr_update_geometry.argtypes = [vp, vp, u32, vp, u32, vp, u32]
         L.vhr_update_per_frame_ubo.argtypes = [vp, vp, sz]
+        L.vhr_upload_texture_from_data.argtypes = [vp, u32, u32, vp, i32, C.POINTER(SamplerInfo)]
+        L.vhr_destroy_textures.argtypes = [vp]
         L.vhr_upload_new_storage_image.argtypes = [vp, u32, u32, i32]
         L.vhr_destroy_storage_image.argtypes = [vp, i32]
         L.vhr_actualize_image.argtypes = [vp, C.c_char_p, u32, u32, i32]
@@ -170,6 +182,25 @@ class Context:
         v = np.ascontiguousarray(vertices); i = np.ascontiguousarray(indices, np.uint32); p = np.ascontiguousarray(primitives)
         assert v.dtype == T.Vertex and p.dtype == T.Primitive
         _check(lib().vhr_update_geometry(self._h, _ptr(v), len(v), _ptr(i), len(i), _ptr(p), len(p)))
+
+    def upload_texture_from_data(self, rgba8, fmt=T.VK_FORMAT_R8G8B8A8_UNORM, sampler=None):
+        """ResourceManager::UploadTextureFromData: [H, W, 4] uint8 -> texture index. sampler = (mag, min, wrap_u, wrap_v) or None."""
+        a = np.ascontiguousarray(rgba8, np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 4
+        si = C.byref(SamplerInfo(*[int(x) for x in sampler])) if sampler is not None else None
+        return _check(lib().vhr_upload_texture_from_data(self._h, a.shape[1], a.shape[0], _ptr(a), int(fmt), si))
+
+    def destroy_textures(self):
+        _check(lib().vhr_destroy_textures(self._h))
+
+    def load_scene(self, scene):
+        """The loader's order (scene_loader.cpp:233-331): textures first, then UpdateGeometry. Texture i of scene.textures
+        must land in slot i (materials name slots), which holds on a context without other textures."""
+        for i, t in enumerate(getattr(scene, "textures", [])):
+            slot = self.upload_texture_from_data(t.rgba, t.format, t.sampler)
+            if slot != i:
+                raise VhrError(f"texture {i} landed in slot {slot}: destroy_textures() first")
+        self.update_geometry(scene.vertices, scene.indices, scene.primitives)
 
     def update_per_frame_ubo(self, pfd):
         pfd = np.ascontiguousarray(pfd)

@@ -190,9 +190,15 @@ __device__ __forceinline__ void expand_leaves(const WideNode *__restrict__ nodes
 
 // while-while traversal (Aila & Laine 2009) over the 8-wide nodes, one ray per lane; every lane of the warp calls
 // trace() together (`alive` = this lane really has a ray) so callers never diverge before the loop.
-template <bool ANY>
+// `accept(tri, u, v)` is the any-hit stage: a candidate it rejects is ignored and the traversal goes on (the G-buffer
+// producer's alpha test, gbuf.frag:27-32). The hybrid path's own rays are gl_RayFlagsOpaqueEXT (raygen.rgen:39,51,64):
+// AcceptAll, which compiles to nothing.
+struct AcceptAll {
+    __device__ __forceinline__ bool operator()(uint32_t, float, float) const { return true; }
+};
+template <bool ANY, class Accept = AcceptAll>
 __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
-                                      uint32_t bias, const Ray &ray, bool alive, Hit &hit) {
+                                      uint32_t bias, const Ray &ray, bool alive, Hit &hit, const Accept accept = Accept()) {
     if (!alive || n_wide == 0) return false;
     const RayPre r = prepare(ray);
     float tmax = ray.tmax;
@@ -221,7 +227,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
                 const float4 *tp = tris + (size_t)(tri_base + j) * 3;
                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
                 float t, u, v;
-                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v)) {
+                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && accept(tri_base + j, u, v)) {
                     if (ANY) return true;
                     tmax = t;
                     hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
@@ -234,7 +240,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Shading of the reflection ray: reflection_hit.rchit:10-72 (constant materials; texture indices treated as -1)
+// Shading of the reflection ray: reflection_hit.rchit:10-72
 // ---------------------------------------------------------------------------------------------------------------
 struct SceneRefs {
     const Vertex *verts;
@@ -245,7 +251,19 @@ struct SceneRefs {
     const float4 *tris;
     uint32_t n_wide;
     uint32_t bias;                // 0x47000000 (see byte_biased)
+    const TextureDesc *textures;  // textures[] (glsl_common.h:104); entries without an image have texels == nullptr
+    const float *lut;             // UNORM / sRGB decode tables (fetch_texel)
+    uint32_t n_textures;
 };
+
+__device__ __forceinline__ bool has_texture(const SceneRefs &s, int idx) {
+    return idx >= 0 && (uint32_t)idx < s.n_textures && s.textures[idx].texels != nullptr;
+}
+// v0.uv0 * b0 + v1.uv0 * b1 + v2.uv0 * b2 (reflection_hit.rchit:22; gbuf.vert:24 + the rasteriser's interpolation)
+__device__ __forceinline__ float2 bary_uv(const Vertex &v0, const Vertex &v1, const Vertex &v2, float b0, float b1, float b2) {
+    return make_float2(add_rn(add_rn(mul_rn(v0.uv0[0], b0), mul_rn(v1.uv0[0], b1)), mul_rn(v2.uv0[0], b2)),
+                       add_rn(add_rn(mul_rn(v0.uv0[1], b0), mul_rn(v1.uv0[1], b1)), mul_rn(v2.uv0[1], b2)));
+}
 
 __device__ __forceinline__ float3 f3(const float *p) { return make_float3(p[0], p[1], p[2]); }
 __device__ __forceinline__ float3 bary3(float3 a, float3 b, float3 c, float b0, float b1, float b2) {
@@ -267,8 +285,21 @@ __device__ float4 reflection_hit(const SceneRefs &s, const PerFrameData &pfd, co
     const float3 pobj = bary3(f3(v0.pos), f3(v1.pos), f3(v2.pos), b0, b1, b2);
     const float4 pw = mul44_rn(prim.transform, make_float4(pobj.x, pobj.y, pobj.z, 1.0f));
     const float3 position = make_float3(pw.x, pw.y, pw.z);
-    const float3 albedo = make_float3(prim.material.base_color[0], prim.material.base_color[1], prim.material.base_color[2]);
+    float3 albedo = make_float3(prim.material.base_color[0], prim.material.base_color[1], prim.material.base_color[2]);
     float metallic = prim.material.metallic_factor, roughness = prim.material.roughness_factor;
+    const bool tex_a = has_texture(s, prim.material.base_color_texture), tex_mr = has_texture(s, prim.material.metallic_roughness_texture);
+    if (tex_a || tex_mr) {                                                                 // reflection_hit.rchit:26-39
+        const float2 uv = bary_uv(v0, v1, v2, b0, b1, b2);
+        if (tex_a) {
+            const float4 c = sample_texture(s.textures, s.lut, prim.material.base_color_texture, uv.x, uv.y);
+            albedo = make_float3(c.x, c.y, c.z);
+        }
+        if (tex_mr) {
+            const float4 c = sample_texture(s.textures, s.lut, prim.material.metallic_roughness_texture, uv.x, uv.y);
+            metallic = mul_rn(metallic, c.y);
+            roughness = mul_rn(roughness, c.z);
+        }
+    }
     const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
     const float3 V = normalize_rn(make_float3(sub_rn(cam.x, position.x), sub_rn(cam.y, position.y), sub_rn(cam.z, position.z)));
     const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
@@ -621,6 +652,30 @@ __device__ __forceinline__ uint32_t unorm8(float f) {
     return (uint32_t)__float2int_rn(f * 255.0f);
 }
 
+// The any-hit stage of the primary ray = the discards of gbuf.frag:19-32: a fragment whose albedo alpha is below the
+// cutoff of an alpha-masked material, or exactly 0, is dropped and whatever lies behind it shows.
+struct AlphaTest {
+    const SceneRefs &s;
+    __device__ __forceinline__ bool operator()(uint32_t tri, float u, float v) const {
+        const float4 *tp = s.tris + (size_t)tri * 3;
+        const uint32_t g = __float_as_uint(__ldg(tp).w), pid = __float_as_uint(__ldg(tp + 1).w);
+        const Primitive &prim = s.prims[g];
+        float alpha = prim.material.base_color[3];
+        if (has_texture(s, prim.material.base_color_texture)) {
+            const Vertex &v0 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 0]];
+            const Vertex &v1 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 1]];
+            const Vertex &v2 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 2]];
+            const float2 uv = bary_uv(v0, v1, v2, sub_rn(sub_rn(1.0f, u), v), u, v);
+            alpha = sample_texture(s.textures, s.lut, prim.material.base_color_texture, uv.x, uv.y).w;
+        }
+        if (prim.material.alpha_mask == 1 && alpha < prim.material.alpha_cutoff) return false;
+        return alpha != 0.0f;
+    }
+};
+__device__ __forceinline__ float3 cross_rn(float3 a, float3 b) {
+    return make_float3(sub_rn(mul_rn(a.y, b.z), mul_rn(a.z, b.y)), sub_rn(mul_rn(a.z, b.x), mul_rn(a.x, b.z)), sub_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x)));
+}
+
 __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ GbufferParams p, const __grid_constant__ PerFrameData pfd) {
     int x, y;
     tile_coords(x, y);
@@ -637,7 +692,7 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
     ray.tmin = 1.0f;
     ray.tmax = 3.0e38f;
     Hit h;
-    const bool found = trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, in_range, h);
+    const bool found = trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, in_range, h, AlphaTest{p.scene});
     if (!in_range) return;
     if (!found) {
         // clear values of hybrid_render_path.cpp:16-19
@@ -655,8 +710,34 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
     const Vertex &v1 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 1]];
     const Vertex &v2 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 2]];
     const float b1 = h.u, b2 = h.v, b0 = sub_rn(sub_rn(1.0f, b1), b2);
-    const float3 nobj = bary3(f3(v0.normal), f3(v1.normal), f3(v2.normal), b0, b1, b2);
+    float3 nobj = bary3(f3(v0.normal), f3(v1.normal), f3(v2.normal), b0, b1, b2);
     const float3 pobj = bary3(f3(v0.pos), f3(v1.pos), f3(v2.pos), b0, b1, b2);
+    const Material &mat = prim.material;
+    const bool tex_a = has_texture(s, mat.base_color_texture), tex_n = has_texture(s, mat.normal_map), tex_mr = has_texture(s, mat.metallic_roughness_texture);
+    float4 albedo = make_float4(mat.base_color[0], mat.base_color[1], mat.base_color[2], mat.base_color[3]);
+    float metallic = mat.metallic_factor, roughness = mat.roughness_factor;
+    if (tex_a || tex_n || tex_mr) {
+        const float2 uv = bary_uv(v0, v1, v2, b0, b1, b2);
+        if (tex_a) albedo = sample_texture(s.textures, s.lut, mat.base_color_texture, uv.x, uv.y);                  // gbuf.frag:24-26
+        if (tex_n) {                                                                                               // gbuf.frag:35-41
+            const float4 c = sample_texture(s.textures, s.lut, mat.normal_map, uv.x, uv.y);
+            const float3 tsn = normalize_rn(make_float3(sub_rn(mul_rn(c.x, 2.0f), 1.0f), sub_rn(mul_rn(c.y, 2.0f), 1.0f), sub_rn(mul_rn(c.z, 2.0f), 1.0f)));
+            const float3 tan3 = bary3(f3(v0.tangent), f3(v1.tangent), f3(v2.tangent), b0, b1, b2);
+            const float tw = add_rn(add_rn(mul_rn(v0.tangent[3], b0), mul_rn(v1.tangent[3], b1)), mul_rn(v2.tangent[3], b2));
+            const float3 cr = cross_rn(tsn, tan3);
+            const float3 bitangent = make_float3(mul_rn(cr.x, tw), mul_rn(cr.y, tw), mul_rn(cr.z, tw));
+            const float tn = dot3_rn(tan3, nobj);
+            const float3 tangent = normalize_rn(make_float3(sub_rn(tan3.x, mul_rn(nobj.x, tn)), sub_rn(tan3.y, mul_rn(nobj.y, tn)), sub_rn(tan3.z, mul_rn(nobj.z, tn))));
+            nobj = make_float3(add_rn(add_rn(mul_rn(tangent.x, tsn.x), mul_rn(bitangent.x, tsn.y)), mul_rn(nobj.x, tsn.z)),
+                               add_rn(add_rn(mul_rn(tangent.y, tsn.x), mul_rn(bitangent.y, tsn.y)), mul_rn(nobj.y, tsn.z)),
+                               add_rn(add_rn(mul_rn(tangent.z, tsn.x), mul_rn(bitangent.z, tsn.y)), mul_rn(nobj.z, tsn.z)));
+        }
+        if (tex_mr) {                                                                                              // gbuf.frag:52-56
+            const float4 c = sample_texture(s.textures, s.lut, mat.metallic_roughness_texture, uv.x, uv.y);
+            metallic = mul_rn(metallic, c.y);
+            roughness = mul_rn(roughness, c.z);
+        }
+    }
     const float *nm = s.normal_mats + (size_t)g * 9;
     float3 nw = make_float3(add_rn(add_rn(mul_rn(nm[0], nobj.x), mul_rn(nm[3], nobj.y)), mul_rn(nm[6], nobj.z)),
                             add_rn(add_rn(mul_rn(nm[1], nobj.x), mul_rn(nm[4], nobj.y)), mul_rn(nm[7], nobj.z)),
@@ -667,12 +748,9 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
     const float4 pclip = mul44_rn(pfd.camera_proj_prev_frame, mul44_rn(pfd.camera_view_prev_frame, pw));
     const float pu = add_rn(mul_rn(__fdiv_rn(pclip.x, pclip.w), 0.5f), 0.5f);
     const float pv = add_rn(mul_rn(__fdiv_rn(pclip.y, pclip.w), 0.5f), 0.5f);
-    if (p.albedo) {
-        const float *bc = prim.material.base_color;
-        p.albedo[pix] = unorm8(bc[2]) | (unorm8(bc[1]) << 8) | (unorm8(bc[0]) << 16) | (unorm8(bc[3]) << 24);
-    }
+    if (p.albedo) p.albedo[pix] = unorm8(albedo.z) | (unorm8(albedo.y) << 8) | (unorm8(albedo.x) << 16) | (unorm8(albedo.w) << 24);
     p.normals[pix] = pack_rgba16f(make_float4(nw.x, nw.y, nw.z, (float)g));
-    p.motion[pix] = pack_rgba16f(make_float4(sub_rn(u, pu), sub_rn(v, pv), prim.material.metallic_factor, prim.material.roughness_factor));
+    p.motion[pix] = pack_rgba16f(make_float4(sub_rn(u, pu), sub_rn(v, pv), metallic, roughness));
     p.depth[pix] = __fdiv_rn(clip.z, clip.w);
 }
 
@@ -712,6 +790,7 @@ SceneRefs scene_refs(vhr_context *ctx) {
     s.normal_mats = ctx->d_normal_mats;
     s.nodes = (const WideNode *)ctx->bvh.wide_nodes; s.tris = ctx->bvh.tri_verts; s.n_wide = ctx->bvh.n_wide;
     s.bias = 0x47000000u;
+    s.textures = ctx->d_textures; s.lut = ctx->d_texel_lut; s.n_textures = ctx->d_textures ? VHR_MAX_GLOBAL_RESOURCES : 0u;
     return s;
 }
 

@@ -2,6 +2,7 @@
 // Each entry point cites the reference call it replaces in the header.
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -169,6 +170,9 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->d_normal_mats) cudaFree(ctx->d_normal_mats);
     if (ctx->d_refl_t) cudaFree(ctx->d_refl_t);
     if (ctx->d_ray_queue) cudaFree(ctx->d_ray_queue);
+    for (TextureDesc &t : ctx->textures) if (t.texels) cudaFree((void *)t.texels);
+    if (ctx->d_textures) cudaFree(ctx->d_textures);
+    if (ctx->d_texel_lut) cudaFree(ctx->d_texel_lut);
     for (cudaEvent_t e : ctx->queries) cudaEventDestroy(e);
     if (ctx->upload_stream) { cudaStreamSynchronize(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream); }
     if (ctx->download_stream) { cudaStreamSynchronize(ctx->download_stream); cudaStreamDestroy(ctx->download_stream); }
@@ -215,6 +219,10 @@ int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_verti
         if ((uint64_t)p.index_offset + p.index_count > n_indices)
             return fail(VHR_ERR_INVALID, "primitive %u: indices [%u, +%u) exceed %u", g, p.index_offset, p.index_count, n_indices);
         if (p.vertex_offset > n_vertices) return fail(VHR_ERR_INVALID, "primitive %u: vertex_offset %u exceeds %u", g, p.vertex_offset, n_vertices);
+        // a material may only name textures that exist (the reference would sample an unwritten descriptor)
+        for (int32_t t : {p.material.base_color_texture, p.material.metallic_roughness_texture, p.material.normal_map})
+            if (t >= 0 && ((size_t)t >= ctx->textures.size() || !ctx->textures[t].texels))
+                return fail(VHR_ERR_INVALID, "primitive %u: material names texture %d, which has not been uploaded (vhr_upload_texture_from_data)", g, t);
         uint32_t lim = n_vertices - p.vertex_offset;
         for (uint32_t k = 0; k < p.index_count; ++k)
             if (indices[p.index_offset + k] >= lim)
@@ -255,6 +263,64 @@ int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_verti
     if (rc) return rc;
     // host arrays may be pageable: make sure the async copies have consumed them before returning
     VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VHR_OK;
+}
+
+int vhr_upload_texture_from_data(vhr_context *ctx, uint32_t width, uint32_t height, const uint8_t *data, int vk_format,
+                                 const vhr_sampler_info *sampler_info) {
+    if (!ctx || !data) return fail(VHR_ERR_INVALID, "NULL argument");
+    VHR_NEED_DEVICE(ctx);
+    if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(VHR_ERR_INVALID, "texture extent %ux%u", width, height);
+    if (vk_format != VHR_FORMAT_R8G8B8A8_UNORM && vk_format != VHR_FORMAT_R8G8B8A8_SRGB)
+        return fail(VHR_ERR_INVALID, "texture format %d (R8G8B8A8_UNORM = 37 and R8G8B8A8_SRGB = 43 are what the scene loader uploads)", vk_format);
+    // default sampler (resource_manager.cpp:58-69): LINEAR / LINEAR / REPEAT / REPEAT
+    vhr_sampler_info si = {VHR_FILTER_LINEAR, VHR_FILTER_LINEAR, VHR_ADDRESS_MODE_REPEAT, VHR_ADDRESS_MODE_REPEAT};
+    if (sampler_info) si = *sampler_info;
+    if ((si.mag_filter != VHR_FILTER_NEAREST && si.mag_filter != VHR_FILTER_LINEAR) || (si.min_filter != VHR_FILTER_NEAREST && si.min_filter != VHR_FILTER_LINEAR) ||
+        si.address_mode_u < 0 || si.address_mode_u > 3 || si.address_mode_v < 0 || si.address_mode_v > 3)
+        return fail(VHR_ERR_INVALID, "sampler (mag %d, min %d, u %d, v %d)", si.mag_filter, si.min_filter, si.address_mode_u, si.address_mode_v);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!ctx->d_textures) {
+        ctx->textures.assign(VHR_MAX_GLOBAL_RESOURCES, TextureDesc{nullptr, 0, 0, 0, 0});
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_textures, sizeof(TextureDesc) * VHR_MAX_GLOBAL_RESOURCES));
+        VHR_CUDA_CHECK(cudaMemset(ctx->d_textures, 0, sizeof(TextureDesc) * VHR_MAX_GLOBAL_RESOURCES));
+        // UNORM8 -> float is c / 255; sRGB8 -> linear is the sRGB EOTF of c / 255 (Khronos Data Format spec 13.3.1), applied per
+        // texel BEFORE filtering as Vulkan requires; evaluated in double, rounded once
+        float lut[512];
+        for (int c = 0; c < 256; ++c) {
+            lut[c] = (float)c / 255.0f;
+            const double e = (double)c / 255.0;
+            lut[256 + c] = (float)(e <= 0.04045 ? e / 12.92 : pow((e + 0.055) / 1.055, 2.4));
+        }
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_texel_lut, sizeof(lut)));
+        VHR_CUDA_CHECK(cudaMemcpy(ctx->d_texel_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
+    int slot = -1;                                   // first free slot, resource_manager.cpp:821-824
+    for (int i = 0; i < VHR_MAX_GLOBAL_RESOURCES; ++i)
+        if (!ctx->textures[i].texels) { slot = i; break; }
+    if (slot < 0) return fail(VHR_ERR_EXHAUSTED, "no free texture slot (%d in use)", VHR_MAX_GLOBAL_RESOURCES);
+    const size_t bytes = (size_t)width * height * 4;
+    void *texels = nullptr;
+    VHR_CUDA_CHECK(cudaMalloc(&texels, bytes));
+    cudaError_t e = cudaMemcpy(texels, data, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(texels); return fail(VHR_ERR_CUDA, "texture upload: %s", cudaGetErrorString(e)); }
+    TextureDesc d;
+    d.texels = (const uint32_t *)texels; d.width = width; d.height = height; d.pad = 0;
+    d.flags = (vk_format == VHR_FORMAT_R8G8B8A8_SRGB ? 1u : 0u) | (si.mag_filter == VHR_FILTER_LINEAR ? 2u : 0u) | (si.min_filter == VHR_FILTER_LINEAR ? 4u : 0u) |
+              ((uint32_t)si.address_mode_u << 4) | ((uint32_t)si.address_mode_v << 6);
+    ctx->textures[slot] = d;
+    VHR_CUDA_CHECK(cudaMemcpy(ctx->d_textures + slot, &d, sizeof(d), cudaMemcpyHostToDevice));
+    return slot;
+}
+
+int vhr_destroy_textures(vhr_context *ctx) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (ctx->device < 0 || !ctx->d_textures) return VHR_OK;
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (TextureDesc &t : ctx->textures)
+        if (t.texels) { cudaFree((void *)t.texels); t = TextureDesc{nullptr, 0, 0, 0, 0}; }
+    VHR_CUDA_CHECK(cudaMemset(ctx->d_textures, 0, sizeof(TextureDesc) * VHR_MAX_GLOBAL_RESOURCES));
     return VHR_OK;
 }
 

@@ -101,6 +101,10 @@ struct vhr_context {
     vhr::Primitive *d_primitives = nullptr;
     uint32_t n_vertices = 0, n_indices = 0, n_primitives = 0;
     float *d_normal_mats = nullptr;                // 9 floats per primitive: inverseTranspose(mat3(transform)), column-major
+    // textures[] (descriptor set 0 binding 4): device table of VHR_MAX_GLOBAL_RESOURCES descriptors + the texel buffers behind it
+    vhr::TextureDesc *d_textures = nullptr;
+    std::vector<vhr::TextureDesc> textures;        // host mirror; texels == nullptr marks a free slot (resource_manager.cpp:821-824)
+    float *d_texel_lut = nullptr;                  // 512 floats: UNORM8 -> float, sRGB8 -> linear float
     float *d_refl_t = nullptr;                     // optional debug image: reflection-ray hit distance per pixel
     uint32_t *d_ray_queue = nullptr;               // head of the persistent ray kernel's pixel queue
     int raygen_blocks = 0;                         // resident grid of the persistent ray kernel (SMs x blocks/SM)

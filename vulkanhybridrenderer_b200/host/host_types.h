@@ -20,11 +20,28 @@
 
 enum VkFormat : int {
     VK_FORMAT_UNDEFINED = 0,
+    VK_FORMAT_R8G8B8A8_UNORM = VHR_FORMAT_R8G8B8A8_UNORM,
+    VK_FORMAT_R8G8B8A8_SRGB = VHR_FORMAT_R8G8B8A8_SRGB,
     VK_FORMAT_B8G8R8A8_UNORM = VHR_FORMAT_B8G8R8A8_UNORM,
     VK_FORMAT_B8G8R8A8_SRGB = VHR_FORMAT_B8G8R8A8_SRGB,
     VK_FORMAT_R16G16_SFLOAT = VHR_FORMAT_R16G16_SFLOAT,
     VK_FORMAT_R16G16B16A16_SFLOAT = VHR_FORMAT_R16G16B16A16_SFLOAT,
     VK_FORMAT_D32_SFLOAT = VHR_FORMAT_D32_SFLOAT,
+};
+
+// vulkan_common.h:21-26; the enumerators carry the Vulkan values
+enum VkFilter : int { VK_FILTER_NEAREST = VHR_FILTER_NEAREST, VK_FILTER_LINEAR = VHR_FILTER_LINEAR };
+enum VkSamplerAddressMode : int {
+    VK_SAMPLER_ADDRESS_MODE_REPEAT = VHR_ADDRESS_MODE_REPEAT,
+    VK_SAMPLER_ADDRESS_MODE_MIRRORED_REPEAT = VHR_ADDRESS_MODE_MIRRORED_REPEAT,
+    VK_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE = VHR_ADDRESS_MODE_CLAMP_TO_EDGE,
+    VK_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER = VHR_ADDRESS_MODE_CLAMP_TO_BORDER,
+};
+struct SamplerInfo {
+    VkFilter mag_filter;
+    VkFilter min_filter;
+    VkSamplerAddressMode address_mode_u;
+    VkSamplerAddressMode address_mode_v;
 };
 
 namespace glmlite {

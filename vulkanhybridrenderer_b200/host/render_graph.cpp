@@ -24,6 +24,13 @@ void ResourceManager::UpdateGeometry(std::vector<Vertex> &vertices, std::vector<
 void ResourceManager::UpdatePerFrameUBO(uint32_t, PerFrameData &per_frame_data) {
     VHR_CHECK(vhr_update_per_frame_ubo(ctx, &per_frame_data, sizeof(PerFrameData)));
 }
+uint32_t ResourceManager::UploadTextureFromData(uint32_t w, uint32_t h, uint8_t *data, VkFormat format, SamplerInfo *sampler_info) {
+    vhr_sampler_info si{};
+    if (sampler_info) si = vhr_sampler_info{sampler_info->mag_filter, sampler_info->min_filter, sampler_info->address_mode_u, sampler_info->address_mode_v};
+    int slot = vhr_upload_texture_from_data(ctx, w, h, data, (int)format, sampler_info ? &si : nullptr);
+    if (slot < 0) throw VhrHostError{slot, std::string("UploadTextureFromData: ") + vhr_last_error()};
+    return (uint32_t)slot;
+}
 uint32_t ResourceManager::UploadNewStorageImage(uint32_t w, uint32_t h, VkFormat format) {
     int slot = vhr_upload_new_storage_image(ctx, w, h, (int)format);
     if (slot < 0) throw VhrHostError{slot, std::string("UploadNewStorageImage: ") + vhr_last_error()};

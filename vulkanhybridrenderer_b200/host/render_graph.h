@@ -25,6 +25,9 @@ public:
 
     void UpdateGeometry(std::vector<Vertex> &vertices, std::vector<uint32_t> &indices, Scene &scene);
     void UpdatePerFrameUBO(uint32_t resource_idx, PerFrameData &per_frame_data);
+    // resource_manager.cpp:152-193 (+ GetSampler :880-910): tightly packed R8G8B8A8 texels -> slot of textures[]
+    uint32_t UploadTextureFromData(uint32_t width, uint32_t height, uint8_t *data, VkFormat format = VK_FORMAT_R8G8B8A8_UNORM,
+                                   SamplerInfo *sampler_info = nullptr);
     uint32_t UploadNewStorageImage(uint32_t width, uint32_t height, VkFormat format);
     void DestroyStorageImage(uint32_t image_idx);
 

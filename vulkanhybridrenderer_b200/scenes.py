@@ -15,14 +15,24 @@ from . import types as T
 from .camera import Camera, directional_light
 
 
+class Texture:
+    """One entry of textures[]: what the loader hands ResourceManager::UploadTextureFromData (scene_loader.cpp:277-309)."""
+
+    def __init__(self, rgba, fmt, sampler=None):
+        self.rgba = np.ascontiguousarray(rgba, np.uint8)       # [H, W, 4]
+        self.format = fmt                                      # VK_FORMAT_R8G8B8A8_SRGB (base colour) / _UNORM
+        self.sampler = sampler                                 # (mag, min, wrap_u, wrap_v) as VkFilter / VkSamplerAddressMode, None = default
+
+
 class Scene:
-    def __init__(self, vertices, indices, primitives, camera, light, name):
+    def __init__(self, vertices, indices, primitives, camera, light, name, textures=None):
         self.vertices = vertices
         self.indices = indices
         self.primitives = primitives
         self.camera = camera
         self.light = light
         self.name = name
+        self.textures = textures or []          # index = the slot the materials name
 
     @property
     def num_triangles(self):
@@ -304,3 +314,61 @@ def tiny_scene(seed=0, width=64, height=48):
                  aspect=width / height, znear=0.1)
     light = directional_light((-0.3, -1.0, 0.2), intensity=30.0)
     return Scene(vertices, indices, primitives, cam, light, "tiny")
+
+
+def add_procedural_textures(scene, seed=11, size=64, fraction=0.6, uv_scale=3.0):
+    """Gives a deterministic subset of the primitives textured materials (no assets ship with the reference): a bank of
+    procedural base-colour (sRGB, some with alpha cut-outs), metallic-roughness and normal-map textures with a mix of
+    samplers, assigned round-robin; uv0 is scaled so REPEAT / MIRRORED_REPEAT / CLAMP addressing all get exercised.
+    Returns the scene (modified in place)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    NEAREST, LINEAR = 0, 1
+    REPEAT, MIRROR, CLAMP, BORDER = 0, 1, 2, 3
+    tex = []
+
+    def rgba(r, g, b, a=None):
+        a = np.full_like(r, 255) if a is None else a
+        return np.stack([r, g, b, a], -1).astype(np.uint8)
+    # base colour (sRGB): checker, stripes with alpha holes, value noise
+    chk = ((xx // 8 + yy // 8) % 2).astype(np.uint8)
+    tex.append(Texture(rgba(60 + 150 * chk, 90 + 100 * chk, 200 - 120 * chk), T.VK_FORMAT_R8G8B8A8_SRGB, (LINEAR, LINEAR, REPEAT, REPEAT)))
+    holes = (((xx % 16) - 8) ** 2 + ((yy % 16) - 8) ** 2 < 20)
+    tex.append(Texture(rgba(200 - 3 * (xx % 32), 80 + 2 * yy, 40 + xx, np.where(holes, 30, 255)), T.VK_FORMAT_R8G8B8A8_SRGB, (LINEAR, LINEAR, MIRROR, REPEAT)))
+    noise = rng.integers(0, 256, (size, size, 3))
+    tex.append(Texture(rgba(noise[..., 0], noise[..., 1], noise[..., 2]), T.VK_FORMAT_R8G8B8A8_SRGB, (NEAREST, NEAREST, REPEAT, CLAMP)))
+    tex.append(Texture(rgba(255 - 2 * xx, 128 + (yy % 64), 2 * yy + 40, 255 - 3 * ((xx + yy) % 64)), T.VK_FORMAT_R8G8B8A8_SRGB, (LINEAR, NEAREST, CLAMP, BORDER)))
+    n_color = len(tex)
+    # metallic-roughness (UNORM; .g = roughness factor... the shader reads metallic from .g and roughness from .b)
+    tex.append(Texture(rgba(0 * xx, 40 + 3 * xx, 255 - 3 * yy), T.VK_FORMAT_R8G8B8A8_UNORM, (LINEAR, LINEAR, REPEAT, REPEAT)))
+    tex.append(Texture(rgba(0 * xx, 255 * chk, 90 + 100 * chk), T.VK_FORMAT_R8G8B8A8_UNORM, (LINEAR, LINEAR, MIRROR, MIRROR)))
+    n_mr = len(tex) - n_color
+    # normal maps (UNORM): sinusoidal bumps, tangent-space
+    ph = 2 * np.pi * xx / 16.0
+    nx, ny = 0.35 * np.cos(ph), 0.35 * np.sin(2 * np.pi * yy / 16.0)
+    nz = np.sqrt(np.maximum(1.0 - nx * nx - ny * ny, 0.0))
+    enc = lambda c: np.clip(np.rint((c * 0.5 + 0.5) * 255.0), 0, 255)
+    tex.append(Texture(rgba(enc(nx), enc(ny), enc(nz)), T.VK_FORMAT_R8G8B8A8_UNORM, (LINEAR, LINEAR, REPEAT, REPEAT)))
+    n_nm = 1
+    scene.textures = tex
+    prims = scene.primitives
+    k = 0
+    for g in range(len(prims)):
+        if rng.uniform() > fraction:
+            continue
+        m = prims[g]["material"]
+        m["base_color_texture"] = k % n_color
+        if k % 2 == 0:
+            m["metallic_roughness_texture"] = n_color + (k // 2) % n_mr
+            m["metallic_factor"] = 1.0
+            m["roughness_factor"] = 1.0
+        if k % 3 == 0:
+            m["normal_map"] = n_color + n_mr + (k // 3) % n_nm
+        if (k % n_color) in (1, 3) and k % 4 != 3:
+            m["alpha_mask"] = 1
+            m["alpha_cutoff"] = 0.5
+        k += 1
+        v0, n = int(prims[g]["vertex_offset"]), None
+        v1 = int(prims[g + 1]["vertex_offset"]) if g + 1 < len(prims) else len(scene.vertices)
+        scene.vertices["uv0"][v0:v1] = (scene.vertices["uv0"][v0:v1] * np.float32(uv_scale) - np.float32(0.6)).astype(np.float32)
+    return scene

@@ -83,6 +83,8 @@ assert SVGFPushConstants.itemsize == 24
 assert SSRPushConstants.itemsize == 16
 
 # VkFormat values used on the hot path (hybrid_render_path.cpp:16-19,109-110,247-261)
+VK_FORMAT_R8G8B8A8_UNORM = 37      # material textures (scene_loader.cpp:249-272)
+VK_FORMAT_R8G8B8A8_SRGB = 43
 VK_FORMAT_B8G8R8A8_UNORM = 44
 VK_FORMAT_B8G8R8A8_SRGB = 50
 VK_FORMAT_R16G16_SFLOAT = 83
