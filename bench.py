@@ -307,27 +307,55 @@ def run_gpu(args):
         pass_ms = path.pass_times_ms(K)            # [K, passes]
         path.timestamps = None
 
-        # ---- next row, timed on its own and NOT part of the step: the composition pass that consumes
-        # the denoised image (composition.frag as a CUDA kernel, B8G8R8A8_SRGB output like the reference's swapchain)
-        comp_ms = None
+        # ---- next rows, each timed on its own and NOT part of the step: the composition pass that consumes the
+        # denoised image (composition.frag, B8G8R8A8_SRGB output like the reference's swapchain), the other per-pixel passes
+        # of the hybrid path (SSAO + blur, SSR) and the G-buffer producer (primary rays on the same BVH)
+        next_ms = {}
         try:
             path_c = HP.HybridRenderPath.__new__(HP.HybridRenderPath)
             path_c.ctx, path_c.W, path_c.H, path_c.gsets = ctx, W, H, path.gsets
-            for n, f in ((HP.N_SSAO, HP.F4), (HP.N_SSR, HP.F4)):
+            path_c.ssao_radius = np.array(0.75, np.float32)
+            path_c.ssr_pc = np.array((25.0, 0.1, 0.5, 10), HP.T.SSRPushConstants)
+            for n, f in ((HP.N_SSAO_RAW, HP.F4), (HP.N_SSAO, HP.F4), (HP.N_SSR, HP.F4)):
                 ctx.actualize_image(n, f)
             ctx.actualize_image(HP.N_SHADOW_MAP, HP.T.VK_FORMAT_D32_SFLOAT, 4096, 4096)
             ctx.actualize_image(HP.N_RENDER_OUTPUT, HP.T.VK_FORMAT_B8G8R8A8_SRGB)
-            for _ in range(3):
-                path_c.composition_pass(0, 0, 0 if refl else 2, denoised=True, gset=0)
-            ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ec0.record(stream)
-            for i in range(20):
-                path_c.composition_pass(0, 0, 0 if refl else 2, denoised=True, gset=i & 1)
-            ec1.record(stream)
-            torch.cuda.synchronize()
-            comp_ms = ec0.elapsed_time(ec1) / 20
-        except capi.VhrError as e:      # never let the extra row break the headline measurement
-            sys.stderr.write(f"bench.py: composition row skipped: {e}\n")
+
+            def time_row(fn, reps=20):
+                ctx.update_per_frame_ubo(pfds[0])
+                for _ in range(3):
+                    fn(0)
+                ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ec0.record(stream)
+                for i in range(reps):
+                    fn(i & 1)
+                ec1.record(stream)
+                torch.cuda.synchronize()
+                return ec0.elapsed_time(ec1) / reps
+
+            def ssao_only(s):
+                g = path.gsets[s]
+                ctx.bind_pass_images([g[HP.N_NORMALS], g[HP.N_DEPTH], HP.N_SSAO_RAW])
+                ctx.dispatch(HP.SHADER_SSAO, HP.groups(W), HP.groups(H), 1, path_c.ssao_radius)
+
+            def blur_only(s):
+                ctx.bind_pass_images([HP.N_SSAO_RAW, HP.N_SSAO])
+                ctx.dispatch(HP.SHADER_SSAO_BLUR, HP.groups(W), HP.groups(H), 1, path_c.ssao_radius)
+
+            def gbuffer_only(s):
+                g = path.gsets[s]
+                ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
+                ctx.gbuffer_pass(W, H)
+
+            next_ms["composition"] = time_row(lambda s: path_c.composition_pass(0, 0, 0 if refl else 2, denoised=True, gset=s))
+            next_ms["ssao"] = time_row(ssao_only)
+            next_ms["ssao_blur"] = time_row(blur_only)
+            next_ms["ssr"] = time_row(lambda s: path_c.ssr_pass(gset=s), reps=6)
+            # the producer rewrites the resident G-buffer of pose 0 with identical values (same camera, same scene)
+            next_ms["gbuffer"] = time_row(lambda s: gbuffer_only(0), reps=6)
+        except capi.VhrError as e:      # never let the extra rows break the headline measurement
+            sys.stderr.write(f"bench.py: next rows skipped: {e}\n")
+        comp_ms = next_ms.get("composition")
 
         # ---- e2e: host G-buffer -> H2D -> frame -> D2H of the denoised + raw shadow/AO images, every step ---------------
         out_den = torch.empty(W * H * 8, dtype=torch.uint8, pin_memory=True)
@@ -464,11 +492,18 @@ def run_gpu(args):
                      "fused_minimum_bytes": svgf_min_bytes, "frac_of_peak_vs_fused_minimum": svgf_min_bytes / (svgf_ms * 1e-3) / 1e9 / peak},
             "bvh": {"triangles": st.n_triangles, "wide_nodes": st.n_wide_nodes, "build_ms": st.build_ms, "sah_cost": st.sah_cost},
         }
-        if comp_ms:
-            cb = px * (HP.BYTES_COMPOSITION + (8 if refl else 0))
-            line["next_rows"] = {"composition": {"kernel": "composition_kernel", "ms": comp_ms, "algorithmic_bytes": cb,
-                                                 "achieved_gbs": cb / (comp_ms * 1e-3) / 1e9, "frac": cb / (comp_ms * 1e-3) / 1e9 / peak,
-                                                 "note": "timed on its own after the frames, not part of the step"}}
+        if next_ms:
+            rows = {"composition": ("composition_kernel", px * (HP.BYTES_COMPOSITION + (8 if refl else 0)), None),
+                    "ssao": ("ssao_kernel", px * HP.BYTES_SSAO, "16 dependent bilinear gathers per pixel: latency-bound"),
+                    "ssao_blur": ("ssao_blur_kernel", px * HP.BYTES_SSAO_BLUR, None),
+                    "ssr": ("ssr_kernel", px * HP.BYTES_SSR, "up to 250 march steps + 10 bisection steps per pixel, each one re-projection + bilinear "
+                            "depth tap in exactly rounded arithmetic: instruction-bound, the HBM fraction is tiny by construction"),
+                    "gbuffer": ("gbuffer_kernel", px * 28, "primary closest-hit rays on the BVH (traversal-bound); 28 B/px of G-buffer written")}
+            line["next_rows"] = {}
+            for key, ms_ in next_ms.items():
+                kname, b_, note = rows[key]
+                line["next_rows"][key] = {"kernel": kname, "ms": ms_, "algorithmic_bytes": b_, "achieved_gbs": b_ / (ms_ * 1e-3) / 1e9,
+                                          "frac": b_ / (ms_ * 1e-3) / 1e9 / peak, "note": (note + "; " if note else "") + "timed on its own after the frames, not part of the step"}
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuArm(wl, args.cpu_rows)
             arm.prepare()

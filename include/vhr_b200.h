@@ -247,7 +247,8 @@ typedef enum vhr_option {
     VHR_OPT_DEBUG_REFLECTION_T = 9,/* 1: the ray pass also records the reflection ray's closest-hit distance */
     VHR_OPT_RAYGEN_VARIANT = 10    /* 0 (default): one thread per pixel, ray kinds in lock step; 1: persistent warps pulling pixels from a
                                       queue, every lane running its pixel's rays back to back. Same images either way; measured
-                                      slower on B200 (desynchronised lanes hit their leaves at different steps), kept for study */
+                                      slower on B200 (desynchronised lanes hit their leaves at different steps), kept for study;
+                                      2 / 3: variant 0 compiled for 8 resident blocks / SM (64 registers) / without a register cap (117) */
 } vhr_option;
 int vhr_set_option(vhr_context *ctx, int option, int64_t value);
 int64_t vhr_get_option(vhr_context *ctx, int option);

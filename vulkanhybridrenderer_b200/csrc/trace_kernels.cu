@@ -339,7 +339,12 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
     y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
 }
 
-__global__ void __launch_bounds__(128) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
+// MIN_BLOCKS is the occupancy target handed to ptxas (__launch_bounds__): 0 = unspecified (ptxas settles on 72 registers, 7
+// blocks / SM: the default); 8 caps the kernel at 64 registers for 8 blocks / SM (VHR_OPT_RAYGEN_VARIANT 2: more warps to hide
+// the node fetches, at the price of ~10 spilled words); 1 lifts the cap (variant 3: 117 registers, 4 blocks / SM, nothing
+// rematerialised). Experiments; same images in every variant.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     int x, y;
     tile_coords(x, y);
     uint32_t *__restrict__ out_sa = p.shadow_ao;
@@ -838,7 +843,7 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         const int mine = (n_blocks - pt.rank + pt.world - 1) / pt.world;          // blocks b = rank, rank + world, ...
         dim3 block(128), grid((width + 15) / 16, mine);
         if (mine > 0) {
-            raygen_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+            raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
             VHR_CUDA_CHECK(cudaGetLastError());
             ctx->launches++;
         }
@@ -859,7 +864,9 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         return VHR_OK;
     }
     dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
-    raygen_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    if (ctx->opt.raygen_variant == 2) raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    else if (ctx->opt.raygen_variant == 3) raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    else raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return VHR_OK;
