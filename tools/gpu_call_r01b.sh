@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box call: the whole -m gpu suite, ray-pass variants at the bench size, a short bench run.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --maxfail=20 -x --durations=8 > gpurun_out/r01b_pytest.log 2>&1
+python -m pytest tests -m gpu -q --maxfail=20 --durations=8 > gpurun_out/r01b_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/r01b_pytest.log
 tail -5 gpurun_out/r01b_pytest.log
 for v in 0 2 3; do
