@@ -103,3 +103,34 @@ def test_reflections_with_textures(textured):
     plain = scenes.sponza_like(40_000, seed=3, width=W, height=H, n_clutter=60)
     rp = O.OracleScene(plain).raygen(pfd, g["depth"], g["normals"], flags=4)
     assert np.abs(refl.astype(np.float32) - rp["reflections"].astype(np.float32)).max() > 0.05
+
+
+def test_gltf_scene_path_renders_like_direct_upload(tmp_path):
+    """SceneLoader::LoadScene (host/scene_loader.cpp) -> textures + UpdateGeometry -> one frame through the C++ render graph must
+    equal the frame of the same scene uploaded array by array (texture slots are renumbered by first use; the images cannot tell)."""
+    from vulkanhybridrenderer_b200 import gltf_export, host_api
+    from vulkanhybridrenderer_b200 import hybrid_path as HP
+    W, H = 160, 96
+    sc = scenes.add_procedural_textures(scenes.sponza_like(12_000, seed=5, width=W, height=H, n_clutter=20), size=32)
+    pfd = camera.FrameSequencer(W, H, sc.light).next(sc.camera)
+    path = gltf_export.export(sc, tmp_path / "scene.glb")
+    outs = []
+    for via_gltf in (False, True):
+        with host_api.Renderer(W, H) as r:
+            if via_gltf:
+                assert r.load_gltf(path) == len(sc.primitives)
+            else:
+                for i, t in enumerate(sc.textures):
+                    assert r.ctx.upload_texture_from_data(t.rgba, t.format, t.sampler) == i
+                r.load_scene(sc)
+            r.set_modes(shadow=0, ao=0, reflection=0, denoise=True)
+            r.set_gbuffer_producer(True)
+            r.render(pfd)
+            outs.append({n: r.ctx.image_download(n) for n in (HP.N_ALBEDO, HP.N_NORMALS, HP.N_MOTION, HP.N_DEPTH, HP.N_RT, HP.N_REFL, HP.N_RENDER_OUTPUT)})
+    for n in outs[0]:
+        a, b = outs[0][n], outs[1][n]
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), n
+    assert outs[1][HP.N_REFL].astype(np.float32).max() > 0
+    # a missing file leaves an empty scene (scene_loader.cpp:344-346), it does not throw
+    with host_api.Renderer(W, H) as r:
+        assert r.load_gltf(tmp_path / "nope.glb") == 0

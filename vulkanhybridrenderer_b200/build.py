@@ -70,7 +70,7 @@ def build_host(force=False):
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [os.path.join(ROOT, "include", "vhr_b200.h")]
     if force or _stale(LIB_HOST, deps + [LIB_CUDA]):
         _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", LIB_HOST] + srcs +
-             ["-L", HERE, "-l:libvhr_b200.so", "-Wl,-rpath,$ORIGIN"])
+             ["-L", HERE, "-l:libvhr_b200.so", "-lz", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST
 
 

@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
     bool found = false;
     float prev_step = 0.0f, final_step = 0.0f;
     float su, sv;
-    for (int i = 0; i < p.n_steps; ++i) {                                            // ssr.comp:89-108
+    // A sky pixel (depth 0 -> w = 0) has a non-finite P: every distance along its ray is inf or NaN, the window test
+    // 0.3 < delta < thickness can never pass, so the march is skipped (same result as walking all of it).
+    const bool finite_p = fabsf(P.x) <= 3.0e38f && fabsf(P.y) <= 3.0e38f && fabsf(P.z) <= 3.0e38f;
+    for (int i = 0; finite_p && i < p.n_steps; ++i) {                                            // ssr.comp:89-108
         const float offset = mul_rn(p.step_size, (float)i);
         const float delta = probe(p, pfd, P, dir, cam, offset, su, sv);
         if (delta > 0.3f && delta < p.thickness) {

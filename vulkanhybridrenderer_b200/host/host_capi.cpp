@@ -5,6 +5,7 @@
 #include <memory>
 
 #include "hybrid_render_path.h"
+#include "scene_loader.h"
 
 struct vhrh_renderer {
     std::unique_ptr<ResourceManager> resource_manager;
@@ -78,6 +79,76 @@ int vhrh_load_scene(vhrh_renderer *r, const void *vertices, uint32_t n_vertices,
         }
         r->resource_manager->UpdateGeometry(v, idx, scene);
     });
+}
+
+// ---- glTF scene path (scene_loader.h) ----------------------------------------------------------------------------------
+struct vhrh_parsed_scene { SceneLoader::ParsedScene parsed; };
+
+// SceneLoader::ParseScene: file -> flat arrays, no GPU involved
+int vhrh_parse_gltf(const char *path, vhrh_parsed_scene **out) {
+    if (!path || !out) return VHR_ERR_INVALID;
+    *out = nullptr;
+    auto p = std::make_unique<vhrh_parsed_scene>();
+    int rc = guarded(nullptr, [&] { SceneLoader::ParseScene(path, p->parsed); });
+    if (rc == VHR_OK) *out = p.release();
+    return rc;
+}
+void vhrh_parsed_scene_destroy(vhrh_parsed_scene *p) { delete p; }
+// counts[5] = vertices, indices, primitives, textures, meshes
+int vhrh_parsed_scene_counts(vhrh_parsed_scene *p, uint32_t *counts) {
+    if (!p || !counts) return VHR_ERR_INVALID;
+    uint32_t prims = 0;
+    for (const Mesh &m : p->parsed.scene.meshes) prims += (uint32_t)m.primitives.size();
+    counts[0] = (uint32_t)p->parsed.vertices.size(); counts[1] = (uint32_t)p->parsed.indices.size(); counts[2] = prims;
+    counts[3] = (uint32_t)p->parsed.textures.size(); counts[4] = (uint32_t)p->parsed.scene.meshes.size();
+    return VHR_OK;
+}
+// copies the flat arrays out (buffers sized from vhrh_parsed_scene_counts); primitives in mesh order = object ids
+int vhrh_parsed_scene_copy(vhrh_parsed_scene *p, void *vertices, uint32_t *indices, void *primitives, uint32_t *prims_per_mesh, void *camera,
+                           void *directional_light) {
+    if (!p) return VHR_ERR_INVALID;
+    const SceneLoader::ParsedScene &s = p->parsed;
+    if (vertices && !s.vertices.empty()) memcpy(vertices, s.vertices.data(), s.vertices.size() * sizeof(Vertex));
+    if (indices && !s.indices.empty()) memcpy(indices, s.indices.data(), s.indices.size() * sizeof(uint32_t));
+    Primitive *out = (Primitive *)primitives;
+    size_t k = 0, mi = 0;
+    for (const Mesh &m : s.scene.meshes) {
+        if (prims_per_mesh) prims_per_mesh[mi] = (uint32_t)m.primitives.size();
+        ++mi;
+        for (const Primitive &pr : m.primitives) { if (out) out[k] = pr; ++k; }
+    }
+    if (camera) memcpy(camera, &s.scene.camera, sizeof(Camera));
+    if (directional_light) memcpy(directional_light, &s.scene.directional_light, sizeof(DirectionalLight));
+    return VHR_OK;
+}
+// info[7] = width, height, VkFormat, mag, min, address u, address v; rgba may be NULL
+int vhrh_parsed_scene_texture(vhrh_parsed_scene *p, uint32_t index, int32_t *info, uint8_t *rgba) {
+    if (!p || index >= p->parsed.textures.size() || !info) return VHR_ERR_INVALID;
+    const SceneLoader::ParsedTexture &t = p->parsed.textures[index];
+    info[0] = (int32_t)t.width; info[1] = (int32_t)t.height; info[2] = (int32_t)t.format;
+    info[3] = t.sampler.mag_filter; info[4] = t.sampler.min_filter; info[5] = t.sampler.address_mode_u; info[6] = t.sampler.address_mode_v;
+    if (rgba) memcpy(rgba, t.rgba.data(), t.rgba.size());
+    return VHR_OK;
+}
+// SceneLoader::LoadScene (scene_loader.cpp:336-349) on the renderer's ResourceManager: textures, then UpdateGeometry.
+// An unreadable file leaves an empty scene, like the reference; returns the number of primitives loaded.
+int vhrh_load_gltf(vhrh_renderer *r, const char *path) {
+    if (!r || !path) return VHR_ERR_INVALID;
+    int n = 0;
+    int rc = guarded(r, [&] {
+        Scene s = SceneLoader::LoadScene(*r->resource_manager, path);
+        for (const Mesh &m : s.meshes) n += (int)m.primitives.size();
+    });
+    return rc == VHR_OK ? n : rc;
+}
+// wh[2] receives the extent; rgba (capacity bytes) the RGBA8 texels when large enough
+int vhrh_decode_png(const uint8_t *data, size_t size, uint32_t *wh, uint8_t *rgba, size_t capacity) {
+    if (!data || !wh) return VHR_ERR_INVALID;
+    std::vector<uint8_t> out;
+    std::string err;
+    if (!SceneLoader::DecodePNG(data, size, wh[0], wh[1], out, err)) { g_host_error = err; return VHR_ERR_INVALID; }
+    if (rgba && capacity >= out.size()) memcpy(rgba, out.data(), out.size());
+    return VHR_OK;
 }
 
 // The ImGui radio buttons of HybridRenderPath::ImGuiDrawSettings (hybrid_render_path.cpp:394-441) + Rebuild().

@@ -72,7 +72,19 @@ struct Material {
 struct Primitive { float transform[16]; Material material; uint32_t vertex_offset, index_offset, index_count; };
 static_assert(sizeof(Primitive) == 120, "Primitive must match glsl_common.h:82-99");
 struct Mesh { std::vector<Primitive> primitives; };
-struct Scene { std::vector<Mesh> meshes; };
+// vulkan_common.h:33-41,68-73; matrices are glm column-major (m[c*4+r])
+struct Camera {
+    float perspective[16];
+    float transform[16];
+    float view[16];
+    float yaw, pitch, roll;
+};
+struct Scene {
+    std::string name;
+    Camera camera{};
+    DirectionalLight directional_light{};
+    std::vector<Mesh> meshes;
+};
 
 struct SVGFPushConstants {
     glmlite::ivec2 integrated_shadow_and_ao;

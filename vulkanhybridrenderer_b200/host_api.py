@@ -15,7 +15,9 @@ from . import types as T
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvhr_host.so")
 SYMBOLS = ["vhrh_last_error", "vhrh_renderer_create", "vhrh_renderer_destroy", "vhrh_context", "vhrh_load_scene", "vhrh_set_modes",
-           "vhrh_set_gbuffer_producer", "vhrh_render", "vhrh_execution_order", "vhrh_pass_time_ms", "vhrh_svgf_push_constants"]
+           "vhrh_set_gbuffer_producer", "vhrh_render", "vhrh_execution_order", "vhrh_pass_time_ms", "vhrh_svgf_push_constants",
+           "vhrh_parse_gltf", "vhrh_parsed_scene_destroy", "vhrh_parsed_scene_counts", "vhrh_parsed_scene_copy", "vhrh_parsed_scene_texture",
+           "vhrh_load_gltf", "vhrh_decode_png"]
 
 SHADOW_MODE_RAYTRACED, SHADOW_MODE_RASTERIZED, SHADOW_MODE_OFF = 0, 1, 2
 AO_MODE_RAYTRACED, AO_MODE_SSAO, AO_MODE_OFF = 0, 1, 2
@@ -48,6 +50,14 @@ def lib():
         L.vhrh_pass_time_ms.argtypes = [vp, C.c_char_p, i32]
         L.vhrh_pass_time_ms.restype = C.c_double
         L.vhrh_svgf_push_constants.argtypes = [vp, vp]
+        L.vhrh_parse_gltf.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.vhrh_parsed_scene_destroy.argtypes = [vp]
+        L.vhrh_parsed_scene_destroy.restype = None
+        L.vhrh_parsed_scene_counts.argtypes = [vp, C.POINTER(u32)]
+        L.vhrh_parsed_scene_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.vhrh_parsed_scene_texture.argtypes = [vp, u32, C.POINTER(C.c_int32), vp]
+        L.vhrh_load_gltf.argtypes = [vp, C.c_char_p]
+        L.vhrh_decode_png.argtypes = [vp, C.c_size_t, C.POINTER(u32), vp, C.c_size_t]
         _lib = L
     return _lib
 
@@ -94,6 +104,10 @@ class Renderer:
         assert v.dtype == T.Vertex and p.dtype == T.Primitive
         _check(lib().vhrh_load_scene(self._r, capi._ptr(v), len(v), capi._ptr(i), len(i), capi._ptr(p), len(p), prims_per_mesh))
 
+    def load_gltf(self, path):
+        """SceneLoader::LoadScene (scene_loader.cpp:336-349): glTF file -> textures + UpdateGeometry. Returns the primitive count."""
+        return _check(lib().vhrh_load_gltf(self._r, str(path).encode()))
+
     def set_modes(self, shadow=SHADOW_MODE_RAYTRACED, ao=AO_MODE_OFF, reflection=REFLECTION_MODE_OFF, denoise=False, svgf_fused=False):
         _check(lib().vhrh_set_modes(self._r, shadow, ao, reflection, int(denoise), int(svgf_fused)))
 
@@ -116,3 +130,44 @@ class Renderer:
         pc = np.zeros((), T.SVGFPushConstants)
         _check(lib().vhrh_svgf_push_constants(self._r, capi._ptr(pc)))
         return pc
+
+
+# Camera of vulkan_common.h:33-41 (column-major matrices)
+CameraPOD = np.dtype([("perspective", np.float32, (4, 4)), ("transform", np.float32, (4, 4)), ("view", np.float32, (4, 4)),
+                      ("yaw", np.float32), ("pitch", np.float32), ("roll", np.float32)])
+
+
+def parse_gltf(path):
+    """SceneLoader::ParseScene through the C++ host: a glTF 2.0 file -> the flat arrays UpdateGeometry consumes. No GPU needed.
+    Returns dict(vertices, indices, primitives, prims_per_mesh, camera, light, textures=[(rgba, format, sampler)])."""
+    from . import scenes
+    h = C.c_void_p()
+    _check(lib().vhrh_parse_gltf(str(path).encode(), C.byref(h)))
+    try:
+        counts = (C.c_uint32 * 5)()
+        _check(lib().vhrh_parsed_scene_counts(h, counts))
+        nv, ni, npr, nt, nm = (int(c) for c in counts)
+        v = np.zeros(nv, T.Vertex); i = np.zeros(ni, np.uint32); p = np.zeros(npr, T.Primitive); ppm = np.zeros(nm, np.uint32)
+        cam = np.zeros((), CameraPOD); light = np.zeros((), T.DirectionalLight)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(lib().vhrh_parsed_scene_copy(h, ptr(v), ptr(i), ptr(p), ptr(ppm), ptr(cam), ptr(light)))
+        textures = []
+        for k in range(nt):
+            info = (C.c_int32 * 7)()
+            _check(lib().vhrh_parsed_scene_texture(h, k, info, None))
+            rgba = np.zeros((info[1], info[0], 4), np.uint8)
+            _check(lib().vhrh_parsed_scene_texture(h, k, info, ptr(rgba)))
+            textures.append(scenes.Texture(rgba, int(info[2]), tuple(int(x) for x in info[3:7])))
+        return dict(vertices=v, indices=i, primitives=p, prims_per_mesh=ppm, camera=cam, light=light, textures=textures)
+    finally:
+        lib().vhrh_parsed_scene_destroy(h)
+
+
+def decode_png(data):
+    """SceneLoader::DecodePNG: bytes -> [H, W, 4] uint8."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    wh = (C.c_uint32 * 2)()
+    _check(lib().vhrh_decode_png(buf.ctypes.data_as(C.c_void_p), buf.size, wh, None, 0))
+    out = np.zeros((wh[1], wh[0], 4), np.uint8)
+    _check(lib().vhrh_decode_png(buf.ctypes.data_as(C.c_void_p), buf.size, wh, out.ctypes.data_as(C.c_void_p), out.nbytes))
+    return out
