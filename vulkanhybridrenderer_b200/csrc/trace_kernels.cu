@@ -239,6 +239,79 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
     return found;
 }
 
+// trace() with POSTPONED LEAVES (Aila & Laine's speculative traversal, adapted to leaf slots that live inside the wide
+// node). The profile of trace() shows the triangle block (leaf-slot decode + fetch + watertight test, ~23 % of all issued
+// instructions) running at 2-4 of 32 lanes: a lane tests its triangles the moment its node reports a leaf hit while the
+// other lanes wait. Here a lane that finds leaf hits only notes them (node index + slot mask, two registers) and keeps
+// traversing; the whole warp runs the triangle block together when a lane cannot go on without it (it found a second
+// leaf node, or it has no nodes left) or when at least `batch` lanes have work noted. Every lane of the warp must call
+// this together (full mask votes); `alive` = this lane really has a ray. Results are identical to trace(): the same
+// nodes' leaves are tested, only later (a postponed any-hit leaf may cost the lane a few extra node steps that the warp
+// was going to issue anyway).
+template <bool ANY, class Accept = AcceptAll>
+__device__ __forceinline__ bool trace_batched(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
+                                              uint32_t bias, const Ray &ray, bool alive, Hit &hit, int batch, const Accept accept = Accept()) {
+    const unsigned FULL = 0xffffffffu;
+    const RayPre r = prepare(ray);
+    float tmax = ray.tmax;
+    bool found = false;
+    bool done = !alive || n_wide == 0;
+    uint2 stack[kStackSize];
+    int sp = 0;
+    uint2 group = make_uint2(0u, 1u);   // (child_base, hit mask over child ordinals): the root
+    uint32_t pend_node = 0u, pend_leaves = 0u;       // postponed leaf work: node index + hit leaf slots
+    while (true) {
+        uint32_t new_node = 0u, new_leaves = 0u;
+        if (!done) {
+            bool have = true;
+            if (group.y == 0u) {
+                if (sp == 0) have = false;
+                else group = stack[--sp];
+            }
+            if (have) {
+                const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
+                group.y &= group.y - 1u;
+                if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
+                const uint32_t node = group.x + k;
+                uint32_t child_base, child_hits, leaf_hits;
+                intersect_node(nodes, node, r, ray.tmin, tmax, bias, child_base, child_hits, leaf_hits);
+                group = make_uint2(child_base, child_hits);
+                new_node = node; new_leaves = leaf_hits;
+            }
+        }
+        const bool more_nodes = !done && (group.y != 0u || sp != 0);
+        bool urgent = false;
+        if (new_leaves) {
+            if (pend_leaves) urgent = true;                       // second leaf node: the noted one has to be tested first
+            else { pend_node = new_node; pend_leaves = new_leaves; new_leaves = 0u; }
+        }
+        if (!done && pend_leaves && !more_nodes) urgent = true;   // nothing left to traverse: the answer hangs on the noted leaves
+        const unsigned pending = __ballot_sync(FULL, !done && pend_leaves != 0u);
+        const bool run = __any_sync(FULL, urgent) || __popc(pending) >= batch;
+        if (run && !done && pend_leaves) {
+            uint32_t tri_base, tri_hits;
+            expand_leaves(nodes, pend_node, pend_leaves, tri_base, tri_hits);
+            do {
+                const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
+                tri_hits &= tri_hits - 1u;
+                const float4 *tp = tris + (size_t)(tri_base + j) * 3;
+                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                float t, u, v;
+                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && accept(tri_base + j, u, v)) {
+                    found = true;
+                    if (ANY) { done = true; break; }
+                    tmax = t;
+                    hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
+                }
+            } while (tri_hits);
+            pend_node = new_node; pend_leaves = new_leaves;       // the leaf node found this round (if any) is noted next
+        }
+        if (!done && !pend_leaves && group.y == 0u && sp == 0) done = true;
+        if (__all_sync(FULL, done)) break;
+    }
+    return found;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shading of the reflection ray: reflection_hit.rchit:10-72
 // ---------------------------------------------------------------------------------------------------------------
@@ -317,6 +390,7 @@ struct RaygenParams {
     int y_begin, y_end;
     int ao_spp;
     int flags;                // bit0 shadows, bit1 AO, bit2 reflections
+    int leaf_batch;           // trace_batched: lanes with noted leaf work that trigger the triangle block
     const uint2 *normals;     // binding 0
     const float *depth;       // binding 1
     uint32_t *shadow_ao;      // binding 2 (RG16F)
@@ -343,7 +417,7 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
 // blocks / SM: the default); 8 caps the kernel at 64 registers for 8 blocks / SM (VHR_OPT_RAYGEN_VARIANT 2: more warps to hide
 // the node fetches, at the price of ~10 spilled words); 1 lifts the cap (variant 3: 117 registers, 4 blocks / SM, nothing
 // rematerialised). Experiments; same images in every variant.
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool BATCHED = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     int x, y;
     tile_coords(x, y);
@@ -389,7 +463,9 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_co
         const float3 cone = normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f));
         ray.d = onb_apply(L, cone);
         ray.tmax = 10000.0f;
-        shadow = trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit) ? 0.0f : 1.0f;
+        const bool occluded = BATCHED ? trace_batched<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
+                                      : trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+        shadow = occluded ? 0.0f : 1.0f;
     }
     // ambient occlusion (raygen.rgen:44-55)
     float ao = 0.0f;
@@ -399,7 +475,9 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_co
         if (p.flags & 2) {
             ray.d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
             ray.tmax = 5.0f;
-            ao = add_rn(ao, trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit) ? 0.0f : 1.0f);
+            const bool occluded = BATCHED ? trace_batched<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
+                                          : trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+            ao = add_rn(ao, occluded ? 0.0f : 1.0f);
         } else {
             ao = add_rn(ao, 1.0f);
         }
@@ -416,7 +494,9 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_co
         const float k2 = mul_rn(2.0f, dot3_rn(N, I));
         ray.d = make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2)));
         ray.tmax = 10000.0f;
-        if (trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit) && lit) {
+        const bool refl_hit = BATCHED ? trace_batched<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
+                                      : trace<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+        if (refl_hit && lit) {
             payload = reflection_hit(p.scene, pfd, hit);
             rt = hit.t;
         }
@@ -864,7 +944,10 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         return VHR_OK;
     }
     dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
-    if (ctx->opt.raygen_variant == 2) raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    p.leaf_batch = getenv("VHR_LEAF_BATCH") ? atoi(getenv("VHR_LEAF_BATCH")) : 12;
+    if (ctx->opt.raygen_variant == 4) raygen_kernel<0, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    else if (ctx->opt.raygen_variant == 5) raygen_kernel<8, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    else if (ctx->opt.raygen_variant == 2) raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     else if (ctx->opt.raygen_variant == 3) raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     else raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());
