@@ -92,6 +92,7 @@ def test_geometry_edge_cases():
         prim["material"]["base_color"] = (1, 1, 1, 1)
         prim["material"]["base_color_texture"] = -1
         prim["material"]["metallic_roughness_texture"] = -1
+        prim["material"]["normal_map"] = -1
         ray_hit = np.array([[0, 0, 0, 0.01, 0, 0, 1, 100]], np.float32)
         ray_miss = np.array([[3, 0, 0, 0.01, 0, 0, 1, 100]], np.float32)
         ray_short = np.array([[0, 0, 0, 0.01, 0, 0, 1, 4.5]], np.float32)
