@@ -163,7 +163,11 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
 
 /* RaytracingExecutionContext::TraceRays (src/render_graph/raytracing_execution_context.cpp:4-13) of the pipeline
  * raygen.rgen + miss.rmiss + reflection_miss.rmiss + reflection_hit.rchit (hybrid_render_path.cpp:111-123).
- * Bound images: 0 normals/object ids, 1 depth, 2 shadow+AO (RG16F), 3 reflections (RGBA16F). */
+ * Bound images: 0 normals/object ids, 1 depth, 2 shadow+AO (RG16F), 3 reflections (RGBA16F).
+ * "Raytracing Pipeline" is the fully ray-traced render path's (src/render_paths/raytraced_render_path.cpp:12-47: raygen.rgen +
+ * closesthit.rchit + miss.rmiss + shadow_miss.rmiss, or the *_test_alpha shaders + shadow_anyhit.rahit with
+ * VHR_OPT_RAYTRACED_ALPHA_TEST): primary ray, textured / normal-mapped Lambert shading, one shadow ray. Bound image: 0
+ * "RaytracedOutput" (B8G8R8A8_UNORM). */
 int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height);
 
 /* GraphicsExecutionContext::Draw (src/render_graph/graphics_execution_context.cpp:38-41) inside
@@ -175,7 +179,9 @@ int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, 
  * 2 motion/metallic-roughness, 3 depth, 4 shadow map, 5 SSAO, 6 SSR, 7 shadow+AO — denoised RGBA16F or raw RG16F —,
  * 8 reflections) followed by colour attachment 0 (RENDER_OUTPUT) at index 9. The attachment may be B8G8R8A8_SRGB (the
  * reference's swapchain: sRGB-encoded on store), B8G8R8A8_UNORM, or R16G16B16A16_SFLOAT (linear HDR radiance, for
- * parity measurements). Any other shader or draw shape fails with VHR_ERR_INVALID (there is no rasteriser). */
+ * parity measurements). "raytraced_render_path/composition.frag" (raytraced_render_path.cpp:49-76; no constants) copies
+ * bound image 0 (RaytracedOutput) to the attachment at index 1, sRGB-encoding when it is B8G8R8A8_SRGB.
+ * Any other shader or draw shape fails with VHR_ERR_INVALID (there is no rasteriser). */
 int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *specialization_constants, uint32_t n_constants,
              uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance);
 
@@ -245,10 +251,13 @@ typedef enum vhr_option {
                                       packed fp32x2 kernel with register-level tap reuse; 3: variant 2's arithmetic in a persistent
                                       CTA with TMA-staged tiles (measured 4-8 % slower than 2 on B200: kept for study) */
     VHR_OPT_DEBUG_REFLECTION_T = 9,/* 1: the ray pass also records the reflection ray's closest-hit distance */
-    VHR_OPT_RAYGEN_VARIANT = 10    /* 0 (default): one thread per pixel, ray kinds in lock step; 1: persistent warps pulling pixels from a
-                                      queue, every lane running its pixel's rays back to back. Same images either way; measured
-                                      slower on B200 (desynchronised lanes hit their leaves at different steps), kept for study;
-                                      2 / 3: variant 0 compiled for 8 resident blocks / SM (64 registers) / without a register cap (117) */
+    VHR_OPT_RAYGEN_VARIANT = 10,   /* 0 (default): one thread per pixel, ray kinds in lock step, built for 8 resident blocks / SM (64 registers);
+                                      1: persistent warps pulling pixels from a queue, every lane running its pixel's rays back to back;
+                                      2 / 3: variant 0 with ptxas' own register choice (72) / without a register cap (117);
+                                      4: variant 0 with postponed leaves (the warp runs the triangle block together).
+                                      Same images in every variant; 1-4 measured slower on B200, kept for study */
+    VHR_OPT_RAYTRACED_ALPHA_TEST = 11 /* the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14): 1 selects the pipeline
+                                      raygen_test_alpha.rgen + closesthit_test_alpha.rchit + shadow_anyhit.rahit */
 } vhr_option;
 int vhr_set_option(vhr_context *ctx, int option, int64_t value);
 int64_t vhr_get_option(vhr_context *ctx, int option);

@@ -84,6 +84,7 @@ def _declare(L):
     L.vo_trace_closest.restype = C.c_int
     L.vo_trace_closest.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp, vp]
     L.vo_raygen.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.vo_raytraced.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.vo_gbuffer.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
 
 
@@ -234,6 +235,12 @@ class OracleScene:
         if want_ids:
             g["ids"] = ids
         return g
+
+    def raytraced(self, pfd, W, H, alpha_test=False):
+        """The fully ray-traced render path's "Raytracing Pass": [H, W, 4] uint8 B8G8R8A8_UNORM "RaytracedOutput"."""
+        out = np.empty((H, W, 4), np.uint8)
+        lib().vo_raytraced(self._s, _p(pfd), W, H, int(bool(alpha_test)), _p(out))
+        return out
 
     def raygen(self, pfd, depth, normals, ao_spp=2, flags=7, rows=None, want_t=False):
         H, W = depth.shape[:2]

@@ -554,6 +554,89 @@ void vo_raygen(const vo_scene *s_, const PerFrameData *pfd_, int W, int H, int y
     if (ray_count) *ray_count = rays;
 }
 
+// The fully ray-traced render path: raytraced_render_path/raygen.rgen:11-23, closesthit.rchit:10-58, miss.rmiss:6-8,
+// shadow_miss.rmiss:6-8; alpha_test != 0 = raygen_test_alpha.rgen / closesthit_test_alpha.rchit / shadow_anyhit.rahit:9-27
+// ("Raytracing Pass", src/render_paths/raytraced_render_path.cpp:12-47). Output: "RaytracedOutput", B8G8R8A8_UNORM.
+void vo_raytraced(const vo_scene *s_, const PerFrameData *pfd_, int W, int H, int alpha_test, uint8_t *out_bgra8) {
+    const Scene &s = *reinterpret_cast<const Scene *>(s_);
+    const PerFrameData &pfd = *pfd_;
+    // shadow_anyhit.rahit:22-26 (the shader samples textures[base_color_texture] unconditionally; index -1 counts as opaque here)
+    auto rahit = [&](uint32_t tri, double hu, double hv) {
+        const Primitive &pr = s.primitives[s.tri_geom[tri]];
+        if (pr.material.alpha_mask != 1 || !has_texture(s, pr.material.base_color_texture)) return true;
+        uint32_t k = s.tri_prim[tri];
+        const Vertex &a0 = s.vertices[pr.vertex_offset + s.indices[pr.index_offset + 3 * k + 0]];
+        const Vertex &a1 = s.vertices[pr.vertex_offset + s.indices[pr.index_offset + 3 * k + 1]];
+        const Vertex &a2 = s.vertices[pr.vertex_offset + s.indices[pr.index_offset + 3 * k + 2]];
+        float c1 = (float)hu, c2 = (float)hv, c0 = 1.0f - c1 - c2;
+        vec2 uvt = {a0.uv0[0] * c0 + a1.uv0[0] * c1 + a2.uv0[0] * c2, a0.uv0[1] * c0 + a1.uv0[1] * c1 + a2.uv0[1] * c2};
+        return !(sample_texture(s, pr.material.base_color_texture, uvt).w < pr.material.alpha_cutoff);
+    };
+    auto opaque = [](uint32_t, double, double) { return true; };
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            vec2 uv_ = {((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H};
+            vec2 uv = {uv_.x * 2.0f - 1.0f, uv_.y * 2.0f - 1.0f};
+            vec4 origin = mul44(pfd.camera_view_inverse, vec4{0, 0, 0, 1});
+            vec4 target = mul44(pfd.camera_proj_inverse, vec4{uv.x, uv.y, 1, 1});
+            vec3 tn = normalize(v3(target.x, target.y, target.z));
+            vec4 direction = mul44(pfd.camera_view_inverse, vec4{tn.x, tn.y, tn.z, 0});
+            vec4 payload = {0.3f, 0.8f, 0.2f, 1.0f};                                              // miss.rmiss:7
+            Hit h;
+            bool hit = alpha_test ? trace_closest_filtered(s, v3(origin.x, origin.y, origin.z), v3(direction.x, direction.y, direction.z), 0.1f, 10000.0f, h, rahit)
+                                  : trace_closest_filtered(s, v3(origin.x, origin.y, origin.z), v3(direction.x, direction.y, direction.z), 0.1f, 10000.0f, h, opaque);
+            if (hit) {
+                uint32_t g = s.tri_geom[h.tri], pid = s.tri_prim[h.tri];
+                const Primitive &prim = s.primitives[g];
+                const Vertex &v0 = s.vertices[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 0]];
+                const Vertex &v1 = s.vertices[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 1]];
+                const Vertex &v2 = s.vertices[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 2]];
+                float b1 = (float)h.u, b2 = (float)h.v, b0 = 1.0f - b1 - b2;
+                vec2 tuv = {v0.uv0[0] * b0 + v1.uv0[0] * b1 + v2.uv0[0] * b2, v0.uv0[1] * b0 + v1.uv0[1] * b1 + v2.uv0[1] * b2};
+                vec3 normal = v3(v0.normal[0], v0.normal[1], v0.normal[2]) * b0 + v3(v1.normal[0], v1.normal[1], v1.normal[2]) * b1 +
+                              v3(v2.normal[0], v2.normal[1], v2.normal[2]) * b2;
+                vec3 pobj = v3(v0.pos[0], v0.pos[1], v0.pos[2]) * b0 + v3(v1.pos[0], v1.pos[1], v1.pos[2]) * b1 +
+                            v3(v2.pos[0], v2.pos[1], v2.pos[2]) * b2;
+                vec4 pw = mul44(prim.transform, vec4{pobj.x, pobj.y, pobj.z, 1.0f});
+                vec3 position = v3(pw.x, pw.y, pw.z);
+                vec3 albedo = v3(prim.material.base_color[0], prim.material.base_color[1], prim.material.base_color[2]);
+                if (has_texture(s, prim.material.base_color_texture)) {
+                    vec4 c = sample_texture(s, prim.material.base_color_texture, tuv);
+                    albedo = v3(c.x, c.y, c.z);
+                }
+                vec3 N = normal;
+                if (has_texture(s, prim.material.normal_map)) {                                   // closesthit.rchit:35-41
+                    vec3 tan3 = v3(v0.tangent[0], v0.tangent[1], v0.tangent[2]) * b0 + v3(v1.tangent[0], v1.tangent[1], v1.tangent[2]) * b1 +
+                                v3(v2.tangent[0], v2.tangent[1], v2.tangent[2]) * b2;
+                    float tw = v0.tangent[3] * b0 + v1.tangent[3] * b1 + v2.tangent[3] * b2;
+                    vec4 c = sample_texture(s, prim.material.normal_map, tuv);
+                    vec3 tsn = normalize(v3(c.x * 2.0f - 1.0f, c.y * 2.0f - 1.0f, c.z * 2.0f - 1.0f));
+                    vec3 bitangent = cross(tsn, tan3) * tw;
+                    vec3 tangent = normalize(tan3 - normal * dot(tan3, normal));
+                    N = tangent * tsn.x + bitangent * tsn.y + normal * tsn.z;
+                }
+                vec3 light_dir = -v3(pfd.directional_light.direction[0], pfd.directional_light.direction[1], pfd.directional_light.direction[2]);
+                vec3 lc = v3(pfd.directional_light.color[0], pfd.directional_light.color[1], pfd.directional_light.color[2]);
+                vec3 li = v3(pfd.directional_light.intensity[0], pfd.directional_light.intensity[1], pfd.directional_light.intensity[2]);
+                Hit sh;
+                bool occluded = alpha_test ? trace_closest_filtered(s, position, light_dir, 0.1f, 10000.0f, sh, rahit) : trace_any(s, position, light_dir, 0.1f, 10000.0f);
+                vec3 albedo_lighting = albedo * (alpha_test ? 0.2f : PI_INVERSE_F);
+                vec3 c = albedo_lighting;
+                if (!occluded) {
+                    float ndl = gl_max(dot(N, light_dir), 0.0f);
+                    vec3 lit = alpha_test ? (albedo * ndl) * lc : ((albedo * ndl) * li) * lc;
+                    c = albedo_lighting + lit;
+                }
+                payload = vec4{c.x, c.y, c.z, 1.0f};
+            }
+            auto q = [](float f) { f = (f == f) ? std::min(std::max(f, 0.0f), 1.0f) : 0.0f; return (uint8_t)std::lrintf(f * 255.0f); };
+            uint8_t *o = out_bgra8 + ((size_t)y * W + x) * 4;
+            o[0] = q(payload.z); o[1] = q(payload.y); o[2] = q(payload.x); o[3] = q(payload.w);
+        }
+    }
+}
+
 // G-buffer scaffolding: primary rays through texel centres stand in for the rasteriser of the "G-Buffer Pass"
 // (hybrid_render_path.cpp:13-56). Encodings follow gbuf.frag:33,43,46-58; clear values hybrid_render_path.cpp:16-19.
 // Also returns the closest-hit record per pixel (tri_geom, tri_prim, t) for debugging when `hit_ids` != NULL.

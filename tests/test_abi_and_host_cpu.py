@@ -108,6 +108,19 @@ def test_execution_order_matches_reference_algorithm(modes, want):
             assert got.index("SSAO Pass") < got.index("SSAO Blur Pass")
 
 
+def test_raytraced_path_graph():
+    """raytraced_render_path.cpp:11-78: two nodes; switching between the render paths re-registers the nodes."""
+    with host_api.Renderer(128, 72, device=host_api.DEVICE_NONE) as r:
+        r.set_raytraced_path(False)
+        assert r.execution_order() == ["Raytracing Pass", "Composition Pass"]
+        r.set_raytraced_path(True)                                   # Rebuild() with the alpha-tested pipeline
+        assert r.execution_order() == ["Raytracing Pass", "Composition Pass"]
+        r.set_modes(shadow=0, ao=0, reflection=0, denoise=True)
+        assert r.execution_order() == [G, RT, SVGF, COMP]
+        r.set_raytraced_path(False)
+        assert r.execution_order() == ["Raytracing Pass", "Composition Pass"]
+
+
 def test_rebuild_recreates_svgf_storage_images():
     with host_api.Renderer(128, 72, device=host_api.DEVICE_NONE) as r:
         r.set_modes(shadow=0, ao=0, reflection=2, denoise=True)

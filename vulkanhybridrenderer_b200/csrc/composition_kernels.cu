@@ -182,6 +182,48 @@ __global__ void __launch_bounds__(256) composition_kernel(const __grid_constant_
     }
 }
 
+// raytraced_render_path/composition.frag:11-13 drawn as the full-screen triangle of composition.vert: out_color = texture(raytraced_output,
+// in_uv) at the pixel centre = the texel, stored to RENDER_OUTPUT (sRGB-encoded when the attachment is B8G8R8A8_SRGB; alpha stays linear).
+struct PresentParams {
+    int W, H, y_begin, y_end, out_format;
+    const uint32_t *in;      // binding 0: RaytracedOutput, B8G8R8A8_UNORM
+    void *out;
+};
+__global__ void __launch_bounds__(256) present_kernel(const __grid_constant__ PresentParams p) {
+    const int x = blockIdx.x * 64 + threadIdx.x, y = p.y_begin + blockIdx.y * 4 + threadIdx.y;
+    if (x >= p.W || y >= p.y_end) return;
+    const size_t pix = (size_t)y * p.W + x;
+    const uint32_t c = __ldg(&p.in[pix]);
+    if (p.out_format == VHR_FORMAT_B8G8R8A8_UNORM) { reinterpret_cast<uint32_t *>(p.out)[pix] = c; return; }
+    const float b = fdiv((float)(c & 0xffu), 255.0f), g = fdiv((float)((c >> 8) & 0xffu), 255.0f), r = fdiv((float)((c >> 16) & 0xffu), 255.0f);
+    if (p.out_format == VHR_FORMAT_R16G16B16A16_SFLOAT) {
+        reinterpret_cast<uint2 *>(p.out)[pix] = pack_rgba16f(make_float4(r, g, b, fdiv((float)(c >> 24), 255.0f)));
+        return;
+    }
+    reinterpret_cast<uint32_t *>(p.out)[pix] = unorm8_rn(srgb_encode(b)) | (unorm8_rn(srgb_encode(g)) << 8) | (unorm8_rn(srgb_encode(r)) << 16) | (c & 0xff000000u);
+}
+
+int launch_present(vhr_context *ctx) {
+    // "Composition Pass" of the ray-traced path (raytraced_render_path.cpp:49-76): 0 RaytracedOutput (sampled), colour attachment 0 at index 1
+    if (ctx->n_bound < 2 || !ctx->bound[0] || !ctx->bound[1]) return fail(VHR_ERR_STATE, "raytraced composition: images not bound (RaytracedOutput + the render output)");
+    Image *in = ctx->bound[0], *out = ctx->bound[1];
+    if (in->format != VHR_FORMAT_B8G8R8A8_UNORM) return fail(VHR_ERR_INVALID, "raytraced composition: binding 0 has format %d", in->format);
+    if (out->format != VHR_FORMAT_B8G8R8A8_SRGB && out->format != VHR_FORMAT_B8G8R8A8_UNORM && out->format != VHR_FORMAT_R16G16B16A16_SFLOAT)
+        return fail(VHR_ERR_INVALID, "raytraced composition: render output format %d", out->format);
+    if (in->width != out->width || in->height != out->height) return fail(VHR_ERR_INVALID, "raytraced composition: image sizes differ");
+    PresentParams p;
+    p.W = (int)out->width; p.H = (int)out->height;
+    p.y_begin = std::max(0, ctx->opt.row_begin);
+    p.y_end = ctx->opt.row_end < 0 ? p.H : std::min(p.H, ctx->opt.row_end);
+    if (p.y_end <= p.y_begin) return VHR_OK;
+    p.out_format = out->format; p.in = (const uint32_t *)in->ptr; p.out = out->ptr;
+    dim3 block(64, 4), grid((p.W + 63) / 64, (p.y_end - p.y_begin + 3) / 4);
+    present_kernel<<<grid, block, 0, ctx->stream>>>(p);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
 int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int reflection_mode) {
     // descriptor set 3 of the "Composition Pass" (hybrid_render_path.cpp:335-349): 0 albedo, 1 normals, 2 motion, 3 depth,
     // 4 shadow map, 5 SSAO, 6 SSR, 7 (denoised) shadow+AO, 8 reflections; colour attachment 0 follows at index 9

@@ -413,10 +413,12 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
     y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
 }
 
-// MIN_BLOCKS is the occupancy target handed to ptxas (__launch_bounds__): 0 = unspecified (ptxas settles on 72 registers, 7
-// blocks / SM: the default); 8 caps the kernel at 64 registers for 8 blocks / SM (VHR_OPT_RAYGEN_VARIANT 2: more warps to hide
-// the node fetches, at the price of ~10 spilled words); 1 lifts the cap (variant 3: 117 registers, 4 blocks / SM, nothing
-// rematerialised). Experiments; same images in every variant.
+// MIN_BLOCKS is the occupancy target handed to ptxas (__launch_bounds__). Measured at 1080p / 3 M triangles (gpurun_out/r01c_trace.log):
+//   8 (default): 64 registers, 8 blocks / SM, ~10 spilled words — 0.879 ms shadow+AO, 2.40 ms shadow + 2 AO + reflection;
+//   0 (VHR_OPT_RAYGEN_VARIANT 2): unspecified, ptxas settles on 72 registers / 7 blocks — 0.883 / 2.47 ms;
+//   1 (variant 3): no cap, 117 registers / 4 blocks — 1.16 / 3.39 ms (fewer warps to hide the node fetches);
+//   BATCHED (variant 4): trace_batched — 1.00 / 2.57 ms: postponing leaves costs the any-hit rays more node steps than the fuller
+//   triangle block saves. Same images in every variant.
 template <int MIN_BLOCKS, bool BATCHED = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     int x, y;
@@ -840,6 +842,124 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const __grid_constant__ Gb
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The fully ray-traced render path: raytraced_render_path/raygen.rgen:11-23 + closesthit.rchit:10-58 +
+// miss.rmiss:6-8 + shadow_miss.rmiss:6-8, and the alpha-tested pipeline raygen_test_alpha.rgen / closesthit_test_alpha.rchit /
+// shadow_anyhit.rahit:9-27 ("Raytracing Pass", src/render_paths/raytraced_render_path.cpp:12-47)
+// ---------------------------------------------------------------------------------------------------------------
+struct RaytracedParams {
+    int W, H;
+    int y_begin, y_end;
+    uint32_t *out;            // binding 0: "RaytracedOutput", B8G8R8A8_UNORM storage image
+    SceneRefs scene;
+};
+
+// shadow_anyhit.rahit:22-26: a candidate whose base-colour texel is below the cutoff of an alpha-masked material is ignored
+// (ignoreIntersectionEXT). The shader samples textures[base_color_texture] unconditionally; without a texture (index -1, an
+// out-of-bounds descriptor in the reference) the candidate counts as opaque here.
+struct RahitAlphaTest {
+    const SceneRefs &s;
+    __device__ __forceinline__ bool operator()(uint32_t tri, float u, float v) const {
+        const float4 *tp = s.tris + (size_t)tri * 3;
+        const uint32_t g = __float_as_uint(__ldg(tp).w), pid = __float_as_uint(__ldg(tp + 1).w);
+        const Primitive &prim = s.prims[g];
+        if (prim.material.alpha_mask != 1 || !has_texture(s, prim.material.base_color_texture)) return true;
+        const Vertex &v0 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 0]];
+        const Vertex &v1 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 1]];
+        const Vertex &v2 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 2]];
+        const float2 uv = bary_uv(v0, v1, v2, sub_rn(sub_rn(1.0f, u), v), u, v);
+        return !(sample_texture(s.textures, s.lut, prim.material.base_color_texture, uv.x, uv.y).w < prim.material.alpha_cutoff);
+    }
+};
+
+template <bool ALPHA>
+__global__ void __launch_bounds__(128) raytraced_kernel(const __grid_constant__ RaytracedParams p, const __grid_constant__ PerFrameData pfd) {
+    int x, y;
+    tile_coords(x, y);
+    y += p.y_begin;
+    const bool in_range = x < p.W && y < p.y_end;       // trace() is warp-synchronous: no early return
+    const SceneRefs &s = p.scene;
+    // raygen.rgen:12-18
+    const float u = sub_rn(mul_rn(__fdiv_rn(add_rn((float)x, 0.5f), (float)p.W), 2.0f), 1.0f);
+    const float v = sub_rn(mul_rn(__fdiv_rn(add_rn((float)y, 0.5f), (float)p.H), 2.0f), 1.0f);
+    const float4 o4 = mul44_rn(pfd.camera_view_inverse, make_float4(0.0f, 0.0f, 0.0f, 1.0f));
+    const float4 target = mul44_rn(pfd.camera_proj_inverse, make_float4(u, v, 1.0f, 1.0f));
+    const float3 tn = normalize_rn(make_float3(target.x, target.y, target.z));
+    const float4 d4 = mul44_rn(pfd.camera_view_inverse, make_float4(tn.x, tn.y, tn.z, 0.0f));
+    Ray ray;
+    ray.o = make_float3(o4.x, o4.y, o4.z);
+    ray.d = make_float3(d4.x, d4.y, d4.z);
+    ray.tmin = 0.1f;
+    ray.tmax = 10000.0f;
+    Hit h;
+    const bool found = ALPHA ? trace<false>(s.nodes, s.tris, s.n_wide, s.bias, ray, in_range, h, RahitAlphaTest{s})
+                             : trace<false>(s.nodes, s.tris, s.n_wide, s.bias, ray, in_range, h);
+    float4 payload = make_float4(0.3f, 0.8f, 0.2f, 1.0f);                                    // miss.rmiss:7
+    Ray sray;
+    sray.o = make_float3(0.0f, 0.0f, 0.0f); sray.d = make_float3(0.0f, 1.0f, 0.0f); sray.tmin = 0.1f; sray.tmax = 10000.0f;
+    float3 albedo = make_float3(0.0f, 0.0f, 0.0f), N = make_float3(0.0f, 0.0f, 0.0f);
+    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+    const bool shade = in_range && found;
+    if (shade) {                                                                             // closesthit.rchit:11-41
+        const float4 *tp = s.tris + (size_t)h.tri * 3;
+        const uint32_t g = __float_as_uint(__ldg(tp).w), pid = __float_as_uint(__ldg(tp + 1).w);
+        const Primitive &prim = s.prims[g];
+        const Vertex &v0 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 0]];
+        const Vertex &v1 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 1]];
+        const Vertex &v2 = s.verts[prim.vertex_offset + s.indices[prim.index_offset + 3 * pid + 2]];
+        const float b1 = h.u, b2 = h.v, b0 = sub_rn(sub_rn(1.0f, b1), b2);
+        const float2 uv = bary_uv(v0, v1, v2, b0, b1, b2);
+        const float3 normal = bary3(f3(v0.normal), f3(v1.normal), f3(v2.normal), b0, b1, b2);
+        const float3 pobj = bary3(f3(v0.pos), f3(v1.pos), f3(v2.pos), b0, b1, b2);
+        const float4 pw = mul44_rn(prim.transform, make_float4(pobj.x, pobj.y, pobj.z, 1.0f));
+        albedo = make_float3(prim.material.base_color[0], prim.material.base_color[1], prim.material.base_color[2]);
+        if (has_texture(s, prim.material.base_color_texture)) {
+            const float4 c = sample_texture(s.textures, s.lut, prim.material.base_color_texture, uv.x, uv.y);
+            albedo = make_float3(c.x, c.y, c.z);
+        }
+        N = normal;
+        if (has_texture(s, prim.material.normal_map)) {
+            const float3 tan3 = bary3(f3(v0.tangent), f3(v1.tangent), f3(v2.tangent), b0, b1, b2);
+            const float tw = add_rn(add_rn(mul_rn(v0.tangent[3], b0), mul_rn(v1.tangent[3], b1)), mul_rn(v2.tangent[3], b2));
+            const float4 c = sample_texture(s.textures, s.lut, prim.material.normal_map, uv.x, uv.y);
+            const float3 tsn = normalize_rn(make_float3(sub_rn(mul_rn(c.x, 2.0f), 1.0f), sub_rn(mul_rn(c.y, 2.0f), 1.0f), sub_rn(mul_rn(c.z, 2.0f), 1.0f)));
+            const float3 cr = cross_rn(tsn, tan3);
+            const float3 bitangent = make_float3(mul_rn(cr.x, tw), mul_rn(cr.y, tw), mul_rn(cr.z, tw));
+            const float tdn = dot3_rn(tan3, normal);
+            const float3 tangent = normalize_rn(make_float3(sub_rn(tan3.x, mul_rn(normal.x, tdn)), sub_rn(tan3.y, mul_rn(normal.y, tdn)), sub_rn(tan3.z, mul_rn(normal.z, tdn))));
+            N = make_float3(add_rn(add_rn(mul_rn(tangent.x, tsn.x), mul_rn(bitangent.x, tsn.y)), mul_rn(normal.x, tsn.z)),
+                            add_rn(add_rn(mul_rn(tangent.y, tsn.x), mul_rn(bitangent.y, tsn.y)), mul_rn(normal.y, tsn.z)),
+                            add_rn(add_rn(mul_rn(tangent.z, tsn.x), mul_rn(bitangent.z, tsn.y)), mul_rn(normal.z, tsn.z)));
+        }
+        sray.o = make_float3(pw.x, pw.y, pw.z);
+        sray.d = L;
+    }
+    // closesthit.rchit:48-50: the shadow ray (miss index 1 clears shadow_payload). Every lane takes part; only shaded ones are alive.
+    Hit sh;
+    const bool occluded = ALPHA ? trace<true>(s.nodes, s.tris, s.n_wide, s.bias, sray, shade, sh, RahitAlphaTest{s})
+                                : trace<true>(s.nodes, s.tris, s.n_wide, s.bias, sray, shade, sh);
+    if (!in_range) return;
+    if (shade) {
+        const float amb = ALPHA ? 0.2f : VHR_PI_INVERSE;                                     // closesthit_test_alpha.rchit:39 / closesthit.rchit:46
+        float3 c = make_float3(mul_rn(amb, albedo.x), mul_rn(amb, albedo.y), mul_rn(amb, albedo.z));
+        if (!occluded) {
+            const float ndl = fmaxf(dot3_rn(N, L), 0.0f);
+            const float *li = pfd.directional_light.intensity, *lc = pfd.directional_light.color;
+            if (ALPHA) {
+                c = make_float3(add_rn(c.x, mul_rn(mul_rn(ndl, albedo.x), lc[0])), add_rn(c.y, mul_rn(mul_rn(ndl, albedo.y), lc[1])),
+                                add_rn(c.z, mul_rn(mul_rn(ndl, albedo.z), lc[2])));
+            } else {
+                c = make_float3(add_rn(c.x, mul_rn(mul_rn(mul_rn(ndl, albedo.x), li[0]), lc[0])), add_rn(c.y, mul_rn(mul_rn(mul_rn(ndl, albedo.y), li[1]), lc[1])),
+                                add_rn(c.z, mul_rn(mul_rn(mul_rn(ndl, albedo.z), li[2]), lc[2])));
+            }
+        }
+        payload = make_float4(c.x, c.y, c.z, 1.0f);
+    }
+    // imageStore to a B8G8R8A8_UNORM image: float -> UNORM8 (NaN -> 0), B in the low byte
+    auto q = [](float f) { f = (f == f) ? fminf(fmaxf(f, 0.0f), 1.0f) : 0.0f; return (uint32_t)__float2int_rn(f * 255.0f); };
+    p.out[(size_t)y * p.W + x] = q(payload.z) | (q(payload.y) << 8) | (q(payload.x) << 16) | (q(payload.w) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // explicit rays (tests)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void trace_explicit_kernel(const float *__restrict__ rays, uint32_t n, int any_hit, SceneRefs s, float *out_t,
@@ -923,7 +1043,7 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         const int mine = (n_blocks - pt.rank + pt.world - 1) / pt.world;          // blocks b = rank, rank + world, ...
         dim3 block(128), grid((width + 15) / 16, mine);
         if (mine > 0) {
-            raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+            raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
             VHR_CUDA_CHECK(cudaGetLastError());
             ctx->launches++;
         }
@@ -944,12 +1064,34 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         return VHR_OK;
     }
     dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
-    p.leaf_batch = getenv("VHR_LEAF_BATCH") ? atoi(getenv("VHR_LEAF_BATCH")) : 12;
-    if (ctx->opt.raygen_variant == 4) raygen_kernel<0, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
-    else if (ctx->opt.raygen_variant == 5) raygen_kernel<8, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
-    else if (ctx->opt.raygen_variant == 2) raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
-    else if (ctx->opt.raygen_variant == 3) raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
-    else raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    p.leaf_batch = getenv("VHR_LEAF_BATCH") ? atoi(getenv("VHR_LEAF_BATCH")) : 16;
+    switch (ctx->opt.raygen_variant) {
+        case 2: raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // ptxas' own register choice (72)
+        case 3: raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // no register cap (117)
+        case 4: raygen_kernel<8, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;    // postponed leaves
+        default: raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;         // 64 registers, 8 blocks / SM
+    }
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
+int launch_raytraced(vhr_context *ctx, uint32_t width, uint32_t height) {
+    // descriptor set 3 of the "Raytracing Pass" (raytraced_render_path.cpp:13-16): 0 RaytracedOutput
+    if (ctx->n_bound < 1 || !ctx->bound[0]) return fail(VHR_ERR_STATE, "Raytracing Pipeline: output image not bound");
+    if (!ctx->d_primitives && ctx->bvh.n_tris) return fail(VHR_ERR_STATE, "TraceRays: geometry not uploaded");
+    Image *out = ctx->bound[0];
+    if (out->format != VHR_FORMAT_B8G8R8A8_UNORM) return fail(VHR_ERR_INVALID, "Raytracing Pipeline: output format %d, expected B8G8R8A8_UNORM", out->format);
+    if (out->width != width || out->height != height)
+        return fail(VHR_ERR_INVALID, "TraceRays: launch size %ux%u differs from image %ux%u", width, height, out->width, out->height);
+    RaytracedParams p;
+    p.W = (int)width; p.H = (int)height;
+    if (!band(ctx, height, p.y_begin, p.y_end)) return VHR_OK;
+    p.out = (uint32_t *)out->ptr;
+    p.scene = scene_refs(ctx);
+    dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
+    if (ctx->opt.raytraced_alpha_test) raytraced_kernel<true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    else raytraced_kernel<false><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return VHR_OK;

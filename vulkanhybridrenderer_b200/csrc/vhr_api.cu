@@ -537,10 +537,11 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
 int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height) {
     if (!ctx || !pipeline_name) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
-    if (strcmp(pipeline_name, "Raytrace Pipeline")) return fail(VHR_ERR_INVALID, "unknown ray-tracing pipeline '%s'", pipeline_name);
+    const bool hybrid = !strcmp(pipeline_name, "Raytrace Pipeline"), full = !strcmp(pipeline_name, "Raytracing Pipeline");
+    if (!hybrid && !full) return fail(VHR_ERR_INVALID, "unknown ray-tracing pipeline '%s'", pipeline_name);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
-    return launch_trace_rays(ctx, width, height);
+    return hybrid ? launch_trace_rays(ctx, width, height) : launch_raytraced(ctx, width, height);
 }
 
 int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *specialization_constants, uint32_t n_constants,
@@ -548,8 +549,15 @@ int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *speci
     if (!ctx || !fragment_shader) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
-    if (strcmp(fragment_shader, "hybrid_render_path/composition.frag"))
-        return fail(VHR_ERR_INVALID, "vhr_draw: no kernel for fragment shader '%s' (only the composition pass is a CUDA kernel)", fragment_shader);
+    const bool present = !strcmp(fragment_shader, "raytraced_render_path/composition.frag");
+    if (!present && strcmp(fragment_shader, "hybrid_render_path/composition.frag"))
+        return fail(VHR_ERR_INVALID, "vhr_draw: no kernel for fragment shader '%s' (only the composition passes are CUDA kernels)", fragment_shader);
+    if (present) {
+        if (vertex_count != 3 || instance_count != 1 || first_vertex != 0 || first_instance != 0)
+            return fail(VHR_ERR_INVALID, "vhr_draw: composition is Draw(3, 1, 0, 0), got (%u, %u, %u, %u)", vertex_count, instance_count, first_vertex, first_instance);
+        VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+        return launch_present(ctx);
+    }
     if (vertex_count != 3 || instance_count != 1 || first_vertex != 0 || first_instance != 0)
         return fail(VHR_ERR_INVALID, "vhr_draw: composition is Draw(3, 1, 0, 0), got (%u, %u, %u, %u)", vertex_count, instance_count, first_vertex, first_instance);
     if (!specialization_constants || n_constants != 3)
@@ -632,8 +640,9 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
         case VHR_OPT_ATROUS_VARIANT:
             if (value < 0 || value > 3) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
+        case VHR_OPT_RAYTRACED_ALPHA_TEST: ctx->opt.raytraced_alpha_test = value != 0; return VHR_OK;
         case VHR_OPT_RAYGEN_VARIANT:
-            if (value < 0 || value > 5) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);
+            if (value < 0 || value > 4) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);
             ctx->opt.raygen_variant = (int)value; return VHR_OK;
         case VHR_OPT_DEBUG_REFLECTION_T:
             ctx->opt.debug_refl_t = value != 0;
@@ -664,6 +673,7 @@ int64_t vhr_get_option(vhr_context *ctx, int option) {
         case VHR_OPT_ATROUS_VARIANT: return ctx->opt.atrous_variant;
         case VHR_OPT_DEBUG_REFLECTION_T: return ctx->opt.debug_refl_t;
         case VHR_OPT_RAYGEN_VARIANT: return ctx->opt.raygen_variant;
+        case VHR_OPT_RAYTRACED_ALPHA_TEST: return ctx->opt.raytraced_alpha_test;
     }
     return -1;
 }

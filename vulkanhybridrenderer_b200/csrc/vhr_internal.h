@@ -63,7 +63,8 @@ struct Options {
     int svgf_fused = 0;
     int atrous_variant = 2;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel, 2 = pixel-pair packed kernel
     int debug_refl_t = 0;        // 1: the ray pass also writes the reflection ray's hit distance (tests)
-    int raygen_variant = 0;      // 0 (default, faster as measured): one thread per pixel, ray kinds in lock step; 1: persistent warps + pixel queue
+    int raytraced_alpha_test = 0; // the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14)
+    int raygen_variant = 0;      // 0 (default, fastest as measured): one thread per pixel, ray kinds in lock step; 1-4: see VHR_OPT_RAYGEN_VARIANT
 };
 
 // Row partition of one frame over the GPUs of a box (vhr_set_partition)
@@ -144,6 +145,8 @@ int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg);
 int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc);
 int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height);
 int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height);
+int launch_raytraced(vhr_context *ctx, uint32_t width, uint32_t height);
+int launch_present(vhr_context *ctx);
 int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int reflection_mode);
 int launch_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_hit, float *out_t, uint32_t *out_ids,
                           float *out_uv);

@@ -5,12 +5,15 @@
 #include <memory>
 
 #include "hybrid_render_path.h"
+#include "raytraced_render_path.h"
 #include "scene_loader.h"
 
 struct vhrh_renderer {
     std::unique_ptr<ResourceManager> resource_manager;
     std::unique_ptr<RenderGraph> render_graph;
     std::unique_ptr<HybridRenderPath> path;
+    std::unique_ptr<RaytracedRenderPath> raytraced_path;
+    RenderPath *active = nullptr;          // the path whose nodes are registered (Renderer::active_render_path, renderer.h)
     std::string error;
     bool built = false;
 };
@@ -46,6 +49,7 @@ int vhrh_renderer_create(int device, void *cuda_stream, uint32_t width, uint32_t
         r->resource_manager = std::make_unique<ResourceManager>(device, cuda_stream, width, height);
         r->render_graph = std::make_unique<RenderGraph>(*r->resource_manager);
         r->path = std::make_unique<HybridRenderPath>(*r->render_graph, *r->resource_manager);
+        r->raytraced_path = std::make_unique<RaytracedRenderPath>(*r->render_graph, *r->resource_manager);
     });
     if (rc == VHR_OK) *out = r.release();
     return rc;
@@ -54,7 +58,7 @@ int vhrh_renderer_create(int device, void *cuda_stream, uint32_t width, uint32_t
 void vhrh_renderer_destroy(vhrh_renderer *r) {
     if (!r) return;
     guarded(r, [&] {
-        if (r->built) r->path->DeregisterPath(*r->render_graph, *r->resource_manager);
+        if (r->built && r->active) r->active->DeregisterPath(*r->render_graph, *r->resource_manager);
     });
     delete r;
 }
@@ -160,7 +164,28 @@ int vhrh_set_modes(vhrh_renderer *r, int shadow_mode, int ambient_occlusion_mode
         r->path->reflection_mode = reflection_mode;
         r->path->denoise_shadow_and_ao = denoise != 0;
         r->path->svgf_fused = svgf_fused != 0;
-        if (r->built) r->path->Rebuild(); else r->path->Build();
+        if (r->built && r->active == r->path.get()) r->path->Rebuild();
+        else {
+            if (r->built && r->active) { VHR_CHECK(vhr_context_synchronize(r->resource_manager->ctx)); r->active->DeregisterPath(*r->render_graph, *r->resource_manager); }
+            r->path->Build();
+        }
+        r->active = r->path.get();
+        r->built = true;
+    });
+}
+
+// Switching the active render path to the fully ray-traced one (Renderer's render-path combo box, user_interface.cpp) and its
+// "Alpha test for shadows" radio buttons (raytraced_render_path.cpp:80-91) + Rebuild().
+int vhrh_set_raytraced_path(vhrh_renderer *r, int use_anyhit_shader) {
+    if (!r) return VHR_ERR_INVALID;
+    return guarded(r, [&] {
+        r->raytraced_path->use_anyhit_shader = use_anyhit_shader != 0;
+        if (r->built && r->active == r->raytraced_path.get()) r->raytraced_path->Rebuild();
+        else {
+            if (r->built && r->active) { VHR_CHECK(vhr_context_synchronize(r->resource_manager->ctx)); r->active->DeregisterPath(*r->render_graph, *r->resource_manager); }
+            r->raytraced_path->Build();
+        }
+        r->active = r->raytraced_path.get();
         r->built = true;
     });
 }

@@ -188,7 +188,9 @@ void RenderGraph::BindPassImages(const RenderPassDescription &pass) {
 }
 
 bool GraphicsExecutionContext::HasKernel(const GraphicsPipelineDescription &pipeline) {
-    return pipeline.fragment_shader && std::string(pipeline.fragment_shader) == "hybrid_render_path/composition.frag";
+    if (!pipeline.fragment_shader) return false;
+    const std::string fs = pipeline.fragment_shader;
+    return fs == "hybrid_render_path/composition.frag" || fs == "raytraced_render_path/composition.frag";
 }
 void GraphicsExecutionContext::Draw(uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance) {
     ++draws;

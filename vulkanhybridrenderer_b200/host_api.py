@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libvhr_host.so")
 SYMBOLS = ["vhrh_last_error", "vhrh_renderer_create", "vhrh_renderer_destroy", "vhrh_context", "vhrh_load_scene", "vhrh_set_modes",
            "vhrh_set_gbuffer_producer", "vhrh_render", "vhrh_execution_order", "vhrh_pass_time_ms", "vhrh_svgf_push_constants",
            "vhrh_parse_gltf", "vhrh_parsed_scene_destroy", "vhrh_parsed_scene_counts", "vhrh_parsed_scene_copy", "vhrh_parsed_scene_texture",
-           "vhrh_load_gltf", "vhrh_decode_png"]
+           "vhrh_load_gltf", "vhrh_decode_png", "vhrh_set_raytraced_path"]
 
 SHADOW_MODE_RAYTRACED, SHADOW_MODE_RASTERIZED, SHADOW_MODE_OFF = 0, 1, 2
 AO_MODE_RAYTRACED, AO_MODE_SSAO, AO_MODE_OFF = 0, 1, 2
@@ -57,6 +57,7 @@ def lib():
         L.vhrh_parsed_scene_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.vhrh_parsed_scene_texture.argtypes = [vp, u32, C.POINTER(C.c_int32), vp]
         L.vhrh_load_gltf.argtypes = [vp, C.c_char_p]
+        L.vhrh_set_raytraced_path.argtypes = [vp, i32]
         L.vhrh_decode_png.argtypes = [vp, C.c_size_t, C.POINTER(u32), vp, C.c_size_t]
         _lib = L
     return _lib
@@ -110,6 +111,10 @@ class Renderer:
 
     def set_modes(self, shadow=SHADOW_MODE_RAYTRACED, ao=AO_MODE_OFF, reflection=REFLECTION_MODE_OFF, denoise=False, svgf_fused=False):
         _check(lib().vhrh_set_modes(self._r, shadow, ao, reflection, int(denoise), int(svgf_fused)))
+
+    def set_raytraced_path(self, use_anyhit_shader=False):
+        """Makes the fully ray-traced render path the active one (raytraced_render_path.cpp:11-78)."""
+        _check(lib().vhrh_set_raytraced_path(self._r, int(bool(use_anyhit_shader))))
 
     def set_gbuffer_producer(self, cuda_primary_rays):
         _check(lib().vhrh_set_gbuffer_producer(self._r, 1 if cuda_primary_rays else 0))
