@@ -73,12 +73,11 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
     for (int i = 0; i < 16; ++i) {
         float ang = mul_rn(mul_rn(random01(rng), 2.0f), VHR_PI);
         float dist = mul_rn(random01(rng), perspective_radius);
-        // ang is in [0, 2 pi): sin / cos on the MUFU unit at ang - pi (inside its accurate range, abs error < 1e-6) with the sign
-        // flipped, instead of the ~45-instruction sincosf. The oracle's libm value differs from either in the last bits; a 1e-6
-        // error moves the tap by 1e-6 * dist in uv, far below a texel, and the result stays inside the 1e-3 parity bar.
+        // full-precision sincosf: MUFU sin / cos (abs error ~5e-7) was measured to break the 1e-3 parity bar — across a depth edge the
+        // bilinear depth tap is unprojected through znear / depth, which amplifies a 1e-6 shift of the tap (1.5e-3 on one pixel of
+        // tests/test_ssao_gpu.py)
         float s, c;
-        __sincosf(ang - VHR_PI, &s, &c);
-        s = -s; c = -c;
+        sincosf(ang, &s, &c);
         float su = add_rn(cu, mul_rn(c, dist)), sv = add_rn(cv, mul_rn(s, dist));
         float3 Q = unproject_rn(pfd.camera_proj_inverse, sample_depth(p, su, sv), su, sv);
         float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
