@@ -48,6 +48,24 @@ def main():
     integ = Hh.noise_integrated(H, W, seed=2)
     np.savez_compressed(os.path.join(OUT, "atrous_noise_96x64.npz"), pfd=pfd, normals=normals, integ=integ,
                         **{f"step{s}": O.svgf_atrous(pfd, normals, integ, s) for s in (1, 2, 3, 4, 8, 16)})
+    # textured scene: G-buffer with alpha cut-outs / normal maps, textured reflections, SSR, the fully ray-traced path
+    tsc = scenes.add_procedural_textures(scenes.sponza_like(6000, seed=21, width=W, height=H, n_clutter=12), size=32)
+    tosc = O.OracleScene(tsc)
+    tseq = camera.FrameSequencer(W, H, tsc.light)
+    tseq.next(tsc.camera)
+    tsc.camera.set_pose(tsc.camera.position + np.array([0.06, 0.0, 0.02]), tsc.camera.yaw + 0.004, tsc.camera.pitch)
+    tpfd = tseq.next(tsc.camera)
+    tg = tosc.gbuffer(tpfd, W, H)
+    trg = tosc.raygen(tpfd, tg["depth"], tg["normals"], want_t=True)
+    tex = {}
+    for i, t in enumerate(tsc.textures):
+        tex[f"tex{i}_rgba"] = t.rgba
+        tex[f"tex{i}_info"] = np.array([t.format, *t.sampler], np.int32)
+    np.savez_compressed(os.path.join(OUT, "textured_frame_96x64.npz"), vertices=tsc.vertices, indices=tsc.indices, primitives=tsc.primitives,
+                        n_textures=len(tsc.textures), pfd=tpfd, depth=tg["depth"], normals=tg["normals"], motion=tg["motion"], albedo=tg["albedo"],
+                        shadow_ao=trg["shadow_ao"], reflections=trg["reflections"], refl_t=trg["refl_t"],
+                        ssr=O.ssr(tpfd, tg["albedo"], tg["normals"], tg["motion"], tg["depth"]),
+                        raytraced=tosc.raytraced(tpfd, W, H, False), raytraced_alpha=tosc.raytraced(tpfd, W, H, True), **tex)
     # RNG / sampling KATs
     import ctypes as C
     seeds = np.array([0, 1, 16221, 0xdeadbeef, 12345678], np.uint32)
