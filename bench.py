@@ -321,7 +321,10 @@ def run_gpu(args):
             ctx.actualize_image(HP.N_SHADOW_MAP, HP.T.VK_FORMAT_D32_SFLOAT, 4096, 4096)
             ctx.actualize_image(HP.N_RENDER_OUTPUT, HP.T.VK_FORMAT_B8G8R8A8_SRGB)
 
+            row_reps = int(os.environ.get("VHR_BENCH_ROW_REPS", "0"))      # profiling runs: a few launches per row are enough
+
             def time_row(fn, reps=20):
+                reps = row_reps or reps
                 ctx.update_per_frame_ubo(pfds[0])
                 for _ in range(3):
                     fn(0)

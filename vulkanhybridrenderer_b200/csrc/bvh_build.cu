@@ -93,16 +93,26 @@ __device__ __forceinline__ uint64_t expand21(uint64_t x) {
     x = (x | x << 2) & 0x1249249249249249ull;
     return x;
 }
+// mode 1 (default): one scale for all axes, the largest extent — cubic grid cells; the short axes leave their top bits at zero,
+// so the first splits of the radix tree only cut the long axes, which is what a surface-area heuristic does with an elongated
+// scene box. mode 0 (VHR_MORTON_MODE=0, the first version): every axis normalised by its own extent, cells with the scene box's
+// aspect ratio (40 x 10 x 16 for the hall). Measured at 1080p / 3 M triangles: SAH cost 35.4 -> 31.9, shadow rays 0.415 -> 0.334 ms,
+// shadow + AO 0.881 -> 0.782 ms, shadow + 2 AO + reflection 2.41 -> 2.29 ms (the closest-hit rays alone lose 5 %).
 __global__ void morton_kernel(const TriRef *__restrict__ tris, uint32_t n, const int *__restrict__ scene_bounds,
-                              uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                              uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int mode) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    float smin[3], inv[3];
+    float smin[3], inv[3], ext[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         smin[a] = ordered_to_float(scene_bounds[a]);
-        float ext = ordered_to_float(scene_bounds[3 + a]) - smin[a];
-        inv[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+        ext[a] = ordered_to_float(scene_bounds[3 + a]) - smin[a];
+    }
+    const float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float e = mode == 1 ? emax : ext[a];
+        inv[a] = e > 0.0f ? 2097152.0f / e : 0.0f;
     }
     const TriRef r = tris[t];
     float c[3];
@@ -225,6 +235,7 @@ struct WidenArgs {
     uint32_t n_in;
     uint32_t *counters;          // [0] wide nodes allocated, [1] triangles emitted, [2] queue_out size
     float *sah;                  // accumulated SAH numerator
+    int child_sort;              // 0: slots in collapse order; 1: largest surface area first
 };
 
 __device__ __forceinline__ bool leaf_like(const Tree2 &t, uint32_t id) { return id >= t.n - 1 || t.cluster[id]; }
@@ -334,7 +345,25 @@ __global__ void widen_kernel(const __grid_constant__ WidenArgs a) {
         kids[best] = t.child_l[id];
         kids[nk++] = t.child_r[id];
     }
-    // internal children first: slot index == child ordinal, and the internal-child mask is a run of low bits
+    // Slot order = visiting order (the traversal pops the lowest set bit first). a.child_sort = 1 (VHR_CHILD_SORT=1, an experiment):
+    // largest surface area first within the internal children and within the leaves, on the idea that an any-hit ray stops at its
+    // first occluder and the largest box is the most likely to hold one. Measured: shadow + AO 0.782 -> 0.800 ms, primary rays
+    // 0.70 -> 0.78 ms, reflections 1.25 -> 1.17 ms — the collapse order (spatially coherent, Morton) stays the default.
+    if (a.child_sort == 1) {
+        float area[8];
+        for (int c = 0; c < nk; ++c) {
+            float4 mn = t.bmin[kids[c]], mx = t.bmax[kids[c]];
+            area[c] = box_half_area(make_float3(mn.x, mn.y, mn.z), make_float3(mx.x, mx.y, mx.z));
+        }
+        for (int i = 1; i < nk; ++i) {          // insertion sort, descending
+            uint32_t kid = kids[i];
+            float ar = area[i];
+            int j = i - 1;
+            while (j >= 0 && area[j] < ar) { kids[j + 1] = kids[j]; area[j + 1] = area[j]; --j; }
+            kids[j + 1] = kid; area[j + 1] = ar;
+        }
+    }
+    // internal children first (stable): slot index == child ordinal, and the internal-child mask is a run of low bits
     {
         uint32_t tmp[8];
         int k = 0;
@@ -434,7 +463,7 @@ int build_bvh(vhr_context *ctx) {
         TRY(dmalloc(&d_keys2, n)); track(d_keys2);
         TRY(dmalloc(&d_vals, n)); track(d_vals);
         TRY(dmalloc(&d_vals2, n)); track(d_vals2);
-        morton_kernel<<<G, B, 0, st>>>(d_tris, n, d_scene, d_keys, d_vals);
+        morton_kernel<<<G, B, 0, st>>>(d_tris, n, d_scene, d_keys, d_vals, getenv("VHR_MORTON_MODE") ? atoi(getenv("VHR_MORTON_MODE")) : 1);
         TRYCUDA(cudaGetLastError()); ctx->launches++;
         size_t tmp_bytes = 0;
         TRYCUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
@@ -474,6 +503,7 @@ int build_bvh(vhr_context *ctx) {
         WidenArgs a;
         a.t = t; a.tris = d_tris; a.order = d_vals2; a.wide = d_wide; a.tris_out = d_tris_out;
         a.counters = d_counters; a.sah = d_sah;
+        a.child_sort = getenv("VHR_CHILD_SORT") ? atoi(getenv("VHR_CHILD_SORT")) : 0;
         uint8_t root_cluster = 0;
         if (n_inner) {
             TRYCUDA(cudaMemcpyAsync(&root_cluster, t.cluster, 1, cudaMemcpyDeviceToHost, st));
