@@ -276,3 +276,48 @@ def test_raygen_kernel_variants_match_default(variant):
     np.testing.assert_array_equal(outs[0][2], outs[1][2])                                  # same closest-hit distance everywhere
     same = np.all(outs[0][1].view(np.uint16) == outs[1][1].view(np.uint16), axis=-1)
     assert same.mean() >= 0.9999, same.mean()
+
+
+def test_ploc_hierarchy_gives_the_same_images(monkeypatch):
+    """The binary hierarchy is built by parallel locally-ordered clustering (default, VHR_BVH_BUILDER=1) or as a radix tree
+    (VHR_BVH_BUILDER=0). Visibility does not depend on the tree: masks and hit distances must be identical, the statistics must
+    describe a complete tree, and two PLOC builds of the same scene must give the same tree (no atomics in the numbering)."""
+    W, H = 203, 117
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, tris=20_000, moving=True)
+    pfd, g = frames[1]
+    outs, stats = [], []
+    for builder in ("0", "1", "1"):
+        monkeypatch.setenv("VHR_BVH_BUILDER", builder)
+        with capi.Context(W, H) as ctx:
+            ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+            st = ctx.bvh_stats()
+            stats.append((st.n_triangles, st.n_wide_nodes, st.sah_cost))
+            ctx.update_per_frame_ubo(pfd)
+            ctx.set_option(capi.OPT_DEBUG_REFLECTION_T, 1)
+            ctx.actualize_image(Hh.N_NORMALS, F4); ctx.actualize_image(Hh.N_DEPTH, T.VK_FORMAT_D32_SFLOAT)
+            ctx.actualize_image(Hh.N_RT, F2); ctx.actualize_image(Hh.N_REFL, F4)
+            ctx.image_upload(Hh.N_NORMALS, g["normals"]); ctx.image_upload(Hh.N_DEPTH, g["depth"])
+            ctx.bind_pass_images([Hh.N_NORMALS, Hh.N_DEPTH, Hh.N_RT, Hh.N_REFL])
+            ctx.trace_rays(W, H)
+            outs.append((ctx.image_download(Hh.N_RT), ctx.image_download(Hh.N_REFL), ctx.download_reflection_t()))
+            # tiny inputs through the same builder
+            v = np.zeros(4, T.Vertex)
+            v["pos"] = [(-1, -1, 5), (1, -1, 5), (0, 1, 5), (0, 0, 5)]
+            prim = np.zeros(1, T.Primitive)
+            prim["transform"] = np.eye(4)
+            for key in ("base_color_texture", "metallic_roughness_texture", "normal_map"):
+                prim["material"][key] = -1
+            for idx in ([0, 1, 2], [0, 1, 2, 0, 1, 3], [0, 1, 2] * 9):
+                prim["index_count"] = len(idx)
+                ctx.update_geometry(v, np.array(idx, np.uint32), prim)
+                t, _, _ = ctx.trace_explicit(np.array([[0, -0.5, 0, 0.01, 0, 0, 1, 100], [3, 0, 0, 0.01, 0, 0, 1, 100]], np.float32), any_hit=False)
+                assert abs(t[0] - 5.0) < 1e-5 and t[1] == -1.0
+    print(f"[ploc] radix tree: {stats[0]}  ploc: {stats[1]}")
+    assert stats[0][0] == stats[1][0]
+    assert stats[1] == stats[2]
+    for a, b in zip(outs[1], outs[2]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert np.mean(outs[0][2] == outs[1][2]) >= 0.9999
+    same = np.all(outs[0][1].view(np.uint16) == outs[1][1].view(np.uint16), axis=-1)
+    assert same.mean() >= 0.999, same.mean()

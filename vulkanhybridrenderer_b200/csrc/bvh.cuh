@@ -30,6 +30,10 @@ static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 
 constexpr int kMaxLeafTris = 3;
 
+// Entries of the per-ray traversal stack. An entry is the not-yet-visited rest of one node's hit children, so a ray holds at most
+// one entry per level of the wide tree: the builder refuses a tree deeper than this instead of letting a ray drop children.
+constexpr int kStackSize = 40;
+
 // Triangle record: three float4, world space. v0.w = geometry index bits, v1.w = primitive id bits, v2.w unused.
 struct TriRef {
     float4 v0, v1, v2;

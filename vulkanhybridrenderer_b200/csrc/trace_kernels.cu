@@ -23,8 +23,6 @@ namespace vhr {
 
 namespace {
 
-constexpr int kStackSize = 40;
-
 struct Ray {
     float3 o, d;
     float tmin, tmax;
