@@ -314,7 +314,7 @@ def test_ploc_hierarchy_gives_the_same_images(monkeypatch):
                 assert abs(t[0] - 5.0) < 1e-5 and t[1] == -1.0
     print(f"[ploc] radix tree: {stats[0]}  ploc: {stats[1]}")
     assert stats[0][0] == stats[1][0]
-    assert stats[1] == stats[2]
+    assert stats[1][:2] == stats[2][:2] and abs(stats[1][2] - stats[2][2]) < 1e-3      # the SAH figure is summed with float atomics
     for a, b in zip(outs[1], outs[2]):
         np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(outs[0][0], outs[1][0])

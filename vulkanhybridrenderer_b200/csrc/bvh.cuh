@@ -13,6 +13,9 @@ namespace vhr {
 
 // 8-wide node with 8-bit quantised child boxes, 80 bytes = five 128-bit loads.
 //   child box i = origin + q{lo,hi}[axis][i] * 2^(e[axis]-127)   (conservative: lo rounded down, hi rounded up)
+//   child_base              bits 0-29: index of the first internal child's node; bits 30-31: the axis the slots are sorted along
+//                           (box centres ascending; 3 = not sorted). A ray whose direction is negative on that axis visits the
+//                           hit children from the highest slot down, so the near side comes first either way.
 //   meta[i] == 0            empty slot (its box is inverted: qlo = 255, qhi = 0)
 //   meta[i] & 0x80          internal child; node index = child_base + (meta[i] & 7)
 //   otherwise               leaf child: triangles [tri_base + (meta[i] & 31), + (meta[i] >> 5)), 1..3 triangles
