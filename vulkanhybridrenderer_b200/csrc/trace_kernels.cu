@@ -417,10 +417,15 @@ struct RaygenParams {
     uint2 *reflections_of[VHR_MAX_RANKS];
 };
 
-// 8x4-pixel warp tiles inside a 16x8 block: neighbouring lanes trace neighbouring pixels.
+// 8x4-pixel warp tiles inside a 16x8-pixel macro block: neighbouring lanes trace neighbouring pixels. A macro block is one CTA of
+// four warps (WPB = 4) or 4 / WPB consecutive CTAs of WPB warps — with one-warp CTAs a finished warp gives its registers back at
+// once instead of waiting for the slowest warp of its CTA.
+template <int WPB = 4>
 __device__ __forceinline__ void tile_coords(int &x, int &y) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    constexpr int kSplit = 4 / WPB;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(blockIdx.x % kSplit) * WPB + (int)(threadIdx.x >> 5);
+    x = (int)(blockIdx.x / kSplit) * 16 + (warp & 1) * 8 + (lane & 7);
     y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
 }
 
@@ -430,10 +435,10 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
 //   1 (variant 3): no cap, 117 registers / 4 blocks — 1.16 / 3.39 ms (fewer warps to hide the node fetches);
 //   BATCHED (variant 4): trace_batched — 1.00 / 2.57 ms: postponing leaves costs the any-hit rays more node steps than the fuller
 //   triangle block saves. Same images in every variant.
-template <int MIN_BLOCKS, bool BATCHED = false>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
+template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4>
+__global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     int x, y;
-    tile_coords(x, y);
+    tile_coords<WPB>(x, y);
     uint32_t *__restrict__ out_sa = p.shadow_ao;
     uint2 *__restrict__ out_refl = p.reflections;
     if (p.world > 0) {
@@ -1080,6 +1085,8 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         case 2: raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // ptxas' own register choice (72)
         case 3: raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // no register cap (117)
         case 4: raygen_kernel<8, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;    // postponed leaves
+        case 6: raygen_kernel<8, false, 1><<<dim3(grid.x * 4, grid.y), 32, 0, ctx->stream>>>(p, ctx->pfd); break;   // one-warp CTAs, 32 / SM
+        case 7: raygen_kernel<8, false, 2><<<dim3(grid.x * 2, grid.y), 64, 0, ctx->stream>>>(p, ctx->pfd); break;   // two-warp CTAs, 16 / SM
         default: raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;         // 64 registers, 8 blocks / SM
     }
     VHR_CUDA_CHECK(cudaGetLastError());
