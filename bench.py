@@ -118,6 +118,9 @@ class CpuArm:
         import oracle_lib as O
         from vulkanhybridrenderer_b200 import camera
         self.O = O
+        # all the host threads this process may use, set explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.cores = O.set_num_threads(avail)
         self.W, self.H, _, self.ao_spp, self.refl = WORKLOADS[wl]
         self.sc, self.poses = make_scene(wl)
         t0 = time.time()
@@ -127,7 +130,6 @@ class CpuArm:
         self.rows = min(band_rows, self.H)
         self.y0 = (self.H - self.rows) // 2
         self.state = O.SvgfState(self.W, self.rows)
-        self.cores = os.cpu_count()
         self.g = None
         self.k = 0
 

@@ -88,6 +88,14 @@ def _declare(L):
     L.vo_gbuffer.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
 
 
+def set_num_threads(n=0):
+    """Sets the OpenMP thread count of the oracle's loops (n <= 0: leave it) and returns the count the runtime will use."""
+    L = lib()
+    L.vo_set_num_threads.restype = C.c_int
+    L.vo_set_num_threads.argtypes = [C.c_int]
+    return int(L.vo_set_num_threads(int(n)))
+
+
 def _h(a):
     """float16 array -> contiguous uint16 view"""
     a = np.ascontiguousarray(a)

@@ -20,6 +20,9 @@
 #include <atomic>
 #include <cfloat>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 using namespace vo;
 
@@ -387,6 +390,18 @@ vec4 reflection_hit(const Scene &s, const PerFrameData &pfd, const Hit &hit) {
 }  // namespace
 
 extern "C" {
+
+// Host threads of every "#pragma omp" loop in the oracle. A launcher may have exported OMP_NUM_THREADS=1 (torchrun does for each rank);
+// bench.py's CPU arm sets the count explicitly and reports what the runtime then uses. Returns omp_get_max_threads().
+int vo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 struct vo_scene;
 
