@@ -198,6 +198,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+FRAMES_IN_FLIGHT_DEFAULT = 1
 METRIC = "shadow+AO Mrays/s (frame = RT shadow+AO pass + SVGF temporal + 5 a-trous)"
 
 
@@ -230,7 +231,10 @@ def run_gpu(args):
     wl = args.workload
     W, H, _, ao_spp, refl = WORKLOADS[wl]
     sc, poses = make_scene(wl, view=rank)
-    stream = torch.cuda.Stream()
+    fif = args.frames_in_flight
+    # queue 0 carries the short SVGF kernels: with two frames in flight it gets the higher priority so that its CTAs are placed as
+    # the long ray kernel's CTAs retire instead of queueing behind that kernel's whole grid
+    stream = torch.cuda.Stream(priority=-1) if fif == 2 else torch.cuda.Stream()
     K, Wm = args.steps, args.warmup
     peak, peak_src = load_peaks()
 
@@ -242,7 +246,7 @@ def run_gpu(args):
         ctx.set_option(capi.OPT_TRACE_AO, 1 if ao_spp else 0)
         ctx.set_option(capi.OPT_AO_SPP, max(ao_spp, 1))
         ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
-        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2)
+        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=fif)
         seq = camera.FrameSequencer(W, H, sc.light)
         cam = sc.camera
 
@@ -273,14 +277,20 @@ def run_gpu(args):
 
         frame_no = [0]
 
-        def step(instrument=True):
+        def step(overlap=True):
             k = frame_no[0]
             s = k & 1
             pfd = pfds[s]
             pfd["frame_index"] = 3 + k
             frame_no[0] += 1
-            path.frame(pfd, gset=s)
+            if fif == 2 and overlap:
+                path.frame_overlapped(pfd, k, gset=s)
+            else:
+                path.frame(pfd, gset=s, rtset=s if fif == 2 else 0)
             return rays_per_frame[s]
+
+        def rt_name(k):
+            return path.rt_sets[(k & 1) if fif == 2 else 0][0]
 
         def barrier():
             if world > 1:
@@ -291,7 +301,8 @@ def run_gpu(args):
         path.timestamps = None
         for _ in range(Wm):
             step()
-        path.enable_timestamps(K)
+        if fif == 1:
+            path.enable_timestamps(K)
         l0 = ctx.kernel_launches
         sampler = ClockSampler(local)
         barrier()
@@ -306,7 +317,16 @@ def run_gpu(args):
         clocks = sampler.stop()
         ms_total = ev0.elapsed_time(ev1)
         launches = ctx.kernel_launches - l0
-        pass_ms = path.pass_times_ms(K)            # [K, passes]
+        if fif == 2:
+            # per-pass times need the passes one after the other: the same frames again, one frame in flight, with timestamps
+            Kb = min(K, 50)
+            path.enable_timestamps(Kb)
+            for _ in range(Kb):
+                step(overlap=False)
+            barrier()
+            pass_ms = path.pass_times_ms(Kb)
+        else:
+            pass_ms = path.pass_times_ms(K)            # [K, passes]
         path.timestamps = None
 
         # ---- next rows, each timed on its own and NOT part of the step: the composition pass that consumes the
@@ -374,9 +394,9 @@ def run_gpu(args):
             g = path.gsets[s]
             for key, t in host_g[s].items():
                 capi._check(capi.lib().vhr_image_upload(ctx._h, g[key].encode(), t.data_ptr(), t.numel()))
-            r = step()
+            r = step(overlap=False)          # blocking copies on queue 0 on both sides: nothing to overlap with
             ctx.image_download_into(HP.N_DENOISED, out_den)
-            ctx.image_download_into(HP.N_RT, out_rt)
+            ctx.image_download_into(rt_name(k), out_rt)
             ctx.synchronize()
             return r
 
@@ -413,10 +433,11 @@ def run_gpu(args):
             upload_async(frame_no[0])
             for i in range(n):
                 upload_async(frame_no[0] + 1)            # next step's inputs (the last one primes the following run)
+                k = frame_no[0]
                 rays_p += step()
                 o = outs[i & 1]
                 t1 = ctx.image_download_async(HP.N_DENOISED, o[0])
-                t2 = ctx.image_download_async(HP.N_RT, o[1])
+                t2 = ctx.image_download_async(rt_name(k), o[1])
                 if prev is not None:
                     ctx.wait_download(prev)
                 prev = max(t1, t2)
@@ -453,11 +474,14 @@ def run_gpu(args):
         pm = dict(zip(labels, (float(x) for x in mean_pass)))
         frame_ms = ms_total / K
         svgf_ms = sum(pm[k] for k in labels if k != "raytrace")
+        # shares are taken of the frame run one pass after the other (with two frames in flight the passes overlap and their
+        # durations no longer add up to the step)
+        share_ms = sum(pm.values()) if fif == 2 else frame_ms
         # per-kernel roofline (HBM): algorithmic bytes / launch = per-pixel bytes x pixels
         kernels = []
         def add(name, ms, bytes_, note=None):
             ach = bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            kernels.append({"kernel": name, "ms": ms, "share": ms / frame_ms, "algorithmic_bytes": bytes_,
+            kernels.append({"kernel": name, "ms": ms, "share": ms / share_ms, "algorithmic_bytes": bytes_,
                             "achieved_gbs": ach, "frac": ach / peak, **({"note": note} if note else {})})
         add("raygen_kernel", pm["raytrace"], px * (HP.BYTES_RAYGEN_IO + (8 if refl else 0)),
             "traversal-bound (software BVH, no RT cores): compulsory G-buffer in + mask out bytes only; see Mrays/s")
@@ -480,7 +504,11 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": rays / (ms_total * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(wl, sc.num_triangles),
+            "dtype": "f32", "data": "synthetic",
+            "config": {**config_dict(wl, sc.num_triangles), "frames_in_flight": fif,
+                       **({"schedule": "Raytrace Pass of frame k+1 on queue 1 under the SVGF pass of frame k (two ray-output image sets); "
+                                       "kernels[] / roofline timed in a separate run with one frame in flight",
+                           "ms_per_step_one_frame_in_flight": share_ms} if fif == 2 else {})},
             "e2e": {"value": rays_e / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "checksum": checksum,
                     "mode": "pipelined: H2D / compute / D2H of consecutive steps overlap on the C-ABI transfer queues, host waits "
@@ -548,7 +576,10 @@ def run_rowband(args):
     wl = args.workload
     W, H, _, ao_spp, refl = WORKLOADS[wl]
     sc, poses = make_scene(wl, view=0)          # every rank renders the SAME view; the scene and BVH are replicated
-    stream = torch.cuda.Stream()
+    fif = args.frames_in_flight
+    # queue 0 carries the short SVGF kernels: with two frames in flight it gets the higher priority so that its CTAs are placed as
+    # the long ray kernel's CTAs retire instead of queueing behind that kernel's whole grid
+    stream = torch.cuda.Stream(priority=-1) if fif == 2 else torch.cuda.Stream()
     K, Wm = args.steps, args.warmup
     y0, y1 = MG.band_rows(H, world, rank)
     with torch.cuda.stream(stream):
@@ -658,6 +689,9 @@ def main():
     ap.add_argument("--workload", default="hybrid_frame_1080p_3Mtri", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-rows", type=int, default=64, help="rows of the frame the CPU arm renders per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=FRAMES_IN_FLIGHT_DEFAULT, choices=[1, 2],
+                    help="2: the Raytrace Pass of frame k+1 is recorded on the context's second queue and runs under the SVGF pass of frame k "
+                         "(HybridRenderPath.frame_overlapped); the per-kernel breakdown then comes from a separate one-frame-at-a-time run")
     ap.add_argument("--partition", default="views", choices=["views", "rows"],
                     help="N>1: independent views per rank (weak scaling, default) or row bands of one frame (strong scaling, NCCL halos)")
     ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],

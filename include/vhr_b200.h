@@ -197,6 +197,22 @@ int vhr_write_timestamp(vhr_context *ctx, uint32_t query);
 /* Blocks until query `last` has been reached, then writes the elapsed milliseconds between `first` and `last`. */
 int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms);
 
+/* ---- two queues inside one context: frames in flight ------------------------------------------------------------
+ * The reference keeps three frames in flight on one queue (renderer.cpp:103-108, 157) and the driver may run the next frame's
+ * first passes under the previous frame's last ones wherever no barrier forbids it. Here that freedom is explicit: queue 0 is
+ * the stream the context was created on, queue 1 a second in-order stream the context creates on first use. Every pass, blit,
+ * copy and timestamp recorded after vhr_select_queue(q) goes to queue q; the two queues are ordered against each other only by
+ * semaphores, like vkQueueSubmit's wait / signal semaphores:
+ *   vhr_queue_signal(s)  semaphore s is signalled when everything recorded so far on the selected queue has finished;
+ *   vhr_queue_wait(s)    work recorded afterwards on the selected queue starts only after the LAST signal of s recorded so far
+ *                        (no-op when s was never signalled).
+ * The caller owns the hazards (the Raytrace Pass of frame k+1 may run under the SVGF pass of frame k when it stores into a second
+ * set of output images: HybridRenderPath::FrameOverlapped in the host mirrors). Not available while a partition is set. */
+#define VHR_MAX_SEMAPHORES 16
+int vhr_select_queue(vhr_context *ctx, int queue);          /* 0 or 1 */
+int vhr_queue_signal(vhr_context *ctx, int semaphore);
+int vhr_queue_wait(vhr_context *ctx, int semaphore);
+
 /* ---- one frame over several GPUs (no counterpart in the reference) ------------------------------------
  * One process per GPU, scene + BVH replicated, every image full-size on every rank. The frame is split by rows:
  *   - SVGF / SSAO / composition work on contiguous row bands: rank r owns rows [band_begin[r], band_begin[r+1]);

@@ -29,8 +29,10 @@ SYMBOLS = [
     "vhr_image_attach_peer_pointer", "vhr_storage_image_attach_peer_pointer", "vhr_sync_attach_peer_pointer",
     "vhr_storage_image_twin_device_ptr", "vhr_sync_device_ptr",
     "vhr_upload_texture_from_data", "vhr_destroy_textures",
+    "vhr_select_queue", "vhr_queue_signal", "vhr_queue_wait",
 ]
 MAX_RANKS = 8
+MAX_SEMAPHORES = 16
 IPC_HANDLE_BYTES = 64
 
 
@@ -131,6 +133,9 @@ def lib():
         L.vhr_debug_download_reflection_t.argtypes = [vp, vp, sz]
         L.vhr_create_query_pool.argtypes = [vp, u32]
         L.vhr_write_timestamp.argtypes = [vp, u32]
+        L.vhr_select_queue.argtypes = [vp, i32]
+        L.vhr_queue_signal.argtypes = [vp, i32]
+        L.vhr_queue_wait.argtypes = [vp, i32]
         L.vhr_get_query_elapsed_ms.argtypes = [vp, u32, u32, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -363,6 +368,16 @@ class Context:
 
     def get_option(self, opt):
         return lib().vhr_get_option(self._h, opt)
+
+    # ---- two queues (frames in flight) --------------------------------------------------------------------------------
+    def select_queue(self, queue):
+        _check(lib().vhr_select_queue(self._h, int(queue)))
+
+    def queue_signal(self, semaphore):
+        _check(lib().vhr_queue_signal(self._h, int(semaphore)))
+
+    def queue_wait(self, semaphore):
+        _check(lib().vhr_queue_wait(self._h, int(semaphore)))
 
     def synchronize(self):
         _check(lib().vhr_context_synchronize(self._h))

@@ -149,6 +149,7 @@ int vhr_context_create(int device, void *cuda_stream, uint32_t width, uint32_t h
         if (e != cudaSuccess) { delete ctx; return fail(VHR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         ctx->own_stream = true;
     }
+    ctx->queue[0] = ctx->stream;
     *out = ctx;
     return VHR_OK;
 }
@@ -157,7 +158,8 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (!ctx) return;
     if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->queue[0]);
+    if (ctx->queue[1]) cudaStreamSynchronize(ctx->queue[1]);
     if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
     if (ctx->download_stream) cudaStreamSynchronize(ctx->download_stream);
     peer_close_all(ctx);
@@ -178,16 +180,49 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->download_stream) { cudaStreamSynchronize(ctx->download_stream); cudaStreamDestroy(ctx->download_stream); }
     if (ctx->compute_tail) cudaEventDestroy(ctx->compute_tail);
     for (cudaEvent_t e : ctx->tickets) cudaEventDestroy(e);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    for (cudaEvent_t e : ctx->semaphores) if (e) cudaEventDestroy(e);
+    if (ctx->queue[1]) cudaStreamDestroy(ctx->queue[1]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->queue[0]);
     delete ctx;
 }
 
 int vhr_context_synchronize(vhr_context *ctx) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     if (ctx->device < 0) return VHR_OK;
-    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->queue[0]));
+    if (ctx->queue[1]) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->queue[1]));
     if (ctx->upload_stream) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->upload_stream));
     if (ctx->download_stream) VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->download_stream));
+    return VHR_OK;
+}
+
+int vhr_select_queue(vhr_context *ctx, int queue) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (queue < 0 || queue > 1) return fail(VHR_ERR_INVALID, "queue %d (0 or 1)", queue);
+    if (ctx->device < 0) return VHR_OK;      // validation-only context: nothing is recorded
+    if (queue == 1 && ctx->part.enabled) return fail(VHR_ERR_STATE, "vhr_select_queue: not available while a partition is set (the peer flag words are ordered on queue 0)");
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (queue == 1 && !ctx->queue[1]) VHR_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->queue[1], cudaStreamNonBlocking));
+    ctx->stream = ctx->queue[queue];
+    return VHR_OK;
+}
+
+int vhr_queue_signal(vhr_context *ctx, int semaphore) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (semaphore < 0 || semaphore >= VHR_MAX_SEMAPHORES) return fail(VHR_ERR_INVALID, "semaphore %d of %d", semaphore, VHR_MAX_SEMAPHORES);
+    if (ctx->device < 0) return VHR_OK;
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!ctx->semaphores[semaphore]) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->semaphores[semaphore], cudaEventDisableTiming));
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->semaphores[semaphore], ctx->stream));
+    ctx->semaphore_signalled[semaphore] = true;
+    return VHR_OK;
+}
+
+int vhr_queue_wait(vhr_context *ctx, int semaphore) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (semaphore < 0 || semaphore >= VHR_MAX_SEMAPHORES) return fail(VHR_ERR_INVALID, "semaphore %d of %d", semaphore, VHR_MAX_SEMAPHORES);
+    if (ctx->device < 0 || !ctx->semaphore_signalled[semaphore]) return VHR_OK;
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->semaphores[semaphore], 0));
     return VHR_OK;
 }
 

@@ -118,6 +118,10 @@ struct vhr_context {
     cudaEvent_t compute_tail = nullptr;            // scratch event: "everything enqueued on the compute stream so far"
     std::vector<cudaEvent_t> tickets;              // ring of download-completion events
     uint32_t next_ticket = 0;
+    // two queues (vhr_select_queue): `stream` is the selected one
+    cudaStream_t queue[2] = {nullptr, nullptr};    // [0] the stream given at creation (or the context's own), [1] created on first use
+    cudaEvent_t semaphores[VHR_MAX_SEMAPHORES] = {};
+    bool semaphore_signalled[VHR_MAX_SEMAPHORES] = {};
     // multi-GPU partition + peer synchronisation (peer.cu)
     vhr::Partition part;
     uint32_t *sync_flags = nullptr;                       // device: [0, MAX) ray-pass arrivals, [MAX, 2 MAX) halo arrivals, by source rank

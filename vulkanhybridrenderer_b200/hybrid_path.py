@@ -175,6 +175,30 @@ class HybridRenderPath:
                                    N_DENOISED if denoised else N_RT, N_REFL, N_RENDER_OUTPUT])
         self.ctx.draw(SHADER_COMPOSITION, (shadow_mode, ao_mode, reflection_mode))
 
+    # semaphores of frame_overlapped, per ray-output set p: the set may be overwritten / the set has been written
+    SEM_RT_SET_FREE, SEM_RT_SET_WRITTEN = (0, 1), (2, 3)
+
+    def frame_overlapped(self, pfd, k, gset=0):
+        """frame() with two frames in flight (needs rt_sets=2): the Raytrace Pass of frame k is recorded on queue 1 into ray-output
+        set k & 1 and only waits for the consumers of that set two frames ago, so it runs under the SVGF Denoise Pass of frame k-1,
+        which is still executing on queue 0. Same kernels, same inputs, same images as frame(): only the schedule differs.
+        The caller keeps the G-buffer of frame k in a set that frame k-1 does not use (gbuffer_sets=2, gset=k & 1) and reads the
+        results of frame k on queue 0 (selected on return) before calling this for frame k+1... or any time before frame k+2."""
+        ctx, p = self.ctx, k & 1
+        assert len(self.rt_sets) >= 2, "frame_overlapped needs rt_sets=2"
+        # everything recorded on queue 0 so far — frame k-1's denoiser and whatever read its images — is what frame k+1's ray pass
+        # (which overwrites set (k-1) & 1) has to wait for
+        ctx.select_queue(0)
+        ctx.queue_signal(self.SEM_RT_SET_FREE[p ^ 1])
+        ctx.select_queue(1)
+        ctx.queue_wait(self.SEM_RT_SET_FREE[p])
+        ctx.update_per_frame_ubo(pfd)
+        self.raytrace_pass(gset, p)
+        ctx.queue_signal(self.SEM_RT_SET_WRITTEN[p])
+        ctx.select_queue(0)
+        ctx.queue_wait(self.SEM_RT_SET_WRITTEN[p])
+        self.svgf_denoise_pass(gset, p)
+
     def frame(self, pfd, gset=0, rtset=0):
         """Raytrace Pass -> SVGF Denoise Pass for one frame whose G-buffer already sits in image set `gset`."""
         self.ctx.update_per_frame_ubo(pfd)
