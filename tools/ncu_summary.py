@@ -1,4 +1,4 @@
-"""Prints a compact per-kernel table from an .ncu-rep (ncu --page raw --csv) for the metrics we track."""
+"""Prints a compact per-kernel table from an .ncu-rep (or its `--page raw --csv` extract) for the metrics we track."""
 import csv, io, subprocess, sys
 
 KEYS = [
@@ -22,7 +22,11 @@ KEYS = [
 
 
 def main(path, extra=()):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):        # an `ncu -i x.ncu-rep --page raw --csv` extract made on the GPU box
+        out = open(path).read()
+        out = out[out.index('"ID"'):]
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
