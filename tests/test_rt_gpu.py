@@ -251,7 +251,7 @@ def test_persistent_raygen_variant_matches_per_pixel_kernel():
     assert outs[0][0][:9].astype(np.float32).sum() == 0 and outs[0][0][101:].astype(np.float32).sum() == 0   # rows outside the band untouched
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 6, 7])
+@pytest.mark.parametrize("variant", [2, 3, 4, 6, 7, 8])
 def test_raygen_kernel_variants_match_default(variant):
     """VHR_OPT_RAYGEN_VARIANT 2 / 3 (other register budgets), 4 (postponed leaves: the warp runs the triangle block together) trace the
     same rays against the same tree: shadow / AO masks are identical; the closest-hit ray may report another triangle only on exact ties."""

@@ -429,14 +429,86 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
     y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
 }
 
+// ---- AO rays sorted by direction inside the CTA (VHR_OPT_RAYGEN_VARIANT 8) -------------------------------------------
+// The AO rays of a warp tile start next to each other but leave over the whole hemisphere (15.7 of 32 lanes active in their node
+// test, against 24.5 for the shadow rays, profiles/r01_ncu_raygen_segments.md). Here the CTA's 128 AO rays are counting-sorted by a
+// 24-valued direction key (cube-map face of the direction x the signs of the two other components) before they are traced: thread t
+// traces the t-th ray in key order and hands the result back to the pixel's thread through shared memory; lanes without a ray
+// (sky, AO off) sort to the end, so whole warps of them do nothing. The rays and their any-hit answers are the same, only the
+// thread that computes each one changes.
+// Measured (gpurun_out/r01r_trace.log, 1080p): AO pass 0.467 -> 0.507 ms at 3 M triangles, 0.393 -> 0.422 ms at 260 k — slower: the rays of
+// a warp now start up to 16 pixels apart, and that costs more than the common direction gains. Kept for study, not the default.
+struct AoSortShared {
+    float4 o[128];            // origin.xyz, tmin
+    float4 d[128];            // direction.xyz, tmax
+    uint16_t warp_count[4][32];
+    uint16_t warp_base[4][32];
+    uint16_t perm[128];
+    uint8_t occluded[128];
+};
+__device__ __forceinline__ uint32_t direction_key(float3 d) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const uint32_t sx = d.x < 0.0f, sy = d.y < 0.0f, sz = d.z < 0.0f;
+    if (ax >= ay && ax >= az) return (0u + sx) * 4u + sy * 2u + sz;
+    if (ay >= az) return (2u + sy) * 4u + sx * 2u + sz;
+    return (4u + sz) * 4u + sx * 2u + sy;
+}
+// Every thread of the 128-thread CTA calls this together. Returns the any-hit answer of THIS thread's ray.
+__device__ __forceinline__ bool trace_any_sorted(const SceneRefs &scene, const Ray &ray, bool alive, AoSortShared &sm) {
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t key = alive ? direction_key(ray.d) : 24u;
+    sm.o[tid] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.tmin);
+    sm.d[tid] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.tmax);
+    sm.warp_count[warp][lane] = 0;
+    __syncwarp();
+    const unsigned same = __match_any_sync(FULL, key);
+    const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+    if (rank == 0u) sm.warp_count[warp][key] = (uint16_t)__popc(same);
+    __syncthreads();
+    if (warp == 0) {
+        // lane = key: total over the four warps, exclusive scan over the keys, then one base per (warp, key) in key-major order
+        const uint32_t c0 = sm.warp_count[0][lane], c1 = sm.warp_count[1][lane], c2 = sm.warp_count[2][lane], c3 = sm.warp_count[3][lane];
+        const uint32_t tot = c0 + c1 + c2 + c3;
+        uint32_t incl = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += v;
+        }
+        uint32_t run = incl - tot;
+        sm.warp_base[0][lane] = (uint16_t)run; run += c0;
+        sm.warp_base[1][lane] = (uint16_t)run; run += c1;
+        sm.warp_base[2][lane] = (uint16_t)run; run += c2;
+        sm.warp_base[3][lane] = (uint16_t)run;
+    }
+    __syncthreads();
+    sm.perm[sm.warp_base[warp][key] + rank] = (uint16_t)tid;
+    const uint32_t n_alive = sm.warp_base[0][24];                 // the rays without work sort last
+    __syncthreads();
+    const int j = sm.perm[tid];
+    const float4 o = sm.o[j], d = sm.d[j];
+    Ray r;
+    r.o = make_float3(o.x, o.y, o.z); r.tmin = o.w;
+    r.d = make_float3(d.x, d.y, d.z); r.tmax = d.w;
+    Hit h;
+    const bool occ = trace<true>(scene.nodes, scene.tris, scene.n_wide, scene.bias, r, (uint32_t)tid < n_alive, h);
+    sm.occluded[j] = occ ? 1 : 0;
+    __syncthreads();
+    const bool mine = sm.occluded[tid] != 0;
+    __syncthreads();                                               // the arrays are reused by the next AO sample
+    return mine;
+}
+
 // MIN_BLOCKS is the occupancy target handed to ptxas (__launch_bounds__). Measured at 1080p / 3 M triangles (gpurun_out/r01c_trace.log):
 //   8 (default): 64 registers, 8 blocks / SM, ~10 spilled words — 0.879 ms shadow+AO, 2.40 ms shadow + 2 AO + reflection;
 //   0 (VHR_OPT_RAYGEN_VARIANT 2): unspecified, ptxas settles on 72 registers / 7 blocks — 0.883 / 2.47 ms;
 //   1 (variant 3): no cap, 117 registers / 4 blocks — 1.16 / 3.39 ms (fewer warps to hide the node fetches);
 //   BATCHED (variant 4): trace_batched — 1.00 / 2.57 ms: postponing leaves costs the any-hit rays more node steps than the fuller
 //   triangle block saves. Same images in every variant.
-template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4>
+template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4, bool SORT_AO = false>
 __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
+    static_assert(!SORT_AO || WPB == 4, "the AO sort works on 128-thread CTAs");
     int x, y;
     tile_coords<WPB>(x, y);
     uint32_t *__restrict__ out_sa = p.shadow_ao;
@@ -493,8 +565,14 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
         if (p.flags & 2) {
             ray.d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
             ray.tmax = 5.0f;
-            const bool occluded = BATCHED ? trace_batched<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
-                                          : trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+            bool occluded;
+            if constexpr (SORT_AO) {
+                __shared__ AoSortShared ao_sort;
+                occluded = trace_any_sorted(p.scene, ray, lit, ao_sort);
+            } else {
+                occluded = BATCHED ? trace_batched<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
+                                   : trace<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+            }
             ao = add_rn(ao, occluded ? 0.0f : 1.0f);
         } else {
             ao = add_rn(ao, 1.0f);
@@ -1085,6 +1163,7 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         case 2: raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // ptxas' own register choice (72)
         case 3: raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // no register cap (117)
         case 4: raygen_kernel<8, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;    // postponed leaves
+        case 8: raygen_kernel<8, false, 4, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;              // AO rays sorted by direction in the CTA
         case 6: raygen_kernel<8, false, 1><<<dim3(grid.x * 4, grid.y), 32, 0, ctx->stream>>>(p, ctx->pfd); break;   // one-warp CTAs, 32 / SM
         case 7: raygen_kernel<8, false, 2><<<dim3(grid.x * 2, grid.y), 64, 0, ctx->stream>>>(p, ctx->pfd); break;   // two-warp CTAs, 16 / SM
         default: raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;         // 64 registers, 8 blocks / SM
