@@ -321,3 +321,41 @@ def test_ploc_hierarchy_gives_the_same_images(monkeypatch):
     assert np.mean(outs[0][2] == outs[1][2]) >= 0.9999
     same = np.all(outs[0][1].view(np.uint16) == outs[1][1].view(np.uint16), axis=-1)
     assert same.mean() >= 0.999, same.mean()
+
+
+def test_strung_out_geometry_falls_back_to_the_radix_tree(monkeypatch):
+    """Tiny triangles on a line with steadily growing gaps: every cluster's nearest neighbour is its left one, so PLOC merges one pair per
+    round and would produce a tree as deep as the line is long. update_geometry must not fail — it rebuilds with the radix tree — and
+    the rays must still find their triangles."""
+    n = 3000
+    x = 0.002 * np.arange(n, dtype=np.float64) ** 2
+    v = np.zeros(3 * n, T.Vertex)
+    pos = np.zeros((n, 3, 3), np.float32)
+    pos[:, :, 2] = 5.0
+    pos[:, 0, 0] = x; pos[:, 1, 0] = x + 0.01; pos[:, 2, 0] = x
+    pos[:, 2, 1] = 0.01
+    v["pos"] = pos.reshape(-1, 3)
+    prim = np.zeros(1, T.Primitive)
+    prim["transform"] = np.eye(4)
+    prim["index_count"] = 3 * n
+    for key in ("base_color_texture", "metallic_roughness_texture", "normal_map"):
+        prim["material"][key] = -1
+    idx = np.arange(3 * n, dtype=np.uint32)
+    pick = np.array([0, 1, 7, 500, 1499, 2998, 2999])
+    rays = np.zeros((len(pick) + 1, 8), np.float32)
+    rays[:-1, 0] = x[pick] + 0.002; rays[:-1, 1] = 0.002
+    rays[-1, 0] = x[10] + 0.02; rays[-1, 1] = 0.002           # between two triangles: a miss
+    rays[:, 3] = 0.01; rays[:, 6] = 1.0; rays[:, 7] = 100.0
+    stats = []
+    for builder in ("1", "0"):
+        monkeypatch.setenv("VHR_BVH_BUILDER", builder)
+        with capi.Context(64, 64) as ctx:
+            ctx.update_geometry(v, idx, prim)
+            st = ctx.bvh_stats()
+            stats.append((st.n_triangles, st.n_wide_nodes, st.wide_depth))
+            t, ids, _ = ctx.trace_explicit(rays, any_hit=False)
+            np.testing.assert_allclose(t[:-1], 5.0, atol=1e-5)
+            assert t[-1] == -1.0
+            t_any, _, _ = ctx.trace_explicit(rays, any_hit=True)
+            assert (t_any[:-1] == 1.0).all() and t_any[-1] == 0.0          # any-hit: 1 = occluded
+    assert stats[0] == stats[1] and stats[0][0] == n and stats[0][2] <= 40, stats

@@ -194,6 +194,8 @@ __device__ __forceinline__ float box_half_area(float3 mn, float3 mx) {
 // union with it has the smallest surface area; mutual nearest neighbours merge into a new internal node; the survivors are
 // compacted. Same Tree2 conventions as the radix tree (internal ids < n-1, root = 0: ids are handed out from n-2 downwards,
 // and the n-1-th merge is the root), so refit / SAH leaf decisions / widening run unchanged on either hierarchy.
+constexpr int kPlocMaxRounds = 512;     // these scenes take 30-45
+
 struct PlocBuf {
     uint32_t *id;      // unified node id of the cluster
     float4 *mn, *mx;   // its box
@@ -515,7 +517,9 @@ void free_bvh(vhr_context *ctx) {
     b = Bvh();
 }
 
-int build_bvh(vhr_context *ctx) {
+// One build with the given hierarchy builder (1 PLOC, 0 radix tree). *retry_radix is set when the failure is one the radix tree does
+// not share: PLOC needing more rounds than allowed, or a tree deeper than the traversal stack.
+static int build_bvh_with(vhr_context *ctx, const int builder, bool *retry_radix) {
     Bvh &bvh = ctx->bvh;
     bvh = Bvh();
     cudaStream_t st = ctx->stream;
@@ -602,7 +606,7 @@ int build_bvh(vhr_context *ctx) {
         TRYCUDA(cudaMemsetAsync(t.cluster, 0, std::max<size_t>(n_inner, 1), st));
         // 1 (default) PLOC, 0 radix tree (Karras). Measured at 1080p, shadow + AO / reflection pass (gpurun_out/r01i_trace.log): 260 k triangles
         // 0.637 -> 0.596 / 0.888 -> 0.795 ms, 1 M 0.716 -> 0.681 / 1.058 -> 0.978 ms, 3 M 0.782 -> 0.756 / 1.25 -> 1.09 ms; build 10 -> 14.5 ms at 3 M.
-        const int builder = getenv("VHR_BVH_BUILDER") ? atoi(getenv("VHR_BVH_BUILDER")) : 1;
+        // (builder: parameter)
         if (n_inner && builder == 1) {
             const int radius = getenv("VHR_PLOC_RADIUS") ? atoi(getenv("VHR_PLOC_RADIUS")) : 8;      // 4 / 8 / 16 / 32 measured: 8 is the fastest to trace
             PlocBuf buf[2];
@@ -624,7 +628,7 @@ int build_bvh(vhr_context *ctx) {
             uint32_t N = n;
             int cur = 0;
             for (int round = 0; N > 1; ++round) {
-                if (round > 4096) { rc = fail(VHR_ERR_CUDA, "PLOC did not converge"); goto done; }
+                if (round > kPlocMaxRounds) { *retry_radix = true; rc = fail(VHR_ERR_INVALID, "PLOC needs more than %d rounds (one merge per round: geometry strung out with growing gaps)", kPlocMaxRounds); goto done; }
                 const uint32_t g = (N + 255) / 256;
                 if (radius >= 32) ploc_nn_kernel<32><<<g, 256, 0, st>>>(buf[cur], N, d_nn);
                 else if (radius >= 16) ploc_nn_kernel<16><<<g, 256, 0, st>>>(buf[cur], N, d_nn);
@@ -690,8 +694,9 @@ int build_bvh(vhr_context *ctx) {
                 TRYCUDA(cudaStreamSynchronize(st));
                 cur ^= 1;
             }
-            if (n_in) { rc = fail(VHR_ERR_CUDA, "BVH widening did not terminate"); goto done; }
+            if (n_in) { *retry_radix = builder == 1; rc = fail(VHR_ERR_CUDA, "BVH widening did not terminate"); goto done; }
             if ((int)bvh.stats.wide_depth > kStackSize) {
+                *retry_radix = builder == 1;
                 rc = fail(VHR_ERR_INVALID, "BVH is %u levels deep, the traversal stack holds %d (degenerate geometry?)", bvh.stats.wide_depth, kStackSize);
                 goto done;
             }
@@ -738,6 +743,20 @@ done:
     return rc;
 #undef TRY
 #undef TRYCUDA
+}
+
+// PLOC by default (VHR_BVH_BUILDER=0: radix tree). Agglomerative clustering degenerates on geometry strung out along a line with
+// steadily growing gaps (every cluster's nearest neighbour is on the same side: one merge per round, a tree as deep as it is long);
+// the radix tree's depth is bounded by the key length, so such a scene is rebuilt with it instead of being refused.
+int build_bvh(vhr_context *ctx) {
+    const int builder = getenv("VHR_BVH_BUILDER") ? atoi(getenv("VHR_BVH_BUILDER")) : 1;
+    bool retry_radix = false;
+    int rc = build_bvh_with(ctx, builder, &retry_radix);
+    if (rc != VHR_OK && retry_radix) {
+        retry_radix = false;
+        rc = build_bvh_with(ctx, 0, &retry_radix);
+    }
+    return rc;
 }
 
 }  // namespace vhr
