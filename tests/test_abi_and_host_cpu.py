@@ -162,3 +162,19 @@ def test_partition_arguments_are_validated():
             with pytest.raises(capi.VhrError) as e:
                 call()
             assert "VHR_DEVICE_NONE" in str(e.value)
+
+
+def test_queue_and_semaphore_arguments_are_validated():
+    """vhr_select_queue / vhr_queue_signal / vhr_queue_wait: argument checks work without a device; on a validation-only context the
+    calls themselves record nothing and succeed."""
+    with capi.Context(64, 48, device=host_api.DEVICE_NONE) as ctx:
+        ctx.select_queue(0); ctx.select_queue(1); ctx.select_queue(0)
+        ctx.queue_signal(0); ctx.queue_wait(0); ctx.queue_wait(capi.MAX_SEMAPHORES - 1)
+        for bad in (-1, 2):
+            with pytest.raises(capi.VhrError):
+                ctx.select_queue(bad)
+        for bad in (-1, capi.MAX_SEMAPHORES):
+            with pytest.raises(capi.VhrError):
+                ctx.queue_signal(bad)
+            with pytest.raises(capi.VhrError):
+                ctx.queue_wait(bad)

@@ -323,3 +323,13 @@ def test_raygen_sky_and_band_consistency():
     bot = osc.raygen(pfd, g["depth"], g["normals"], rows=(20, H))
     np.testing.assert_array_equal(np.concatenate([top["shadow_ao"][:20], bot["shadow_ao"][20:]]), full["shadow_ao"])
     np.testing.assert_array_equal(np.concatenate([top["reflections"][:20], bot["reflections"][20:]]), full["reflections"])
+
+
+def test_oracle_thread_count_can_be_set_explicitly():
+    """bench.py's CPU arm sets the OpenMP thread count itself (torchrun exports OMP_NUM_THREADS=1 to every rank) and reports what
+    the runtime then uses."""
+    before = O.set_num_threads(0)
+    assert before >= 1
+    assert O.set_num_threads(2) == 2
+    assert O.set_num_threads(0) == 2
+    O.set_num_threads(before)
