@@ -113,13 +113,6 @@ __device__ __forceinline__ bool intersect_tri(const RayPre &r, float tmin, float
 __device__ __forceinline__ float byte_biased(uint32_t w, int i, uint32_t bias) {
     return __uint_as_float(__byte_perm(w, bias, 0x7604u | ((uint32_t)i << 4)));
 }
-// (a <= b) ? 0xffffffff : 0 in one instruction (FSET.BF), so a hit bit costs FSET + LOP3 instead of FSETP + SEL + IADD3
-__device__ __forceinline__ uint32_t set_le(float a, float b) {
-    uint32_t r;
-    asm("set.le.u32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
-    return r;
-}
-
 struct Hit {
     float t, u, v;
     uint32_t tri;
@@ -157,26 +150,36 @@ __device__ __forceinline__ void intersect_node(const WideNode *__restrict__ node
     const uint32_t nearx[2] = {nx ? n3.z : n2.x, nx ? n3.w : n2.y}, farx[2] = {nx ? n2.x : n3.z, nx ? n2.y : n3.w};
     const uint32_t neary[2] = {ny ? n4.x : n2.z, ny ? n4.y : n2.w}, fary[2] = {ny ? n2.z : n4.x, ny ? n2.w : n4.y};
     const uint32_t nearz[2] = {nz ? n4.z : n3.x, nz ? n4.w : n3.y}, farz[2] = {nz ? n3.x : n4.z, nz ? n3.y : n4.w};
-    uint32_t hits = 0u;
+    uint32_t miss = 0u;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 7; s >= 0; --s) {
         const int w = s >> 2, b = s & 3;
         const float tnx = fmaf(byte_biased(nearx[w], b, bias), ax, bnx), tfx = fmaf(byte_biased(farx[w], b, bias), afx, bfx);
         const float tny = fmaf(byte_biased(neary[w], b, bias), ay, bny), tfy = fmaf(byte_biased(fary[w], b, bias), afy, bfy);
         const float tnz = fmaf(byte_biased(nearz[w], b, bias), az, bnz), tfz = fmaf(byte_biased(farz[w], b, bias), afz, bfz);
         const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
         const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-        // empty slots carry an inverted box (qlo = 255, qhi = 0) and can never pass this test
-        hits |= set_le(tn, tf) & (1u << s);
+        // empty slots carry an inverted box (qlo = 255, qhi = 0) and can never pass this test.
+        // tn <= tf  <=>  the sign bit of tf - tn is clear (x - x = +0 under round-to-nearest; both are finite); a funnel shift moves
+        // that bit into the mask: FADD + SHF per child instead of FSETP + SEL + LOP3. Slots go 7 -> 0 so slot 0 ends in bit 0.
+        miss = __funnelshift_l(__float_as_uint(tf - tn), miss, 1);
     }
+    const uint32_t hits = ~miss & 0xffu;
     const uint32_t imask = n0.w >> 24;
     child_hits = hits & imask;
     leaf_hits = hits & ~imask;
 }
 
 // Takes the next child out of a (base | reverse << 31, hit mask) group: lowest slot first, or highest first when the node's slots are
-// sorted along an axis the ray runs against.
+// sorted along an axis the ray runs against. FIXED_ORDER (any-hit rays: their groups never carry the reverse bit) is the two-instruction
+// lowest-first pop.
+template <bool FIXED_ORDER>
 __device__ __forceinline__ uint32_t pop_child(uint2 &group) {
+    if (FIXED_ORDER) {
+        const uint32_t k = (uint32_t)__ffs((int)group.y) - 1u;
+        group.y &= group.y - 1u;
+        return k;
+    }
     const uint32_t k = (group.x >> 31) ? 31u - (uint32_t)__clz((int)group.y) : (uint32_t)__ffs((int)group.y) - 1u;
     group.y &= ~(1u << k);
     return k;
@@ -220,9 +223,9 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
             if (sp == 0) break;
             group = stack[--sp];
         }
-        const uint32_t k = pop_child(group);
+        const uint32_t k = pop_child<ANY>(group);
         if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
-        const uint32_t node = (group.x & 0x7fffffffu) + k;
+        const uint32_t node = (ANY ? group.x : (group.x & 0x7fffffffu)) + k;
         uint32_t child_base, child_hits, leaf_hits;
         intersect_node(nodes, node, r, ray.tmin, tmax, bias, child_base, child_hits, leaf_hits);
         // any-hit rays keep one fixed order (lowest slot first): measured faster than near-side-first for the incoherent AO rays
@@ -280,9 +283,9 @@ __device__ __forceinline__ bool trace_batched(const WideNode *__restrict__ nodes
                 else group = stack[--sp];
             }
             if (have) {
-                const uint32_t k = pop_child(group);
+                const uint32_t k = pop_child<ANY>(group);
                 if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
-                const uint32_t node = (group.x & 0x7fffffffu) + k;
+                const uint32_t node = (ANY ? group.x : (group.x & 0x7fffffffu)) + k;
                 uint32_t child_base, child_hits, leaf_hits;
                 intersect_node(nodes, node, r, ray.tmin, tmax, bias, child_base, child_hits, leaf_hits);
                 if (ANY) child_base &= 0x7fffffffu;           // same order policy as trace()
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(128) raygen_persistent_kernel(const __grid_con
                 else group = stack[--sp];
             }
             if (!done) {
-                const uint32_t k = pop_child(group);
+                const uint32_t k = pop_child<false>(group);
                 if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
                 const uint32_t node = (group.x & 0x7fffffffu) + k;
                 uint32_t child_base, child_hits, leaf_hits;
