@@ -499,6 +499,11 @@ def run_gpu(args):
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "ms_per_launch": dom["ms"],
                     "share_of_step": dom["share"]}
+        if dom["kernel"] == "raygen_kernel":
+            # the contract's roofline is HBM or tensor; a software BVH traversal is bound by neither — say what does bound it
+            roofline["note"] = ("not an HBM-bound kernel: ncu (profiles/r01_ncu_final_summary.md) has it at 75 % instruction-issue "
+                                "utilisation and 64 % ALU pipe with 15.3 of 32 lanes active per instruction (software BVH traversal, "
+                                "no RT cores on B200), DRAM at 2 % of peak; the figure of merit is rt_pass.mrays_s")
         svgf_bytes = px * (HP.BYTES_TEMPORAL + 5 * HP.BYTES_ATROUS + 3 * HP.BYTES_BLIT)
         svgf_min_bytes = px * 148
         line = {
