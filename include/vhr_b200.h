@@ -291,6 +291,8 @@ typedef struct vhr_bvh_stats {
     float scene_max[3];
     float build_ms;              /* device time of the last build */
     uint32_t wide_depth;         /* levels of the wide tree (bounds the traversal stack) */
+    uint32_t n_used_slots;       /* child slots in use over all wide nodes (internal children + leaves): n_used_slots / (8 n_wide_nodes) is the
+                                    fill rate — every slot of a visited node is slab-tested whether it is used or not */
 } vhr_bvh_stats;
 int vhr_get_bvh_stats(vhr_context *ctx, vhr_bvh_stats *out);
 

@@ -26,7 +26,7 @@ def main(tris=260_000, W=1920, H=1080, reps=10):
         t0 = time.time()
         ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
         st = ctx.bvh_stats()
-        print(f"update_geometry {time.time()-t0:.3f}s wall; build {st.build_ms:.2f} ms device; wide nodes {st.n_wide_nodes}; depth {st.wide_depth}; sah {st.sah_cost:.1f}")
+        print(f"update_geometry {time.time()-t0:.3f}s wall; build {st.build_ms:.2f} ms device; wide nodes {st.n_wide_nodes}; depth {st.wide_depth}; slots in use {st.n_used_slots / max(8 * st.n_wide_nodes, 1) * 100:.1f}%; sah {st.sah_cost:.1f}")
         ctx.update_per_frame_ubo(pfd)
         ctx.set_option(capi.OPT_RAYGEN_VARIANT, int(os.environ.get('VHR_RAYGEN_VARIANT', '1')))
         for n, f in GB.items():

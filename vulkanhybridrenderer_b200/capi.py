@@ -58,7 +58,7 @@ ADDRESS_MODE_REPEAT, ADDRESS_MODE_MIRRORED_REPEAT, ADDRESS_MODE_CLAMP_TO_EDGE, A
 class BvhStats(C.Structure):
     _fields_ = [("n_triangles", C.c_uint32), ("n_bvh2_nodes", C.c_uint32), ("n_wide_nodes", C.c_uint32),
                 ("max_leaf_size", C.c_uint32), ("sah_cost", C.c_float), ("scene_min", C.c_float * 3),
-                ("scene_max", C.c_float * 3), ("build_ms", C.c_float), ("wide_depth", C.c_uint32)]
+                ("scene_max", C.c_float * 3), ("build_ms", C.c_float), ("wide_depth", C.c_uint32), ("n_used_slots", C.c_uint32)]
 
 
 class VhrError(RuntimeError):

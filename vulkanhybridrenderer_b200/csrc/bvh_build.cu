@@ -314,7 +314,7 @@ struct WidenArgs {
     const uint2 *queue_in;       // (binary node, wide node index)
     uint2 *queue_out;
     uint32_t n_in;
-    uint32_t *counters;          // [0] wide nodes allocated, [1] triangles emitted, [2] queue_out size
+    uint32_t *counters;          // [0] wide nodes allocated, [1] triangles emitted, [2] queue_out size, [3] child slots in use
     float *sah;                  // accumulated SAH numerator
     int child_sort;              // 0: slots in collapse order; 1: largest surface area first; 2: ascending along the axis of largest spread
 };
@@ -404,6 +404,7 @@ __device__ void emit_wide_node(const WidenArgs &a, uint32_t wide_idx, const uint
     }
     a.wide[wide_idx] = w;
     atomicAdd(a.sah, sah);
+    atomicAdd(&a.counters[3], (uint32_t)nk);
 }
 
 __global__ void widen_kernel(const __grid_constant__ WidenArgs a) {
@@ -727,6 +728,7 @@ static int build_bvh_with(vhr_context *ctx, const int builder, bool *retry_radix
         bvh.stats.sah_cost = root_area > 0.0f ? sah_num / root_area : 0.0f;
         bvh.stats.n_bvh2_nodes = bvh.n_nodes2;
         bvh.stats.n_wide_nodes = bvh.n_wide;
+        bvh.stats.n_used_slots = counters[3];
         TRYCUDA(cudaEventRecord(ev1, st));
         TRYCUDA(cudaEventSynchronize(ev1));
         float ms = 0.0f;
