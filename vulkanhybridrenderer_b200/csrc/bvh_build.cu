@@ -8,7 +8,8 @@
 //   4. hierarchy binary tree over the sorted triangles: PLOC (parallel locally-ordered clustering, Meister & Bittner 2018; default:
 //                3-12 % faster to trace) or the radix tree over the codes (Karras 2012; VHR_BVH_BUILDER=0)
 //   5. refit     bottom-up AABBs + SAH cost; subtrees of <= 3 triangles collapse into leaves when SAH prefers it
-//   6. widen     level-synchronous collapse of the binary tree into 8-wide nodes (largest-area child opened first),
+//   5b. collapse which binary nodes become wide nodes / leaves: cost-optimal dynamic programme (default) or greedy (VHR_COLLAPSE=0)
+//   6. widen     level-synchronous emission of the 8-wide nodes, slots sorted along the axis of largest spread,
 //                child boxes quantised to 8 bits (conservative), leaf triangles rewritten contiguously per node
 #include <stdlib.h>
 #include <cub/cub.cuh>
