@@ -17,8 +17,9 @@ namespace vhr {
 //                           (box centres ascending; 3 = not sorted). A ray whose direction is negative on that axis visits the
 //                           hit children from the highest slot down, so the near side comes first either way.
 //   meta[i] == 0            empty slot (its box is inverted: qlo = 255, qhi = 0)
-//   meta[i] & 0x80          internal child; node index = child_base + (meta[i] & 7)
-//   otherwise               leaf child: triangles [tri_base + (meta[i] & 31), + (meta[i] >> 5)), 1..3 triangles
+//   slot i internal          bit i of imask (the traversal tells internal from leaf by imask only); meta[i] = 0x80 | ordinal,
+//                           node index = child_base + ordinal
+//   otherwise               leaf child: triangles [tri_base + (meta[i] & 31), + (meta[i] >> 5)), 1..3 triangles (4 with VHR_MAX_LEAF_TRIS=4)
 struct __align__(16) WideNode {
     float origin[3];
     uint8_t e[3];

@@ -270,7 +270,7 @@ __global__ void ploc_merge_kernel(PlocBuf in, PlocBuf out, uint32_t N, const uin
 
 // ---- 5. refit + SAH --------------------------------------------------------------------------------------------
 
-__global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__restrict__ order, Tree2 t, float tri_cost) {
+__global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__restrict__ order, Tree2 t, float tri_cost, uint32_t max_leaf) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= t.n) return;
     const TriRef r = tris[order[j]];
@@ -295,7 +295,7 @@ __global__ void refit_kernel(const TriRef *__restrict__ tris, const uint32_t *__
         float area = box_half_area(mn, mx);
         float cost_inner = area * 1.0f + lmn.w + rmn.w;       // node cost 1, triangle cost 1
         float cost_leaf = area * (float)cnt * tri_cost;
-        bool cl = cnt <= (uint32_t)kMaxLeafTris && cost_leaf <= cost_inner;
+        bool cl = cnt <= max_leaf && cost_leaf <= cost_inner;
         t.cluster[p] = cl ? 1 : 0;
         t.lcount[p] = cl ? 1u : __ldcg(&t.lcount[l]) + __ldcg(&t.lcount[rr]);
         t.bmin[p] = make_float4(mn.x, mn.y, mn.z, cl ? cost_leaf : cost_inner);
@@ -323,7 +323,7 @@ __device__ __forceinline__ float dp_cost_of(const Tree2 &t, const DpTables &d, u
     return id >= t.n - 1 ? __ldcg(&t.bmin[id]).w : __ldcg(&d.cost[(size_t)id * 7 + (i - 1)]);
 }
 
-__global__ void collapse_dp_kernel(Tree2 t, DpTables d, float node_cost, float tri_cost) {
+__global__ void collapse_dp_kernel(Tree2 t, DpTables d, float node_cost, float tri_cost, uint32_t max_leaf) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= t.n || t.n == 1) return;
     uint32_t p = t.parent[t.n - 1 + j];
@@ -352,7 +352,7 @@ __global__ void collapse_dp_kernel(Tree2 t, DpTables d, float node_cost, float t
             D[jj] = best; K[jj] = bk;
         }
         const float c_int = area * node_cost + D[8];
-        const float c_leaf = cnt <= (uint32_t)kMaxLeafTris ? area * (float)cnt * tri_cost : 3.0e38f;
+        const float c_leaf = cnt <= max_leaf ? area * (float)cnt * tri_cost : 3.0e38f;
         const bool leaf = c_leaf <= c_int;
         float prev = leaf ? c_leaf : c_int;
         d.cost[(size_t)p * 7] = prev;
@@ -757,7 +757,10 @@ static int build_bvh_with(vhr_context *ctx, const int builder, bool *retry_radix
             TRYCUDA(cudaGetLastError()); ctx->launches++;
         }
         const float tri_cost = getenv("VHR_BVH_CT") ? (float)atof(getenv("VHR_BVH_CT")) : 1.0f;
-        refit_kernel<<<G, B, 0, st>>>(d_tris, d_vals2, t, tri_cost);
+        // triangles per leaf slot: kMaxLeafTris (3) by default; VHR_MAX_LEAF_TRIS=1..4 for study (8 slots x 4 = the 32-bit triangle mask of a node)
+        const uint32_t max_leaf = (uint32_t)std::min(4, std::max(1, getenv("VHR_MAX_LEAF_TRIS") ? atoi(getenv("VHR_MAX_LEAF_TRIS")) : kMaxLeafTris));
+        bvh.stats.max_leaf_size = max_leaf;
+        refit_kernel<<<G, B, 0, st>>>(d_tris, d_vals2, t, tri_cost, max_leaf);
         TRYCUDA(cudaGetLastError()); ctx->launches++;
         // VHR_COLLAPSE: 1 (default) cost-optimal collapse (collapse_dp_kernel), 0 the greedy one; VHR_DP_NODE_COST = cost of visiting one
         // 8-wide node in units of one triangle test per unit area (0.5 / 1 / 2 measured: 1). Measured at 1080p (gpurun_out/r01v_trace.log):
@@ -769,7 +772,7 @@ static int build_bvh_with(vhr_context *ctx, const int builder, bool *retry_radix
             TRY(dmalloc(&dp.cost, (size_t)n_inner * 7)); track(dp.cost);
             TRY(dmalloc(&dp.dec, (size_t)n_inner * 8)); track(dp.dec);
             TRYCUDA(cudaMemsetAsync(t.visit, 0, (size_t)n_inner * sizeof(int), st));
-            collapse_dp_kernel<<<G, B, 0, st>>>(t, dp, getenv("VHR_DP_NODE_COST") ? (float)atof(getenv("VHR_DP_NODE_COST")) : 1.0f, tri_cost);
+            collapse_dp_kernel<<<G, B, 0, st>>>(t, dp, getenv("VHR_DP_NODE_COST") ? (float)atof(getenv("VHR_DP_NODE_COST")) : 1.0f, tri_cost, max_leaf);
             TRYCUDA(cudaGetLastError()); ctx->launches++;
         }
 
