@@ -159,3 +159,68 @@ def test_png_from_independent_encoder():
         assert np.array_equal(got, np.asarray(im.convert("RGBA"))), mode
     with pytest.raises(capi.VhrError):
         host_api.decode_png(b"\xff\xd8\xff\xe0 not a png")      # JPEG magic: rejected loudly
+
+
+def _hand_built_gltf(tmp_path, index_type):
+    """Two triangles in one interleaved vertex buffer view (byteStride 28: POSITION f32x3, NORMAL f32x3, TEXCOORD_0 normalised u16x2),
+    indices as u8 / u16 / u32, the mesh under a child node (matrix) of a parent node (TRS), plus a second primitive without normals."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float32)
+    nrm = np.array([[0, 0, 1]] * 4, np.float32)
+    uv16 = np.array([[0, 0], [65535, 0], [0, 65535], [65535, 32768]], np.uint16)
+    inter = bytearray()
+    for i in range(4):
+        inter += pos[i].tobytes() + nrm[i].tobytes() + uv16[i].tobytes()
+    assert len(inter) == 4 * 28
+    idx = np.array([0, 1, 2, 2, 1, 3], {5121: np.uint8, 5123: np.uint16, 5125: np.uint32}[index_type])
+    pos2 = (pos + np.float32(10)).astype(np.float32)
+    blob = bytes(inter)
+    off_idx = len(blob); blob += idx.tobytes(); blob += b"\0" * (-len(blob) % 4)
+    off_pos2 = len(blob); blob += pos2.tobytes()
+    (tmp_path / "hand.bin").write_bytes(blob)
+    q = [0.0, float(np.sin(np.pi / 4)), 0.0, float(np.cos(np.pi / 4))]          # 90 degrees about +Y
+    child = np.eye(4, dtype=np.float32); child[:3, 3] = [0.5, 0.0, 0.0]          # translation, written column-major below
+    doc = {
+        "asset": {"version": "2.0"},
+        "buffers": [{"uri": "hand.bin", "byteLength": len(blob)}],
+        "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 4 * 28, "byteStride": 28},
+                        {"buffer": 0, "byteOffset": off_idx, "byteLength": idx.nbytes},
+                        {"buffer": 0, "byteOffset": off_pos2, "byteLength": pos2.nbytes}],
+        "accessors": [{"bufferView": 0, "byteOffset": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+                      {"bufferView": 0, "byteOffset": 12, "componentType": 5126, "count": 4, "type": "VEC3"},
+                      {"bufferView": 0, "byteOffset": 24, "componentType": 5123, "normalized": True, "count": 4, "type": "VEC2"},
+                      {"bufferView": 1, "componentType": index_type, "count": 6, "type": "SCALAR"},
+                      {"bufferView": 2, "componentType": 5126, "count": 4, "type": "VEC3"}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3},
+                                   {"attributes": {"POSITION": 4}, "indices": 3}]}],
+        "nodes": [{"children": [1], "translation": [1.0, 2.0, 3.0], "rotation": q, "scale": [2.0, 2.0, 2.0]},
+                  {"mesh": 0, "matrix": [float(x) for x in child.T.reshape(-1)]}],
+        "scenes": [{"nodes": [0]}], "scene": 0,
+    }
+    path = tmp_path / "hand.gltf"
+    path.write_text(json.dumps(doc))
+    return path, pos, nrm, uv16, idx, pos2, child
+
+
+@pytest.mark.parametrize("index_type", [5121, 5123, 5125])
+def test_interleaved_views_index_types_and_node_hierarchy(tmp_path, index_type):
+    path, pos, nrm, uv16, idx, pos2, child = _hand_built_gltf(tmp_path, index_type)
+    got = host_api.parse_gltf(path)
+    v = got["vertices"]
+    assert len(v) == 8 and len(got["indices"]) == 12 and len(got["primitives"]) == 2
+    np.testing.assert_array_equal(v["pos"][:4], pos)
+    np.testing.assert_array_equal(v["normal"][:4], nrm)
+    np.testing.assert_allclose(v["uv0"][:4], uv16.astype(np.float32) / np.float32(65535), rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(v["pos"][4:], pos2)
+    assert np.all(v["normal"][4:] == 0) and np.all(v["uv0"][4:] == 0) and np.all(v["tangent"] == 0)     # absent attributes stay zero (:150-173)
+    np.testing.assert_array_equal(got["indices"], np.concatenate([idx, idx]).astype(np.uint32))         # relative to vertex_offset
+    p = got["primitives"]
+    assert list(p["vertex_offset"]) == [0, 4] and list(p["index_offset"]) == [0, 6] and list(p["index_count"]) == [6, 6]
+    # world transform = parent TRS * child matrix (column-major in Primitive.transform): T(1,2,3) * Ry(90) * S(2) * T(0.5,0,0)
+    ry = np.array([[0, 0, 1, 0], [0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 0, 1]], np.float64)
+    trs = np.eye(4); trs[:3, 3] = [1, 2, 3]
+    world = trs @ ry @ np.diag([2.0, 2.0, 2.0, 1.0]) @ child.astype(np.float64)
+    for k in range(2):
+        np.testing.assert_allclose(np.asarray(p["transform"][k], np.float64).reshape(4, 4).T, world, atol=1e-6)
+    # no material: factors 1, no textures, opaque
+    m = p["material"]
+    assert np.all(m["base_color"] == 1.0) and np.all(m["base_color_texture"] == -1) and np.all(m["alpha_mask"] == 0)
