@@ -497,7 +497,7 @@ __device__ void finish_wide_node(const WidenArgs &a, const uint2 item, uint32_t 
     }
     // a.child_sort = 2 (default): slots ascending by box centre along the axis on which the centres spread the most; the axis goes into
     // the node and a closest-hit ray pops the children low-to-high or high-to-low by the sign of its direction on that axis (near side
-    // first, so tmax shrinks early). Measured against the collapse order at 1080p (gpurun_out/r01j_trace.log, r01k_trace.log):
+    // first, so tmax shrinks early). Measured against the collapse order at 1080p (profiles/traces/r01j_trace.log, r01k_trace.log):
     // reflection pass 1.13 -> 0.91 ms (3 M triangles), 0.83 -> 0.69 ms (260 k); primary rays 0.675 -> 0.583 ms; shadow + AO unchanged
     // (0.780 -> 0.770 ms) with the any-hit rays popping lowest-first regardless of direction.
     uint32_t order_axis = 3u;
@@ -708,7 +708,7 @@ static int build_bvh_with(vhr_context *ctx, const int builder, bool *retry_radix
         TRY(dmalloc(&t.lcount, 2 * (size_t)n)); track(t.lcount);
         TRYCUDA(cudaMemsetAsync(t.visit, 0, std::max<size_t>(n_inner, 1) * sizeof(int), st));
         TRYCUDA(cudaMemsetAsync(t.cluster, 0, std::max<size_t>(n_inner, 1), st));
-        // 1 (default) PLOC, 0 radix tree (Karras). Measured at 1080p, shadow + AO / reflection pass (gpurun_out/r01i_trace.log): 260 k triangles
+        // 1 (default) PLOC, 0 radix tree (Karras). Measured at 1080p, shadow + AO / reflection pass (profiles/traces/r01i_trace.log): 260 k triangles
         // 0.637 -> 0.596 / 0.888 -> 0.795 ms, 1 M 0.716 -> 0.681 / 1.058 -> 0.978 ms, 3 M 0.782 -> 0.756 / 1.25 -> 1.09 ms; build 10 -> 14.5 ms at 3 M.
         // (builder: parameter)
         if (n_inner && builder == 1) {
@@ -763,7 +763,7 @@ static int build_bvh_with(vhr_context *ctx, const int builder, bool *retry_radix
         refit_kernel<<<G, B, 0, st>>>(d_tris, d_vals2, t, tri_cost, max_leaf);
         TRYCUDA(cudaGetLastError()); ctx->launches++;
         // VHR_COLLAPSE: 1 (default) cost-optimal collapse (collapse_dp_kernel), 0 the greedy one; VHR_DP_NODE_COST = cost of visiting one
-        // 8-wide node in units of one triangle test per unit area (0.5 / 1 / 2 measured: 1). Measured at 1080p (gpurun_out/r01v_trace.log):
+        // 8-wide node in units of one triangle test per unit area (0.5 / 1 / 2 measured: 1). Measured at 1080p (profiles/traces/r01v_trace.log):
         // slots in use 69.5 -> 89.1 %, SAH 31.8 -> 30.5, shadow + AO pass 0.721 -> 0.702 ms at 3 M triangles and 0.581 -> 0.562 ms at 260 k,
         // reflection pass 0.890 -> 0.876 / 0.691 -> 0.646 ms, primary rays 0.554 -> 0.552 / 0.428 -> 0.406 ms; build + 1 ms.
         const int collapse = getenv("VHR_COLLAPSE") ? atoi(getenv("VHR_COLLAPSE")) : 1;

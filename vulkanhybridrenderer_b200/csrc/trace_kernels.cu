@@ -229,7 +229,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
         uint32_t child_base, child_hits, leaf_hits;
         intersect_node(nodes, node, r, ray.tmin, tmax, bias, child_base, child_hits, leaf_hits);
         // any-hit rays keep one fixed order (lowest slot first): measured faster than near-side-first for the incoherent AO rays
-        // (0.496 -> 0.472 ms at 3 M triangles, gpurun_out/r01k_trace.log) — neighbouring lanes then fetch the same children
+        // (0.496 -> 0.472 ms at 3 M triangles, profiles/traces/r01k_trace.log) — neighbouring lanes then fetch the same children
         if (ANY) child_base &= 0x7fffffffu;
         group = make_uint2(child_base, child_hits);
         if (leaf_hits) {
@@ -439,7 +439,7 @@ __device__ __forceinline__ void tile_coords(int &x, int &y) {
 // traces the t-th ray in key order and hands the result back to the pixel's thread through shared memory; lanes without a ray
 // (sky, AO off) sort to the end, so whole warps of them do nothing. The rays and their any-hit answers are the same, only the
 // thread that computes each one changes.
-// Measured (gpurun_out/r01r_trace.log, 1080p): AO pass 0.467 -> 0.507 ms at 3 M triangles, 0.393 -> 0.422 ms at 260 k — slower: the rays of
+// Measured (profiles/traces/r01r_trace.log, 1080p): AO pass 0.467 -> 0.507 ms at 3 M triangles, 0.393 -> 0.422 ms at 260 k — slower: the rays of
 // a warp now start up to 16 pixels apart, and that costs more than the common direction gains. Kept for study, not the default.
 struct AoSortShared {
     float4 o[128];            // origin.xyz, tmin
@@ -503,7 +503,7 @@ __device__ __forceinline__ bool trace_any_sorted(const SceneRefs &scene, const R
     return mine;
 }
 
-// MIN_BLOCKS is the occupancy target handed to ptxas (__launch_bounds__). Measured at 1080p / 3 M triangles (gpurun_out/r01c_trace.log):
+// MIN_BLOCKS is the occupancy target handed to ptxas (__launch_bounds__). Measured at 1080p / 3 M triangles (profiles/traces/r01c_trace.log):
 //   8 (default): 64 registers, 8 blocks / SM, ~10 spilled words — 0.879 ms shadow+AO, 2.40 ms shadow + 2 AO + reflection;
 //   0 (VHR_OPT_RAYGEN_VARIANT 2): unspecified, ptxas settles on 72 registers / 7 blocks — 0.883 / 2.47 ms;
 //   1 (variant 3): no cap, 117 registers / 4 blocks — 1.16 / 3.39 ms (fewer warps to hide the node fetches);
