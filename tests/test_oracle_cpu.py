@@ -333,3 +333,95 @@ def test_oracle_thread_count_can_be_set_explicitly():
     assert O.set_num_threads(2) == 2
     assert O.set_num_threads(0) == 2
     O.set_num_threads(before)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent scalar transcription of the WHOLE of svgf.comp (motion, 2x2 taps, 3x3 retry), written from the shader text
+# ---------------------------------------------------------------------------------------------------------------
+def _svgf_comp_scalar(pfd, normals, motion, rt, prev_normals, history, moments):
+    """svgf.comp:16-145 one pixel at a time in float32, separate multiplies and adds, GLSL conversions (int() and ivec2() truncate,
+    fract = x - floor(x), mix(a, b, t) = a (1 - t) + b t). The moments image is RG16F: a load returns (x, y, 0, 1), a store keeps .xy."""
+    H, W = rt.shape[:2]
+    dsx, dsy = f32(pfd["display_size"][0]), f32(pfd["display_size"][1])
+    n32, m32, r32 = normals.astype(f32), motion.astype(f32), rt.astype(f32)
+    pn32, h32, mo32 = prev_normals.astype(f32), history.astype(f32), moments.astype(f32)
+    integ = np.zeros((H, W, 4), np.float16)
+    mom_out = np.zeros((H, W, 2), np.float16)
+    one, cos_pi_4 = f32(1), f32(0.70710678118654752440084)
+
+    def valid(px, py, cur_id, cur_n):
+        if px < 0 or py < 0 or f32(px) >= dsx or f32(py) >= dsy:
+            return False
+        p = pn32[py, px]
+        if cur_id != int(p[3]):
+            return False
+        d = f32(f32(f32(cur_n[0] * p[0]) + f32(cur_n[1] * p[1])) + f32(cur_n[2] * p[2]))
+        return not (d < cos_pi_4)
+
+    for cy in range(H):
+        for cx in range(W):
+            cur_n, cur_id = n32[cy, cx, :3], int(n32[cy, cx, 3])
+            mvx, mvy = m32[cy, cx, 0], m32[cy, cx, 1]
+            cs, ca = r32[cy, cx, 0], r32[cy, cx, 1]
+            pcx = f32(f32(f32(cx) - f32(mvx * dsx)) + f32(0.5))
+            pcy = f32(f32(f32(cy) - f32(mvy * dsy)) + f32(0.5))
+            x, y = f32(pcx - np.floor(pcx)), f32(pcy - np.floor(pcy))
+            ax, ay = int(pcx), int(pcy)                                     # ivec2(): towards zero
+            w4 = [f32(f32(one - x) * f32(one - y)), f32(x * f32(one - y)), f32(f32(one - x) * y), f32(x * y)]
+            ps = pa = f32(0); psm = [f32(0), f32(0)]; pam = [f32(0), f32(0)]; s = f32(0)
+            for i, (ox, oy) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+                sx, sy = ax + ox, ay + oy
+                if valid(sx, sy, cur_id, cur_n):
+                    hv, mv = h32[sy, sx], (mo32[sy, sx, 0], mo32[sy, sx, 1], f32(0), f32(1))
+                    ps = f32(ps + f32(w4[i] * hv[0])); pa = f32(pa + f32(w4[i] * hv[1]))
+                    psm = [f32(psm[0] + f32(w4[i] * mv[0])), f32(psm[1] + f32(w4[i] * mv[1]))]
+                    pam = [f32(pam[0] + f32(w4[i] * mv[2])), f32(pam[1] + f32(w4[i] * mv[3]))]
+                    s = f32(s + w4[i])
+            ok = s > f32(1e-6)
+            if not ok:                                                      # accumulators are NOT reset (svgf.comp:81-97)
+                for oy in (-1, 0, 1):
+                    for ox in (-1, 0, 1):
+                        sx, sy = ax + ox, ay + oy
+                        if valid(sx, sy, cur_id, cur_n):
+                            hv, mv = h32[sy, sx], (mo32[sy, sx, 0], mo32[sy, sx, 1], f32(0), f32(1))
+                            ps = f32(ps + hv[0]); pa = f32(pa + hv[1])
+                            psm = [f32(psm[0] + mv[0]), f32(psm[1] + mv[1])]
+                            pam = [f32(pam[0] + mv[2]), f32(pam[1] + mv[3])]
+                            s = f32(s + one)
+                ok = s > f32(1e-6)
+            sm = [cs, f32(cs * cs)]; am = [ca, f32(ca * ca)]
+            mix = lambda a, b, t: f32(f32(a * f32(one - t)) + f32(b * t))
+            if ok:
+                al = f32(0.2)
+                ps = f32(ps / s); pa = f32(pa / s)
+                psm = [f32(psm[0] / s), f32(psm[1] / s)]; pam = [f32(pam[0] / s), f32(pam[1] / s)]
+                sm = [mix(psm[0], sm[0], al), mix(psm[1], sm[1], al)]
+                am = [mix(pam[0], am[0], al), mix(pam[1], am[1], al)]
+                vs = max(f32(0), f32(sm[1] - f32(sm[0] * sm[0]))); va = max(f32(0), f32(am[1] - f32(am[0] * am[0])))
+                integ[cy, cx] = (mix(ps, cs, al), mix(pa, ca, al), vs, va)
+            else:
+                vs = max(f32(0), f32(sm[1] - f32(sm[0] * sm[0]))); va = max(f32(0), f32(am[1] - f32(am[0] * am[0])))
+                integ[cy, cx] = (cs, ca, vs, va)
+            mom_out[cy, cx] = (sm[0], sm[1])
+    return integ, mom_out
+
+
+def test_temporal_oracle_vs_scalar_transcription_with_motion():
+    W, H = 40, 28
+    _, _, frames = Hh.scene_and_gbuffer(W, H, tris=6000, moving=True)
+    (_, g0), (pfd, g1) = frames[0], frames[1]
+    rng = np.random.default_rng(9)
+    rt = np.stack([rng.integers(0, 2, (H, W)), rng.integers(0, 3, (H, W)) * 0.5], -1).astype(np.float16)
+    hist = np.zeros((H, W, 4), np.float16)
+    hist[..., :2] = rng.uniform(0, 1, (H, W, 2))
+    mom = rng.uniform(0, 1, (H, W, 2)).astype(np.float16)
+    # larger motion than the 0.05-unit camera step gives, so taps leave the image and the 3x3 retry is exercised
+    motion = g1["motion"].copy()
+    motion[..., 0] = (motion[..., 0].astype(f32) * f32(6) + f32(0.02)).astype(np.float16)
+    motion[..., 1] = (motion[..., 1].astype(f32) * f32(6) - f32(0.03)).astype(np.float16)
+    got_i, got_m = O.svgf_temporal(pfd, g1["normals"], motion, rt, g0["normals"], hist, mom)
+    want_i, want_m = _svgf_comp_scalar(pfd, g1["normals"], motion, rt, g0["normals"], hist, mom)
+    valid_px = (got_i[..., 0] != rt[..., 0]) | (got_i[..., 2] != 0)
+    assert 0.2 < valid_px.mean() < 0.98                  # both outcomes of the reprojection occur
+    np.testing.assert_array_equal(got_i.view(np.uint16), want_i.view(np.uint16))
+    np.testing.assert_array_equal(got_m.view(np.uint16), want_m.view(np.uint16))
