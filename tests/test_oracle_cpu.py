@@ -499,3 +499,91 @@ def test_ssao_oracle_vs_scalar_transcription():
     assert (diff <= 1e-3).mean() >= 0.99, (diff <= 1e-3).mean()
     assert (got == want.astype(np.float16).astype(f32)).mean() >= 0.97      # measured: every pixel equal after the fp16 store
     assert (got > 0).mean() > 0.3 and (got < 1).mean() > 0.3     # a real AO image, not a constant
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent transcription of raygen.rgen's ray generation (seed rule, cone / hemisphere samples, Frisvad basis, origin offset)
+# with brute-force float64 visibility: pins which rays the oracle traces, not only how it intersects them
+# ---------------------------------------------------------------------------------------------------------------
+def _onb(n):                                           # common.glsl:80-93, columns M[0], M[1], M[2]
+    if n[2] < f32(-0.9999999):
+        return np.array([0, -1, 0], f32), np.array([-1, 0, 0], f32), n
+    a = f32(f32(1) / f32(f32(1) + n[2]))
+    b = f32(f32(-n[0] * n[1]) * a)
+    return (np.array([f32(f32(1) - f32(f32(n[0] * n[0]) * a)), b, -n[0]], f32),
+            np.array([b, f32(f32(1) - f32(f32(n[1] * n[1]) * a)), -n[1]], f32), n)
+
+
+def _raygen_rays_scalar(pfd, depth, normals, x, y):
+    """raygen.rgen:14-55 for one pixel -> [(origin, direction, tmax)] for the shadow ray and the two AO rays, or None for sky."""
+    H, W = depth.shape
+    d = depth[y, x]                                                          # LINEAR sampler at the texel centre = the texel
+    if d == 0:
+        return None
+    u, v = f32(f32(x + f32(0.5)) / f32(W)), f32(f32(y + f32(0.5)) / f32(H))
+    inv = np.asarray(pfd["camera_viewproj_inverse"], f32).reshape(4, 4).T
+    p = inv @ np.array([f32(u * f32(2) - f32(1)), f32(v * f32(2) - f32(1)), d, f32(1)], f32)
+    P = (p[:3] / p[3]).astype(f32)
+    L = (-np.asarray(pfd["directional_light"]["direction"], f32)[:3]).astype(f32)
+    N = normals[y, x, :3].astype(f32)
+    origin = (P + N * f32(0.1)).astype(f32)
+    s = np.uint32((np.uint32(y) * np.uint32(H) + np.uint32(x)) * np.uint32(int(pfd["frame_index"])))     # LaunchSize.y, not .x
+    s = np.uint32((s ^ np.uint32(61)) ^ (s >> np.uint32(16))); s = np.uint32(s * np.uint32(9))
+    s = np.uint32(s ^ (s >> np.uint32(4))); s = np.uint32(s * np.uint32(0x27d4eb2d)); s = np.uint32(s ^ (s >> np.uint32(15)))
+    state = [s]
+
+    def rnd01():
+        t = state[0]
+        t = np.uint32(t ^ np.uint32(t << np.uint32(13))); t = np.uint32(t ^ (t >> np.uint32(17))); t = np.uint32(t ^ np.uint32(t << np.uint32(5)))
+        state[0] = t
+        return f32(np.array([np.uint32(0x3f800000) | (t >> np.uint32(9))], np.uint32).view(f32)[0] - f32(1))
+    two_pi = f32(6.28318530717958647692528)
+    r1, r2 = rnd01(), rnd01()
+    ct = f32(f32(f32(1) - r1) + f32(r1 * f32(0.999995)))
+    st = f32(np.sqrt(f32(f32(1) - f32(ct * ct))))
+    phi = f32(r2 * two_pi)
+    cone = np.array([f32(np.cos(phi) * st), f32(np.sin(phi) * st), ct], f32)
+    cone = (cone / f32(np.sqrt(f32(cone @ cone)))).astype(f32)
+    m0, m1, m2 = _onb(L)
+    rays = [(origin, (m0 * cone[0] + m1 * cone[1] + m2 * cone[2]).astype(f32), 10000.0)]
+    for _ in range(2):
+        r1, r2 = rnd01(), rnd01()
+        hx = f32(f32(np.sqrt(r1)) * f32(np.cos(f32(two_pi * r2))))
+        hy = f32(f32(np.sqrt(r1)) * f32(np.sin(f32(two_pi * r2))))
+        hz = f32(np.sqrt(f32(f32(1) - r1)))
+        m0, m1, m2 = _onb(N)
+        rays.append((origin, (m0 * hx + m1 * hy + m2 * hz).astype(f32), 5.0))
+    return rays
+
+
+def test_raygen_oracle_vs_scalar_ray_generation_and_brute_force():
+    W, H = 40, 30
+    sc = scenes.tiny_scene(width=W, height=H)
+    osc = O.OracleScene(sc)
+    tris = Hh.world_triangles(sc)
+    seq = camera.FrameSequencer(W, H, sc.light)
+    seq.next(sc.camera)
+    pfd = seq.next(sc.camera)                              # frame_index 1: per-pixel seeds (frame 0 seeds every pixel alike, Q5)
+    assert int(pfd["frame_index"]) > 0
+    g = osc.gbuffer(pfd, W, H)
+    got = osc.raygen(pfd, g["depth"], g["normals"], ao_spp=2, flags=3)["shadow_ao"].astype(f32)
+    checked = agree_s = agree_a = 0
+    for y in range(0, H, 2):
+        for x in range(0, W, 2):
+            with np.errstate(over="ignore"):             # uint32 wrap-around is the point of the hash
+                rays = _raygen_rays_scalar(pfd, g["depth"], g["normals"], x, y)
+            if rays is None:
+                assert got[y, x, 0] == 1.0 and got[y, x, 1] == 1.0
+                continue
+            res, grazing = [], False
+            for o, d, tmax in rays:
+                hit, _, margin = Hh.brute_force_hits(tris, o, d, 0.01, tmax)
+                grazing |= margin < 1e-5
+                res.append(0.0 if hit else 1.0)            # miss.rmiss writes 1 (visible), a hit leaves the payload at 0
+            if grazing:
+                continue
+            checked += 1
+            agree_s += got[y, x, 0] == res[0]
+            agree_a += got[y, x, 1] == (res[1] + res[2]) / 2
+    assert checked > 100
+    assert agree_s == checked and agree_a == checked, (checked, agree_s, agree_a)
