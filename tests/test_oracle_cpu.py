@@ -587,3 +587,105 @@ def test_raygen_oracle_vs_scalar_ray_generation_and_brute_force():
             agree_a += got[y, x, 1] == (res[1] + res[2]) / 2
     assert checked > 100
     assert agree_s == checked and agree_a == checked, (checked, agree_s, agree_a)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent transcription of the reflection ray + reflection_hit.rchit (float64, constant materials)
+# ---------------------------------------------------------------------------------------------------------------
+def _closest_hit_f64(tris64, o, d, tmin, tmax):
+    e1 = tris64[:, 1] - tris64[:, 0]; e2 = tris64[:, 2] - tris64[:, 0]
+    pv = np.cross(d[None, :], e2)
+    det = np.einsum("ij,ij->i", e1, pv)
+    ok = np.abs(det) > 0
+    inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+    tv = o[None, :] - tris64[:, 0]
+    u = np.einsum("ij,ij->i", tv, pv) * inv
+    qv = np.cross(tv, e1)
+    v = np.einsum("j,ij->i", d, qv) * inv
+    t = np.einsum("ij,ij->i", e2, qv) * inv
+    inside = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > tmin) & (t < tmax)
+    if not inside.any():
+        return None
+    tt = np.where(inside, t, np.inf)
+    k = int(np.argmin(tt))
+    second = np.partition(tt, 1)[1] if len(tt) > 1 else np.inf
+    edge = min(u[k], v[k], 1 - u[k] - v[k])
+    return k, float(u[k]), float(v[k]), float(tt[k]), float(second - tt[k]), float(edge)
+
+
+def _reflection_hit_f64(pfd, sc, g, prim_id, b1, b2, cam):
+    """reflection_hit.rchit:10-72 in float64 for a primitive with constant material (no textures)."""
+    p = sc.primitives[g]
+    base = int(p["index_offset"]) + 3 * prim_id
+    vi = [int(p["vertex_offset"]) + int(sc.indices[base + k]) for k in range(3)]
+    bary = np.array([1.0 - b1 - b2, b1, b2])
+    normal = sum(sc.vertices["normal"][vi[k]].astype(np.float64) * bary[k] for k in range(3))      # not transformed, not normalised
+    lp = sum(sc.vertices["pos"][vi[k]].astype(np.float64) * bary[k] for k in range(3))
+    M = np.asarray(p["transform"], np.float64).reshape(4, 4).T
+    position = (M @ np.append(lp, 1.0))[:3]
+    m = p["material"]
+    assert int(m["base_color_texture"]) == -1 and int(m["metallic_roughness_texture"]) == -1
+    albedo = np.asarray(m["base_color"], np.float64)[:3]
+    metallic, roughness = float(m["metallic_factor"]), float(m["roughness_factor"])
+    V = cam - position; V /= np.linalg.norm(V)
+    L = -np.asarray(pfd["directional_light"]["direction"], np.float64)[:3]
+    N = normal
+    Hv = L + V; Hv /= np.linalg.norm(Hv)
+    roughness = min(max(roughness, 0.04), 1.0); metallic = min(max(metallic, 0.0), 1.0)
+    f0 = 0.04 * (1 - metallic) + albedo * metallic
+    hv = max(Hv @ V, 0.0)
+    F = f0 + (1 - f0) * (1 - hv) ** 5
+    a2 = roughness * roughness
+    ndh = max(N @ Hv, 0.0)
+    f = ndh * ndh * (a2 - 1) + 1
+    D = a2 / (np.pi * f * f)
+    k = (roughness + 1) ** 2 * 0.125
+    ndv, ndl = max(N @ V, 0.0), max(N @ L, 0.0)
+    G = ndv / (ndv * (1 - k) + k) * (ndl / (ndl * (1 - k) + k))
+    spec = D * G * F / max(4.0 * ndv * ndl, 1e-6)
+    diff = (1 - F) * (1 - metallic) * albedo / np.pi
+    li = np.asarray(pfd["directional_light"]["intensity"], np.float64)[:3]
+    lc = np.asarray(pfd["directional_light"]["color"], np.float64)[:3]
+    return albedo * (0.2 / np.pi) + (diff + spec) * ndl * li * lc
+
+
+def test_reflection_oracle_vs_scalar_transcription():
+    W, H = 40, 30
+    sc = scenes.tiny_scene(width=W, height=H)
+    osc = O.OracleScene(sc)
+    tris64 = Hh.world_triangles(sc).astype(np.float64)
+    counts = np.array([int(p["index_count"]) // 3 for p in sc.primitives])
+    first = np.concatenate([[0], np.cumsum(counts)])
+    seq = camera.FrameSequencer(W, H, sc.light)
+    pfd = seq.next(sc.camera)
+    g = osc.gbuffer(pfd, W, H)
+    got = osc.raygen(pfd, g["depth"], g["normals"], ao_spp=2, flags=4)["reflections"].astype(np.float64)
+    inv = np.asarray(pfd["camera_viewproj_inverse"], np.float64).reshape(4, 4).T
+    cam = np.asarray(pfd["camera_view_inverse"], np.float64).reshape(4, 4).T[:3, 3]
+    n_hit = n_miss = 0
+    for y in range(H):
+        for x in range(W):
+            d = float(g["depth"][y, x])
+            if d == 0:
+                assert not got[y, x].any()
+                continue
+            u, v = (x + 0.5) / W, (y + 0.5) / H
+            p = inv @ np.array([u * 2 - 1, v * 2 - 1, d, 1.0])
+            P = p[:3] / p[3]
+            N = g["normals"][y, x, :3].astype(np.float64)
+            I = P - cam; I /= np.linalg.norm(I)
+            R = I - 2.0 * (N @ I) * N
+            hit = _closest_hit_f64(tris64, P + 0.1 * N, R, 0.01, 10000.0)
+            if hit is None:
+                if not got[y, x].any():
+                    n_miss += 1
+                continue
+            k, b1, b2, t, gap, edge = hit
+            if gap < 1e-4 * max(1.0, t) or edge < 1e-4:
+                continue                                    # two surfaces at the same distance / an edge: either answer is legitimate
+            gi = int(np.searchsorted(first, k, side="right") - 1)
+            want = _reflection_hit_f64(pfd, sc, gi, k - int(first[gi]), b1, b2, cam)
+            assert got[y, x, 3] == 1.0, (x, y)
+            np.testing.assert_allclose(got[y, x, :3], want, rtol=3e-3, atol=2e-3, err_msg=f"pixel {x},{y}")
+            n_hit += 1
+    assert n_hit > 60 and n_miss > 60, (n_hit, n_miss)
