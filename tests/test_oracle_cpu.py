@@ -689,3 +689,67 @@ def test_reflection_oracle_vs_scalar_transcription():
             np.testing.assert_allclose(got[y, x, :3], want, rtol=3e-3, atol=2e-3, err_msg=f"pixel {x},{y}")
             n_hit += 1
     assert n_hit > 60 and n_miss > 60, (n_hit, n_miss)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent transcription of the G-buffer encodings (gbuf.vert:19-28, gbuf.frag:17-59, clear values hybrid_render_path.cpp:16-19)
+# ---------------------------------------------------------------------------------------------------------------
+def test_gbuffer_oracle_vs_scalar_transcription():
+    W, H = 40, 30
+    sc = scenes.tiny_scene(width=W, height=H)
+    osc = O.OracleScene(sc)
+    tris64 = Hh.world_triangles(sc).astype(np.float64)
+    counts = np.array([int(p["index_count"]) // 3 for p in sc.primitives])
+    first = np.concatenate([[0], np.cumsum(counts)])
+    seq = camera.FrameSequencer(W, H, sc.light)
+    cam = sc.camera
+    seq.next(cam)
+    cam.set_pose(cam.position + np.array([0.05, 0.0, 0.01]), cam.yaw + 0.002, cam.pitch)      # previous != current camera
+    pfd = seq.next(cam)
+    g = osc.gbuffer(pfd, W, H)
+    col = lambda name: np.asarray(pfd[name], np.float64).reshape(4, 4).T
+    vp, vp_prev, vp_inv = col("camera_proj") @ col("camera_view"), col("camera_proj_prev_frame") @ col("camera_view_prev_frame"), col("camera_viewproj_inverse")
+    eye = col("camera_view_inverse")[:3, 3]
+    dsi = np.asarray(pfd["display_size_inverse"], np.float64)
+    n_hit = n_sky = 0
+    for y in range(H):
+        for x in range(W):
+            u, v = (x + 0.5) / W, (y + 0.5) / H
+            far = vp_inv @ np.array([u * 2 - 1, v * 2 - 1, 0.5, 1.0])                           # any depth on the pixel's line of sight
+            d = far[:3] / far[3] - eye
+            d /= np.linalg.norm(d)
+            hit = _closest_hit_f64(tris64, eye, d, 0.0, 1e9)
+            if hit is None:
+                # clear values: albedo 0, normals / id 0, motion (0, 0, -1, -1), depth 0
+                if g["depth"][y, x] == 0:
+                    assert not g["albedo"][y, x].any() and not g["normals"][y, x].any()
+                    assert tuple(g["motion"][y, x].astype(f32)) == (0.0, 0.0, -1.0, -1.0)
+                    n_sky += 1
+                continue
+            k, b1, b2, t, gap, edge = hit
+            if gap < 1e-4 * max(1.0, t) or edge < 1e-3:
+                continue                                                                      # silhouettes: coverage may differ
+            gi = int(np.searchsorted(first, k, side="right") - 1)
+            p = sc.primitives[gi]
+            base = int(p["index_offset"]) + 3 * (k - int(first[gi]))
+            vi = [int(p["vertex_offset"]) + int(sc.indices[base + j]) for j in range(3)]
+            bary = np.array([1.0 - b1 - b2, b1, b2])
+            lp = sum(sc.vertices["pos"][vi[j]].astype(np.float64) * bary[j] for j in range(3))
+            ln = sum(sc.vertices["normal"][vi[j]].astype(np.float64) * bary[j] for j in range(3))
+            M = np.asarray(p["transform"], np.float64).reshape(4, 4).T
+            world = M @ np.append(lp, 1.0)
+            clip, clip_prev = vp @ world, vp_prev @ world
+            nrm = np.linalg.inv(M[:3, :3]).T @ ln                                              # glm::inverseTranspose(mat3(transform))
+            nrm /= np.linalg.norm(nrm)
+            m = p["material"]
+            assert g["depth"][y, x] > 0, (x, y)
+            np.testing.assert_allclose(g["depth"][y, x], clip[2] / clip[3], rtol=2e-4, err_msg=f"depth {x},{y}")
+            np.testing.assert_allclose(g["normals"][y, x, :3].astype(np.float64), nrm, atol=2e-3, err_msg=f"normal {x},{y}")
+            assert float(g["normals"][y, x, 3]) == float(gi)
+            want_mv = np.array([x + 0.5, y + 0.5]) * dsi - ((clip_prev[:2] / clip_prev[3]) * 0.5 + 0.5)
+            np.testing.assert_allclose(g["motion"][y, x, :2].astype(np.float64), want_mv, atol=1e-3, err_msg=f"motion {x},{y}")
+            np.testing.assert_allclose(g["motion"][y, x, 2:].astype(np.float64), [float(m["metallic_factor"]), float(m["roughness_factor"])], atol=1e-3)
+            want_bgra = np.round(np.asarray(m["base_color"], np.float64)[[2, 1, 0, 3]] * 255.0)
+            assert np.all(np.abs(g["albedo"][y, x].astype(np.float64) - want_bgra) <= 1), (x, y)
+            n_hit += 1
+    assert n_hit > 300 and n_sky > 20, (n_hit, n_sky)
