@@ -753,3 +753,63 @@ def test_gbuffer_oracle_vs_scalar_transcription():
             assert np.all(np.abs(g["albedo"][y, x].astype(np.float64) - want_bgra) <= 1), (x, y)
             n_hit += 1
     assert n_hit > 300 and n_sky > 20, (n_hit, n_sky)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent transcription of the fully ray-traced path (raytraced_render_path/raygen.rgen, closesthit.rchit, miss shaders)
+# ---------------------------------------------------------------------------------------------------------------
+def test_raytraced_path_oracle_vs_scalar_transcription():
+    W, H = 40, 30
+    sc = scenes.tiny_scene(width=W, height=H)
+    osc = O.OracleScene(sc)
+    tris64 = Hh.world_triangles(sc).astype(np.float64)
+    counts = np.array([int(p["index_count"]) // 3 for p in sc.primitives])
+    first = np.concatenate([[0], np.cumsum(counts)])
+    seq = camera.FrameSequencer(W, H, sc.light)
+    pfd = seq.next(sc.camera)
+    got = osc.raytraced(pfd, W, H)                                   # B8G8R8A8_UNORM
+    col = lambda name: np.asarray(pfd[name], np.float64).reshape(4, 4).T
+    view_inv, proj_inv = col("camera_view_inverse"), col("camera_proj_inverse")
+    light_dir = -np.asarray(pfd["directional_light"]["direction"], np.float64)[:3]
+    li = np.asarray(pfd["directional_light"]["intensity"], np.float64)[:3]
+    lc = np.asarray(pfd["directional_light"]["color"], np.float64)[:3]
+    to_bgra8 = lambda rgba: np.round(np.clip(np.asarray(rgba, np.float64), 0, 1)[[2, 1, 0, 3]] * 255.0)
+    n_hit = n_miss = n_lit = n_shadowed = 0
+    for y in range(H):
+        for x in range(W):
+            ndc = np.array([(x + 0.5) / W, (y + 0.5) / H]) * 2.0 - 1.0
+            origin = (view_inv @ np.array([0, 0, 0, 1.0]))[:3]
+            target = proj_inv @ np.array([ndc[0], ndc[1], 1.0, 1.0])
+            tdir = target[:3] / np.linalg.norm(target[:3])
+            direction = (view_inv @ np.append(tdir, 0.0))[:3]
+            hit = _closest_hit_f64(tris64, origin, direction, 0.1, 10000.0)
+            if hit is None:
+                if np.all(np.abs(got[y, x].astype(np.float64) - to_bgra8([0.3, 0.8, 0.2, 1.0])) <= 1):
+                    n_miss += 1
+                continue
+            k, b1, b2, t, gap, edge = hit
+            if gap < 1e-4 * max(1.0, t) or edge < 1e-3:
+                continue
+            gi = int(np.searchsorted(first, k, side="right") - 1)
+            p = sc.primitives[gi]
+            base = int(p["index_offset"]) + 3 * (k - int(first[gi]))
+            vi = [int(p["vertex_offset"]) + int(sc.indices[base + j]) for j in range(3)]
+            bary = np.array([1.0 - b1 - b2, b1, b2])
+            normal = sum(sc.vertices["normal"][vi[j]].astype(np.float64) * bary[j] for j in range(3))
+            lp = sum(sc.vertices["pos"][vi[j]].astype(np.float64) * bary[j] for j in range(3))
+            position = (np.asarray(p["transform"], np.float64).reshape(4, 4).T @ np.append(lp, 1.0))[:3]
+            albedo = np.asarray(p["material"]["base_color"], np.float64)[:3]
+            shadow = _closest_hit_f64(tris64, position, light_dir, 0.1, 10000.0)
+            if shadow is not None and shadow[5] < 1e-3:
+                continue                                             # the shadow ray grazes an edge
+            ambient = albedo / np.pi
+            if shadow is None:
+                rgb = ambient + max(normal @ light_dir, 0.0) * albedo * li * lc
+                n_lit += 1
+            else:
+                rgb = ambient
+                n_shadowed += 1
+            want = to_bgra8(np.append(rgb, 1.0))
+            assert np.all(np.abs(got[y, x].astype(np.float64) - want) <= 1), (x, y, got[y, x], want)
+            n_hit += 1
+    assert n_hit > 300 and n_miss > 20 and n_lit > 20 and n_shadowed > 20, (n_hit, n_miss, n_lit, n_shadowed)
