@@ -122,3 +122,97 @@ def test_gbuffer_and_reflections_use_textures(textured):
     # reflections: textured hits change the radiance
     r, rp = osc.raygen(pfd, g["depth"], g["normals"], flags=4), oplain.raygen(pfd, g["depth"], g["normals"], flags=4)
     assert np.abs(r["reflections"].astype(np.float32) - rp["reflections"].astype(np.float32)).max() > 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The alpha-tested ray-traced pipeline (raygen_test_alpha.rgen, closesthit_test_alpha.rchit, shadow_anyhit.rahit) transcribed in
+# float64 with np_sample() above as texture(): candidate hits in distance order, the any-hit shader drops the ones whose base-colour
+# alpha is below the cutoff, for the primary ray AND the shadow ray (gl_RayFlagsNoOpaqueEXT on both)
+# ---------------------------------------------------------------------------------------------------------------
+def _hits_in_order(tris64, o, d, tmin, tmax):
+    e1 = tris64[:, 1] - tris64[:, 0]; e2 = tris64[:, 2] - tris64[:, 0]
+    pv = np.cross(d[None, :], e2)
+    det = np.einsum("ij,ij->i", e1, pv)
+    ok = np.abs(det) > 0
+    inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+    tv = o[None, :] - tris64[:, 0]
+    u = np.einsum("ij,ij->i", tv, pv) * inv
+    qv = np.cross(tv, e1)
+    v = np.einsum("j,ij->i", d, qv) * inv
+    t = np.einsum("ij,ij->i", e2, qv) * inv
+    inside = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > tmin) & (t < tmax)
+    idx = np.nonzero(inside)[0]
+    idx = idx[np.argsort(t[idx])]
+    return [(int(k), float(u[k]), float(v[k]), float(t[k]), float(min(u[k], v[k], 1 - u[k] - v[k]))) for k in idx]
+
+
+def test_alpha_tested_raytraced_pipeline_vs_transcription(textured):
+    import helpers as Hh
+    W, H, sc, osc = textured
+    tris64 = Hh.world_triangles(sc).astype(np.float64)
+    counts = np.array([int(p["index_count"]) // 3 for p in sc.primitives])
+    first = np.concatenate([[0], np.cumsum(counts)])
+    pfd = camera.FrameSequencer(W, H, sc.light).next(sc.camera)
+    got = osc.raytraced(pfd, W, H, alpha_test=True)
+    col = lambda name: np.asarray(pfd[name], np.float64).reshape(4, 4).T
+    view_inv, proj_inv = col("camera_view_inverse"), col("camera_proj_inverse")
+    light_dir = -np.asarray(pfd["directional_light"]["direction"], np.float64)[:3]
+    lc = np.asarray(pfd["directional_light"]["color"], np.float64)[:3]
+    to_bgra8 = lambda rgba: np.round(np.clip(np.asarray(rgba, np.float64), 0, 1)[[2, 1, 0, 3]] * 255.0)
+
+    def surface(k, b1, b2):
+        gi = int(np.searchsorted(first, k, side="right") - 1)
+        p = sc.primitives[gi]
+        base = int(p["index_offset"]) + 3 * (k - int(first[gi]))
+        vi = [int(p["vertex_offset"]) + int(sc.indices[base + j]) for j in range(3)]
+        bary = np.array([1.0 - b1 - b2, b1, b2])
+        mix = lambda field: sum(sc.vertices[field][vi[j]].astype(np.float64) * bary[j] for j in range(3))
+        return p, mix("uv0"), mix("normal"), (np.asarray(p["transform"], np.float64).reshape(4, 4).T @ np.append(mix("pos"), 1.0))[:3]
+
+    def first_accepted(o, d):
+        """Closest hit the any-hit shader keeps; ambiguous = a candidate grazes an edge or sits on the cutoff."""
+        ambiguous = False
+        cands = _hits_in_order(tris64, o, d, 0.1, 10000.0)
+        for n, (k, b1, b2, t, edge) in enumerate(cands):
+            p, uv, _, _ = surface(k, b1, b2)
+            m = p["material"]
+            ambiguous |= edge < 1e-3
+            if n + 1 < len(cands) and cands[n + 1][3] - t < 1e-4 * max(1.0, t):
+                ambiguous = True                           # coincident surfaces: either one may win
+            if int(m["alpha_mask"]) == 1 and int(m["base_color_texture"]) >= 0:
+                a = float(np_sample(sc.textures[int(m["base_color_texture"])], uv[0], uv[1])[3])
+                ambiguous |= abs(a - float(m["alpha_cutoff"])) < 2e-2
+                if a < float(m["alpha_cutoff"]):
+                    continue                               # ignoreIntersectionEXT
+            return (k, b1, b2), ambiguous
+        return None, ambiguous
+
+    n_checked = n_through = n_shadow_through = 0
+    for y in range(0, H, 3):
+        for x in range(0, W, 3):
+            ndc = np.array([(x + 0.5) / W, (y + 0.5) / H]) * 2.0 - 1.0
+            origin = (view_inv @ np.array([0, 0, 0, 1.0]))[:3]
+            target = proj_inv @ np.array([ndc[0], ndc[1], 1.0, 1.0])
+            direction = (view_inv @ np.append(target[:3] / np.linalg.norm(target[:3]), 0.0))[:3]
+            cands = _hits_in_order(tris64, origin, direction, 0.1, 10000.0)
+            hit, amb = first_accepted(origin, direction)
+            if hit is None or amb:
+                continue
+            p, uv, normal, position = surface(*hit)
+            m = p["material"]
+            if int(m["base_color_texture"]) < 0 or int(m["normal_map"]) >= 0:
+                continue                                   # closesthit_test_alpha.rchit samples textures[base_color_texture] unconditionally
+            n_through += hit[0] != cands[0][0]
+            albedo = np_sample(sc.textures[int(m["base_color_texture"])], uv[0], uv[1])[:3].astype(np.float64)
+            occluder, amb_s = first_accepted(position, light_dir)
+            if amb_s:
+                continue
+            n_shadow_through += occluder is None and len(_hits_in_order(tris64, position, light_dir, 0.1, 10000.0)) > 0
+            rgb = 0.2 * albedo
+            if occluder is None:
+                rgb = rgb + max(normal @ light_dir, 0.0) * albedo * lc      # no light_intensity in the alpha-tested shader
+            want = to_bgra8(np.append(rgb, 1.0))
+            assert np.all(np.abs(got[y, x].astype(np.float64) - want) <= 1), (x, y, got[y, x], want)
+            n_checked += 1
+    assert n_checked > 60, n_checked
+    assert n_through + n_shadow_through > 0, "no ray passed through a cut-out: the any-hit path was not exercised"
