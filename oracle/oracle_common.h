@@ -1,9 +1,13 @@
 // oracle/oracle_common.h — TEST INFRASTRUCTURE ONLY (CPU restatement of the reference shaders).
 //
-// PARITY UNPINNED: the reference (RMichelsen/VulkanHybridRenderer) ships no tests, golden images or
-// known-answer vectors, and its ray/triangle arithmetic lives in the Vulkan driver.
-// This oracle restates the GLSL line by line; the only pins are the KATs derived from the restatement
-// itself (tests/golden/) and the shader text cited beside every function.
+// PINNED BY oracle/_ref: the reference (RMichelsen/VulkanHybridRenderer) ships no tests, golden images or known-answer
+// vectors, but its shader files themselves compile for the CPU through oracle/ref_shim.h + the reference's vendored glm
+// (oracle/make_ref.py -> oracle/_ref/libvhr_ref.so). tests/test_ref_pinning_cpu.py holds this restatement BIT-IDENTICAL to
+// those compiled shaders for every pass both cover (common.glsl helpers, svgf.comp, svgf_atrous_filter.comp, ssao.comp,
+// ssao_blur.comp, ssr.comp, composition.frag, raygen.rgen + miss shaders + reflection_hit.rchit), and tests/golden/ holds
+// outputs of the compiled shaders. Still third-party and NOT pinned: the driver's BVH traversal / ray-triangle arithmetic
+// behind traceRayEXT — both sides query the double-precision BVH of oracle_rt.cpp — and the rasteriser
+// (the G-buffer producer restates gbuf.vert / gbuf.frag encodings on primary rays).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
 // library. The product path (vulkanhybridrenderer_b200/) never links or calls it.
@@ -176,19 +180,21 @@ static inline vec3 operator*(vec3 a, vec3 b) { return {a.x * b.x, a.y * b.y, a.z
 static inline vec3 operator-(vec3 a) { return {-a.x, -a.y, -a.z}; }
 static inline float dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline float length(vec3 a) { return std::sqrt(dot(a, a)); }
-// GLSL normalize(): v * inversesqrt(dot(v,v)); restated with an IEEE divide (implementation-defined in GLSL).
-static inline vec3 normalize(vec3 a) { float l = length(a); return {a.x / l, a.y / l, a.z / l}; }
+// GLSL normalize() = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x): the formula of the reference's own math library
+// (dependencies/glm/detail/func_geometric.inl:88, func_exponential.inl:138), which is what oracle/_ref compiles the shaders with.
+static inline vec3 normalize(vec3 a) { float r = 1.0f / std::sqrt(dot(a, a)); return {a.x * r, a.y * r, a.z * r}; }
 static inline vec3 cross(vec3 a, vec3 b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 
-// mat4 * vec4, column-major, accumulated left to right (col0*x + col1*y + col2*z + col3*w).
+// mat4 * vec4, column-major, summed pairwise: (col0*x + col1*y) + (col2*z + col3*w) — the order of the reference's own math library
+// (dependencies/glm/detail/type_mat4x4.inl:561-571), i.e. of oracle/_ref. (GLSL itself leaves the order to the compiler.)
 static inline vec4 mul44(const float *m, vec4 v) {
     vec4 r;
-    r.x = m[0] * v.x + m[4] * v.y + m[8]  * v.z + m[12] * v.w;
-    r.y = m[1] * v.x + m[5] * v.y + m[9]  * v.z + m[13] * v.w;
-    r.z = m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * v.w;
-    r.w = m[3] * v.x + m[7] * v.y + m[11] * v.z + m[15] * v.w;
+    r.x = (m[0] * v.x + m[4] * v.y) + (m[8]  * v.z + m[12] * v.w);
+    r.y = (m[1] * v.x + m[5] * v.y) + (m[9]  * v.z + m[13] * v.w);
+    r.z = (m[2] * v.x + m[6] * v.y) + (m[10] * v.z + m[14] * v.w);
+    r.w = (m[3] * v.x + m[7] * v.y) + (m[11] * v.z + m[15] * v.w);
     return r;
 }
 // mat3(m4) * vec3

@@ -17,7 +17,11 @@ using namespace vo;
 namespace {
 inline int wrap(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 inline void bilinear_setup(float u, int n, int &i0, int &i1, float &a) {
-    float uu = u * (float)n - 0.5f;
+    // NVIDIA texture units — the hardware the reference needs (RTX) — hold the filter coordinate in fixed point with 8 fractional bits
+    // (VkPhysicalDeviceLimits::subTexelPrecisionBits = 8; CUDA C Programming Guide, "Linear Filtering": 9-bit fixed point with 8 bits of
+    // fractional value, 1.0 exactly representable). Consequence: a lookup at a texel centre returns that texel even when
+    // fl(fl((x + .5) / W) * W) is an ulp off x + .5 (51 of the 1920 columns at 1080p) — SURVEY Q17.
+    float uu = std::floor((u * (float)n - 0.5f) * 256.0f + 0.5f) * 0.00390625f;
     float fl = std::floor(uu);
     a = uu - fl;
     int i = (fl == fl && std::fabs(fl) < 1e9f) ? (int)fl : 0;

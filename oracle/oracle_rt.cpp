@@ -88,7 +88,8 @@ inline vec4 sample_texture(const Scene &s, int idx, vec2 uv) {
         int i = texel_index(std::floor(uv.x * (float)W)), j = texel_index(std::floor(uv.y * (float)H));
         return fetch_texel(t, wrap_texel(i, W, t.wrap_u), wrap_texel(j, H, t.wrap_v));
     }
-    float uu = uv.x * (float)W - 0.5f, vv = uv.y * (float)H - 0.5f;
+    // 8 fractional bits of sub-texel precision, rounded to nearest (see oracle_svgf.cpp bilinear_setup)
+    float uu = std::floor((uv.x * (float)W - 0.5f) * 256.0f + 0.5f) * 0.00390625f, vv = std::floor((uv.y * (float)H - 0.5f) * 256.0f + 0.5f) * 0.00390625f;
     float fu = std::floor(uu), fv = std::floor(vv);
     float a = uu - fu, b = vv - fv;
     int i = texel_index(fu), j = texel_index(fv);

@@ -39,7 +39,7 @@ def assert_parity(gpu, ref, what, max_abs=MAX_ABS_TOL, min_psnr=PSNR_MIN_DB):
 @functools.lru_cache(maxsize=8)
 def scene_and_gbuffer(width, height, tris=20000, seed=3, moving=False):
     """Scene + oracle G-buffers of two consecutive frames (CPU primary rays; test scaffolding)."""
-    import oracle_lib as O
+    import checker as O
     sc = scenes.sponza_like(tris, seed=seed, width=width, height=height, n_clutter=40)
     osc = O.OracleScene(sc)
     seq = camera.FrameSequencer(width, height, sc.light)

@@ -433,7 +433,9 @@ def test_temporal_oracle_vs_scalar_transcription_with_motion():
 def _texture_linear_repeat(img, u, v):
     """texture() through the default sampler (LINEAR, REPEAT, one mip): Vulkan spec 16.6-16.8 in float32."""
     H, W = img.shape[:2]
+    # filter coordinate in fixed point with 8 fractional bits, rounded to nearest (subTexelPrecisionBits = 8)
     x, y = f32(f32(u * f32(W)) - f32(0.5)), f32(f32(v * f32(H)) - f32(0.5))
+    x, y = f32(np.floor(f32(f32(x * f32(256.0)) + f32(0.5))) * f32(0.00390625)), f32(np.floor(f32(f32(y * f32(256.0)) + f32(0.5))) * f32(0.00390625))
     fx, fy = np.floor(x), np.floor(y)
     a, b = f32(x - fx), f32(y - fy)
     x0, y0 = int(fx) % W, int(fy) % H

@@ -3,7 +3,7 @@ C-ABI) vs the CPU oracle, both pipelines (opaque / alpha-tested), on a textured 
 import numpy as np
 import pytest
 
-import oracle_lib as O
+import checker as O
 from vulkanhybridrenderer_b200 import camera, capi, host_api, scenes
 from vulkanhybridrenderer_b200 import types as T
 

@@ -17,6 +17,7 @@ def _wrap(i, n):
 
 def _taps(u, v, W, H):
     uu = f32(f32(u * f32(W)) - f32(0.5)); vv = f32(f32(v * f32(H)) - f32(0.5))
+    uu, vv = f32(np.floor(f32(f32(uu * f32(256.0)) + f32(0.5))) * f32(0.00390625)), f32(np.floor(f32(f32(vv * f32(256.0)) + f32(0.5))) * f32(0.00390625))      # 8 fractional bits of sub-texel precision
     fx, fy = np.floor(uu), np.floor(vv)
     a, b = f32(uu - fx), f32(vv - fy)
     ix = int(fx) if np.isfinite(fx) and abs(fx) < 1e9 else 0

@@ -42,6 +42,7 @@ def np_sample(tex, u, v):
         i, j = int(np.floor(f32(u * f32(W)))), int(np.floor(f32(v * f32(H))))
         return np_texel(tex, np_wrap(i, W, wu), np_wrap(j, H, wv))
     uu, vv = f32(f32(u * f32(W)) - f32(0.5)), f32(f32(v * f32(H)) - f32(0.5))
+    uu, vv = f32(np.floor(f32(f32(uu * f32(256.0)) + f32(0.5))) * f32(0.00390625)), f32(np.floor(f32(f32(vv * f32(256.0)) + f32(0.5))) * f32(0.00390625))      # 8 fractional bits of sub-texel precision
     fu, fv = np.floor(uu), np.floor(vv)
     a, b = f32(uu - fu), f32(vv - fv)
     i, j = int(fu), int(fv)

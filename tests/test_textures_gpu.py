@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import helpers as Hh
-import oracle_lib as O
+import checker as O
 from vulkanhybridrenderer_b200 import camera, capi, scenes
 from vulkanhybridrenderer_b200 import types as T
 

@@ -1,8 +1,11 @@
-"""Generates tests/golden/*.npz — small frozen input/output vectors of the CPU oracle for every hot-path kernel.
+"""Generates tests/golden/*.npz — small frozen input/output vectors for every hot-path kernel.
 
-The reference ships no fixtures and cannot run here, so these are NOT reference outputs: they freeze the
-oracle (so an edit cannot drift silently) and give the CUDA path committed vectors to match. Regenerate only when the
-oracle is deliberately changed:  python tools/make_golden.py
+The reference ships no fixtures. The shader-pass outputs stored here (shadow/AO, reflections, temporal, a-trous, denoised,
+SSAO, SSR) are OUTPUTS OF THE REFERENCE'S OWN SHADERS: oracle/_ref compiles the GLSL files of /root/reference for the CPU
+(oracle/make_ref.py) and this script runs them in this container, where /root/reference exists; the hand-written oracle is asserted
+bit-identical on the way. The G-buffer inputs, hit distances and the fully ray-traced path come from the oracle (no reference shader
+produces them from arrays). tests/test_ref_pinning_cpu.py re-derives every stored shader output from the stored inputs.
+Regenerate only when the oracle or the shim is deliberately changed:  python tools/make_golden.py
 """
 import os
 import sys
@@ -14,9 +17,16 @@ import numpy as np
 
 import helpers as Hh
 import oracle_lib as O
+import ref_lib as R
 from vulkanhybridrenderer_b200 import camera, scenes
 
 OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def same(a, b, what):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"oracle and oracle/_ref differ on {what}"
+    return b
 
 
 def main():
@@ -25,7 +35,7 @@ def main():
     osc = O.OracleScene(sc)
     seq = camera.FrameSequencer(W, H, sc.light)
     cam = sc.camera
-    st = O.SvgfState(W, H)
+    st, st_ref = O.SvgfState(W, H), R.SvgfState(W, H)
     frames = []
     for f in range(3):
         if f:
@@ -33,11 +43,14 @@ def main():
         pfd = seq.next(cam)
         g = osc.gbuffer(pfd, W, H)
         rg = osc.raygen(pfd, g["depth"], g["normals"], want_t=True)
-        den, iters, temporal = st.run(pfd, g["normals"], g["motion"], rg["shadow_ao"])
-        ssao_raw = O.ssao(pfd, g["depth"], g["normals"], 0.75)
+        rr = R.raygen(sc, osc, pfd, g["depth"], g["normals"])                    # the reference's Raytrace Pipeline
+        shadow_ao, reflections = same(rg["shadow_ao"], rr["shadow_ao"], "shadow/AO"), same(rg["reflections"], rr["reflections"], "reflections")
+        den, iters, temporal = (same(a, b, "SVGF") for a, b in zip(st.run(pfd, g["normals"], g["motion"], shadow_ao),
+                                                                   st_ref.run(pfd, g["normals"], g["motion"], shadow_ao)))
+        ssao_raw = same(O.ssao(pfd, g["depth"], g["normals"], 0.75), R.ssao(pfd, g["depth"], g["normals"], 0.75), "ssao")
         frames.append(dict(pfd=pfd, depth=g["depth"], normals=g["normals"], motion=g["motion"], albedo=g["albedo"],
-                           shadow_ao=rg["shadow_ao"], reflections=rg["reflections"], refl_t=rg["refl_t"], temporal=temporal,
-                           atrous=iters, denoised=den, ssao_raw=ssao_raw, ssao=O.ssao_blur(pfd, ssao_raw)))
+                           shadow_ao=shadow_ao, reflections=reflections, refl_t=rg["refl_t"], temporal=temporal,
+                           atrous=iters, denoised=den, ssao_raw=ssao_raw, ssao=same(O.ssao_blur(pfd, ssao_raw), R.ssao_blur(pfd, ssao_raw), "ssao blur")))
     flat = {}
     for i, fr in enumerate(frames):
         for k, v in fr.items():
@@ -47,7 +60,7 @@ def main():
     pfd, normals = frames[0]["pfd"], frames[0]["normals"]
     integ = Hh.noise_integrated(H, W, seed=2)
     np.savez_compressed(os.path.join(OUT, "atrous_noise_96x64.npz"), pfd=pfd, normals=normals, integ=integ,
-                        **{f"step{s}": O.svgf_atrous(pfd, normals, integ, s) for s in (1, 2, 3, 4, 8, 16)})
+                        **{f"step{s}": same(O.svgf_atrous(pfd, normals, integ, s), R.svgf_atrous(pfd, normals, integ, s), "a-trous") for s in (1, 2, 3, 4, 8, 16)})
     # textured scene: G-buffer with alpha cut-outs / normal maps, textured reflections, SSR, the fully ray-traced path
     tsc = scenes.add_procedural_textures(scenes.sponza_like(6000, seed=21, width=W, height=H, n_clutter=12), size=32)
     tosc = O.OracleScene(tsc)
@@ -57,6 +70,8 @@ def main():
     tpfd = tseq.next(tsc.camera)
     tg = tosc.gbuffer(tpfd, W, H)
     trg = tosc.raygen(tpfd, tg["depth"], tg["normals"], want_t=True)
+    trr = R.raygen(tsc, tosc, tpfd, tg["depth"], tg["normals"])
+    same(trg["shadow_ao"], trr["shadow_ao"], "textured shadow/AO"); same(trg["reflections"], trr["reflections"], "textured reflections")
     tex = {}
     for i, t in enumerate(tsc.textures):
         tex[f"tex{i}_rgba"] = t.rgba
@@ -64,7 +79,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "textured_frame_96x64.npz"), vertices=tsc.vertices, indices=tsc.indices, primitives=tsc.primitives,
                         n_textures=len(tsc.textures), pfd=tpfd, depth=tg["depth"], normals=tg["normals"], motion=tg["motion"], albedo=tg["albedo"],
                         shadow_ao=trg["shadow_ao"], reflections=trg["reflections"], refl_t=trg["refl_t"],
-                        ssr=O.ssr(tpfd, tg["albedo"], tg["normals"], tg["motion"], tg["depth"]),
+                        ssr=same(O.ssr(tpfd, tg["albedo"], tg["normals"], tg["motion"], tg["depth"]),
+                                 R.ssr(tpfd, tg["albedo"], tg["normals"], tg["motion"], tg["depth"]), "ssr"),
                         raytraced=tosc.raytraced(tpfd, W, H, False), raytraced_alpha=tosc.raytraced(tpfd, W, H, True), **tex)
     # RNG / sampling KATs
     import ctypes as C
