@@ -246,7 +246,7 @@ def run_gpu(args):
         ctx.set_option(capi.OPT_TRACE_AO, 1 if ao_spp else 0)
         ctx.set_option(capi.OPT_AO_SPP, max(ao_spp, 1))
         ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
-        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=fif)
+        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=fif, svgf_fused=args.svgf == "fused", blit_alias=args.svgf != "reference")
         seq = camera.FrameSequencer(W, H, sc.light)
         cam = sc.camera
 
@@ -510,7 +510,7 @@ def run_gpu(args):
             "metric": METRIC, "value": rays / (ms_total * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {**config_dict(wl, sc.num_triangles), "frames_in_flight": fif,
+            "config": {**config_dict(wl, sc.num_triangles), "frames_in_flight": fif, "svgf_mode": args.svgf,
                        **({"schedule": "Raytrace Pass of frame k+1 on queue 1 under the SVGF pass of frame k (two ray-output image sets); "
                                        "kernels[] / roofline timed in a separate run with one frame in flight",
                            "ms_per_step_one_frame_in_flight": share_ms} if fif == 2 else {})},
@@ -697,6 +697,10 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=FRAMES_IN_FLIGHT_DEFAULT, choices=[1, 2],
                     help="2: the Raytrace Pass of frame k+1 is recorded on the context's second queue and runs under the SVGF pass of frame k "
                          "(HybridRenderPath.frame_overlapped); the per-kernel breakdown then comes from a separate one-frame-at-a-time run")
+    ap.add_argument("--svgf", default="alias", choices=["reference", "alias", "fused"],
+                    help="how the library answers the SVGF node's (unchanged) call sequence: reference = temporal kernel, five a-trous kernels, three "
+                         "copies; alias = the three blits alias buffers copy-on-write (VHR_OPT_BLIT_ALIAS); fused = alias + svgf.comp and a-trous "
+                         "iteration 0 in one kernel (VHR_OPT_SVGF_FUSED). Same images in all three (tests/test_svgf_gpu.py)")
     ap.add_argument("--partition", default="views", choices=["views", "rows"],
                     help="N>1: independent views per rank (weak scaling, default) or row bands of one frame (strong scaling, NCCL halos)")
     ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],

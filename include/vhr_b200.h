@@ -262,7 +262,12 @@ typedef enum vhr_option {
     VHR_OPT_TRACE_REFLECTIONS = 4, /* 1 (reference) / 0: skip the closest-hit ray, write 0 */
     VHR_OPT_ROW_BEGIN = 5,         /* row band [begin, end) this context renders (multi-GPU split); default 0 */
     VHR_OPT_ROW_END = 6,           /* default = image height */
-    VHR_OPT_SVGF_FUSED = 7,        /* 1: temporal pass also produces a-trous iteration 0 (fused kernel) */
+    VHR_OPT_SVGF_FUSED = 7,        /* 1: Dispatch("hybrid_render_path/svgf.comp") runs ONE kernel that does the temporal pass and a-trous
+                                      iteration 0 (the tile's integrated[0] texels are computed into shared memory instead of being read
+                                      back); the Dispatch("...svgf_atrous_filter.comp") with atrous_step 1 on the same slots that follows
+                                      it in the reference's sequence (hybrid_render_path.cpp:299-307) then returns without a launch. The
+                                      call sequence and every image are unchanged. Falls back to the two kernels for banded / partitioned
+                                      dispatches. Default 0 */
     VHR_OPT_ATROUS_VARIANT = 8,    /* 0: direct-load kernel (the reference's dataflow); 1: tiled kernel; 2 (default): pixel-pair
                                       packed fp32x2 kernel with register-level tap reuse; 3: variant 2's arithmetic in a persistent
                                       CTA with TMA-staged tiles (measured 4-8 % slower than 2 on B200: kept for study) */
@@ -274,8 +279,14 @@ typedef enum vhr_option {
                                       6 / 7: variant 0 launched as one-warp / two-warp CTAs (32 / 16 resident per SM);
                                       8: variant 0 with the CTA's AO rays counting-sorted by direction before they are traced.
                                       Same images in every variant; 1-4 measured slower on B200, kept for study */
-    VHR_OPT_RAYTRACED_ALPHA_TEST = 11 /* the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14): 1 selects the pipeline
+    VHR_OPT_RAYTRACED_ALPHA_TEST = 11,/* the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14): 1 selects the pipeline
                                       raygen_test_alpha.rgen + closesthit_test_alpha.rchit + shadow_anyhit.rahit */
+    VHR_OPT_BLIT_ALIAS = 12        /* 1: the three vhr_blit_* calls stop copying. After a blit source and destination show one buffer;
+                                      whichever of the two is written next (a kernel output, an upload, another blit) takes the
+                                      allocation the destination gave up, so every image always holds what the copy would have left
+                                      (copy-on-write). Removes the three copies of the SVGF pass (hybrid_render_path.cpp:309-325: 48 B/px).
+                                      Device pointers obtained through vhr_*_device_ptr are invalidated by blits and writes while it is on;
+                                      ignored (real copies) while a multi-GPU partition is installed. Default 0 */
 } vhr_option;
 int vhr_set_option(vhr_context *ctx, int option, int64_t value);
 int64_t vhr_get_option(vhr_context *ctx, int option);

@@ -120,3 +120,53 @@ def test_svgf_pass_sequence_three_frames():
                 Hh.assert_parity(iters[i], ref_iters[i], f"frame {f} atrous it{i}")
             Hh.assert_parity(den, ref_den, f"frame {f} denoised (= it3, SURVEY Q1)")
             assert np.array_equal(den.view(np.uint16), iters[3].view(np.uint16))
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_copy_free_blits_and_fused_kernel_leave_every_image_unchanged(fused):
+    """VHR_OPT_BLIT_ALIAS (the three blits of the pass alias buffers copy-on-write) and VHR_OPT_SVGF_FUSED (svgf.comp's dispatch also runs
+    a-trous iteration 0): the reference's call sequence is issued unchanged, and after every frame all five persistent images, the
+    Denoised image and the normals image hold bit for bit what the copying / unfused build leaves — also when images are re-uploaded,
+    read back or blitted again in between."""
+    W, H = 328, 200
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, moving=True)
+    ctxs = [capi.Context(W, H), capi.Context(W, H)]
+    try:
+        passes = [Hh.SvgfPassCABI(c, W, H) for c in ctxs]
+        ctxs[1].set_option(capi.OPT_BLIT_ALIAS, 1)
+        ctxs[1].set_option(capi.OPT_SVGF_FUSED, fused)
+        rng = np.random.default_rng(3)
+        for f in range(6):
+            pfd, g = frames[f % len(frames)]
+            rt = np.stack([rng.integers(0, 2, (H, W)), rng.integers(0, 3, (H, W)) * 0.5], -1).astype(np.float16)
+            outs = []
+            for ctx, p in zip(ctxs, passes):
+                ctx.update_per_frame_ubo(pfd)
+                ctx.image_upload(Hh.N_NORMALS, g["normals"]); ctx.image_upload(Hh.N_MOTION, g["motion"]); ctx.image_upload(Hh.N_RT, rt)
+                den, iters, temporal = p.run(want_iters=(f % 2 == 0))
+                pc = p.pc
+                imgs = {"denoised": den, "normals": ctx.image_download(Hh.N_NORMALS)}
+                for k in ("prev_frame_normals_and_object_ids", "shadow_and_ao_history", "shadow_and_ao_moments_history"):
+                    imgs[k] = ctx.storage_image_download(int(pc[k]))
+                imgs["integrated0"] = ctx.storage_image_download(int(pc["integrated_shadow_and_ao"][0]))
+                imgs["integrated1"] = ctx.storage_image_download(int(pc["integrated_shadow_and_ao"][1]))
+                if iters is not None:
+                    imgs["iters"], imgs["temporal"] = iters, temporal
+                if f == 3:      # a second blit of the same pair and a partial overwrite of a lender must not disturb the borrower
+                    ctx.blit_transient_to_storage(Hh.N_NORMALS, int(pc["prev_frame_normals_and_object_ids"]))
+                    ctx.set_option(capi.OPT_ROW_END, H // 2)
+                    ctx.bind_pass_images([Hh.N_NORMALS, Hh.N_MOTION, Hh.N_DEPTH, Hh.N_RT, Hh.N_DENOISED])
+                    pc2 = pc.copy(); pc2["atrous_step"] = 2
+                    ctx.dispatch("hybrid_render_path/svgf_atrous_filter.comp", _groups(W), _groups(H), 1, pc2)
+                    ctx.set_option(capi.OPT_ROW_END, -1)
+                    imgs["after_partial_out"] = ctx.storage_image_download(int(pc["integrated_shadow_and_ao"][1]))
+                    imgs["after_partial_den"] = ctx.image_download(Hh.N_DENOISED)
+                outs.append(imgs)
+            for k in outs[0]:
+                a, b = outs[0][k], outs[1][k]
+                assert np.array_equal(a.view(np.uint16), b.view(np.uint16)), f"frame {f}: image '{k}' differs with blit aliasing (fused={fused})"
+        if fused:
+            assert ctxs[1].kernel_launches < ctxs[0].kernel_launches, "the fused build should launch fewer kernels"
+    finally:
+        for c in ctxs:
+            c.close()

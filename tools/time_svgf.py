@@ -34,7 +34,7 @@ def main(W=1920, H=1080, reps=20):
         ctx.bind_pass_images(["n"])
         capi._check(capi.lib().vhr_create_query_pool(ctx._h, 2))
         gx, gy = (W + 7) // 8, (H + 7) // 8
-        for variant in (1, 2, 3):
+        for variant in [int(v) for v in os.environ.get("VHR_TIME_VARIANTS", "1,2,3").split(",")]:
             ctx.set_option(capi.OPT_ATROUS_VARIANT, variant)
             for step in (1, 2, 4, 8, 16):
                 pc = np.zeros((), T.SVGFPushConstants); pc["integrated_shadow_and_ao"] = (a, b); pc["atrous_step"] = step

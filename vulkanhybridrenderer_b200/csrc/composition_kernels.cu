@@ -211,6 +211,7 @@ int launch_present(vhr_context *ctx) {
     if (out->format != VHR_FORMAT_B8G8R8A8_SRGB && out->format != VHR_FORMAT_B8G8R8A8_UNORM && out->format != VHR_FORMAT_R16G16B16A16_SFLOAT)
         return fail(VHR_ERR_INVALID, "raytraced composition: render output format %d", out->format);
     if (in->width != out->width || in->height != out->height) return fail(VHR_ERR_INVALID, "raytraced composition: image sizes differ");
+    if (int rc = make_writable(ctx, out, covers_image(ctx, out, out->width, out->height))) return rc;
     PresentParams p;
     p.W = (int)out->width; p.H = (int)out->height;
     p.y_begin = std::max(0, ctx->opt.row_begin);
@@ -246,6 +247,7 @@ int launch_composition(vhr_context *ctx, int shadow_mode, int ao_mode, int refle
         return fail(VHR_ERR_INVALID, "composition: render output format %d", out->format);
     if (shadow_mode < 0 || shadow_mode > 2 || ao_mode < 0 || ao_mode > 2 || reflection_mode < 0 || reflection_mode > 2)
         return fail(VHR_ERR_INVALID, "composition: specialisation constants (%d, %d, %d)", shadow_mode, ao_mode, reflection_mode);
+    if (int rc = make_writable(ctx, out, covers_image(ctx, out, out->width, out->height))) return rc;
     CompositionParams p;
     p.W = (int)out->width; p.H = (int)out->height;
     p.y_begin = std::max(0, ctx->opt.row_begin);

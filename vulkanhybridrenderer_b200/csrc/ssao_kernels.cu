@@ -149,6 +149,7 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     if (depth->width != normals->width || depth->height != normals->height || out->width != normals->width ||
         out->height != normals->height)
         return fail(VHR_ERR_INVALID, "ssao.comp: image sizes differ");
+    if (int rc = make_writable(ctx, out, covers_image(ctx, out, (uint64_t)xg * 8, (uint64_t)yg * 8))) return rc;
     SsaoParams p;
     p.W = (int)normals->width; p.H = (int)normals->height;
     if (!dispatch_range(ctx, normals, xg, yg, p.x_end, p.y_begin, p.y_end)) return VHR_OK;
@@ -176,6 +177,7 @@ int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg) {
     if (in->width != out->width || in->height != out->height) return fail(VHR_ERR_INVALID, "ssao_blur.comp: image sizes differ");
     if (ctx->pfd.display_size[0] != (float)in->width || ctx->pfd.display_size[1] != (float)in->height)
         return fail(VHR_ERR_INVALID, "ssao_blur.comp: PerFrameData.display_size does not match the images");
+    if (int rc = make_writable(ctx, out, covers_image(ctx, out, (uint64_t)xg * 8, (uint64_t)yg * 8))) return rc;
     BlurParams p;
     p.W = (int)in->width; p.H = (int)in->height;
     if (!dispatch_range(ctx, in, xg, yg, p.x_end, p.y_begin, p.y_end)) return VHR_OK;

@@ -177,6 +177,7 @@ int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstant
     const float q = pc.ray_distance / pc.step_size;
     if (!(q == q) || q > 1048576.0f) return fail(VHR_ERR_INVALID, "ssr.comp: ray_distance / step_size = %g", (double)q);
     if (pc.bsearch_steps < 0 || pc.bsearch_steps > 4096) return fail(VHR_ERR_INVALID, "ssr.comp: bsearch_steps = %d", pc.bsearch_steps);
+    if (int rc = make_writable(ctx, b[4], covers_image(ctx, b[4], (uint64_t)xg * 8, (uint64_t)yg * 8))) return rc;
     SsrParams p;
     p.W = (int)b[4]->width; p.H = (int)b[4]->height;
     p.x_end = (int)std::min<uint64_t>(b[4]->width, (uint64_t)xg * 8);

@@ -47,13 +47,13 @@ __device__ __forceinline__ bool is_valid_reprojection(const TemporalParams &p, i
 
 __device__ __forceinline__ float mix_rn(float a, float b, float t) { return add_rn(mul_rn(a, sub_rn(1.0f, t)), mul_rn(b, t)); }
 
-__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ TemporalParams p) {
-    const int cx = blockIdx.x * 32 + threadIdx.x;
-    const int cy = p.y_begin + blockIdx.y * 8 + threadIdx.y;
-    if (cx >= p.x_end || cy >= p.y_end) return;
+// svgf.comp:41-145 for one pixel: the integrated[0] texel (shadow, ao, var_shadow, var_ao) and the moments texel, both as stored (fp16 RTE).
+// `ntexel` = the pixel's normal / object-id texel (the caller has loaded it already).
+struct TemporalOut { uint2 integ; uint32_t mom; };
+__device__ __forceinline__ TemporalOut temporal_pixel(const TemporalParams &p, int cx, int cy, uint2 ntexel) {
     const size_t pix = (size_t)cy * p.W + cx;
 
-    float4 cn = unpack_rgba16f(__ldg(&p.normals[pix]));
+    float4 cn = unpack_rgba16f(ntexel);
     float3 cur_n = make_float3(cn.x, cn.y, cn.z);
     int cur_id = f2i_rz(cn.w);
     float2 mv = unpack_rg16f(__ldg(reinterpret_cast<const uint32_t *>(&p.motion[pix])));   // .xy only
@@ -141,8 +141,20 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
         float av = fmaxf(0.0f, sub_rn(am1, mul_rn(am0, am0)));
         out = make_float4(cur.x, cur.y, sv, av);
     }
-    const uint2 o = pack_rgba16f(out);
-    const uint32_t m = pack_rg16f(sm0, sm1);      // RG16F keeps the shadow moments only (Q2)
+    TemporalOut r;
+    r.integ = pack_rgba16f(out);
+    r.mom = pack_rg16f(sm0, sm1);      // RG16F keeps the shadow moments only (Q2)
+    return r;
+}
+
+__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ TemporalParams p) {
+    const int cx = blockIdx.x * 32 + threadIdx.x;
+    const int cy = p.y_begin + blockIdx.y * 8 + threadIdx.y;
+    if (cx >= p.x_end || cy >= p.y_end) return;
+    const size_t pix = (size_t)cy * p.W + cx;
+    const TemporalOut r = temporal_pixel(p, cx, cy, __ldg(&p.normals[pix]));
+    const uint2 o = r.integ;
+    const uint32_t m = r.mom;
     p.integrated_out[pix] = o;
     p.moments_out[pix] = m;
     if (p.push_integ.rows | p.push_mom.rows) {    // halo exchange fused into the kernel: the next pass on the neighbour reads these rows
@@ -408,9 +420,16 @@ static int launch_tiled(vhr_context *ctx, const AtrousParams &p, int x_pixels, i
 //     tap and pixel, ran no faster than variant 1), so the arithmetic itself is cut: kernel weight, d^128 (a cubic in
 //     d - 1 for 128 log2 d) and both luminance stops fold into the argument of ONE ex2 per channel, the id stop is an
 //     integer compare + select on the ALU pipe. 18 FP32 ops + 2 MUFU.EX2 + 2 ALU ops per tap and pixel.
+// Degree of the polynomial for 128 log2(1 + e) in the tap weight (see pair_compute). 2: the cubic term is dropped — it only matters where
+// the weight is already small: the absolute weight error 2^(184.7 e) * ln 2 * 61.6 |e|^3 peaks at 2.7e-5 (e = -0.023) before the kernel
+// factor h <= 3/32, i.e. < 3e-6 per tap against a weight sum >= 1. One FFMA2 per tap and pixel pair less.
+#ifndef VHR_ATROUS_POLY_DEGREE
+#define VHR_ATROUS_POLY_DEGREE 2
+#endif
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void upk_u32(u64 v, uint32_t &lo, uint32_t &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 pmul(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 padd(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 pfma(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
@@ -425,14 +444,20 @@ struct PairCfg {
     static constexpr int LR = TR * RY;           // lattice rows (S apart) per CTA
     static constexpr int SR = LR + 4;            // staged rows
     static constexpr int THREADS = PD * TR;
-    static constexpr size_t SMEM = (size_t)4 * SR * PC * sizeof(ulonglong2);
+    static constexpr size_t PLANES = (size_t)4 * SR * PC * sizeof(ulonglong2);
+    // S > 1: the 3x3 variance gaussian reads rows y - 1 and y + 1 of every output row, which are not lattice rows of the tile; their
+    // (var_shadow, var_ao) half pairs are staged raw, 2 LR rows of XW = 2 PD + 2 pixels (columns x0 - 1 .. x0 + 2 PD)
+    static constexpr int XW = 2 * PD + 2;
+    static constexpr size_t VXROWS = (S > 1) ? (size_t)2 * LR * XW * sizeof(uint32_t) : 0;
+    static constexpr size_t SMEM = PLANES + VXROWS;
 };
 
 // Taps + normalisation + store for one staged tile (shared by the direct-staging and the TMA-staged kernels): thread
 // (tx, ty) owns pixel columns x0 + tx and x0 + tx + PD on the RY lattice rows ty*RY.. of the tile whose first row is yb.
-template <int S, int PD, int RY, int TR>
+template <int S, int PD, int RY, int TR, bool VX = false>
 __device__ __forceinline__ void pair_compute(const AtrousParams &p, const ulonglong2 *__restrict__ sN0, const ulonglong2 *__restrict__ sN1,
-                                             const ulonglong2 *__restrict__ sL, const ulonglong2 *__restrict__ sV, int x0, int yb, int tx, int ty) {
+                                             const ulonglong2 *__restrict__ sL, const ulonglong2 *__restrict__ sV, int x0, int yb, int tx, int ty,
+                                             const uint32_t *__restrict__ sVx = nullptr) {
     typedef PairCfg<S, PD, RY, TR> C;
     constexpr int PC = C::PC;
     const int ca = x0 + tx, cb = ca + PD;
@@ -451,7 +476,7 @@ __device__ __forceinline__ void pair_compute(const AtrousParams &p, const ulongl
         const int oc = (lr0 + i + 2) * PC + jc;
         const ulonglong2 n0 = sN0[oc], n1 = sN1[oc], l = sL[oc], v = sV[oc];
         pnx[i] = n0.x; pny[i] = n0.y; pnz[i] = n1.x;
-        ida[i] = (uint32_t)n1.y; idb[i] = (uint32_t)(n1.y >> 32);
+        upk_u32(n1.y, ida[i], idb[i]);
         float a, b;
         upk(l.x, a, b); nls[i] = pk(-a, -b);
         upk(l.y, a, b); nla[i] = pk(-a, -b);
@@ -470,6 +495,11 @@ __device__ __forceinline__ void pair_compute(const AtrousParams &p, const ulongl
                 if (S == 1 || y == 0) {
                     const ulonglong2 t = sV[oc + y * PC + x];          // OOB texels staged as 0
                     qs = t.x; qa = t.y;
+                } else if (VX) {
+                    // rows y - 1 / y + 1 staged by the kernel (out-of-image texels as 0)
+                    const uint32_t *rowp = sVx + ((lr0 + i) * 2 + (y > 0 ? 1 : 0)) * C::XW + tx + x + 1;
+                    const float2 ta = unpack_rg16f(rowp[0]), tb = unpack_rg16f(rowp[PD]);
+                    qs = pk(ta.x, tb.x); qa = pk(ta.y, tb.y);
                 } else {
                     const int sy = cy + y;
                     float2 ta = make_float2(0.0f, 0.0f), tb = ta;
@@ -504,14 +534,17 @@ __device__ __forceinline__ void pair_compute(const AtrousParams &p, const ulongl
     const u64 M1 = pk(-1.0f, -1.0f);
     const u64 C1 = pk(184.66496523378731f, 184.66496523378731f);
     const u64 C2 = pk(-92.33248261689366f, -92.33248261689366f);
+#if VHR_ATROUS_POLY_DEGREE >= 3
     const u64 C3 = pk(61.55498841126244f, 61.55498841126244f);
+#endif
 #pragma unroll
     for (int tr = 0; tr < RY + 4; ++tr) {
 #pragma unroll
         for (int x = -2; x <= 2; ++x) {
             const int o = (lr0 + tr) * PC + jc + x * S;
             const ulonglong2 n0 = sN0[o], n1 = sN1[o], l = sL[o], v = sV[o];
-            const uint32_t qa = (uint32_t)n1.y, qb = (uint32_t)(n1.y >> 32);
+            uint32_t qa, qb;
+            upk_u32(n1.y, qa, qb);      // (a plain shift makes ptxas compare 64-bit values: three ISETP per pair instead of two)
 #pragma unroll
             for (int i = 0; i < RY; ++i) {
                 const int y = tr - 2 - i;                       // this texel is tap (x, y) of output row i
@@ -522,8 +555,12 @@ __device__ __forceinline__ void pair_compute(const AtrousParams &p, const ulongl
                 u64 e = pfma(pnx[i], n0.x, M1);
                 e = pfma(pny[i], n0.y, e);
                 e = pfma(pnz[i], n1.x, e);
+#if VHR_ATROUS_POLY_DEGREE >= 3
                 u64 u = pfma(C3, e, C2);
                 u = pfma(u, e, C1);
+#else
+                const u64 u = pfma(C2, e, C1);
+#endif
                 const u64 g = pfma(u, e, pk(lgh, lgh));
                 float ga, gb, da, db;
                 upk(g, ga, gb);
@@ -568,12 +605,25 @@ __global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair
     ulonglong2 *sN1 = psm + SR * PC;       // (nz_a, nz_b), (id_a, id_b)
     ulonglong2 *sL = psm + 2 * SR * PC;    // (shadow_a, shadow_b), (ao_a, ao_b)
     ulonglong2 *sV = psm + 3 * SR * PC;    // (var_shadow_a, var_shadow_b), (var_ao_a, var_ao_b)
+    uint32_t *sVx = reinterpret_cast<uint32_t *>(psm + 4 * SR * PC);   // S > 1: raw (var_shadow, var_ao) of the rows above / below every lattice row
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * PD + tx;
     const int x0 = blockIdx.x * (2 * PD);
     const int k = blockIdx.y / S, r = blockIdx.y % S;       // (super-tile, residue): rows y = yb + S*j
     const int yb = p.y_begin + k * (S * LR) + r;
+    constexpr int NVX = (S > 1) ? (2 * LR * C::XW + C::THREADS - 1) / C::THREADS : 0;
+    uint32_t rvx[NVX > 0 ? NVX : 1];
+    if (S > 1) {
+#pragma unroll
+        for (int it = 0; it < NVX; ++it) {
+            const int idx = tid + it * C::THREADS;
+            const int e = idx / C::XW, c = idx - e * C::XW;
+            const int gy = yb + (e >> 1) * S + ((e & 1) ? 1 : -1), gx = x0 - 1 + c;
+            rvx[it] = 0u;
+            if (idx < 2 * LR * C::XW && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) rvx[it] = __ldg(reinterpret_cast<const uint32_t *>(p.integ_in + (size_t)gy * p.W + gx) + 1);
+        }
+    }
 
     // ---- stage: every texel converted to fp32 once, pixel a = column j, pixel b = column j + PD ------------------
     // Two sweeps (all loads, then convert + store) so that every global load of the tile is in flight at once: the
@@ -606,9 +656,67 @@ __global__ void __launch_bounds__(PD * TR, (PD * TR <= 128) ? 4 : 2) atrous_pair
             sV[idx] = make_ulonglong2(pk(va.z, vb.z), pk(va.w, vb.w));
         }
     }
+    if (S > 1) {
+#pragma unroll
+        for (int it = 0; it < NVX; ++it) {
+            const int idx = tid + it * C::THREADS;
+            if (idx < 2 * LR * C::XW) sVx[idx] = rvx[it];
+        }
+    }
     __syncthreads();
 
-    pair_compute<S, PD, RY, TR>(p, sN0, sN1, sL, sV, x0, yb, tx, ty);
+    pair_compute<S, PD, RY, TR, (S > 1)>(p, sN0, sN1, sL, sV, x0, yb, tx, ty, sVx);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// svgf.comp + the first a-trous iteration in ONE kernel (VHR_OPT_SVGF_FUSED, north_star "fused reprojection + variance + first
+// a-trous step"; reference sequence hybrid_render_path.cpp:299-307)
+// ---------------------------------------------------------------------------------------------------------------
+// The pair kernel's staging sweep does not LOAD the integrated[0] texels of its tile + 2-pixel halo, it COMPUTES them: every staged
+// pixel runs temporal_pixel() (the whole of svgf.comp), the result is rounded to fp16 exactly as the image store would and goes
+// straight into the shared-memory planes; pixels inside the tile also write integrated[0] and the moments image, so every image
+// ends up bit-identical to the two-kernel sequence. Halo pixels are recomputed by the neighbouring CTAs ((PD + 4) (LR + 4) 2 evaluations
+// per 2 PD LR outputs = 1.59x for the 128 x 8 tile). What it saves: one launch, the re-read of integrated[0] and of the normals.
+template <int PD, int RY, int TR>
+__global__ void __launch_bounds__(PD * TR, 2) svgf_fused_kernel(const __grid_constant__ TemporalParams t, const __grid_constant__ AtrousParams p) {
+    typedef PairCfg<1, PD, RY, TR> C;
+    constexpr int PC = C::PC, SR = C::SR, LR = C::LR;
+    extern __shared__ ulonglong2 psm[];
+    ulonglong2 *sN0 = psm, *sN1 = psm + SR * PC, *sL = psm + 2 * SR * PC, *sV = psm + 3 * SR * PC;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * PD + tx;
+    const int x0 = blockIdx.x * (2 * PD);
+    const int yb = p.y_begin + blockIdx.y * LR;
+    for (int idx = tid; idx < SR * PC; idx += C::THREADS) {
+        const int row = idx / PC, j = idx - row * PC;
+        const int gy = yb + row - 2;
+        // one staged pixel: the tile's own pixels also leave the kernel (side a owns columns [x0, x0 + PD), side b [x0 + PD, x0 + 2 PD))
+        auto stage = [&](int gx, int c0, float4 &n, float4 &v) {
+            n = make_float4(0.0f, 0.0f, 0.0f, 0.0f);        // out of bounds: zero normal => weight 0 ("skipped")
+            v = n;
+            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+                const size_t pix = (size_t)gy * p.W + gx;
+                const uint2 nt = __ldg(&p.normals[pix]);
+                const TemporalOut r = temporal_pixel(t, gx, gy, nt);
+                if (row >= 2 && row < 2 + LR && gy < t.y_end && gx >= c0 && gx < c0 + PD && gx < t.x_end) {
+                    t.integrated_out[pix] = r.integ;
+                    t.moments_out[pix] = r.mom;
+                }
+                n = unpack_rgba16f(nt);
+                v = unpack_rgba16f(r.integ);
+            }
+        };
+        float4 na, va, nb, vb;
+        stage(x0 - 2 + j, x0, na, va);
+        stage(x0 - 2 + j + PD, x0 + PD, nb, vb);
+        const int ia = f2i_rz(na.w), ib = f2i_rz(nb.w);
+        sN0[idx] = make_ulonglong2(pk(na.x, nb.x), pk(na.y, nb.y));
+        sN1[idx] = make_ulonglong2(pk(na.z, nb.z), (u64)(uint32_t)ia | ((u64)(uint32_t)ib << 32));
+        sL[idx] = make_ulonglong2(pk(va.x, vb.x), pk(va.y, vb.y));
+        sV[idx] = make_ulonglong2(pk(va.z, vb.z), pk(va.w, vb.w));
+    }
+    __syncthreads();
+    pair_compute<1, PD, RY, TR>(p, sN0, sN1, sL, sV, x0, yb, tx, ty);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -731,10 +839,10 @@ template <int S, int PD, int RY, int TR>
 static int launch_pair(vhr_context *ctx, const AtrousParams &p, int x_pixels, int y_pixels) {
     typedef PairCfg<S, PD, RY, TR> C;
     static_assert(C::SMEM <= 110 * 1024, "two CTAs per SM must fit in shared memory");
-    static bool configured = false;     // per (kernel instantiation, process); the attribute is per function, not per device context
-    if (!configured) {
+    static uint64_t configured = 0;     // bit d: done on device d (function attributes live in the device's context, not in the process)
+    if (!(configured >> (ctx->device & 63) & 1ull)) {
         VHR_CUDA_CHECK(cudaFuncSetAttribute(atrous_pair_kernel<S, PD, RY, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     dim3 block(PD, TR);
     dim3 grid((x_pixels + 2 * PD - 1) / (2 * PD), ((y_pixels + S * C::LR - 1) / (S * C::LR)) * S);
@@ -776,13 +884,14 @@ static int launch_tma(vhr_context *ctx, const AtrousParams &p, const Image *norm
     typedef PairCfg<S, PD, RY, TR> C;
     typedef TmaCfg<S, PD, RY, TR> T;
     static_assert(T::SMEM <= 112 * 1024, "two CTAs per SM must fit in shared memory");
-    static bool configured = false;
-    static int sms = 0;
-    if (!configured) {
+    static uint64_t configured = 0;     // bit d: done on device d
+    static int sms_of[64] = {};
+    if (!(configured >> (ctx->device & 63) & 1ull)) {
         VHR_CUDA_CHECK(cudaFuncSetAttribute(atrous_tma_kernel<S, PD, RY, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-        VHR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        configured = true;
+        VHR_CUDA_CHECK(cudaDeviceGetAttribute(&sms_of[ctx->device & 63], cudaDevAttrMultiProcessorCount, ctx->device));
+        configured |= 1ull << (ctx->device & 63);
     }
+    const int sms = sms_of[ctx->device & 63];
     CUtensorMap map_n, map_i;
     if (int rc = make_tensor_map(&map_n, normals, S, T::PCT, C::SR)) return rc;
     if (int rc = make_tensor_map(&map_i, in, S, T::PCT, C::SR)) return rc;
@@ -836,6 +945,7 @@ int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFP
         VHR_CUDA_CHECK(cudaMalloc(&mom->twin, mom->bytes));
         VHR_CUDA_CHECK(cudaMemsetAsync(mom->twin, 0, mom->bytes, ctx->stream));
     }
+    if ((rc = make_writable(ctx, integ0, covers_image(ctx, integ0, (uint64_t)xg * 8, (uint64_t)yg * 8)))) return rc;
     TemporalParams p;
     p.W = (int)normals->width; p.H = (int)normals->height;
     if (!dispatch_range(ctx, normals, xg, yg, p.x_end, p.y_begin, p.y_end)) return VHR_OK;
@@ -847,9 +957,35 @@ int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFP
     // reads `motion_halo` rows of these moments
     p.push_integ = halo_push_for(ctx, integ0, false, 2);
     p.push_mom = halo_push_for(ctx, mom, true, ctx->part.motion_halo);
-    dim3 block(32, 8), grid((p.x_end + 31) / 32, (p.y_end - p.y_begin + 7) / 8);
-    svgf_temporal_kernel<<<grid, block, 0, ctx->stream>>>(p);
-    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->fused_it0.valid = false;
+    Image *integ1 = storage_slot(ctx, pc.integrated_shadow_and_ao[1]);
+    const bool full = covers_image(ctx, integ0, (uint64_t)xg * 8, (uint64_t)yg * 8);
+    if (ctx->opt.svgf_fused && full && ctx->opt.atrous_variant >= 2 && integ1 && integ1 != integ0 && p.dsx == (float)p.W && p.dsy == (float)p.H &&
+        !check_image(integ1, VHR_FORMAT_R16G16B16A16_SFLOAT, normals, "svgf.comp integrated[1]")) {
+        // fused temporal + a-trous iteration 0 (step 1): the reference's next call, Dispatch(svgf_atrous_filter.comp) with atrous_step 1 on
+        // the same slots, is then answered without a launch (launch_svgf_atrous)
+        typedef PairCfg<1, 64, 2, 4> C;
+        if ((rc = make_writable(ctx, integ1, true))) return rc;
+        static uint64_t configured = 0;
+        if (!(configured >> (ctx->device & 63) & 1ull)) {
+            VHR_CUDA_CHECK(cudaFuncSetAttribute(svgf_fused_kernel<64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+            configured |= 1ull << (ctx->device & 63);
+        }
+        AtrousParams a;
+        a.W = p.W; a.H = p.H; a.x_end = p.x_end; a.y_begin = p.y_begin; a.y_end = p.y_end; a.step = 1; a.dsx = p.dsx; a.dsy = p.dsy;
+        a.normals = p.normals; a.integ_in = (const uint2 *)integ0->ptr; a.integ_out = (uint2 *)integ1->ptr;
+        dim3 block(64, 4), grid((p.x_end + 127) / 128, (p.y_end - p.y_begin + C::LR - 1) / C::LR);
+        svgf_fused_kernel<64, 2, 4><<<grid, block, C::SMEM, ctx->stream>>>(p, a);
+        VHR_CUDA_CHECK(cudaGetLastError());
+        ctx->fused_it0.valid = true;
+        ctx->fused_it0.in_slot = pc.integrated_shadow_and_ao[0];
+        ctx->fused_it0.out_slot = pc.integrated_shadow_and_ao[1];
+        ctx->fused_it0.epoch = ctx->epoch;
+    } else {
+        dim3 block(32, 8), grid((p.x_end + 31) / 32, (p.y_end - p.y_begin + 7) / 8);
+        svgf_temporal_kernel<<<grid, block, 0, ctx->stream>>>(p);
+        VHR_CUDA_CHECK(cudaGetLastError());
+    }
     ctx->launches++;
     std::swap(mom->ptr, mom->twin);   // this frame's moments become "the" moments image
     for (int r = 0; r < VHR_MAX_RANKS; ++r) std::swap(mom->peer[r], mom->peer_twin[r]);
@@ -867,6 +1003,7 @@ static int atrous_launch_only(vhr_context *ctx, uint32_t xg, uint32_t yg, const 
     if ((rc = check_image(out, VHR_FORMAT_R16G16B16A16_SFLOAT, normals, "atrous integrated[1]"))) return rc;
     if (in == out) return fail(VHR_ERR_INVALID, "atrous: integrated[0] and [1] are the same image");
     if (pc.atrous_step < 1) return fail(VHR_ERR_INVALID, "atrous: step %d < 1", pc.atrous_step);
+    if ((rc = make_writable(ctx, out, covers_image(ctx, out, (uint64_t)xg * 8, (uint64_t)yg * 8)))) return rc;
     AtrousParams p;
     p.W = (int)normals->width; p.H = (int)normals->height;
     if (!dispatch_range(ctx, normals, xg, yg, p.x_end, p.y_begin, p.y_end)) return VHR_OK;
@@ -882,6 +1019,16 @@ static int atrous_launch_only(vhr_context *ctx, uint32_t xg, uint32_t yg, const 
     // the same thing whenever the UBO matches the images, which the tiled path requires.
     bool tiled_ok = ctx->opt.atrous_variant >= 1 && p.dsx == (float)p.W && p.dsy == (float)p.H;
     static const int dev_tr = getenv("VHR_ATROUS_TR") ? atoi(getenv("VHR_ATROUS_TR")) : 4;     // development A/B switch
+    if (tiled_ok && ctx->opt.atrous_variant >= 2 && dev_tr == 3) {      // three rows per thread, 192-thread CTAs (168 registers): 22 % fewer shared-memory loads per tap
+        int xp = p.x_end, yp = p.y_end - p.y_begin;
+        switch (p.step) {
+            case 1: return launch_pair<1, 64, 3, 3>(ctx, p, xp, yp);
+            case 2: return launch_pair<2, 64, 3, 3>(ctx, p, xp, yp);
+            case 4: return launch_pair<4, 64, 3, 3>(ctx, p, xp, yp);
+            case 8: return launch_pair<8, 64, 3, 3>(ctx, p, xp, yp);
+            default: break;
+        }
+    }
     if (tiled_ok && ctx->opt.atrous_variant >= 2 && dev_tr == 2) {
         int xp = p.x_end, yp = p.y_end - p.y_begin;
         switch (p.step) {
@@ -932,6 +1079,12 @@ static int atrous_launch_only(vhr_context *ctx, uint32_t xg, uint32_t yg, const 
 }
 
 int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc) {
+    if (ctx->fused_it0.valid) {       // iteration 0 came out of the fused svgf.comp kernel one call ago: nothing left to launch
+        const bool same = ctx->fused_it0.epoch + 1 == ctx->epoch && pc.atrous_step == 1 && pc.integrated_shadow_and_ao[0] == ctx->fused_it0.in_slot &&
+                          pc.integrated_shadow_and_ao[1] == ctx->fused_it0.out_slot;
+        ctx->fused_it0.valid = false;
+        if (same) return VHR_OK;
+    }
     bool pushed = false;
     if (int rc = atrous_launch_only(ctx, xg, yg, pc, pushed)) return rc;
     return pushed ? peer_sync_neighbours(ctx) : VHR_OK;

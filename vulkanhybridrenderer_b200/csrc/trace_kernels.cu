@@ -1115,6 +1115,8 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
     for (Image *im : {normals, depth, sa, refl})
         if (im->width != width || im->height != height)
             return fail(VHR_ERR_INVALID, "TraceRays: launch size %ux%u differs from image %ux%u", width, height, im->width, im->height);
+    for (Image *im : {sa, refl})
+        if (int rc = make_writable(ctx, im, covers_image(ctx, im, width, height))) return rc;
     RaygenParams p;
     p.W = (int)width; p.H = (int)height;
     if (!band(ctx, height, p.y_begin, p.y_end)) return VHR_OK;
@@ -1184,6 +1186,7 @@ int launch_raytraced(vhr_context *ctx, uint32_t width, uint32_t height) {
     if (out->format != VHR_FORMAT_B8G8R8A8_UNORM) return fail(VHR_ERR_INVALID, "Raytracing Pipeline: output format %d, expected B8G8R8A8_UNORM", out->format);
     if (out->width != width || out->height != height)
         return fail(VHR_ERR_INVALID, "TraceRays: launch size %ux%u differs from image %ux%u", width, height, out->width, out->height);
+    if (int rc = make_writable(ctx, out, covers_image(ctx, out, width, height))) return rc;
     RaytracedParams p;
     p.W = (int)width; p.H = (int)height;
     if (!band(ctx, height, p.y_begin, p.y_end)) return VHR_OK;
@@ -1205,6 +1208,8 @@ int launch_gbuffer(vhr_context *ctx, uint32_t width, uint32_t height) {
         return fail(VHR_ERR_INVALID, "G-buffer pass: unexpected image formats");
     for (Image *im : {albedo, normals, motion, depth})
         if (im->width != width || im->height != height) return fail(VHR_ERR_INVALID, "G-buffer pass: image size mismatch");
+    for (Image *im : {albedo, normals, motion, depth})      // e.g. the normals image still shared with the SVGF pass's previous-frame copy
+        if (int rc = make_writable(ctx, im, covers_image(ctx, im, width, height))) return rc;
     GbufferParams p;
     p.W = (int)width; p.H = (int)height;
     if (!band(ctx, height, p.y_begin, p.y_end)) return VHR_OK;

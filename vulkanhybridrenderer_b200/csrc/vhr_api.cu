@@ -40,6 +40,13 @@ static int alloc_image(vhr_context *ctx, Image &im, uint32_t w, uint32_t h, int 
     return VHR_OK;
 }
 static void free_image(Image &im) {
+    if (im.shares_with) {          // the partner keeps the shared buffer; the idle allocation goes
+        Image *o = im.shares_with;
+        void *sp = im.spare ? im.spare : o->spare;
+        if (sp) cudaFree(sp);
+        o->spare = nullptr; o->shares_with = nullptr;
+        im.ptr = nullptr; im.spare = nullptr; im.shares_with = nullptr;
+    }
     if (im.ptr) cudaFree(im.ptr);
     if (im.twin) cudaFree(im.twin);
     if (im.staging) cudaFree(im.staging);
@@ -71,6 +78,7 @@ static int copy_in(vhr_context *ctx, Image *im, const void *host, size_t bytes, 
     if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
     if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", what, bytes, im->bytes);
     if (int rc = consume_upload(ctx, im)) return rc;
+    if (int rc = make_writable(ctx, im, true)) return rc;
     VHR_CUDA_CHECK(cudaMemcpyAsync(im->ptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return VHR_OK;
 }
@@ -81,6 +89,22 @@ static int copy_out(vhr_context *ctx, Image *im, void *host, size_t bytes, const
     VHR_CUDA_CHECK(cudaMemcpyAsync(host, im->ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return VHR_OK;
 }
+}  // namespace vhr (anonymous part)
+
+int vhr::make_writable(vhr_context *ctx, Image *im, bool whole) {
+    if (!im || !im->shares_with) return VHR_OK;
+    Image *o = im->shares_with;
+    void *sp = im->spare ? im->spare : o->spare;
+    void *shared = im->ptr;
+    im->ptr = sp;
+    im->spare = o->spare = nullptr;
+    im->shares_with = o->shares_with = nullptr;
+    // everything that read the idle allocation was enqueued before the blit that idled it, i.e. earlier on this stream
+    if (!whole) VHR_CUDA_CHECK(cudaMemcpyAsync(im->ptr, shared, im->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return VHR_OK;
+}
+
+namespace vhr {
 static int blit(vhr_context *ctx, Image *src, Image *dst, const char *what) {
     if (!src || !dst) return fail(VHR_ERR_INVALID, "%s: unknown image", what);
     // compute_execution_context.cpp:128-129,179-180 assert equal extents; the blit is NEAREST same-size = copy
@@ -89,13 +113,24 @@ static int blit(vhr_context *ctx, Image *src, Image *dst, const char *what) {
                     src->height, src->format, dst->width, dst->height, dst->format);
     if (int rc = consume_upload(ctx, src)) return rc;
     if (int rc = consume_upload(ctx, dst)) return rc;
+    if (src == dst || (dst->shares_with == src && dst->ptr == src->ptr)) return VHR_OK;      // already the same texels
     if (ctx->part.enabled && ctx->part.world > 1 && src->height == ctx->height) {
+        if (int rc = make_writable(ctx, dst, false)) return rc;
         // a rank only ever reads its band and the halo rows around it: copy those (band +- 64 rows)
         const int y0 = std::max(0, ctx->part.band_begin[ctx->part.rank] - 64);
         const int y1 = std::min((int)src->height, ctx->part.band_begin[ctx->part.rank + 1] + 64);
         const size_t row = src->bytes / src->height;
         VHR_CUDA_CHECK(cudaMemcpyAsync((char *)dst->ptr + y0 * row, (const char *)src->ptr + y0 * row, (size_t)(y1 - y0) * row,
                                        cudaMemcpyDeviceToDevice, ctx->stream));
+        return VHR_OK;
+    }
+    if (int rc = make_writable(ctx, dst, true)) return rc;                                   // dst is overwritten: it leaves its old partner
+    if (ctx->opt.blit_alias && !src->shares_with && !src->twin && !dst->twin && !src->staging_busy) {
+        // copy-free: dst shows src's buffer until one of the two is written again (see Image::shares_with)
+        dst->spare = dst->ptr;
+        dst->ptr = src->ptr;
+        dst->shares_with = src;
+        src->shares_with = dst;
         return VHR_OK;
     }
     VHR_CUDA_CHECK(cudaMemcpyAsync(dst->ptr, src->ptr, src->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -236,6 +271,7 @@ uint64_t vhr_kernel_launch_count(vhr_context *ctx) { return ctx ? ctx->launches 
 
 int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_vertices, const uint32_t *indices,
                         uint32_t n_indices, const void *primitives, uint32_t n_primitives) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     if ((n_vertices && !vertices) || (n_indices && !indices) || (n_primitives && !primitives))
@@ -360,6 +396,7 @@ int vhr_destroy_textures(vhr_context *ctx) {
 }
 
 int vhr_update_per_frame_ubo(vhr_context *ctx, const void *per_frame_data, size_t size) {
+    if (ctx) ctx->epoch++;
     if (!ctx || !per_frame_data) return fail(VHR_ERR_INVALID, "NULL argument");
     if (size != sizeof(PerFrameData)) return fail(VHR_ERR_INVALID, "PerFrameData is %zu bytes, got %zu", sizeof(PerFrameData), size);
     memcpy(&ctx->pfd, per_frame_data, sizeof(PerFrameData));
@@ -368,6 +405,7 @@ int vhr_update_per_frame_ubo(vhr_context *ctx, const void *per_frame_data, size_
 }
 
 int vhr_upload_new_storage_image(vhr_context *ctx, uint32_t width, uint32_t height, int vk_format) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     if (ctx->device >= 0) VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     for (int i = 0; i < VHR_MAX_GLOBAL_RESOURCES; ++i) {
@@ -380,6 +418,7 @@ int vhr_upload_new_storage_image(vhr_context *ctx, uint32_t width, uint32_t heig
 }
 
 int vhr_destroy_storage_image(vhr_context *ctx, int slot) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     Image *im = storage_slot(ctx, slot);
     if (!im) return fail(VHR_ERR_INVALID, "storage image %d does not exist", slot);
@@ -416,6 +455,7 @@ int vhr_destroy_transient_resources(vhr_context *ctx) {
 }
 
 int vhr_image_upload(vhr_context *ctx, const char *name, const void *host, size_t bytes) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return copy_in(ctx, find_transient(ctx, name), host, bytes, name ? name : "(null)");
@@ -426,6 +466,7 @@ int vhr_image_download(vhr_context *ctx, const char *name, void *host, size_t by
     return copy_out(ctx, find_transient(ctx, name), host, bytes, name ? name : "(null)");
 }
 int vhr_storage_image_upload(vhr_context *ctx, int slot, const void *host, size_t bytes) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return copy_in(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
@@ -436,6 +477,7 @@ int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t by
     return copy_out(ctx, storage_slot(ctx, slot), host, bytes, "storage image");
 }
 int vhr_image_upload_async(vhr_context *ctx, const char *name, const void *host, size_t bytes) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     Image *im = find_transient(ctx, name);
@@ -443,6 +485,7 @@ int vhr_image_upload_async(vhr_context *ctx, const char *name, const void *host,
     if (!host || bytes != im->bytes) return fail(VHR_ERR_INVALID, "%s: %zu bytes given, image holds %zu", name, bytes, im->bytes);
     VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (int rc = ensure_transfer_queues(ctx)) return rc;
+    if (int rc = make_writable(ctx, im, true)) return rc;
     if (!im->upload_done) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->upload_done, cudaEventDisableTiming));
     // the copy may only start once every pass enqueued so far (the image's last readers) has finished
     VHR_CUDA_CHECK(cudaEventRecord(ctx->compute_tail, ctx->stream));
@@ -513,6 +556,7 @@ void *vhr_storage_image_device_ptr(vhr_context *ctx, int slot, uint32_t *width, 
 }
 
 int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, uint32_t count) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     if (count > VHR_MAX_PASS_BINDINGS) return fail(VHR_ERR_INVALID, "%u bindings (max %d)", count, VHR_MAX_PASS_BINDINGS);
     for (uint32_t i = 0; i < count; ++i) {
@@ -528,6 +572,7 @@ int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, 
 
 int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
                  const void *push_constants, size_t push_constants_size) {
+    if (ctx) ctx->epoch++;
     if (!ctx || !shader_path) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
@@ -570,6 +615,7 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
 }
 
 int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height) {
+    if (ctx) ctx->epoch++;
     if (!ctx || !pipeline_name) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     const bool hybrid = !strcmp(pipeline_name, "Raytrace Pipeline"), full = !strcmp(pipeline_name, "Raytracing Pipeline");
@@ -581,6 +627,7 @@ int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, 
 
 int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *specialization_constants, uint32_t n_constants,
              uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance) {
+    if (ctx) ctx->epoch++;
     if (!ctx || !fragment_shader) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
@@ -602,6 +649,7 @@ int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *speci
 }
 
 int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
@@ -618,16 +666,19 @@ int vhr_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_
 }
 
 int vhr_blit_storage_to_transient(vhr_context *ctx, int src_slot, const char *dst_name) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return blit(ctx, storage_slot(ctx, src_slot), find_transient(ctx, dst_name), "BlitImageStorageToTransient");
 }
 int vhr_blit_transient_to_storage(vhr_context *ctx, const char *src_name, int dst_slot) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return blit(ctx, find_transient(ctx, src_name), storage_slot(ctx, dst_slot), "BlitImageTransientToStorage");
 }
 int vhr_blit_storage_to_storage(vhr_context *ctx, int src_slot, int dst_slot) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return blit(ctx, storage_slot(ctx, src_slot), storage_slot(ctx, dst_slot), "BlitImageStorageToStorage");
@@ -661,10 +712,12 @@ int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, do
 }
 
 int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
+    if (ctx) ctx->epoch++;
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     switch (option) {
         case VHR_OPT_AO_SPP:
-            if (value < 0 || value > 64) return fail(VHR_ERR_INVALID, "ao_spp %lld out of [0, 64]", (long long)value);
+            // 0 would make the kernel average zero samples (0 / 0 = NaN into the RG16F image); VHR_OPT_TRACE_AO = 0 switches AO off
+            if (value < 1 || value > 64) return fail(VHR_ERR_INVALID, "ao_spp %lld out of [1, 64]", (long long)value);
             ctx->opt.ao_spp = (int)value; return VHR_OK;
         case VHR_OPT_TRACE_SHADOWS: ctx->opt.trace_shadows = value != 0; return VHR_OK;
         case VHR_OPT_TRACE_AO: ctx->opt.trace_ao = value != 0; return VHR_OK;
@@ -672,6 +725,7 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
         case VHR_OPT_ROW_BEGIN: ctx->opt.row_begin = (int)value; return VHR_OK;
         case VHR_OPT_ROW_END: ctx->opt.row_end = (int)value; return VHR_OK;
         case VHR_OPT_SVGF_FUSED: ctx->opt.svgf_fused = value != 0; return VHR_OK;
+        case VHR_OPT_BLIT_ALIAS: ctx->opt.blit_alias = value != 0; return VHR_OK;
         case VHR_OPT_ATROUS_VARIANT:
             if (value < 0 || value > 3) return fail(VHR_ERR_INVALID, "atrous variant %lld", (long long)value);
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
@@ -705,6 +759,7 @@ int64_t vhr_get_option(vhr_context *ctx, int option) {
         case VHR_OPT_ROW_BEGIN: return ctx->opt.row_begin;
         case VHR_OPT_ROW_END: return ctx->opt.row_end;
         case VHR_OPT_SVGF_FUSED: return ctx->opt.svgf_fused;
+        case VHR_OPT_BLIT_ALIAS: return ctx->opt.blit_alias;
         case VHR_OPT_ATROUS_VARIANT: return ctx->opt.atrous_variant;
         case VHR_OPT_DEBUG_REFLECTION_T: return ctx->opt.debug_refl_t;
         case VHR_OPT_RAYGEN_VARIANT: return ctx->opt.raygen_variant;

@@ -29,6 +29,11 @@ struct Image {
     // multi-GPU: the same image in the other ranks' HBM, mapped through CUDA IPC (NVLink peer memory); index = rank
     void *peer[VHR_MAX_RANKS] = {};
     void *peer_twin[VHR_MAX_RANKS] = {};
+    // copy-free blits (VHR_OPT_BLIT_ALIAS): after blit(src -> dst) both images show ONE buffer (ptr == shares_with->ptr) and the
+    // allocation dst gave up waits in `spare` (held by exactly one of the two); whoever is written first takes the spare
+    // (make_writable) — the copy a blit would do never happens, the image contents are what a copy would have left.
+    Image *shares_with = nullptr;
+    void *spare = nullptr;
 };
 
 inline int format_texel_bytes(int fmt) {
@@ -61,6 +66,7 @@ struct Options {
     int row_begin = 0;
     int row_end = -1;            // -1 = image height
     int svgf_fused = 0;
+    int blit_alias = 0;          // 1: same-size blits alias buffers copy-on-write instead of copying (VHR_OPT_BLIT_ALIAS)
     int atrous_variant = 2;      // 0 = direct-load reference-like kernel, 1 = shared-memory tiled kernel, 2 = pixel-pair packed kernel
     int debug_refl_t = 0;        // 1: the ray pass also writes the reflection ray's hit distance (tests)
     int raytraced_alpha_test = 0; // the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14)
@@ -112,6 +118,11 @@ struct vhr_context {
     vhr::Bvh bvh;
     vhr::Options opt;
     uint64_t launches = 0;
+    // VHR_OPT_SVGF_FUSED: svgf.comp's dispatch has already produced a-trous iteration 0 for these storage slots; the step-1
+    // dispatch that follows it in the reference's sequence finds this note and launches nothing. `epoch` counts the calls that can
+    // change an image, a binding or the per-frame constants: the note only holds for the very next such call.
+    uint64_t epoch = 0;
+    struct { bool valid = false; int in_slot = -1, out_slot = -1; uint64_t epoch = 0; } fused_it0;
     std::vector<cudaEvent_t> queries;              // timestamp query pool
     // transfer queues: copies that overlap the compute stream (the reference's frames in flight, renderer.cpp:103-108)
     cudaStream_t upload_stream = nullptr, download_stream = nullptr;
@@ -159,6 +170,13 @@ int peer_sync_neighbours(vhr_context *ctx);   // after a kernel that pushed halo
 int peer_sync_all(vhr_context *ctx);          // after the ray pass scattered its rows to their owners: all ranks <-> all ranks
 HaloPush halo_push_for(vhr_context *ctx, Image *out, bool twin, int rows);
 void peer_close_all(vhr_context *ctx);
+// Call before enqueueing work that writes `im`: an image that shares its buffer with a blit partner gets the spare allocation
+// (its old content is copied over first unless the write covers the `whole` image). No-op for images that share nothing.
+int make_writable(vhr_context *ctx, Image *im, bool whole);
+// does a pass dispatched over xg x yg groups of 8 x 8 (or a w x h launch) overwrite every texel of `im`?
+inline bool covers_image(const vhr_context *ctx, const Image *im, uint64_t w, uint64_t h) {
+    return !ctx->part.enabled && ctx->opt.row_begin <= 0 && (ctx->opt.row_end < 0 || ctx->opt.row_end >= (int)im->height) && w >= im->width && h >= im->height;
+}
 int build_bvh(vhr_context *ctx);
 void free_bvh(vhr_context *ctx);
 

@@ -127,7 +127,10 @@ void HybridRenderPath::RegisterPath(RenderGraph &rg, ResourceManager &rm) {
         pc.shadow_and_ao_history = (int)rm.UploadNewStorageImage(rm.width, rm.height, F4);
         pc.shadow_and_ao_moments_history = (int)rm.UploadNewStorageImage(rm.width, rm.height, F2);
         svgf_textures_created = true;
+        // B200 mode of the node (not in the reference): the pass body below stays the reference's call sequence; the library answers
+        // svgf.comp + the step-1 a-trous dispatch with one fused kernel and the three blits by aliasing buffers copy-on-write
         VHR_CHECK(vhr_set_option(rm.ctx, VHR_OPT_SVGF_FUSED, svgf_fused ? 1 : 0));
+        VHR_CHECK(vhr_set_option(rm.ctx, VHR_OPT_BLIT_ALIAS, svgf_fused ? 1 : 0));
 
         rg.AddComputePass(
             "SVGF Denoise Pass",

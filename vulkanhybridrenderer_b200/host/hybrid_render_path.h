@@ -35,7 +35,8 @@ public:
     int ambient_occlusion_mode = AMBIENT_OCCLUSION_MODE_OFF;
     int reflection_mode = REFLECTION_MODE_OFF;
     bool denoise_shadow_and_ao = false;
-    // B200 addition (not in the reference): run the SVGF node as the fused / blit-free kernel sequence.
+    // B200 addition (not in the reference): VHR_OPT_SVGF_FUSED + VHR_OPT_BLIT_ALIAS for the SVGF node — same call sequence, one fused
+    // temporal + a-trous-0 kernel and copy-free blits inside the library.
     bool svgf_fused = false;
 
     SVGFPushConstants svgf_push_constants{};

@@ -61,10 +61,15 @@ def groups(n):
 class HybridRenderPath:
     """Owns the images of the hot-path passes on one context and replays the reference's per-frame call sequence."""
 
-    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False, composition=None, shadow_map_size=(4096, 4096), rt_sets=1):
+    def __init__(self, ctx, width, height, gbuffer_sets=1, ssao=False, composition=None, shadow_map_size=(4096, 4096), rt_sets=1, svgf_fused=False,
+                 blit_alias=None):
         """composition: None (no composition pass) or the VkFormat of RENDER_OUTPUT (B8G8R8A8_SRGB = the reference's
         swapchain; R16G16B16A16_SFLOAT = linear HDR radiance for parity measurements)."""
         self.ctx, self.W, self.H = ctx, width, height
+        # B200 modes of the SVGF node (HybridRenderPath::svgf_fused of host/hybrid_render_path.h): the call sequence below stays the
+        # reference's; the library fuses svgf.comp with a-trous iteration 0 and turns the three blits into copy-on-write aliases
+        ctx.set_option(capi.OPT_SVGF_FUSED, int(bool(svgf_fused)))
+        ctx.set_option(capi.OPT_BLIT_ALIAS, int(bool(svgf_fused if blit_alias is None else blit_alias)))
         self.gsets = []
         for s in range(gbuffer_sets):
             sfx = "" if s == 0 else f" [{s}]"
