@@ -141,6 +141,11 @@ int vhr_storage_image_download(vhr_context *ctx, int slot, void *host, size_t by
 int vhr_image_upload_async(vhr_context *ctx, const char *name, const void *host, size_t bytes);
 int vhr_image_download_async(vhr_context *ctx, const char *name, void *host, size_t bytes, uint32_t *ticket);
 int vhr_wait_download(vhr_context *ctx, uint32_t ticket);
+/* Rows [y0, y1) only (`host_rows` points at row y0): what a rank of the row-band partition moves — its band of the G-buffer up, its band
+ * of the result down. The upload follows the rules of vhr_image_upload_async. The download reads the image itself (no device-side
+ * snapshot): the compute queue is made to wait for it before anything enqueued later runs. */
+int vhr_image_upload_rows_async(vhr_context *ctx, const char *name, const void *host_rows, uint32_t y0, uint32_t y1);
+int vhr_image_download_rows_async(vhr_context *ctx, const char *name, void *host_rows, uint32_t y0, uint32_t y1, uint32_t *ticket);
 /* Device pointer of a named image (zero-copy interop, e.g. NCCL halo exchange); NULL if unknown. */
 void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format);
 void *vhr_storage_image_device_ptr(vhr_context *ctx, int slot, uint32_t *width, uint32_t *height, int *vk_format);
@@ -193,6 +198,11 @@ int vhr_blit_storage_to_storage(vhr_context *ctx, int src_slot, int dst_slot);
 /* Per-pass GPU timestamps (render_graph.cpp:143-148 vkCreateQueryPool, :167-182 vkCmdWriteTimestamp, :189-201
  * vkGetQueryPoolResults): a pool of `count` CUDA events recorded on the context's stream. */
 int vhr_create_query_pool(vhr_context *ctx, uint32_t count);
+/* vkCmdBeginDebugUtilsLabelEXT / vkCmdEndDebugUtilsLabelEXT around every pass node (render_graph.cpp:160-164, :184): an NVTX range named
+ * after the pass ("Raytrace Pass", "SVGF Denoise Pass", ...). The kernel-launching calls open their own nested ranges named after the
+ * shader path / pipeline name they were given. */
+int vhr_cmd_begin_debug_label(vhr_context *ctx, const char *label);
+int vhr_cmd_end_debug_label(vhr_context *ctx);
 int vhr_write_timestamp(vhr_context *ctx, uint32_t query);
 /* Blocks until query `last` has been reached, then writes the elapsed milliseconds between `first` and `last`. */
 int vhr_get_query_elapsed_ms(vhr_context *ctx, uint32_t first, uint32_t last, double *out_ms);

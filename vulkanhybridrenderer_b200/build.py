@@ -57,7 +57,7 @@ def build_cuda(force=False, verbose=False):
             if verbose:
                 print(out)
     if jobs or _stale(LIB_CUDA, objs):
-        _run([NVCC, "-shared", "-o", LIB_CUDA] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        _run([NVCC, "-shared", "-o", LIB_CUDA] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])    # -ldl: NVTX loads its injection library lazily
     return LIB_CUDA
 
 

@@ -30,6 +30,7 @@ SYMBOLS = [
     "vhr_storage_image_twin_device_ptr", "vhr_sync_device_ptr",
     "vhr_upload_texture_from_data", "vhr_destroy_textures",
     "vhr_select_queue", "vhr_queue_signal", "vhr_queue_wait",
+    "vhr_image_upload_rows_async", "vhr_image_download_rows_async", "vhr_cmd_begin_debug_label", "vhr_cmd_end_debug_label",
 ]
 MAX_RANKS = 8
 MAX_SEMAPHORES = 16
@@ -98,6 +99,10 @@ def lib():
         L.vhr_image_upload_async.argtypes = [vp, C.c_char_p, vp, sz]
         L.vhr_image_download_async.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(u32)]
         L.vhr_wait_download.argtypes = [vp, u32]
+        L.vhr_image_upload_rows_async.argtypes = [vp, C.c_char_p, vp, u32, u32]
+        L.vhr_image_download_rows_async.argtypes = [vp, C.c_char_p, vp, u32, u32, C.POINTER(u32)]
+        L.vhr_cmd_begin_debug_label.argtypes = [vp, C.c_char_p]
+        L.vhr_cmd_end_debug_label.argtypes = [vp]
         L.vhr_storage_image_upload.argtypes = [vp, i32, vp, sz]
         L.vhr_storage_image_download.argtypes = [vp, i32, vp, sz]
         L.vhr_image_device_ptr.argtypes = [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(i32)]
@@ -250,6 +255,29 @@ class Context:
         t = C.c_uint32()
         _check(lib().vhr_image_download_async(self._h, name.encode(), a, n, C.byref(t)))
         return t.value
+
+    def image_upload_rows_async(self, name, host_rows, y0, y1):
+        """Rows [y0, y1) of `name` from pinned host memory (host_rows starts at row y0) on the transfer queue."""
+        a, _ = _addr(host_rows)
+        _check(lib().vhr_image_upload_rows_async(self._h, name.encode(), a, int(y0), int(y1)))
+
+    def image_download_rows_async(self, name, host_rows, y0, y1):
+        a, _ = _addr(host_rows)
+        t = C.c_uint32()
+        _check(lib().vhr_image_download_rows_async(self._h, name.encode(), a, int(y0), int(y1), C.byref(t)))
+        return t.value
+
+    def debug_label(self, label):
+        """Context manager: an NVTX range named after a pass node (vkCmdBegin/EndDebugUtilsLabelEXT, render_graph.cpp:160-164,184)."""
+        ctx = self
+
+        class _L:
+            def __enter__(self_inner):
+                _check(lib().vhr_cmd_begin_debug_label(ctx._h, label.encode()))
+
+            def __exit__(self_inner, *a):
+                _check(lib().vhr_cmd_end_debug_label(ctx._h))
+        return _L()
 
     def wait_download(self, ticket):
         _check(lib().vhr_wait_download(self._h, int(ticket)))

@@ -123,7 +123,12 @@ extern "C" {
 
 int vhr_set_partition(vhr_context *ctx, const vhr_partition *p) {
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
-    if (!p) { ctx->part = Partition(); return VHR_OK; }
+    if (!p) {      // back to single-GPU behaviour: the whole image is the dispatch range again
+        ctx->part = Partition();
+        ctx->opt.row_begin = 0;
+        ctx->opt.row_end = -1;
+        return VHR_OK;
+    }
     if (ctx->stream != ctx->queue[0]) return fail(VHR_ERR_STATE, "partition: select queue 0 first (the peer flag words are ordered on it)");
     if (p->world < 1 || p->world > VHR_MAX_RANKS || p->rank >= p->world) return fail(VHR_ERR_INVALID, "partition: rank %u of %u (max %d ranks)", p->rank, p->world, VHR_MAX_RANKS);
     if (p->band_begin[0] != 0 || p->band_begin[p->world] != ctx->height) return fail(VHR_ERR_INVALID, "partition: bands must cover rows [0, %u)", ctx->height);

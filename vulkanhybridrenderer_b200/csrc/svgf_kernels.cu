@@ -955,6 +955,11 @@ int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFP
     p.moments_in = (const uint32_t *)mom->ptr; p.integrated_out = (uint2 *)integ0->ptr; p.moments_out = (uint32_t *)mom->twin;
     // multi-GPU: iteration 0 on the neighbours reads 2 rows of this output beyond their band, their next temporal pass
     // reads `motion_halo` rows of these moments
+    // Without the interleaved ray pass (ray_block_rows = 0) nothing orders this kernel's halo stores into the neighbours' integrated[0]
+    // after THEIR last a-trous iteration of the previous frame, which still reads that image and exchanges nothing: one
+    // flag round trip first. With ray_block_rows = 8 the ray pass's all-ranks exchange already sits in between.
+    if (ctx->part.enabled && ctx->part.world > 1 && ctx->part.ray_block_rows == 0)
+        if ((rc = peer_sync_neighbours(ctx))) return rc;
     p.push_integ = halo_push_for(ctx, integ0, false, 2);
     p.push_mom = halo_push_for(ctx, mom, true, ctx->part.motion_halo);
     ctx->fused_it0.valid = false;

@@ -10,6 +10,17 @@
 
 #include "vhr_internal.h"
 
+// NVTX ranges (header-only nvtx3; visible in Nsight Systems / Compute): one range per pass node (vhr_cmd_begin_debug_label, the
+// counterpart of the vkCmdBeginDebugUtilsLabelEXT per pass at render_graph.cpp:160-164) and one per kernel-launching entry point,
+// named after the reference's shader path / pipeline name.
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name ? name : "(null)"); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+
 namespace vhr {
 
 static thread_local char g_error[512] = "";
@@ -272,6 +283,7 @@ uint64_t vhr_kernel_launch_count(vhr_context *ctx) { return ctx ? ctx->launches 
 int vhr_update_geometry(vhr_context *ctx, const void *vertices, uint32_t n_vertices, const uint32_t *indices,
                         uint32_t n_indices, const void *primitives, uint32_t n_primitives) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range("UpdateGeometry + BVH build");
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     if ((n_vertices && !vertices) || (n_indices && !indices) || (n_primitives && !primitives))
@@ -573,6 +585,7 @@ int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, 
 int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
                  const void *push_constants, size_t push_constants_size) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range(shader_path);
     if (!ctx || !shader_path) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
@@ -616,6 +629,7 @@ int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, u
 
 int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, uint32_t height) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range(pipeline_name);
     if (!ctx || !pipeline_name) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     const bool hybrid = !strcmp(pipeline_name, "Raytrace Pipeline"), full = !strcmp(pipeline_name, "Raytracing Pipeline");
@@ -628,6 +642,7 @@ int vhr_trace_rays(vhr_context *ctx, const char *pipeline_name, uint32_t width, 
 int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *specialization_constants, uint32_t n_constants,
              uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range(fragment_shader);
     if (!ctx || !fragment_shader) return fail(VHR_ERR_INVALID, "NULL argument");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
@@ -650,6 +665,7 @@ int vhr_draw(vhr_context *ctx, const char *fragment_shader, const int32_t *speci
 
 int vhr_gbuffer_pass(vhr_context *ctx, uint32_t width, uint32_t height) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range("G-Buffer Pass (primary rays)");
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     if (!ctx->pfd_set) return fail(VHR_ERR_STATE, "vhr_update_per_frame_ubo has not been called");
@@ -667,21 +683,89 @@ int vhr_trace_explicit(vhr_context *ctx, const float *rays, uint32_t n, int any_
 
 int vhr_blit_storage_to_transient(vhr_context *ctx, int src_slot, const char *dst_name) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range("BlitImageStorageToTransient");
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return blit(ctx, storage_slot(ctx, src_slot), find_transient(ctx, dst_name), "BlitImageStorageToTransient");
 }
 int vhr_blit_transient_to_storage(vhr_context *ctx, const char *src_name, int dst_slot) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range("BlitImageTransientToStorage");
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return blit(ctx, find_transient(ctx, src_name), storage_slot(ctx, dst_slot), "BlitImageTransientToStorage");
 }
 int vhr_blit_storage_to_storage(vhr_context *ctx, int src_slot, int dst_slot) {
     if (ctx) ctx->epoch++;
+    NvtxRange nvtx_range("BlitImageStorageToStorage");
     if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
     VHR_NEED_DEVICE(ctx);
     return blit(ctx, storage_slot(ctx, src_slot), storage_slot(ctx, dst_slot), "BlitImageStorageToStorage");
+}
+
+int vhr_cmd_begin_debug_label(vhr_context *ctx, const char *label) {
+    if (!ctx || !label) return fail(VHR_ERR_INVALID, "NULL argument");
+    nvtxRangePushA(label);
+    ctx->debug_label_depth++;
+    return VHR_OK;
+}
+int vhr_cmd_end_debug_label(vhr_context *ctx) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    if (ctx->debug_label_depth == 0) return fail(VHR_ERR_STATE, "vhr_cmd_end_debug_label without a matching begin");
+    nvtxRangePop();
+    ctx->debug_label_depth--;
+    return VHR_OK;
+}
+
+// Rows [y0, y1) of an image, on the transfer queues (the row-band partition moves only a band of the G-buffer up and a band of the
+// result down). Same ordering rules as the whole-image calls above.
+int vhr_image_upload_rows_async(vhr_context *ctx, const char *name, const void *host_rows, uint32_t y0, uint32_t y1) {
+    if (ctx) ctx->epoch++;
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
+    Image *im = find_transient(ctx, name);
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", name ? name : "(null)");
+    if (!host_rows || y0 >= y1 || y1 > im->height) return fail(VHR_ERR_INVALID, "%s: rows [%u, %u) of %u", name, y0, y1, im->height);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_transfer_queues(ctx)) return rc;
+    if (int rc = make_writable(ctx, im, false)) return rc;
+    if (!im->upload_done) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->upload_done, cudaEventDisableTiming));
+    const size_t row = im->bytes / im->height;
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->compute_tail, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->upload_stream, ctx->compute_tail, 0));
+    VHR_CUDA_CHECK(cudaMemcpyAsync((char *)im->ptr + (size_t)y0 * row, host_rows, (size_t)(y1 - y0) * row, cudaMemcpyHostToDevice, ctx->upload_stream));
+    VHR_CUDA_CHECK(cudaEventRecord(im->upload_done, ctx->upload_stream));
+    im->upload_pending = true;
+    return VHR_OK;
+}
+// Reads rows [y0, y1) straight from the image (no device-side snapshot): the caller must not enqueue anything that rewrites the image
+// before vhr_wait_download(ticket) — true for an image that is only written once per frame when the host waits for frame k's read-back
+// before it records frame k+1's writer, which is what a frame loop with one frame of latency does.
+int vhr_image_download_rows_async(vhr_context *ctx, const char *name, void *host_rows, uint32_t y0, uint32_t y1, uint32_t *ticket) {
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
+    Image *im = find_transient(ctx, name);
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", name ? name : "(null)");
+    if (!host_rows || !ticket || y0 >= y1 || y1 > im->height) return fail(VHR_ERR_INVALID, "%s: rows [%u, %u) of %u", name, y0, y1, im->height);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_transfer_queues(ctx)) return rc;
+    if (int rc = consume_upload(ctx, im)) return rc;
+    const size_t row = im->bytes / im->height;
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->compute_tail, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->download_stream, ctx->compute_tail, 0));
+    VHR_CUDA_CHECK(cudaMemcpyAsync(host_rows, (const char *)im->ptr + (size_t)y0 * row, (size_t)(y1 - y0) * row, cudaMemcpyDeviceToHost, ctx->download_stream));
+    if (ctx->tickets.empty()) {
+        ctx->tickets.resize(64);
+        for (auto &e : ctx->tickets) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint32_t t = ctx->next_ticket++;
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->tickets[t % ctx->tickets.size()], ctx->download_stream));
+    // the next writer of the image on the compute stream must come after this read
+    if (!im->staging_free) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->staging_free, cudaEventDisableTiming));
+    VHR_CUDA_CHECK(cudaEventRecord(im->staging_free, ctx->download_stream));
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, im->staging_free, 0));
+    *ticket = t;
+    return VHR_OK;
 }
 
 int vhr_create_query_pool(vhr_context *ctx, uint32_t count) {

@@ -118,6 +118,7 @@ struct vhr_context {
     vhr::Bvh bvh;
     vhr::Options opt;
     uint64_t launches = 0;
+    uint32_t debug_label_depth = 0;                // open vhr_cmd_begin_debug_label ranges
     // VHR_OPT_SVGF_FUSED: svgf.comp's dispatch has already produced a-trous iteration 0 for these storage slots; the step-1
     // dispatch that follows it in the reference's sequence finds this note and launches nothing. `epoch` counts the calls that can
     // change an image, a binding or the per-frame constants: the note only holds for the very next such call.

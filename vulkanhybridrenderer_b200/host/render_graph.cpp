@@ -208,6 +208,7 @@ void RenderGraph::Execute(uint32_t resource_idx) {
     vhr_context *ctx = resource_manager.ctx;
     for (size_t i = 0; i < execution_order.size(); ++i) {
         const RenderPassDescription &pass = pass_descriptions[execution_order[i]];
+        VHR_CHECK(vhr_cmd_begin_debug_label(ctx, pass.name));      // render_graph.cpp:160-164
         VHR_CHECK(vhr_write_timestamp(ctx, (uint32_t)i * 2));
         if (auto *g = std::get_if<GraphicsPassDescription>(&pass.description)) {
             auto hook = graphics_hooks.find(pass.name);
@@ -266,6 +267,7 @@ void RenderGraph::Execute(uint32_t resource_idx) {
             c.callback(ec);
         }
         VHR_CHECK(vhr_write_timestamp(ctx, (uint32_t)i * 2 + 1));
+        VHR_CHECK(vhr_cmd_end_debug_label(ctx));                             // render_graph.cpp:184
     }
     timestamps_pending = true;
 }

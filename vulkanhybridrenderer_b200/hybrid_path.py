@@ -135,8 +135,9 @@ class HybridRenderPath:
     # ---- passes ---------------------------------------------------------------------------------------------------
     def raytrace_pass(self, gset=0, rtset=0):
         g = self.gsets[gset]
-        self.ctx.bind_pass_images([g[N_NORMALS], g[N_DEPTH], *self.rt_sets[rtset]])
-        self.ctx.trace_rays(self.W, self.H)
+        with self.ctx.debug_label("Raytrace Pass"):
+            self.ctx.bind_pass_images([g[N_NORMALS], g[N_DEPTH], *self.rt_sets[rtset]])
+            self.ctx.trace_rays(self.W, self.H)
 
     def ssao_passes(self, gset=0):
         g = self.gsets[gset]
@@ -154,6 +155,10 @@ class HybridRenderPath:
         self.ctx.dispatch(SHADER_SSR, groups(self.W), groups(self.H), 1, self.ssr_pc)
 
     def svgf_denoise_pass(self, gset=0, rtset=0):
+        with self.ctx.debug_label("SVGF Denoise Pass"):
+            self._svgf_denoise_body(gset, rtset)
+
+    def _svgf_denoise_body(self, gset=0, rtset=0):
         """hybrid_render_path.cpp:288-330, statement by statement."""
         ctx, pc, g = self.ctx, self.pc, self.gsets[gset]
         gx, gy = groups(self.W), groups(self.H)
