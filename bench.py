@@ -213,10 +213,371 @@ def config_dict(wl, n_tris):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def pinned_bytes(torch, n, write_combined=False):
+    """Pinned host buffer of n bytes as a uint8 tensor. write_combined: cudaHostAllocWriteCombined — an upload source the CPU only ever
+    writes (by DMA at set-up); the PCIe reads then skip the snoop of the CPU caches."""
+    if not write_combined:
+        return torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    p = C.c_void_p()
+    rc = rt.cudaHostAlloc(C.byref(p), C.c_size_t(n), C.c_uint(0x01 | 0x04))       # cudaHostAllocPortable | cudaHostAllocWriteCombined
+    if rc != 0 or not p.value:
+        return torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    return torch.frombuffer((C.c_ubyte * n).from_address(p.value), dtype=torch.uint8)        # lives until the process exits
+
+
+def bind_rank_to_cores(world, local):
+    """One slice of the visible CPUs per rank: the ranks' host threads (launch loop + copy submission) do not migrate onto each other."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // max(world, 1))
+        mine = cpus[local * per:(local + 1) * per]
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return len(mine)
+    except (AttributeError, OSError):
+        return None
+
+
+def load_counters():
+    """Per-launch ncu counters of the committed profile (profiles/kernel_counters.json): DRAM bytes and warp instructions."""
+    for name in ("kernel_counters.json", "dram_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                d = json.load(f)
+            return {k: (v if isinstance(v, dict) else {"dram_bytes": v}) for k, v in d.items()}
+    return {}
+
+
+class GpuFrameLoop:
+    """One context + HybridRenderPath rendering the workload's frames: set-up (scene, BVH, G-buffers of the two alternating poses in HBM and
+    in pinned host memory) and the step functions the measurements time."""
+
+    def __init__(self, torch, wl, local, stream, view, svgf_mode, fif=1, host_copies=True):
+        from vulkanhybridrenderer_b200 import camera, capi
+        from vulkanhybridrenderer_b200 import hybrid_path as HP
+        self.torch, self.capi, self.HP, self.stream, self.fif = torch, capi, HP, stream, fif
+        self.W, self.H, _, self.ao_spp, self.refl = WORKLOADS[wl]
+        W, H = self.W, self.H
+        self.sc, self.poses = make_scene(wl, view=view)
+        ctx = self.ctx = capi.Context(W, H, device=local, stream=stream.cuda_stream)
+        ctx.update_geometry(self.sc.vertices, self.sc.indices, self.sc.primitives)
+        self.bvh = ctx.bvh_stats()
+        ctx.set_option(capi.OPT_TRACE_SHADOWS, 1)
+        ctx.set_option(capi.OPT_TRACE_AO, 1 if self.ao_spp else 0)
+        ctx.set_option(capi.OPT_AO_SPP, max(self.ao_spp, 1))
+        ctx.set_option(capi.OPT_TRACE_REFLECTIONS, self.refl)
+        self.path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=2 if fif == 2 else 1, svgf_fused=svgf_mode == "fused",
+                                        blit_alias=svgf_mode != "reference")
+        self.seq = camera.FrameSequencer(W, H, self.sc.light)
+        self.cam = self.sc.camera
+        self.pfds, self.host_g, nonsky = [None, None], [None, None], []
+        for s in (1, 0, 1):           # pose 1 first so that pose 0's "previous camera" is pose 1 and vice versa
+            self.cam.set_pose(*self.poses[s])
+            pfd = self.seq.next(self.cam)
+            self.gbuffer_pass(pfd, s)
+            self.pfds[s] = pfd
+        for s in (0, 1):
+            g, hg = self.path.gsets[s], {}
+            for key in (HP.N_DEPTH, HP.N_NORMALS, HP.N_MOTION):
+                _, w, h, f = ctx.image_info(g[key])
+                t = pinned_bytes(torch, h * w * HP.T.FORMAT_TEXEL_BYTES[f])
+                ctx.image_download_into(g[key], t)
+                hg[key] = t
+            ctx.synchronize()
+            nonsky.append(int((hg[HP.N_DEPTH].view(torch.float32) > 0).sum()))
+            if host_copies:       # the upload sources: write-combined copies of the same bytes
+                for key in list(hg):
+                    wc = pinned_bytes(torch, hg[key].numel(), write_combined=True)
+                    wc.copy_(hg[key])
+                    hg[key] = wc
+            self.host_g[s] = hg
+        self.rays_per_frame = [n * (1 + self.ao_spp + self.refl) for n in nonsky]
+        self.h2d_bytes = sum(t.numel() for t in self.host_g[0].values())
+        self.frame_no = 0
+
+    def gbuffer_pass(self, pfd, s):
+        HP, g = self.HP, self.path.gsets[s]
+        self.ctx.update_per_frame_ubo(pfd)
+        with self.ctx.debug_label("G-Buffer Pass"):
+            self.ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
+            self.ctx.gbuffer_pass(self.W, self.H)
+
+    def next_pfd(self):
+        k = self.frame_no
+        s = k & 1
+        pfd = self.pfds[s]
+        pfd["frame_index"] = 3 + k
+        self.frame_no += 1
+        return k, s, pfd
+
+    def step(self, overlap=True):
+        k, s, pfd = self.next_pfd()
+        if self.fif == 2 and overlap:
+            self.path.frame_overlapped(pfd, k, gset=s)
+        else:
+            self.path.frame(pfd, gset=s, rtset=s if self.fif == 2 else 0)
+        return self.rays_per_frame[s]
+
+    def step_camera_in(self):
+        """The path driven from a CAMERA: the per-frame constants (584 B) are the only input that crosses PCIe; the G-buffer producer pass
+        (primary rays on the same BVH) runs inside the step."""
+        k, s, pfd = self.next_pfd()
+        self.gbuffer_pass(pfd, s)
+        self.path.frame(pfd, gset=s, rtset=0)
+        return self.rays_per_frame[s]
+
+    def upload_async(self, k):
+        g = self.path.gsets[k & 1]
+        for key, t in self.host_g[k & 1].items():
+            self.ctx.image_upload_async(g[key], t)
+
+    def close(self):
+        self.ctx.close()
+
+
+def timed(torch, stream, barrier, fn, n):
+    """n calls of fn between two CUDA events on `stream`, barrier + synchronize on both sides. Returns (ms, sum of fn's return values)."""
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tot = 0
+    for _ in range(n):
+        tot += fn()
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1), tot
+
+
+def measure_e2e(torch, loop, barrier, K, Wm):
+    """End to end through the C-ABI from HOST buffers, every step: 41.5 MB (1080p) of G-buffer up from pinned memory, the denoised image
+    down. serial = blocking copies around the frame; pipelined (headline) = the same copies on the transfer queues, step k+1's upload
+    and step k-1's read-back under step k's kernels, the host waiting for the previous read-back every step; camera_in = the per-frame
+    constants are the only upload, the G-buffer producer pass runs inside the step."""
+    ctx, HP, W, H, stream = loop.ctx, loop.HP, loop.W, loop.H, loop.stream
+    capi = loop.capi
+    out_den = pinned_bytes(torch, W * H * 8)
+    d2h = out_den.numel()
+
+    def step_serial():
+        g = loop.path.gsets[loop.frame_no & 1]
+        for key, t in loop.host_g[loop.frame_no & 1].items():
+            capi._check(capi.lib().vhr_image_upload(ctx._h, g[key].encode(), t.data_ptr(), t.numel()))
+        r = loop.step(overlap=False)
+        ctx.image_download_into(HP.N_DENOISED, out_den)
+        ctx.synchronize()
+        return r
+
+    for _ in range(max(2, Wm // 2)):
+        step_serial()
+    serial_ms, rays_serial = timed(torch, stream, barrier, step_serial, K)
+    checksum_serial = float(out_den.view(torch.float16)[::4097].float().nan_to_num().sum())
+
+    outs = [pinned_bytes(torch, W * H * 8) for _ in range(2)]
+
+    def run_pipelined(n, step_fn, upload):
+        rays_p, prev = 0, None
+        if upload:
+            loop.upload_async(loop.frame_no)
+        for i in range(n):
+            if upload:
+                loop.upload_async(loop.frame_no + 1)        # next step's inputs (the last one primes the following run)
+            rays_p += step_fn()
+            t1 = ctx.image_download_async(HP.N_DENOISED, outs[i & 1])
+            if prev is not None:
+                ctx.wait_download(prev)
+            prev = t1
+        ctx.wait_download(prev)
+        return rays_p
+
+    res = {}
+    for name, step_fn, upload in (("pipelined", lambda: loop.step(overlap=False), True), ("camera_in", loop.step_camera_in, False)):
+        run_pipelined(max(3, Wm // 2), step_fn, upload)
+        ctx.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rays_e = run_pipelined(K, step_fn, upload)
+        e1.record(stream)          # the host has already waited for the last read-back: this stamps its completion
+        ctx.synchronize()
+        barrier()
+        res[name] = {"ms": max(e0.elapsed_time(e1), 0.0), "wall_ms": (time.perf_counter() - t0) * 1e3, "rays": rays_e,
+                     "checksum": float(outs[(K - 1) & 1].view(torch.float16)[::4097].float().nan_to_num().sum())}
+    res["serial"] = {"ms": serial_ms, "rays": rays_serial, "checksum": checksum_serial}
+    res["d2h"] = d2h
+    return res
+
+
+def measure_next_rows(torch, loop):
+    """SURVEY 8f rows, each timed on its own and NOT part of the step."""
+    ctx, HP, W, H, stream, path, capi = loop.ctx, loop.HP, loop.W, loop.H, loop.stream, loop.path, loop.capi
+    next_ms = {}
+    try:
+        path_c = HP.HybridRenderPath.__new__(HP.HybridRenderPath)
+        path_c.ctx, path_c.W, path_c.H, path_c.gsets = ctx, W, H, path.gsets
+        path_c.ssao_radius = np.array(0.75, np.float32)
+        path_c.ssr_pc = np.array((25.0, 0.1, 0.5, 10), HP.T.SSRPushConstants)
+        for n, f in ((HP.N_SSAO_RAW, HP.F4), (HP.N_SSAO, HP.F4), (HP.N_SSR, HP.F4)):
+            ctx.actualize_image(n, f)
+        ctx.actualize_image(HP.N_SHADOW_MAP, HP.T.VK_FORMAT_D32_SFLOAT, 4096, 4096)
+        ctx.actualize_image(HP.N_RENDER_OUTPUT, HP.T.VK_FORMAT_B8G8R8A8_SRGB)
+        row_reps = int(os.environ.get("VHR_BENCH_ROW_REPS", "0"))      # profiling runs: a few launches per row are enough
+
+        def time_row(fn, reps=20):
+            reps = row_reps or reps
+            ctx.update_per_frame_ubo(loop.pfds[0])
+            for _ in range(3):
+                fn(0)
+            ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ec0.record(stream)
+            for i in range(reps):
+                fn(i & 1)
+            ec1.record(stream)
+            torch.cuda.synchronize()
+            return ec0.elapsed_time(ec1) / reps
+
+        def ssao_only(s):
+            g = path.gsets[s]
+            ctx.bind_pass_images([g[HP.N_NORMALS], g[HP.N_DEPTH], HP.N_SSAO_RAW])
+            ctx.dispatch(HP.SHADER_SSAO, HP.groups(W), HP.groups(H), 1, path_c.ssao_radius)
+
+        def blur_only(s):
+            ctx.bind_pass_images([HP.N_SSAO_RAW, HP.N_SSAO])
+            ctx.dispatch(HP.SHADER_SSAO_BLUR, HP.groups(W), HP.groups(H), 1, path_c.ssao_radius)
+
+        def gbuffer_only(s):
+            g = path.gsets[s]
+            ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
+            ctx.gbuffer_pass(W, H)
+
+        next_ms["composition"] = time_row(lambda s: path_c.composition_pass(0, 0, 0 if loop.refl else 2, denoised=True, gset=s))
+        next_ms["ssao"] = time_row(ssao_only)
+        next_ms["ssao_blur"] = time_row(blur_only)
+        next_ms["ssr"] = time_row(lambda s: path_c.ssr_pass(gset=s), reps=6)
+        # the producer rewrites the resident G-buffer of pose 0 with identical values (same camera, same scene)
+        next_ms["gbuffer"] = time_row(lambda s: gbuffer_only(0), reps=6)
+    except capi.VhrError as e:      # never let the extra rows break the headline measurement
+        sys.stderr.write(f"bench.py: next rows skipped: {e}\n")
+    return next_ms
+
+
+def measure_strong_4k(torch, dist, args, local, rank, world, stream, barrier):
+    """BASELINE config 4 / north_star's multi-GPU claim: ONE 3840x2160 frame (shadow + 2 AO + reflection rays per pixel, 5-iteration SVGF,
+    3 M triangles) over the N GPUs of the box: fused partition (ray pass in 8-row blocks dealt round-robin with the results stored into the
+    owners' images over NVLink peer memory, SVGF on row bands with halo rows pushed by the kernels, flag words; no collective in the frame).
+    The one-GPU time of the SAME frame is measured first, on every rank at once (max over ranks), so the speed-up is self-contained."""
+    from vulkanhybridrenderer_b200 import capi
+    from vulkanhybridrenderer_b200 import hybrid_path as HP
+    from vulkanhybridrenderer_b200 import multi_gpu as MG
+    wl = "full_frame_4k_3Mtri"
+    W, H, _, ao_spp, refl = WORKLOADS[wl]
+    K1, K2, Wm = 8, max(10, min(args.steps, 30)), 3
+    # ---- one GPU: the unpartitioned frame, best single-GPU configuration --------------------------------------------------------------
+    one = GpuFrameLoop(torch, wl, local, stream, 0, "alias", host_copies=False)
+    for _ in range(Wm):
+        one.step()
+    ms1, _ = timed(torch, stream, barrier, one.step, K1)
+    host_g, rays_frame, pfds, n_tris = one.host_g, one.rays_per_frame, one.pfds, one.sc.num_triangles
+    one.close()
+    # ---- N GPUs ----------------------------------------------------------------------------------------------------------------------
+    sc, poses = make_scene(wl, view=0)
+    y0, y1 = MG.band_rows(H, world, rank)
+    ctx = capi.Context(W, H, device=local, stream=stream.cuda_stream)
+    ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+    ctx.set_option(capi.OPT_TRACE_AO, 1); ctx.set_option(capi.OPT_AO_SPP, ao_spp); ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
+    path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=2)
+    for s in (0, 1):       # full G-buffer of both poses into HBM (set-up, untimed), from the host copies of the one-GPU run
+        for key, t in host_g[s].items():
+            capi._check(capi.lib().vhr_image_upload(ctx._h, path.gsets[s][key].encode(), t.data_ptr(), t.numel()))
+    mv = max(float(host_g[s][HP.N_MOTION].view(torch.float16).view(H, W, 4)[..., 1].float().abs().max()) for s in (0, 1))
+    motion_halo = min(64, MG.required_motion_halo(mv, H))
+    MG.setup_fused_partition(ctx, path, world, rank, motion_halo=motion_halo)
+    frame_no = [0]
+
+    def step():
+        k = frame_no[0]; s = k & 1
+        pfd = pfds[s]; pfd["frame_index"] = 3 + k
+        frame_no[0] += 1
+        path.frame(pfd, gset=s, rtset=k & 1)          # the plain single-GPU call sequence
+        return 0
+
+    for _ in range(Wm):
+        step()
+    l0 = ctx.kernel_launches
+    msN, _ = timed(torch, stream, barrier, step, K2)
+    launches = ctx.kernel_launches - l0
+    # ---- e2e: every step this rank uploads the G-buffer rows it consumes and reads its band of the results back -----------------------
+    #   depth + normals of the 8-row blocks it ray-traces (one strided DMA each), normals + motion of its SVGF band +- halo rows;
+    #   down: its band of the denoised image and of the reflections. Pipelined on the transfer queues like the 1-GPU e2e.
+    blocks = [b for b in range((H + 7) // 8) if b % world == rank and b * 8 + 8 <= H]
+    halo = MG.GBUFFER_HALO
+    b0, b1 = max(0, y0 - halo), min(H, y1 + halo)
+    row = {HP.N_DEPTH: W * 4, HP.N_NORMALS: W * 8, HP.N_MOTION: W * 8}
+    outs = [(pinned_bytes(torch, (y1 - y0) * W * 8), pinned_bytes(torch, (y1 - y0) * W * 8)) for _ in range(2)]
+    h2d = len(blocks) * 8 * (row[HP.N_DEPTH] + row[HP.N_NORMALS]) + (b1 - b0) * (row[HP.N_NORMALS] + row[HP.N_MOTION])
+    d2h = 2 * (y1 - y0) * W * 8
+
+    def upload(k):
+        s = k & 1
+        g = path.gsets[s]
+        if blocks:
+            for key in (HP.N_DEPTH, HP.N_NORMALS):
+                ctx.image_upload_blocks_async(g[key], host_g[s][key], blocks[0] * 8, 8, world * 8, len(blocks))
+        for key in (HP.N_NORMALS, HP.N_MOTION):
+            ctx.image_upload_rows_async(g[key], host_g[s][key][b0 * row[key]:], b0, b1)
+
+    def run_e2e(n):
+        prev = None
+        upload(frame_no[0])
+        for i in range(n):
+            upload(frame_no[0] + 1)
+            k = frame_no[0]
+            step()
+            o = outs[i & 1]
+            t1 = ctx.image_download_rows_async(HP.N_DENOISED, o[0], y0, y1)
+            t2 = ctx.image_download_rows_async(path.rt_sets[k & 1][1], o[1], y0, y1)
+            if prev is not None:
+                ctx.wait_download(prev)
+            prev = max(t1, t2)
+        ctx.wait_download(prev)
+        return 0
+
+    run_e2e(3)
+    ctx.synchronize()
+    msE, _ = timed(torch, stream, barrier, lambda: run_e2e(K2), 1)
+    den = torch.as_tensor(MG._DeviceRows(ctx.image_info(HP.N_DENOISED)[0], H, W * 4), device="cuda")
+    band_sum = den[y0:y1].float().nan_to_num().sum().double()
+    t = torch.tensor([ms1 / K1, msN / K2, msE / K2], device="cuda", dtype=torch.float64)
+    tmax, tmin = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    r = torch.tensor([float(band_sum), float(launches), float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    ctx.close()
+    rays = float(np.mean(rays_frame))
+    ms1f, msNf, msEf = (float(x) for x in tmax.cpu())
+    return {
+        "workload": wl, "scaling": "strong", "n_gpus": world, "width": W, "height": H, "triangles": int(n_tris), "rays_per_frame": rays,
+        "partition": "fused: ray pass in 8-row blocks dealt round-robin, results stored into the owners' images over NVLink peer memory; SVGF on row "
+                     "bands, halo rows pushed by the kernels; stream-ordered flag words; no collective in the frame",
+        "motion_halo_rows": motion_halo,
+        "ms_per_frame_1gpu": ms1f, "ms_per_frame": msNf, "speedup_vs_1gpu": ms1f / msNf, "efficiency": ms1f / msNf / world,
+        "mrays_s_1gpu": rays / ms1f / 1e3, "mrays_s": rays / msNf / 1e3,
+        "ms_per_frame_min_over_ranks": float(tmin.cpu()[1]), "frames_timed": K2, "gpu_launches_all_ranks": int(r[1]),
+        "e2e": {"ms_per_frame": msEf, "mrays_s": rays / msEf / 1e3, "speedup_vs_1gpu_device_time": ms1f / msEf,
+                "h2d_bytes_per_step_all_ranks": int(r[2]), "d2h_bytes_per_step_all_ranks": int(r[3]),
+                "what": "per rank and step: depth + normals of its ray blocks (strided DMA), normals + motion of its band +- 64 rows up; its band of the "
+                        "denoised image and of the reflections down; copies on the transfer queues under the kernels"},
+        "denoised_checksum": float(r[0]),
+    }
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from vulkanhybridrenderer_b200 import camera, capi
     from vulkanhybridrenderer_b200 import hybrid_path as HP
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,12 +586,12 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    cores = bind_rank_to_cores(world, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = args.workload
     W, H, _, ao_spp, refl = WORKLOADS[wl]
-    sc, poses = make_scene(wl, view=rank)
     fif = args.frames_in_flight
     # queue 0 carries the short SVGF kernels: with two frames in flight it gets the higher priority so that its CTAs are placed as
     # the long ray kernel's CTAs retire instead of queueing behind that kernel's whole grid
@@ -238,234 +599,57 @@ def run_gpu(args):
     K, Wm = args.steps, args.warmup
     peak, peak_src = load_peaks()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     with torch.cuda.stream(stream):
-        ctx = capi.Context(W, H, device=local, stream=stream.cuda_stream)
-        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
-        st = ctx.bvh_stats()
-        ctx.set_option(capi.OPT_TRACE_SHADOWS, 1)
-        ctx.set_option(capi.OPT_TRACE_AO, 1 if ao_spp else 0)
-        ctx.set_option(capi.OPT_AO_SPP, max(ao_spp, 1))
-        ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
-        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, rt_sets=fif, svgf_fused=args.svgf == "fused", blit_alias=args.svgf != "reference")
-        seq = camera.FrameSequencer(W, H, sc.light)
-        cam = sc.camera
-
-        # ---- set-up (untimed): the G-buffer producer pass renders both poses into the two resident image sets -------
-        pfds, host_g = [None, None], [None, None]
-        for s in (1, 0, 1):           # pose 1 first so that pose 0's "previous camera" is pose 1 and vice versa
-            cam.set_pose(*poses[s])
-            pfd = seq.next(cam)
-            ctx.update_per_frame_ubo(pfd)
-            g = path.gsets[s]
-            ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
-            ctx.gbuffer_pass(W, H)
-            pfds[s] = pfd
-        nonsky = []
-        for s in (0, 1):
-            g = path.gsets[s]
-            hg = {}
-            for key in (HP.N_DEPTH, HP.N_NORMALS, HP.N_MOTION):
-                _, w, h, f = ctx.image_info(g[key])
-                tb = HP.T.FORMAT_TEXEL_BYTES[f]
-                t = torch.empty(h * w * tb, dtype=torch.uint8, pin_memory=True)
-                ctx.image_download_into(g[key], t)
-                hg[key] = t
-            ctx.synchronize()
-            host_g[s] = hg
-            nonsky.append(int((hg[HP.N_DEPTH].view(torch.float32) > 0).sum()))
-        rays_per_frame = [n * (1 + ao_spp + refl) for n in nonsky]
-
-        frame_no = [0]
-
-        def step(overlap=True):
-            k = frame_no[0]
-            s = k & 1
-            pfd = pfds[s]
-            pfd["frame_index"] = 3 + k
-            frame_no[0] += 1
-            if fif == 2 and overlap:
-                path.frame_overlapped(pfd, k, gset=s)
-            else:
-                path.frame(pfd, gset=s, rtset=s if fif == 2 else 0)
-            return rays_per_frame[s]
-
-        def rt_name(k):
-            return path.rt_sets[(k & 1) if fif == 2 else 0][0]
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
+        loop = GpuFrameLoop(torch, wl, local, stream, rank, args.svgf, fif)
+        ctx, path, sc, st = loop.ctx, loop.path, loop.sc, loop.bvh
 
         # ---- value: inputs resident in HBM ----------------------------------------------------------------------------
         path.timestamps = None
         for _ in range(Wm):
-            step()
+            loop.step()
         if fif == 1:
             path.enable_timestamps(K)
         l0 = ctx.kernel_launches
         sampler = ClockSampler(local)
         barrier()
         sampler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        rays = 0
-        for _ in range(K):
-            rays += step()
-        ev1.record(stream)
-        barrier()
+        ms_total, rays = timed(torch, stream, barrier, loop.step, K)
         clocks = sampler.stop()
-        ms_total = ev0.elapsed_time(ev1)
         launches = ctx.kernel_launches - l0
         if fif == 2:
             # per-pass times need the passes one after the other: the same frames again, one frame in flight, with timestamps
             Kb = min(K, 50)
             path.enable_timestamps(Kb)
             for _ in range(Kb):
-                step(overlap=False)
+                loop.step(overlap=False)
             barrier()
             pass_ms = path.pass_times_ms(Kb)
         else:
             pass_ms = path.pass_times_ms(K)            # [K, passes]
         path.timestamps = None
 
-        # ---- next rows, each timed on its own and NOT part of the step: the composition pass that consumes the
-        # denoised image (composition.frag, B8G8R8A8_SRGB output like the reference's swapchain), the other per-pixel passes
-        # of the hybrid path (SSAO + blur, SSR) and the G-buffer producer (primary rays on the same BVH)
-        next_ms = {}
-        try:
-            path_c = HP.HybridRenderPath.__new__(HP.HybridRenderPath)
-            path_c.ctx, path_c.W, path_c.H, path_c.gsets = ctx, W, H, path.gsets
-            path_c.ssao_radius = np.array(0.75, np.float32)
-            path_c.ssr_pc = np.array((25.0, 0.1, 0.5, 10), HP.T.SSRPushConstants)
-            for n, f in ((HP.N_SSAO_RAW, HP.F4), (HP.N_SSAO, HP.F4), (HP.N_SSR, HP.F4)):
-                ctx.actualize_image(n, f)
-            ctx.actualize_image(HP.N_SHADOW_MAP, HP.T.VK_FORMAT_D32_SFLOAT, 4096, 4096)
-            ctx.actualize_image(HP.N_RENDER_OUTPUT, HP.T.VK_FORMAT_B8G8R8A8_SRGB)
-
-            row_reps = int(os.environ.get("VHR_BENCH_ROW_REPS", "0"))      # profiling runs: a few launches per row are enough
-
-            def time_row(fn, reps=20):
-                reps = row_reps or reps
-                ctx.update_per_frame_ubo(pfds[0])
-                for _ in range(3):
-                    fn(0)
-                ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ec0.record(stream)
-                for i in range(reps):
-                    fn(i & 1)
-                ec1.record(stream)
-                torch.cuda.synchronize()
-                return ec0.elapsed_time(ec1) / reps
-
-            def ssao_only(s):
-                g = path.gsets[s]
-                ctx.bind_pass_images([g[HP.N_NORMALS], g[HP.N_DEPTH], HP.N_SSAO_RAW])
-                ctx.dispatch(HP.SHADER_SSAO, HP.groups(W), HP.groups(H), 1, path_c.ssao_radius)
-
-            def blur_only(s):
-                ctx.bind_pass_images([HP.N_SSAO_RAW, HP.N_SSAO])
-                ctx.dispatch(HP.SHADER_SSAO_BLUR, HP.groups(W), HP.groups(H), 1, path_c.ssao_radius)
-
-            def gbuffer_only(s):
-                g = path.gsets[s]
-                ctx.bind_pass_images([g[HP.N_ALBEDO], g[HP.N_NORMALS], g[HP.N_MOTION], g[HP.N_DEPTH]])
-                ctx.gbuffer_pass(W, H)
-
-            next_ms["composition"] = time_row(lambda s: path_c.composition_pass(0, 0, 0 if refl else 2, denoised=True, gset=s))
-            next_ms["ssao"] = time_row(ssao_only)
-            next_ms["ssao_blur"] = time_row(blur_only)
-            next_ms["ssr"] = time_row(lambda s: path_c.ssr_pass(gset=s), reps=6)
-            # the producer rewrites the resident G-buffer of pose 0 with identical values (same camera, same scene)
-            next_ms["gbuffer"] = time_row(lambda s: gbuffer_only(0), reps=6)
-        except capi.VhrError as e:      # never let the extra rows break the headline measurement
-            sys.stderr.write(f"bench.py: next rows skipped: {e}\n")
-        comp_ms = next_ms.get("composition")
-
-        # ---- e2e: host G-buffer -> H2D -> frame -> D2H of the denoised + raw shadow/AO images, every step ---------------
-        out_den = torch.empty(W * H * 8, dtype=torch.uint8, pin_memory=True)
-        out_rt = torch.empty(W * H * 4, dtype=torch.uint8, pin_memory=True)
-        h2d = sum(t.numel() for t in host_g[0].values())
-        d2h = out_den.numel() + out_rt.numel()
-
-        def step_e2e():
-            k = frame_no[0]
-            s = k & 1
-            g = path.gsets[s]
-            for key, t in host_g[s].items():
-                capi._check(capi.lib().vhr_image_upload(ctx._h, g[key].encode(), t.data_ptr(), t.numel()))
-            r = step(overlap=False)          # blocking copies on queue 0 on both sides: nothing to overlap with
-            ctx.image_download_into(HP.N_DENOISED, out_den)
-            ctx.image_download_into(rt_name(k), out_rt)
-            ctx.synchronize()
-            return r
-
-        for _ in range(max(2, Wm // 2)):
-            step_e2e()
+        next_ms = measure_next_rows(torch, loop) if world == 1 or rank == 0 else {}
         barrier()
-        t0 = time.perf_counter()
-        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ee0.record(stream)
-        rays_serial = 0
-        for _ in range(K):
-            rays_serial += step_e2e()
-        ee1.record(stream)
-        barrier()
-        e2e_serial_wall_ms = (time.perf_counter() - t0) * 1e3
-        e2e_serial_ms = max(ee0.elapsed_time(ee1), 0.0)
-        checksum_serial = float(out_den.view(torch.float16)[::4097].float().nan_to_num().sum())
-
-        # ---- e2e, pipelined (the headline): the same copies on the C-ABI's transfer queues. Step k's G-buffer goes up
-        # while step k-1 is still computing, step k's results come down while step k+1 computes; the host blocks on the
-        # previous step's read-back every step (one frame of latency, the reference keeps three frames in flight). Every
-        # step still uploads its own 41.5 MB and reads back its own 24.9 MB inside the timed region.
-        outs = [(torch.empty(W * H * 8, dtype=torch.uint8, pin_memory=True), torch.empty(W * H * 4, dtype=torch.uint8, pin_memory=True))
-                for _ in range(2)]
-
-        def upload_async(k):
-            s = k & 1
-            g = path.gsets[s]
-            for key, t in host_g[s].items():
-                ctx.image_upload_async(g[key], t)
-
-        def run_pipelined(n):
-            rays_p, prev = 0, None
-            upload_async(frame_no[0])
-            for i in range(n):
-                upload_async(frame_no[0] + 1)            # next step's inputs (the last one primes the following run)
-                k = frame_no[0]
-                rays_p += step()
-                o = outs[i & 1]
-                t1 = ctx.image_download_async(HP.N_DENOISED, o[0])
-                t2 = ctx.image_download_async(rt_name(k), o[1])
-                if prev is not None:
-                    ctx.wait_download(prev)
-                prev = max(t1, t2)
-            ctx.wait_download(prev)
-            return rays_p
-
-        run_pipelined(max(3, Wm // 2))
-        ctx.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        ee0.record(stream)
-        rays_e = run_pipelined(K)
-        ee1.record(stream)          # the host has already waited for the last read-back: this stamps its completion
-        ctx.synchronize()
-        barrier()
-        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-        e2e_ms = max(ee0.elapsed_time(ee1), 0.0)
-        last = outs[(K - 1) & 1][0]
-        checksum = float(last.view(torch.float16)[::4097].float().nan_to_num().sum())
+        e2e = measure_e2e(torch, loop, barrier, K, Wm)
+        h2d = loop.h2d_bytes
+        loop.close()
+        strong = measure_strong_4k(torch, dist, args, local, rank, world, stream, barrier) if world > 1 and not args.no_strong else None
 
     # ---- reduce over ranks: max time, summed rays ------------------------------------------------------------------------
+    e2e_ms, e2e_wall_ms, e2e_serial_ms, cam_ms = e2e["pipelined"]["ms"], e2e["pipelined"]["wall_ms"], e2e["serial"]["ms"], e2e["camera_in"]["ms"]
+    rays_e, rays_serial, rays_cam = e2e["pipelined"]["rays"], e2e["serial"]["rays"], e2e["camera_in"]["rays"]
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms, e2e_wall_ms, e2e_serial_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_ms, e2e_wall_ms, e2e_serial_ms, cam_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, e2e_wall_ms, e2e_serial_ms = (float(x) for x in t.cpu())
-        r = torch.tensor([rays, rays_e, launches, rays_serial], device="cuda", dtype=torch.float64)
+        ms_total, e2e_ms, e2e_wall_ms, e2e_serial_ms, cam_ms = (float(x) for x in t.cpu())
+        r = torch.tensor([rays, rays_e, launches, rays_serial, rays_cam], device="cuda", dtype=torch.float64)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        rays, rays_e, launches, rays_serial = (float(x) for x in r.cpu())
+        rays, rays_e, launches, rays_serial, rays_cam = (float(x) for x in r.cpu())
 
     if rank == 0:
         px = W * H
@@ -477,33 +661,47 @@ def run_gpu(args):
         # shares are taken of the frame run one pass after the other (with two frames in flight the passes overlap and their
         # durations no longer add up to the step)
         share_ms = sum(pm.values()) if fif == 2 else frame_ms
-        # per-kernel roofline (HBM): algorithmic bytes / launch = per-pixel bytes x pixels
+        counters = load_counters()
+        sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        # per-kernel roofline (HBM): algorithmic bytes / launch = per-pixel bytes x pixels; plus, where the committed ncu profile has
+        # the kernel's warp-instruction count, the fraction of the machine's issue slots (148 SMs x 4 schedulers x SM clock) the launch used
         kernels = []
+
         def add(name, ms, bytes_, note=None):
             ach = bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            kernels.append({"kernel": name, "ms": ms, "share": ms / share_ms, "algorithmic_bytes": bytes_,
-                            "achieved_gbs": ach, "frac": ach / peak, **({"note": note} if note else {})})
+            k = {"kernel": name, "ms": ms, "share": ms / share_ms, "algorithmic_bytes": bytes_, "achieved_gbs": ach, "frac": ach / peak}
+            c = counters.get(name.split(" ")[0], {})
+            if c.get("inst_executed") and ms > 0:
+                k["issue"] = {"warp_instructions_per_launch": c["inst_executed"], "achieved_ginst_s": c["inst_executed"] / (ms * 1e-3) / 1e9,
+                              "peak_ginst_s": 148 * 4 * sm_clock_hz / 1e9, "frac": c["inst_executed"] / (ms * 1e-3) / (148 * 4 * sm_clock_hz),
+                              "source": "instruction count from the committed ncu profile (profiles/kernel_counters.json), duration live"}
+            if note:
+                k["note"] = note
+            kernels.append(k)
         add("raygen_kernel", pm["raytrace"], px * (HP.BYTES_RAYGEN_IO + (8 if refl else 0)),
-            "traversal-bound (software BVH, no RT cores): compulsory G-buffer in + mask out bytes only; see Mrays/s")
-        add("svgf_temporal_kernel", pm["svgf_temporal"], px * HP.BYTES_TEMPORAL)
+            "traversal-bound (software BVH, no RT cores): compulsory G-buffer in + mask out bytes only; see Mrays/s and issue.frac")
+        fused = args.svgf == "fused"
+        add("svgf_fused_kernel (svgf.comp + a-trous iteration 0)" if fused else "svgf_temporal_kernel", pm["svgf_temporal"],
+            px * (HP.BYTES_TEMPORAL + (8 if fused else 0)))
         at_ms = float(np.mean([pm[f"atrous{i}"] for i in (1, 2, 3, 4)]))
         add("atrous_pair_kernel (mean of iterations 1-4)", at_ms, px * HP.BYTES_ATROUS)
-        add("atrous iteration 0 + history blit", pm["atrous0"], px * (HP.BYTES_ATROUS + HP.BYTES_BLIT))
-        add("blits (prev-normals, denoised)", pm["blits"], px * 2 * HP.BYTES_BLIT)
+        if not fused:
+            add("atrous_pair_kernel (iteration 0, + the history blit of the reference sequence)", pm["atrous0"],
+                px * (HP.BYTES_ATROUS + (HP.BYTES_BLIT if args.svgf == "reference" else 0)))
+        add("blits (prev-normals, denoised)" + ("" if args.svgf == "reference" else ": copy-on-write aliases, no copy"), pm["blits"],
+            px * 2 * HP.BYTES_BLIT if args.svgf == "reference" else 0)
         dom = max(kernels[:3], key=lambda k: k["ms"])
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(dom["kernel"].split(" ")[0])
+        cdom = counters.get(dom["kernel"].split(" ")[0], {})
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "ms_per_launch": dom["ms"],
+                    "frac": dom["frac"], "traffic": cdom.get("dram_bytes"), "peak_source": peak_src, "ms_per_launch": dom["ms"],
                     "share_of_step": dom["share"]}
+        if "issue" in dom:
+            roofline["issue"] = dom["issue"]
         if dom["kernel"] == "raygen_kernel":
             # the contract's roofline is HBM or tensor; a software BVH traversal is bound by neither — say what does bound it
-            roofline["note"] = ("not an HBM-bound kernel: ncu (profiles/r01_ncu_final_summary.md) has it at 75 % instruction-issue "
-                                "utilisation and 64 % ALU pipe with 15.3 of 32 lanes active per instruction (software BVH traversal, "
-                                "no RT cores on B200), DRAM at 2 % of peak; the figure of merit is rt_pass.mrays_s")
+            roofline["note"] = ("not an HBM-bound kernel: software BVH traversal (no RT cores on B200) bound by instruction issue and node-fetch latency "
+                                "at ~15 of 32 lanes active per instruction (ncu, profiles/), DRAM at 2 % of peak; the figures of merit are "
+                                "rt_pass.mrays_s and roofline.issue.frac. The HBM-bound part of the step is the SVGF chain: svgf.frac_of_peak_vs_fused_minimum")
         svgf_bytes = px * (HP.BYTES_TEMPORAL + 5 * HP.BYTES_ATROUS + 3 * HP.BYTES_BLIT)
         svgf_min_bytes = px * 148
         line = {
@@ -511,15 +709,22 @@ def run_gpu(args):
             "warmup": Wm, "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {**config_dict(wl, sc.num_triangles), "frames_in_flight": fif, "svgf_mode": args.svgf,
+                       **({"multi_gpu": "one independent view of the replicated scene per rank, no data-path collective (BASELINE config 5 style); the "
+                                        "strong-scaling 4K row-band frame of config 4 is measured in the same run: key strong_4k",
+                           "host_cores_per_rank": cores} if world > 1 else {}),
                        **({"schedule": "Raytrace Pass of frame k+1 on queue 1 under the SVGF pass of frame k (two ray-output image sets); "
                                        "kernels[] / roofline timed in a separate run with one frame in flight",
                            "ms_per_step_one_frame_in_flight": share_ms} if fif == 2 else {})},
-            "e2e": {"value": rays_e / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "checksum": checksum,
-                    "mode": "pipelined: H2D / compute / D2H of consecutive steps overlap on the C-ABI transfer queues, host waits "
-                            "for step k-1's read-back during step k",
+            "e2e": {"value": rays_e / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e["d2h"],
+                    "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "checksum": e2e["pipelined"]["checksum"],
+                    "mode": "pipelined: G-buffer (depth, normals, motion) up from write-combined pinned memory and the denoised image down on the C-ABI "
+                            "transfer queues, copies of consecutive steps under the kernels, host waits for step k-1's read-back during step k",
                     "serial_ms_per_step": e2e_serial_ms / K, "serial_value": rays_serial / (e2e_serial_ms * 1e-3) / 1e6,
-                    "serial_checksum": checksum_serial},
+                    "serial_checksum": e2e["serial"]["checksum"],
+                    "camera_in": {"value": rays_cam / (cam_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": cam_ms / K, "h2d_bytes_per_step": 584,
+                                  "d2h_bytes_per_step": e2e["d2h"], "checksum": e2e["camera_in"]["checksum"],
+                                  "what": "the path driven from a camera: only the per-frame constants go up, the G-buffer producer pass (primary rays, "
+                                          "SURVEY 8f rank 2) runs inside the step, the denoised image comes down"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -530,9 +735,12 @@ def run_gpu(args):
                      "fused_minimum_bytes": svgf_min_bytes, "frac_of_peak_vs_fused_minimum": svgf_min_bytes / (svgf_ms * 1e-3) / 1e9 / peak},
             "bvh": {"triangles": st.n_triangles, "wide_nodes": st.n_wide_nodes, "build_ms": st.build_ms, "sah_cost": st.sah_cost},
         }
+        if strong:
+            line["strong_4k"] = strong
         if next_ms:
             rows = {"composition": ("composition_kernel", px * (HP.BYTES_COMPOSITION + (8 if refl else 0)), None),
-                    "ssao": ("ssao_kernel", px * HP.BYTES_SSAO, "16 samples per pixel, each an exactly rounded unprojection (three IEEE divisions) + full-precision sincosf + software bilinear depth tap: issue-bound (87 % issue active, L2 hit 96 %)"),
+                    "ssao": ("ssao_kernel", px * HP.BYTES_SSAO, "16 samples per pixel: full-precision sincosf (the sample position must be exact: the filter coordinate "
+                             "is quantised to 1/256 texel), software bilinear depth tap, unprojection: issue-bound, L2 hit 96 %"),
                     "ssao_blur": ("ssao_blur_kernel", px * HP.BYTES_SSAO_BLUR, None),
                     "ssr": ("ssr_kernel", px * HP.BYTES_SSR, "up to 250 march steps + 10 bisection steps per pixel, each one re-projection + bilinear "
                             "depth tap in exactly rounded arithmetic: instruction-bound, the HBM fraction is tiny by construction"),
@@ -555,7 +763,6 @@ def run_gpu(args):
                                     "sample": arm.sample_desc() + f", {n} samples",
                                     "svgf_ms_per_full_frame_extrapolated": svgf_s / n * 1e3 * H / arm.rows}
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -701,6 +908,7 @@ def main():
                     help="how the library answers the SVGF node's (unchanged) call sequence: reference = temporal kernel, five a-trous kernels, three "
                          "copies; alias = the three blits alias buffers copy-on-write (VHR_OPT_BLIT_ALIAS); fused = alias + svgf.comp and a-trous "
                          "iteration 0 in one kernel (VHR_OPT_SVGF_FUSED). Same images in all three (tests/test_svgf_gpu.py)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling 4K frame (key strong_4k)")
     ap.add_argument("--partition", default="views", choices=["views", "rows"],
                     help="N>1: independent views per rank (weak scaling, default) or row bands of one frame (strong scaling, NCCL halos)")
     ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],

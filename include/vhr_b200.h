@@ -146,6 +146,10 @@ int vhr_wait_download(vhr_context *ctx, uint32_t ticket);
  * snapshot): the compute queue is made to wait for it before anything enqueued later runs. */
 int vhr_image_upload_rows_async(vhr_context *ctx, const char *name, const void *host_rows, uint32_t y0, uint32_t y1);
 int vhr_image_download_rows_async(vhr_context *ctx, const char *name, void *host_rows, uint32_t y0, uint32_t y1, uint32_t *ticket);
+/* `n_blocks` blocks of `block_rows` rows, one every `stride_rows` rows from `first_row`, out of a FULL host image (same row pitch): the rows a
+ * rank of the fused partition ray-traces (8-row blocks dealt round-robin) in one strided DMA. */
+int vhr_image_upload_blocks_async(vhr_context *ctx, const char *name, const void *host_image, uint32_t first_row, uint32_t block_rows,
+                                  uint32_t stride_rows, uint32_t n_blocks);
 /* Device pointer of a named image (zero-copy interop, e.g. NCCL halo exchange); NULL if unknown. */
 void *vhr_image_device_ptr(vhr_context *ctx, const char *name, uint32_t *width, uint32_t *height, int *vk_format);
 void *vhr_storage_image_device_ptr(vhr_context *ctx, int slot, uint32_t *width, uint32_t *height, int *vk_format);

@@ -85,6 +85,9 @@ def _declare(L):
     L.vo_trace_closest.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp, vp]
     L.vo_raygen.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
     L.vo_raytraced.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.vo_raygen_pixel_rays.restype = C.c_int
+    L.vo_raygen_pixel_rays.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp]
+    L.vo_brute_force.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp]
     L.vo_gbuffer.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
 
 
@@ -192,6 +195,15 @@ def composition(pfd, albedo, normals, motion, depth, rt, shadow_mode=0, ao_mode=
     return out
 
 
+def raygen_pixel_rays(pfd, depth, normals, x, y, ao_spp=2):
+    """The shadow ray and the `ao_spp` AO rays raygen.rgen generates for pixel (x, y): array [n, 8] (origin, tMin, direction, tMax)."""
+    H, W = depth.shape[:2]
+    rays = np.zeros((1 + ao_spp, 8), np.float32)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = lib().vo_raygen_pixel_rays(_p(pfd), W, H, int(x), int(y), _p(d), _p(_h(normals)), int(ao_spp), _p(rays))
+    return rays[:n]
+
+
 class OracleScene:
     def __init__(self, scene):
         v = np.ascontiguousarray(scene.vertices)
@@ -231,6 +243,13 @@ class OracleScene:
         tuv = np.zeros(3, np.float64); gp = np.zeros(2, np.uint32)
         hit = lib().vo_trace_closest(self._s, _p(o), _p(d), tmin, tmax, _p(tuv), _p(gp))
         return (tuv, gp) if hit else None
+
+    def brute_force(self, o, d, tmin, tmax):
+        """One ray against every triangle in double precision: (any_hit, closest_t, margin). See vo_brute_force."""
+        o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)
+        out = np.zeros(3, np.float64)
+        lib().vo_brute_force(self._s, _p(o), _p(d), float(tmin), float(tmax), _p(out))
+        return bool(out[0]), float(out[1]), float(out[2])
 
     def gbuffer(self, pfd, W, H, want_ids=False):
         albedo = np.empty((H, W, 4), np.uint8)

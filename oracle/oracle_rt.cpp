@@ -570,6 +570,75 @@ void vo_raygen(const vo_scene *s_, const PerFrameData *pfd_, int W, int H, int y
     if (ray_count) *ray_count = rays;
 }
 
+// The rays raygen.rgen:26-55 generates for ONE pixel, exactly as vo_raygen does (same statements, same order): ray 0 = shadow, rays
+// 1..ao_spp = ambient occlusion; 8 floats each (origin xyz, tMin, direction xyz, tMax). Returns the number of rays (0 for a sky pixel).
+// Tests use it to re-trace the pixels on which a GPU mask and the oracle disagree and to classify them (vo_brute_force).
+int vo_raygen_pixel_rays(const PerFrameData *pfd_, int W, int H, int x, int y, const float *depth, const uint16_t *normals, int ao_spp, float *out_rays) {
+    const PerFrameData &pfd = *pfd_;
+    vec2 uv = {((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H};
+    uint32_t rng = seed_thread(((uint32_t)y * (uint32_t)H + (uint32_t)x) * pfd.frame_index);
+    float current_depth = depth[(size_t)y * W + x];
+    if (current_depth == 0.0f) return 0;
+    vec3 P = get_world_space_position(pfd, current_depth, uv);
+    vec3 L = -v3(pfd.directional_light.direction[0], pfd.directional_light.direction[1], pfd.directional_light.direction[2]);
+    vec4 n4 = load_rgba16f(normals, W, x, y);
+    vec3 N = v3(n4.x, n4.y, n4.z);
+    vec3 origin = P + N * 0.1f;
+    auto put = [&](int i, vec3 d, float tmax) {
+        float *r = out_rays + 8 * i;
+        r[0] = origin.x; r[1] = origin.y; r[2] = origin.z; r[3] = 0.01f; r[4] = d.x; r[5] = d.y; r[6] = d.z; r[7] = tmax;
+    };
+    float rnd1 = random01(rng), rnd2 = random01(rng);
+    put(0, mul(onb_from_unit_vector(L), normalize(uniform_sample_cone(vec2{rnd1, rnd2}, 0.999995f))), 10000.0f);
+    for (int i = 0; i < ao_spp; ++i) {
+        rnd1 = random01(rng); rnd2 = random01(rng);
+        put(1 + i, mul(onb_from_unit_vector(N), uniform_sample_cosine_weighted_hemisphere(vec2{rnd1, rnd2})), 5.0f);
+    }
+    return 1 + ao_spp;
+}
+
+// One ray against EVERY triangle in double precision (Moller-Trumbore, no acceleration structure): out[0] = 1 if any triangle is hit in
+// (tmin, tmax), out[1] = closest such t (-1: none), out[2] = margin = the smallest distance of a nearby candidate from flipping its
+// classification (normalised barycentric distance to an edge, or relative distance of t to an end of the interval). A small margin
+// means the ray grazes an edge or an interval end: the self-intersection-epsilon / grazing cases north_star confines mismatches to.
+void vo_brute_force(const vo_scene *s_, const float *o_, const float *d_, float tmin, float tmax, double *out) {
+    const Scene &s = *reinterpret_cast<const Scene *>(s_);
+    const double o[3] = {o_[0], o_[1], o_[2]}, d[3] = {d_[0], d_[1], d_[2]};
+    int any = 0;
+    double best = -1.0, margin = 1.0;
+#pragma omp parallel
+    {
+        int l_any = 0;
+        double l_best = -1.0, l_margin = 1.0;
+#pragma omp for nowait
+        for (long long i = 0; i < (long long)s.n_tris; ++i) {
+            const float *t = &s.tri[(size_t)i * 9];
+            const double v0[3] = {t[0], t[1], t[2]}, e1[3] = {t[3] - v0[0], t[4] - v0[1], t[5] - v0[2]}, e2[3] = {t[6] - v0[0], t[7] - v0[1], t[8] - v0[2]};
+            const double pv[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+            const double det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+            if (det == 0.0) continue;
+            const double inv = 1.0 / det, tv[3] = {o[0] - v0[0], o[1] - v0[1], o[2] - v0[2]};
+            const double u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv;
+            const double qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+            const double v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv;
+            const double tt = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv, w = 1.0 - u - v;
+            if (u >= 0 && v >= 0 && w >= 0 && tt > tmin && tt < tmax) { l_any = 1; if (l_best < 0 || tt < l_best) l_best = tt; }
+            if (u > -1e-3 && v > -1e-3 && w > -1e-3 && tt > tmin - 1e-3 && tt < tmax + 1e-3) {
+                const double bm = std::min(std::min(std::fabs(u), std::fabs(v)), std::fabs(w));
+                const double tm = std::min(std::fabs(tt - tmin), std::fabs(tt - tmax)) / std::max(1.0, std::fabs(tt));
+                l_margin = std::min(l_margin, std::min(bm, tm));
+            }
+        }
+#pragma omp critical
+        {
+            any |= l_any;
+            if (l_best >= 0 && (best < 0 || l_best < best)) best = l_best;
+            margin = std::min(margin, l_margin);
+        }
+    }
+    out[0] = any; out[1] = best; out[2] = margin;
+}
+
 // The fully ray-traced render path: raytraced_render_path/raygen.rgen:11-23, closesthit.rchit:10-58, miss.rmiss:6-8,
 // shadow_miss.rmiss:6-8; alpha_test != 0 = raygen_test_alpha.rgen / closesthit_test_alpha.rchit / shadow_anyhit.rahit:9-27
 // ("Raytracing Pass", src/render_paths/raytraced_render_path.cpp:12-47). Output: "RaytracedOutput", B8G8R8A8_UNORM.

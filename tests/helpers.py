@@ -165,3 +165,24 @@ def brute_force_hits(tris, o, d, tmin, tmax):
     near = ok & (u > -1e-3) & (v > -1e-3) & (w > -1e-3) & (t > tmin - 1e-3) & (t < tmax + 1e-3)
     margin = float(np.min(np.minimum(bary_margin, t_margin)[near])) if near.any() else 1.0
     return bool(inside.any()), (float(t[inside].min()) if inside.any() else -1.0), margin
+
+
+def classify_mask_mismatches(osc, pfd, depth, normals, gpu_sa, ref_sa, ao_spp, what, flags=3, max_margin=1e-4, max_checked=64):
+    """north_star: visibility-mask mismatches must be "confined to self-intersection-epsilon / grazing cases". Every pixel on which the GPU's
+    shadow / AO texel differs from the checker's is re-traced here: the pixel's rays are regenerated (oracle, same statements as raygen.rgen) and
+    each one is tested against EVERY triangle in double precision; a mismatching pixel must own at least one ray whose nearest candidate lies
+    within `max_margin` of flipping (barycentric distance to an edge, or relative distance of t to tMin / tMax). Returns the number classified."""
+    import oracle_lib as OL
+    bad = np.argwhere(np.any(np.asarray(gpu_sa).view(np.uint16) != np.asarray(ref_sa).view(np.uint16), axis=-1))
+    worst = 0.0
+    for y, x in bad[:max_checked]:
+        rays = OL.raygen_pixel_rays(pfd, depth, normals, x, y, ao_spp)
+        use = [i for i in range(len(rays)) if (i == 0 and flags & 1) or (i > 0 and flags & 2)]
+        margins = [osc.brute_force(rays[i, :3], rays[i, 4:7], rays[i, 3], rays[i, 7])[2] for i in use]
+        assert margins, (what, x, y)
+        m = min(margins)
+        worst = max(worst, m)
+        assert m <= max_margin, f"{what}: pixel ({x}, {y}) differs but none of its rays grazes anything (smallest margin {m:.3e}): a real miss, not an epsilon case"
+    print(f"[masks] {what}: {len(bad)} mismatching pixels of {gpu_sa.shape[0] * gpu_sa.shape[1]}, {min(len(bad), max_checked)} re-traced by brute force, "
+          f"all grazing (largest margin {worst:.2e})")
+    return len(bad)

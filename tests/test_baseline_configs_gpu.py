@@ -94,6 +94,7 @@ def test_config2_shadows_1080p_260k():
             lit = g["depth"] > 0
             print(f"[config2] frame_index {frame}: shadow mask agreement {agree * 100:.4f}% over {int(lit.sum())} rays, lit fraction {float(ref[..., 0].astype(np.float32)[lit].mean()):.3f}")
             assert agree >= MASK_MIN
+            Hh.classify_mask_mismatches(osc, pfd, g["depth"], g["normals"], sa[..., :1], ref[..., :1], 0, f"config2 frame_index {frame}", flags=1)
             assert np.all(sa[..., 1].astype(np.float32) == 1.0)                       # AO off: written as 1
             assert np.all(sa[~lit].astype(np.float32) == 1.0)                         # sky rule (raygen.rgen:20-24)
             path.raytrace_pass()                                                       # determinism
@@ -125,6 +126,7 @@ def test_config3_ao4_temporal_1080p_1M():
             q = np.unique(sa[..., 1].astype(np.float32))
             print(f"[config3] frame {f}: AO agreement {agree * 100:.4f}% (8.29 M rays), levels {q.tolist()}")
             assert agree >= MASK_MIN
+            Hh.classify_mask_mismatches(osc, pfd, g["depth"], g["normals"], sa[..., 1:], ref[..., 1:], 4, f"config3 frame {f}", flags=2)
             assert set(q.tolist()) <= {0.0, 0.25, 0.5, 0.75, 1.0}                      # mean of 4 binary samples
             # temporal accumulation + variance (svgf.comp) on the GPU's own ray output vs the oracle on the same inputs
             gx, gy = HP.groups(W), HP.groups(H)
@@ -179,6 +181,28 @@ def test_config4_full_frame_4k_3M_partitioned_equals_single():
             agree = float(np.mean(np.all(want["rt"][rows[0]:rows[1]] == ref["shadow_ao"][rows[0]:rows[1]], axis=-1)))
             print(f"[config4] frame {f}: partitioned == single (bit-exact); oracle band rows {rows}: mask agreement {agree * 100:.4f}%")
             assert agree >= MASK_MIN
+            band = slice(rows[0], rows[1])
+            full_gpu, full_ref = np.ones_like(want["rt"]), np.ones_like(want["rt"])
+            full_gpu[band], full_ref[band] = want["rt"][band], ref["shadow_ao"][band]
+            Hh.classify_mask_mismatches(osc, pfd, g["depth"], g["normals"], full_gpu, full_ref, 2, f"config4 frame {f} rows {rows}")
+            # 4K reflections on the band: same hit point => radiance within 2e-3 relative (HDR values, fp16 ulp above 1.0 exceeds 1e-3)
+            a, b = want["refl"][band].astype(np.float32), ref["reflections"][band].astype(np.float32)
+            err = np.abs(a - b) / np.maximum(1.0, np.abs(b) / 2.0)
+            frac_ok = float(np.mean(err.max(axis=-1) <= 2e-3))
+            print(f"[config4] frame {f}: 4K reflections within tolerance on {frac_ok * 100:.3f}% of the band's pixels")
+            assert frac_ok >= 0.995
+            # 4K denoised on the band: the checker's SVGF pass over rows [y0 - 72, y1 + 72) of the GPU's own ray output (the five a-trous
+            # iterations reach 62 rows, the variance gaussian 1 more; frame 0 has no history to reproject)
+            if f == 0:
+                m = 72
+                sub_ = slice(rows[0] - m, rows[1] + m)
+                bpfd = pfd.copy()
+                bpfd["display_size"] = (W, sub_.stop - sub_.start)
+                bpfd["display_size_inverse"] = (np.float32(1) / np.float32(W), np.float32(1) / np.float32(sub_.stop - sub_.start))
+                st = O.SvgfState(W, sub_.stop - sub_.start)
+                den_ref, _, _ = st.run(bpfd, np.ascontiguousarray(g["normals"][sub_]), np.ascontiguousarray(g["motion"][sub_]),
+                                       np.ascontiguousarray(want["rt"][sub_]), want_iters=False)
+                Hh.assert_parity(want["den"][band], den_ref[m:-m], f"config4 frame {f} 4K denoised, rows {rows}")
             assert np.isfinite(want["den"].astype(np.float32)).all()
     finally:
         for c in ctxs + [ref_ctx]:
@@ -192,6 +216,7 @@ def test_config5_view_batch_is_partitioned_exactly_and_views_render():
         assert seen == list(range(64))
     W, H = 1920, 1080
     sc = scenes.sponza_like(260_000, seed=3, width=W, height=H)
+    osc = O.OracleScene(sc)
     seq = camera.FrameSequencer(W, H, sc.light)
     cam = sc.camera
     base = cam.position.copy()
@@ -203,8 +228,19 @@ def test_config5_view_batch_is_partitioned_exactly_and_views_render():
         for view in MG.views_for_rank(64, 8, 3)[:3]:                 # rank 3 of 8 renders views 3, 11, 19, ...
             cam.set_pose(base + np.array([0.9 * view / 8.0, 0.0, 0.0]), cam.yaw + 0.01 * view, cam.pitch)
             pfd = seq.next(cam)
-            _gbuffer_on_gpu(ctx, path, pfd, W, H)
+            g = _gbuffer_on_gpu(ctx, path, pfd, W, H)
             path.frame(pfd)
+            # every view against the checker on a 96-row band: masks (mismatches classified) ...
+            rows = (492, 588)
+            sa = ctx.image_download(HP.N_RT)
+            ref = osc.raygen(pfd, g["depth"], g["normals"], ao_spp=1, flags=3, rows=rows)["shadow_ao"]
+            band = slice(*rows)
+            agree = float(np.mean(np.all(sa[band] == ref[band], axis=-1)))
+            print(f"[config5] view {view}: mask agreement {agree * 100:.4f}% on rows {rows}")
+            assert agree >= MASK_MIN
+            full_gpu, full_ref = np.ones_like(sa), np.ones_like(sa)
+            full_gpu[band], full_ref[band] = sa[band], ref[band]
+            Hh.classify_mask_mismatches(osc, pfd, g["depth"], g["normals"], full_gpu, full_ref, 1, f"config5 view {view}")
             den = ctx.image_download(HP.N_DENOISED).astype(np.float32)
             assert np.isfinite(den).all() and 0.0 <= den[..., :2].min() and den[..., :2].max() <= 1.0 + 1e-3
             sums.append(float(den[..., :2].sum()))

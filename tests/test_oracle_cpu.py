@@ -815,3 +815,29 @@ def test_raytraced_path_oracle_vs_scalar_transcription():
             assert np.all(np.abs(got[y, x].astype(np.float64) - want) <= 1), (x, y, got[y, x], want)
             n_hit += 1
     assert n_hit > 300 and n_miss > 20 and n_lit > 20 and n_shadowed > 20, (n_hit, n_miss, n_lit, n_shadowed)
+
+
+def test_pixel_ray_regenerator_reproduces_the_masks_and_brute_force_agrees_with_the_bvh():
+    """vo_raygen_pixel_rays (used to classify GPU / checker mask mismatches) generates exactly vo_raygen's rays: tracing them one by one gives
+    vo_raygen's image; vo_brute_force (every triangle, double precision) agrees with the BVH query on every ray that does not graze."""
+    W, H = 64, 40
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, tris=4000)
+    pfd, g = frames[1]
+    for spp in (2, 4):
+        ref = osc.raygen(pfd, g["depth"], g["normals"], ao_spp=spp, flags=3)["shadow_ao"].astype(np.float32)
+        got = np.ones((H, W, 2), np.float32)
+        checked = 0
+        for y in range(H):
+            for x in range(W):
+                rays = O.raygen_pixel_rays(pfd, g["depth"], g["normals"], x, y, spp)
+                if len(rays) == 0:
+                    continue
+                vis = [0.0 if osc.trace_any(r[:3], r[4:7], float(r[3]), float(r[7])) else 1.0 for r in rays]
+                got[y, x] = (vis[0], np.float32(sum(vis[1:])) / np.float32(spp))
+                if (x + 7 * y) % 29 == 0:
+                    for r, v in zip(rays, vis):
+                        hit, _, margin = osc.brute_force(r[:3], r[4:7], r[3], r[7])
+                        assert margin < 1e-6 or hit == (v == 0.0)
+                        checked += 1
+        assert np.array_equal(got.astype(np.float16), ref.astype(np.float16)), f"regenerated rays give another image (ao_spp {spp})"
+        assert checked > 100

@@ -148,6 +148,7 @@ def test_raygen_masks_and_reflections(size, tris, ao_spp):
           f"  (lit {ref['shadow_ao'][..., 0].astype(np.float32).mean():.3f}, ao {ref['shadow_ao'][..., 1].astype(np.float32).mean():.3f})")
     assert shadow_agree >= MASK_AGREEMENT_MIN
     assert ao_agree >= MASK_AGREEMENT_MIN
+    Hh.classify_mask_mismatches(osc, pfd, g["depth"], g["normals"], sa, ref["shadow_ao"], ao_spp, f"raygen {W}x{H} ao_spp={ao_spp}")
     # reflection hit distance: same hit/miss classification and t within 1e-3 relative on >= 99.9 % of pixels
     ref_t = ref["refl_t"]
     same_class = (rt >= 0) == (ref_t >= 0)

@@ -30,7 +30,7 @@ SYMBOLS = [
     "vhr_storage_image_twin_device_ptr", "vhr_sync_device_ptr",
     "vhr_upload_texture_from_data", "vhr_destroy_textures",
     "vhr_select_queue", "vhr_queue_signal", "vhr_queue_wait",
-    "vhr_image_upload_rows_async", "vhr_image_download_rows_async", "vhr_cmd_begin_debug_label", "vhr_cmd_end_debug_label",
+    "vhr_image_upload_rows_async", "vhr_image_download_rows_async", "vhr_image_upload_blocks_async", "vhr_cmd_begin_debug_label", "vhr_cmd_end_debug_label",
 ]
 MAX_RANKS = 8
 MAX_SEMAPHORES = 16
@@ -101,6 +101,7 @@ def lib():
         L.vhr_wait_download.argtypes = [vp, u32]
         L.vhr_image_upload_rows_async.argtypes = [vp, C.c_char_p, vp, u32, u32]
         L.vhr_image_download_rows_async.argtypes = [vp, C.c_char_p, vp, u32, u32, C.POINTER(u32)]
+        L.vhr_image_upload_blocks_async.argtypes = [vp, C.c_char_p, vp, u32, u32, u32, u32]
         L.vhr_cmd_begin_debug_label.argtypes = [vp, C.c_char_p]
         L.vhr_cmd_end_debug_label.argtypes = [vp]
         L.vhr_storage_image_upload.argtypes = [vp, i32, vp, sz]
@@ -260,6 +261,11 @@ class Context:
         """Rows [y0, y1) of `name` from pinned host memory (host_rows starts at row y0) on the transfer queue."""
         a, _ = _addr(host_rows)
         _check(lib().vhr_image_upload_rows_async(self._h, name.encode(), a, int(y0), int(y1)))
+
+    def image_upload_blocks_async(self, name, host_image, first_row, block_rows, stride_rows, n_blocks):
+        """Blocks of `block_rows` rows every `stride_rows` rows from `first_row`, out of the FULL pinned host image, in one strided DMA."""
+        a, _ = _addr(host_image)
+        _check(lib().vhr_image_upload_blocks_async(self._h, name.encode(), a, int(first_row), int(block_rows), int(stride_rows), int(n_blocks)))
 
     def image_download_rows_async(self, name, host_rows, y0, y1):
         a, _ = _addr(host_rows)

@@ -738,6 +738,32 @@ int vhr_image_upload_rows_async(vhr_context *ctx, const char *name, const void *
     im->upload_pending = true;
     return VHR_OK;
 }
+// Every `stride_rows`-th block of `block_rows` rows starting at row `first_row`, `n_blocks` of them, from a host image of the same row
+// pitch (host_image points at row 0 of the FULL host image): the rows a rank of the fused partition ray-traces (8-row blocks dealt
+// round-robin). One strided DMA (cudaMemcpy2DAsync) instead of n_blocks copies.
+int vhr_image_upload_blocks_async(vhr_context *ctx, const char *name, const void *host_image, uint32_t first_row, uint32_t block_rows,
+                                  uint32_t stride_rows, uint32_t n_blocks) {
+    if (ctx) ctx->epoch++;
+    if (!ctx) return fail(VHR_ERR_INVALID, "ctx is NULL");
+    VHR_NEED_DEVICE(ctx);
+    Image *im = find_transient(ctx, name);
+    if (!im) return fail(VHR_ERR_INVALID, "%s: unknown image", name ? name : "(null)");
+    if (!host_image || block_rows == 0 || stride_rows < block_rows || n_blocks == 0 ||
+        (uint64_t)first_row + (uint64_t)(n_blocks - 1) * stride_rows + block_rows > im->height)
+        return fail(VHR_ERR_INVALID, "%s: blocks of %u rows every %u rows from row %u x %u exceed %u rows", name, block_rows, stride_rows, first_row, n_blocks, im->height);
+    VHR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_transfer_queues(ctx)) return rc;
+    if (int rc = make_writable(ctx, im, false)) return rc;
+    if (!im->upload_done) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->upload_done, cudaEventDisableTiming));
+    const size_t row = im->bytes / im->height;
+    VHR_CUDA_CHECK(cudaEventRecord(ctx->compute_tail, ctx->stream));
+    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->upload_stream, ctx->compute_tail, 0));
+    VHR_CUDA_CHECK(cudaMemcpy2DAsync((char *)im->ptr + (size_t)first_row * row, (size_t)stride_rows * row, (const char *)host_image + (size_t)first_row * row,
+                                     (size_t)stride_rows * row, (size_t)block_rows * row, n_blocks, cudaMemcpyHostToDevice, ctx->upload_stream));
+    VHR_CUDA_CHECK(cudaEventRecord(im->upload_done, ctx->upload_stream));
+    im->upload_pending = true;
+    return VHR_OK;
+}
 // Reads rows [y0, y1) straight from the image (no device-side snapshot): the caller must not enqueue anything that rewrites the image
 // before vhr_wait_download(ticket) — true for an image that is only written once per frame when the host waits for frame k's read-back
 // before it records frame k+1's writer, which is what a frame loop with one frame of latency does.
