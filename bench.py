@@ -513,11 +513,13 @@ def measure_strong_4k(torch, dist, args, local, rank, world, stream, barrier):
     #   depth + normals of the 8-row blocks it ray-traces (one strided DMA each), normals + motion of its SVGF band +- halo rows;
     #   down: its band of the denoised image and of the reflections. Pipelined on the transfer queues like the 1-GPU e2e.
     blocks = [b for b in range((H + 7) // 8) if b % world == rank and b * 8 + 8 <= H]
-    halo = MG.GBUFFER_HALO
-    b0, b1 = max(0, y0 - halo), min(H, y1 + halo)
+    # normals: the a-trous taps of the widest iteration reach 32 rows beyond the band, and the band's copy into the previous-frame normals is
+    # read up to motion_halo + 1 rows beyond it by the next temporal pass; motion vectors are only read at the pixel itself
+    halo = max(32, motion_halo + 1) + 8
+    n0, n1 = max(0, y0 - halo), min(H, y1 + halo)
     row = {HP.N_DEPTH: W * 4, HP.N_NORMALS: W * 8, HP.N_MOTION: W * 8}
     outs = [(pinned_bytes(torch, (y1 - y0) * W * 8), pinned_bytes(torch, (y1 - y0) * W * 8)) for _ in range(2)]
-    h2d = len(blocks) * 8 * (row[HP.N_DEPTH] + row[HP.N_NORMALS]) + (b1 - b0) * (row[HP.N_NORMALS] + row[HP.N_MOTION])
+    h2d = len(blocks) * 8 * (row[HP.N_DEPTH] + row[HP.N_NORMALS]) + (n1 - n0) * row[HP.N_NORMALS] + (y1 - y0) * row[HP.N_MOTION]
     d2h = 2 * (y1 - y0) * W * 8
 
     def upload(k):
@@ -526,8 +528,8 @@ def measure_strong_4k(torch, dist, args, local, rank, world, stream, barrier):
         if blocks:
             for key in (HP.N_DEPTH, HP.N_NORMALS):
                 ctx.image_upload_blocks_async(g[key], host_g[s][key], blocks[0] * 8, 8, world * 8, len(blocks))
-        for key in (HP.N_NORMALS, HP.N_MOTION):
-            ctx.image_upload_rows_async(g[key], host_g[s][key][b0 * row[key]:], b0, b1)
+        ctx.image_upload_rows_async(g[HP.N_NORMALS], host_g[s][HP.N_NORMALS][n0 * row[HP.N_NORMALS]:], n0, n1)
+        ctx.image_upload_rows_async(g[HP.N_MOTION], host_g[s][HP.N_MOTION][y0 * row[HP.N_MOTION]:], y0, y1)
 
     def run_e2e(n):
         prev = None
@@ -569,8 +571,8 @@ def measure_strong_4k(torch, dist, args, local, rank, world, stream, barrier):
         "ms_per_frame_min_over_ranks": float(tmin.cpu()[1]), "frames_timed": K2, "gpu_launches_all_ranks": int(r[1]),
         "e2e": {"ms_per_frame": msEf, "mrays_s": rays / msEf / 1e3, "speedup_vs_1gpu_device_time": ms1f / msEf,
                 "h2d_bytes_per_step_all_ranks": int(r[2]), "d2h_bytes_per_step_all_ranks": int(r[3]),
-                "what": "per rank and step: depth + normals of its ray blocks (strided DMA), normals + motion of its band +- 64 rows up; its band of the "
-                        "denoised image and of the reflections down; copies on the transfer queues under the kernels"},
+                "what": "per rank and step: depth + normals of its ray blocks (strided DMA), normals of its band +- (a-trous / motion halo) rows and motion "
+                        "vectors of its band up; its band of the denoised image and of the reflections down; copies on the transfer queues under the kernels"},
         "denoised_checksum": float(r[0]),
     }
 

@@ -69,7 +69,10 @@ def build_host(force=False):
         return None
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [os.path.join(ROOT, "include", "vhr_b200.h")]
     if force or _stale(LIB_HOST, deps + [LIB_CUDA]):
-        _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", LIB_HOST] + srcs +
+        # the reference's vendored third-party headers (stb_image.h), used where they lie: include path only, nothing copied
+        ref_deps = os.path.join(os.environ.get("VHR_REFERENCE_ROOT", "/root/reference"), "dependencies")
+        extra = ["-I", ref_deps] if os.path.isfile(os.path.join(ref_deps, "stb", "stb_image.h")) else []
+        _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include")] + extra + ["-o", LIB_HOST] + srcs +
              ["-L", HERE, "-l:libvhr_b200.so", "-lz", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST
 

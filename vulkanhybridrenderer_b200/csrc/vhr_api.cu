@@ -64,6 +64,7 @@ static void free_image(Image &im) {
     if (im.upload_done) cudaEventDestroy(im.upload_done);
     if (im.staged) cudaEventDestroy(im.staged);
     if (im.staging_free) cudaEventDestroy(im.staging_free);
+    if (im.direct_read_done) cudaEventDestroy(im.direct_read_done);
     im = Image();
 }
 // Orders the compute stream after an asynchronous upload into `im` that it has not consumed yet.
@@ -103,6 +104,10 @@ static int copy_out(vhr_context *ctx, Image *im, void *host, size_t bytes, const
 }  // namespace vhr (anonymous part)
 
 int vhr::make_writable(vhr_context *ctx, Image *im, bool whole) {
+    if (im && im->direct_read_pending) {      // a row read-back straight from the image (vhr_image_download_rows_async) is still in flight
+        VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, im->direct_read_done, 0));
+        im->direct_read_pending = false;
+    }
     if (!im || !im->shares_with) return VHR_OK;
     Image *o = im->shares_with;
     void *sp = im->spare ? im->spare : o->spare;
@@ -786,10 +791,11 @@ int vhr_image_download_rows_async(vhr_context *ctx, const char *name, void *host
     }
     const uint32_t t = ctx->next_ticket++;
     VHR_CUDA_CHECK(cudaEventRecord(ctx->tickets[t % ctx->tickets.size()], ctx->download_stream));
-    // the next writer of the image on the compute stream must come after this read
-    if (!im->staging_free) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->staging_free, cudaEventDisableTiming));
-    VHR_CUDA_CHECK(cudaEventRecord(im->staging_free, ctx->download_stream));
-    VHR_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, im->staging_free, 0));
+    // the next WRITER of this image on the compute stream must come after this read (make_writable, which every writer calls, waits for
+    // it); everything else enqueued on the compute stream runs under the copy
+    if (!im->direct_read_done) VHR_CUDA_CHECK(cudaEventCreateWithFlags(&im->direct_read_done, cudaEventDisableTiming));
+    VHR_CUDA_CHECK(cudaEventRecord(im->direct_read_done, ctx->download_stream));
+    im->direct_read_pending = true;
     *ticket = t;
     return VHR_OK;
 }

@@ -26,6 +26,8 @@ struct Image {
     cudaEvent_t staged = nullptr;        // snapshot written (compute stream)
     cudaEvent_t staging_free = nullptr;  // snapshot read back (download stream)
     bool staging_busy = false;
+    cudaEvent_t direct_read_done = nullptr;   // last vhr_image_download_rows_async (reads the image itself): writers wait for it
+    bool direct_read_pending = false;
     // multi-GPU: the same image in the other ranks' HBM, mapped through CUDA IPC (NVLink peer memory); index = rank
     void *peer[VHR_MAX_RANKS] = {};
     void *peer_twin[VHR_MAX_RANKS] = {};

@@ -11,7 +11,34 @@
 #include <map>
 #include <memory>
 
+// Image decoding = the reference's own decoder, stb_image.h (scene_loader.cpp:284,290: stbi_load / stbi_load_from_memory with
+// STBI_rgb_alpha), taken from the reference's vendored copy THROUGH THE INCLUDE PATH (-I /root/reference/dependencies; nothing is copied
+// into this repository): PNG, JPEG (Sponza / Bistro ship both), BMP, TGA, ... Where that tree is not on the include path the library is
+// built with this file's own PNG decoder only and says so (HasStbImage()).
+#if defined(__has_include)
+#if __has_include("stb/stb_image.h")
+#define VHR_HAVE_STB_IMAGE 1
+#define STB_IMAGE_IMPLEMENTATION
+#define STB_IMAGE_STATIC
+#define STBI_NO_STDIO
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wunused-function"
+#pragma GCC diagnostic ignored "-Wunused-but-set-variable"
+#pragma GCC diagnostic ignored "-Wmisleading-indentation"
+#pragma GCC diagnostic ignored "-Wsign-compare"
+#include "stb/stb_image.h"
+#pragma GCC diagnostic pop
+#endif
+#endif
+
 namespace SceneLoader {
+bool HasStbImage() {
+#ifdef VHR_HAVE_STB_IMAGE
+    return true;
+#else
+    return false;
+#endif
+}
 namespace {
 
 [[noreturn]] void bad(const std::string &msg) { throw VhrHostError{VHR_ERR_INVALID, "scene loader: " + msg}; }
@@ -623,7 +650,21 @@ void ParseScene(const char *path, ParsedScene &out) {
         }
         ParsedTexture pt;
         std::string err;
-        if (!DecodePNG(bytes.data(), bytes.size(), pt.width, pt.height, pt.rgba, err)) bad("image " + std::to_string(img) + ": " + err);
+        bool decoded = false;
+#ifdef VHR_HAVE_STB_IMAGE
+        {   // scene_loader.cpp:284-290: four channels whatever the file holds
+            int x = 0, y = 0, n = 0;
+            if (uint8_t *px = stbi_load_from_memory(bytes.data(), (int)bytes.size(), &x, &y, &n, STBI_rgb_alpha)) {
+                pt.width = (uint32_t)x; pt.height = (uint32_t)y;
+                pt.rgba.assign(px, px + (size_t)x * y * 4);
+                stbi_image_free(px);
+                decoded = true;
+            } else {
+                err = std::string("stb_image: ") + (stbi_failure_reason() ? stbi_failure_reason() : "unknown failure");
+            }
+        }
+#endif
+        if (!decoded && !DecodePNG(bytes.data(), bytes.size(), pt.width, pt.height, pt.rgba, err)) bad("image " + std::to_string(img) + ": " + err);
         pt.format = tu.second;
         pt.name = image.str("name", image.str("uri"));
         const int smp = tex.integer("sampler", -1);

@@ -18,6 +18,8 @@
 #include "render_graph.h"
 
 namespace SceneLoader {
+// true when the library was built against the reference's vendored stb_image.h (JPEG / PNG / ... textures); false: own PNG decoder only
+bool HasStbImage();
 
 struct ParsedTexture {
     uint32_t width = 0, height = 0;

@@ -168,6 +168,13 @@ def parse_gltf(path):
         lib().vhrh_parsed_scene_destroy(h)
 
 
+def has_stb_image():
+    """True when libvhr_host.so was built against the reference's vendored stb_image.h (JPEG and the other stb formats load)."""
+    L = lib()
+    L.vhrh_has_stb_image.restype = C.c_int
+    return bool(L.vhrh_has_stb_image())
+
+
 def decode_png(data):
     """SceneLoader::DecodePNG: bytes -> [H, W, 4] uint8."""
     buf = np.frombuffer(bytes(data), np.uint8)
