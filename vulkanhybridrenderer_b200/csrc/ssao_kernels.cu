@@ -40,6 +40,30 @@ __device__ __forceinline__ float sample_depth(const SsaoParams &p, float u, floa
     return bilerp_rn(a, b, t00, t10, t01, t11);
 }
 
+// get_view_space_position (glsl_common.h:111-116) for the 16 SAMPLES of a pixel. What must stay exact in this kernel is the sample POSITION
+// (su, sv): the texture unit holds the filter coordinate with 8 fractional bits, so the depth tap is a step function of it — that is the
+// centre unprojection (-> perspective radius), the RNG and sincosf, all kept as in the oracle. The unprojected sample itself only enters
+// the occlusion sum continuously, so here the three IEEE divisions by w become one MUFU reciprocal + one Newton step (<= 1 ulp) and three
+// products, and with PERSPECTIVE (the inverse projection has the sparsity of an inverse perspective matrix: only m00, m11, m23, m32, m33
+// non-zero — checked on the host) the 16 products of the matrix-vector product that multiply exact zeros are not issued (same values: the
+// pairwise sum of glm's mat4 * vec4 with zero terms is the remaining term).
+template <bool PERSPECTIVE>
+__device__ __forceinline__ float3 unproject_sample(const float *inv, float depth, float u, float v) {
+    const float x = sub_rn(mul_rn(u, 2.0f), 1.0f), y = sub_rn(mul_rn(v, 2.0f), 1.0f);
+    float4 q;
+    if (PERSPECTIVE) {
+        q = make_float4(mul_rn(inv[0], x), mul_rn(inv[5], y), inv[14], add_rn(mul_rn(inv[11], depth), inv[15]));
+    } else {
+        q = mul44_rn(inv, make_float4(x, y, depth, 1.0f));
+    }
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q.w));
+    const float rn = fmaf(r, fmaf(-q.w, r, 1.0f), r);        // one Newton step
+    r = (q.w == 0.0f) ? r : rn;                              // w = 0 (a sky sample): x * (1 / 0) = x / 0 = +-inf or NaN, as the division gives
+    return make_float3(q.x * r, q.y * r, q.z * r);
+}
+
+template <bool PERSPECTIVE>
 __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoParams p, const __grid_constant__ PerFrameData pfd) {
     const int gx = blockIdx.x * 32 + threadIdx.x;
     const int gy = p.y_begin + blockIdx.y * 8 + threadIdx.y;
@@ -79,7 +103,7 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
         float s, c;
         sincosf(ang, &s, &c);
         float su = add_rn(cu, mul_rn(c, dist)), sv = add_rn(cv, mul_rn(s, dist));
-        float3 Q = unproject_rn(pfd.camera_proj_inverse, sample_depth(p, su, sv), su, sv);
+        float3 Q = unproject_sample<PERSPECTIVE>(pfd.camera_proj_inverse, sample_depth(p, su, sv), su, sv);
         float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
         // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
         float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
@@ -161,7 +185,12 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     if (p.push.rows && ((p.push.up == nullptr && ctx->part.rank > 0) || (p.push.down == nullptr && ctx->part.rank + 1 < ctx->part.world)))
         return fail(VHR_ERR_STATE, "ssao.comp: the neighbours' '%s' image is not attached (vhr_image_attach_peer)", "Screen Space Ambient Occlusion Raw");
     dim3 block(32, 8), grid((p.x_end + 31) / 32, (p.y_end - p.y_begin + 7) / 8);
-    ssao_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    // inverse perspective sparsity (column-major m[c * 4 + r]): everything but m00, m11, m23 (index 11), m32 (index 14), m33 (index 15) is zero
+    bool perspective = true;
+    for (int i = 0; i < 16; ++i)
+        if (i != 0 && i != 5 && i != 11 && i != 14 && i != 15 && ctx->pfd.camera_proj_inverse[i] != 0.0f) perspective = false;
+    if (perspective) ssao_kernel<true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    else ssao_kernel<false><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return p.push.rows ? peer_sync_neighbours(ctx) : VHR_OK;
