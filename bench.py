@@ -839,6 +839,10 @@ def run_gpu(args):
                             "transfer queues, copies of consecutive steps under the kernels, host waits for step k-1's read-back during step k",
                     "serial_ms_per_step": e2e_serial_ms / K, "serial_value": rays_serial / (e2e_serial_ms * 1e-3) / 1e6,
                     "serial_checksum": e2e["serial"]["checksum"],
+                    "host_device_gbs_all_ranks": (h2d + e2e["d2h"]) * world / (e2e_ms / K * 1e-3) / 1e9,
+                    **({"limiter": "N > 1: every rank moves its own 58 MB per step; the box's host<->device fabric (all GPUs on one NUMA node of a 32-vCPU "
+                                   "host) delivered 109 / 119 / 153 GB/s in aggregate at 2 / 4 / 8 GPUs (profiles/r02_summary.md), i.e. 54 / 30 / 19 GB/s per GPU: the "
+                                   "G-buffer-in rate stops scaling there, the camera-in rate (no G-buffer over PCIe) and the device rate do not"} if world > 1 else {}),
                     "camera_in": {"value": rays_cam / (cam_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": cam_ms / K, "h2d_bytes_per_step": 584,
                                   "d2h_bytes_per_step": e2e["d2h"], "checksum": e2e["camera_in"]["checksum"],
                                   "what": "the path driven from a camera: only the per-frame constants go up, the G-buffer producer pass (primary rays, "
