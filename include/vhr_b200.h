@@ -291,8 +291,10 @@ typedef enum vhr_option {
                                       2 / 3: variant 0 with ptxas' own register choice (72) / without a register cap (117);
                                       4: variant 0 with postponed leaves (the warp runs the triangle block together);
                                       6 / 7: variant 0 launched as one-warp / two-warp CTAs (32 / 16 resident per SM);
-                                      8: variant 0 with the CTA's AO rays counting-sorted by direction before they are traced.
-                                      Same images in every variant; 1-4 measured slower on B200, kept for study */
+                                      8: variant 0 with the CTA's AO rays counting-sorted by direction before they are traced;
+                                      9: two-phase kernel — the shadow + AO rays of a 16 x 8 pixel block are generated into shared memory, then traversed with
+                                         RAY-level lane refill from that queue (ao_spp 1, 2 or 4; reflections through variant 0 afterwards).
+                                      Same images in every variant; 1-4, 8 and 9 measured slower on B200, kept for study */
     VHR_OPT_RAYTRACED_ALPHA_TEST = 11,/* the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14): 1 selects the pipeline
                                       raygen_test_alpha.rgen + closesthit_test_alpha.rchit + shadow_anyhit.rahit */
     VHR_OPT_BLIT_ALIAS = 12        /* 1: the three vhr_blit_* calls stop copying. After a blit source and destination show one buffer;

@@ -252,6 +252,41 @@ def test_persistent_raygen_variant_matches_per_pixel_kernel():
     assert outs[0][0][:9].astype(np.float32).sum() == 0 and outs[0][0][101:].astype(np.float32).sum() == 0   # rows outside the band untouched
 
 
+@pytest.mark.parametrize("ao_spp,shadows,ao,refl,band", [(1, 1, 1, 0, None), (2, 1, 1, 1, None), (4, 1, 1, 0, (9, 101)), (2, 0, 1, 1, None), (1, 1, 0, 0, (16, 64)), (2, 1, 1, 1, (5, 117))])
+def test_ray_queue_variant_matches_per_pixel_kernel(ao_spp, shadows, ao, refl, band):
+    """VHR_OPT_RAYGEN_VARIANT 9 (two-phase kernel: rays generated into shared memory, traversal with ray-level lane refill; the reflection ray, if on,
+    through the per-pixel kernel afterwards) traces exactly the rays of variant 0: every image is bit-identical, also on a ragged band of rows and
+    with ray kinds switched off."""
+    W, H = 203, 117
+    sc, osc, frames = Hh.scene_and_gbuffer(W, H, tris=20_000, moving=True)
+    pfd, g = frames[1]
+    outs = []
+    with capi.Context(W, H) as ctx:
+        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+        ctx.update_per_frame_ubo(pfd)
+        ctx.set_option(capi.OPT_DEBUG_REFLECTION_T, 1)
+        ctx.set_option(capi.OPT_AO_SPP, ao_spp); ctx.set_option(capi.OPT_TRACE_SHADOWS, shadows); ctx.set_option(capi.OPT_TRACE_AO, ao)
+        ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
+        if band:
+            ctx.set_option(capi.OPT_ROW_BEGIN, band[0]); ctx.set_option(capi.OPT_ROW_END, band[1])
+        ctx.actualize_image(Hh.N_NORMALS, F4); ctx.actualize_image(Hh.N_DEPTH, T.VK_FORMAT_D32_SFLOAT)
+        ctx.actualize_image(Hh.N_RT, F2); ctx.actualize_image(Hh.N_REFL, F4)
+        ctx.image_upload(Hh.N_NORMALS, g["normals"]); ctx.image_upload(Hh.N_DEPTH, g["depth"])
+        ctx.bind_pass_images([Hh.N_NORMALS, Hh.N_DEPTH, Hh.N_RT, Hh.N_REFL])
+        for v in (0, 9):
+            ctx.set_option(capi.OPT_RAYGEN_VARIANT, v)
+            ctx.image_upload(Hh.N_RT, np.full((H, W, 2), 0.25, np.float16)); ctx.image_upload(Hh.N_REFL, np.full((H, W, 4), 0.25, np.float16))
+            ctx.trace_rays(W, H)
+            outs.append((ctx.image_download(Hh.N_RT), ctx.image_download(Hh.N_REFL), ctx.download_reflection_t()))
+    assert np.array_equal(outs[0][0].view(np.uint16), outs[1][0].view(np.uint16)), "shadow / AO image differs"
+    assert np.array_equal(outs[0][1].view(np.uint16), outs[1][1].view(np.uint16)), "reflection image differs"
+    if band is None:
+        np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    if shadows and ao:
+        rows = slice(*band) if band else slice(None)
+        assert len(np.unique(outs[1][0][rows, :, 1].astype(np.float32))) >= 2 and len(np.unique(outs[1][0][rows, :, 0].astype(np.float32))) == 2
+
+
 @pytest.mark.parametrize("variant", [2, 3, 4, 6, 7, 8])
 def test_raygen_kernel_variants_match_default(variant):
     """VHR_OPT_RAYGEN_VARIANT 2 / 3 (other register budgets), 4 (postponed leaves: the warp runs the triangle block together) trace the

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
     const float depth = in_range ? __ldg(&p.depth[pix]) : 0.0f;                                  // texel centre: exact texel (Q17)
     const bool lit = in_range && depth != 0.0f;
     if (in_range && !lit) {                                                                      // raygen.rgen:20-24
-        out_sa[pix] = pack_rg16f(1.0f, 1.0f);
+        if (!(p.flags & 8)) out_sa[pix] = pack_rg16f(1.0f, 1.0f);
         out_refl[pix] = make_uint2(0u, 0u);
         if (p.refl_t) p.refl_t[pix] = -1.0f;
     }
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
         }
     }
     ao = __fdiv_rn(ao, (float)p.ao_spp);
-    if (lit) out_sa[pix] = pack_rg16f(shadow, ao);
+    if (lit && !(p.flags & 8)) out_sa[pix] = pack_rg16f(shadow, ao);      // bit 3: another kernel owns the shadow / AO texel (variant 9)
 
     // mirror reflection (raygen.rgen:59-65)
     if (p.flags & 4) {
@@ -823,6 +823,172 @@ __global__ void __launch_bounds__(128) raygen_persistent_kernel(const __grid_con
                 ++stage;
                 ray_active = false;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// raygen, two-phase variant with RAY-level lane refill (VHR_OPT_RAYGEN_VARIANT 9): any-hit rays (shadow + AO)
+// ---------------------------------------------------------------------------------------------------------------
+// The per-pixel kernel traces one ray kind at a time and a warp iterates until its slowest ray is done: 15 of 32 lanes are active in an
+// average instruction. The persistent variant above refills lanes with PIXELS, so its refill path carries the whole of raygen.rgen's ray
+// generation at low utilisation and its per-lane state costs 96 registers (5 blocks / SM). Here the two jobs are separated:
+//   A  every lane generates the rays of four pixels (its warp owns a 16 x 8 pixel block = four 8 x 4 tiles) exactly as raygen_kernel does —
+//      same statements, same RNG order — and parks them in shared memory: origin per pixel, one direction per ray (12 B each);
+//   B  the warp traverses its (1 + ao_spp) x 128 rays with per-lane refill: a lane whose ray is done takes the next ray of the warp's queue
+//      (shadow rays of all lit pixels first, then the AO samples; a warp-uniform counter, no atomics) as soon as kRefill lanes are idle;
+//      fetching a ray is two shared-memory loads + prepare(), nothing else. Any-hit answers land in a byte array;
+//   C  every lane combines the answers of its four pixels and stores the texels.
+// Same rays, same answers as raygen_kernel (an any-hit answer does not depend on when the ray is traced). Reflections (closest hit +
+// shading) are not part of it: with them switched on the launcher runs raygen_kernel for that ray kind afterwards.
+constexpr int kQueuePixels = 128;          // pixels per warp
+struct QueueShared {                       // per warp; dynamic shared memory, sized by the launcher for (1 + ao_spp) ray kinds
+    float o[kQueuePixels][3];              // origin = P + 0.1 N
+    uint8_t list[kQueuePixels];            // lit pixels in queue order
+};
+template <int KINDS>                       // 1 + ao_spp (2, 3 or 5): ray kind 0 = shadow, k = AO sample k - 1
+__global__ void __launch_bounds__(128, 8) raygen_queue_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd, const int kRefill,
+                                                              const int kBurst) {
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr size_t PER_WARP = sizeof(QueueShared) + (size_t)KINDS * kQueuePixels * 12 + (size_t)KINDS * kQueuePixels;
+    unsigned char *base = qsm + (size_t)warp * ((PER_WARP + 15) & ~(size_t)15);
+    QueueShared &q = *reinterpret_cast<QueueShared *>(base);
+    float (*dirs)[3] = reinterpret_cast<float (*)[3]>(base + sizeof(QueueShared));                     // [KINDS * 128][3]
+    uint8_t *occluded = base + sizeof(QueueShared) + (size_t)KINDS * kQueuePixels * 12;                // [KINDS * 128]
+    // this warp's 16 x 8 pixel block inside the CTA's 32 x 16
+    const int bx = blockIdx.x * 32 + (warp & 1) * 16, by = p.y_begin + blockIdx.y * 16 + (warp >> 1) * 8;
+    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+
+    // ---- A: ray generation (raygen.rgen:15-55), four pixels per lane -------------------------------------------------------------------
+    int n_lit = 0;
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+        const int i = t * 32 + lane;
+        const int x = bx + (t & 1) * 8 + (lane & 7), y = by + (t >> 1) * 4 + (lane >> 3);
+        const bool in_range = x < p.W && y < p.y_end;
+        const size_t pix = in_range ? (size_t)y * p.W + x : 0;
+        const float depth = in_range ? __ldg(&p.depth[pix]) : 0.0f;
+        const bool lit = in_range && depth != 0.0f;
+        if (in_range && !lit) {                                                                      // raygen.rgen:20-24
+            p.shadow_ao[pix] = pack_rg16f(1.0f, 1.0f);
+            p.reflections[pix] = make_uint2(0u, 0u);
+            if (p.refl_t) p.refl_t[pix] = -1.0f;
+        }
+        if (lit) {
+            const float u = __fdiv_rn(add_rn((float)x, 0.5f), (float)p.W), v = __fdiv_rn(add_rn((float)y, 0.5f), (float)p.H);
+            uint32_t rng = seed_thread(((uint32_t)y * (uint32_t)p.H + (uint32_t)x) * pfd.frame_index);
+            const float3 P = unproject_rn(pfd.camera_viewproj_inverse, depth, u, v);
+            const float4 n4 = unpack_rgba16f(__ldg(&p.normals[pix]));
+            const float3 N = make_float3(n4.x, n4.y, n4.z);
+            q.o[i][0] = add_rn(P.x, mul_rn(N.x, 0.1f)); q.o[i][1] = add_rn(P.y, mul_rn(N.y, 0.1f)); q.o[i][2] = add_rn(P.z, mul_rn(N.z, 0.1f));
+            float rnd1 = random01(rng), rnd2 = random01(rng);
+            float3 d = onb_apply(L, normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f)));
+            dirs[i][0] = d.x; dirs[i][1] = d.y; dirs[i][2] = d.z;
+#pragma unroll
+            for (int k = 1; k < KINDS; ++k) {
+                rnd1 = random01(rng); rnd2 = random01(rng);
+                d = onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
+                dirs[k * kQueuePixels + i][0] = d.x; dirs[k * kQueuePixels + i][1] = d.y; dirs[k * kQueuePixels + i][2] = d.z;
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, lit);
+        if (lit) q.list[n_lit + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
+        n_lit += __popc(m);
+    }
+    __syncwarp();
+
+    // ---- B: traversal with ray-level refill ------------------------------------------------------------------------------------------------
+    // queue entry j: kind j / n_lit (skipping the kinds that are switched off), pixel list[j % n_lit]
+    const int first_kind = (p.flags & 1) ? 0 : 1, end_kind = (p.flags & 2) ? KINDS : 1;
+    const int n_rays = n_lit * max(end_kind - first_kind, 0);
+    int next = 0;                                   // warp-uniform queue head
+    bool active = false;
+    int slot = 0;                                   // kind * 128 + pixel of the ray in flight
+    RayPre r;
+    r.o = make_float3(0.f, 0.f, 0.f); r.idir = r.o; r.kx = 0; r.ky = 1; r.kz = 2; r.Sx = r.Sy = r.Sz = 0.f; r.neg = 0u;
+    float tmax = 0.0f;
+    uint2 stack[kStackSize];
+    int sp = 0;
+    uint2 group = make_uint2(0u, 0u);
+    const WideNode *__restrict__ nodes = p.scene.nodes;
+    const float4 *__restrict__ tris = p.scene.tris;
+    const uint32_t bias = p.scene.bias;
+    while (true) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle == FULL || (next < n_rays && __popc(idle) >= kRefill)) {
+            if (next >= n_rays) break;              // nothing in flight, nothing queued
+            if (!active) {
+                const int j = next + __popc(idle & ((1u << lane) - 1u));
+                if (j < n_rays) {
+                    const int kind = first_kind + j / n_lit, pixel = q.list[j - (j / n_lit) * n_lit];
+                    slot = kind * kQueuePixels + pixel;
+                    Ray ray;
+                    ray.o = make_float3(q.o[pixel][0], q.o[pixel][1], q.o[pixel][2]);
+                    ray.d = make_float3(dirs[slot][0], dirs[slot][1], dirs[slot][2]);
+                    ray.tmin = 0.01f;
+                    tmax = kind == 0 ? 10000.0f : 5.0f;
+                    r = prepare(ray);
+                    sp = 0;
+                    group = make_uint2(0u, p.scene.n_wide ? 1u : 0u);
+                    active = true;
+                }
+            }
+            next += __popc(idle);
+        }
+#pragma unroll 1
+        for (int it = 0; it < kBurst && active; ++it) {
+            bool done = false, hit_any = false;
+            if (group.y == 0u) {
+                if (sp == 0) done = true;
+                else group = stack[--sp];
+            }
+            if (!done) {
+                const uint32_t k = pop_child<true>(group);
+                if (group.y != 0u && sp < kStackSize) stack[sp++] = group;
+                const uint32_t node = group.x + k;
+                uint32_t child_base, child_hits, leaf_hits;
+                intersect_node(nodes, node, r, 0.01f, tmax, bias, child_base, child_hits, leaf_hits);
+                group = make_uint2(child_base & 0x7fffffffu, child_hits);
+                if (leaf_hits) {
+                    uint32_t tri_base, tri_hits;
+                    expand_leaves(nodes, node, leaf_hits, tri_base, tri_hits);
+                    do {
+                        const uint32_t jt = (uint32_t)__ffs((int)tri_hits) - 1u;
+                        tri_hits &= tri_hits - 1u;
+                        const float4 *tp = tris + (size_t)(tri_base + jt) * 3;
+                        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                        float tt, uu, vv;
+                        if (intersect_tri(r, 0.01f, tmax, v0, v1, v2, tt, uu, vv)) { hit_any = true; done = true; break; }
+                    } while (tri_hits);
+                }
+            }
+            if (done) {
+                occluded[slot] = hit_any ? 1 : 0;
+                active = false;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- C: miss.rmiss / payload arithmetic of raygen.rgen:41-57 and the stores --------------------------------------------------------------
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+        const int i = t * 32 + lane;
+        const int x = bx + (t & 1) * 8 + (lane & 7), y = by + (t >> 1) * 4 + (lane >> 3);
+        if (!(x < p.W && y < p.y_end)) continue;
+        const size_t pix = (size_t)y * p.W + x;
+        if (__ldg(&p.depth[pix]) == 0.0f) continue;
+        const float shadow = (p.flags & 1) ? (occluded[i] ? 0.0f : 1.0f) : 1.0f;
+        float ao = 0.0f;
+#pragma unroll
+        for (int k = 1; k < KINDS; ++k) ao = add_rn(ao, (p.flags & 2) ? (occluded[k * kQueuePixels + i] ? 0.0f : 1.0f) : 1.0f);
+        ao = __fdiv_rn(ao, (float)(KINDS - 1));
+        p.shadow_ao[pix] = pack_rg16f(shadow, ao);
+        if (!(p.flags & 4)) {
+            p.reflections[pix] = make_uint2(0u, 0u);
+            if (p.refl_t) p.refl_t[pix] = -1.0f;
         }
     }
 }
@@ -1173,6 +1339,39 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
     }
     dim3 block(128), grid((width + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
     p.leaf_batch = getenv("VHR_LEAF_BATCH") ? atoi(getenv("VHR_LEAF_BATCH")) : 16;
+    if (ctx->opt.raygen_variant == 9 && (p.ao_spp == 1 || p.ao_spp == 2 || p.ao_spp == 4) && (p.flags & 3)) {
+        // any-hit rays through the ray queue kernel; the reflection ray (closest hit + shading), if on, through the per-pixel kernel afterwards
+        const int kinds = 1 + p.ao_spp;
+        const size_t per_warp = (sizeof(QueueShared) + (size_t)kinds * kQueuePixels * 12 + (size_t)kinds * kQueuePixels + 15) & ~(size_t)15;
+        const size_t smem = 4 * per_warp;
+        const int refill = getenv("VHR_REFILL_IDLE") ? atoi(getenv("VHR_REFILL_IDLE")) : 8, burst = getenv("VHR_BURST") ? atoi(getenv("VHR_BURST")) : 4;
+        dim3 qgrid((width + 31) / 32, (p.y_end - p.y_begin + 15) / 16);
+        RaygenParams pq = p;
+        pq.flags = p.flags & 7;
+#define VHR_LAUNCH_QUEUE(K)                                                                                                         \
+        do {                                                                                                                        \
+            static uint64_t configured = 0;                                                                                         \
+            if (!(configured >> (ctx->device & 63) & 1ull)) {                                                                       \
+                VHR_CUDA_CHECK(cudaFuncSetAttribute(raygen_queue_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                configured |= 1ull << (ctx->device & 63);                                                                           \
+            }                                                                                                                       \
+            raygen_queue_kernel<K><<<qgrid, block, smem, ctx->stream>>>(pq, ctx->pfd, refill, burst);                               \
+        } while (0)
+        if (kinds == 2) VHR_LAUNCH_QUEUE(2);
+        else if (kinds == 3) VHR_LAUNCH_QUEUE(3);
+        else VHR_LAUNCH_QUEUE(5);
+#undef VHR_LAUNCH_QUEUE
+        VHR_CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        if (p.flags & 4) {
+            RaygenParams pr = p;
+            pr.flags = 4 | 8;                      // reflection ray only, leave the shadow / AO texel alone
+            raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(pr, ctx->pfd);
+            VHR_CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+        }
+        return VHR_OK;
+    }
     switch (ctx->opt.raygen_variant) {
         case 2: raygen_kernel<0><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // ptxas' own register choice (72)
         case 3: raygen_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;          // no register cap (117)
