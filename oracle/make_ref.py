@@ -496,6 +496,82 @@ extern "C" void vr_raygen(const void *scene, void *trace_any, void *trace_closes
 """
 
 
+# vkCmdTraceRaysKHR of the fully ray-traced path's "Raytracing Pipeline" (src/render_paths/raytraced_render_path.cpp:12-47): raygen.rgen /
+# raygen_test_alpha.rgen, miss.rmiss (index 0), shadow_miss.rmiss (index 1), one hit group: closesthit.rchit, or closesthit_test_alpha.rchit +
+# shadow_anyhit.rahit. The closest-hit shader itself calls traceRayEXT (the shadow ray, payload location 1 = a bool).
+def harness_raytraced(sfx, alpha):
+    anyhit = """
+static int run_anyhit(void *, uint32_t geometry_index, uint32_t primitive_id, double u, double v) {
+    namespace A = ref_rtp%(sfx)s_ahit;
+    A::gl_GeometryIndexEXT = (int)geometry_index; A::gl_PrimitiveID = (int)primitive_id;
+    A::hit_attribs = glm::vec3((float)u, (float)v, 0.0f);
+    A::gl_IgnoreIntersection = false;
+    A::shader_main();
+    return A::gl_IgnoreIntersection ? 0 : 1;
+}
+""" % dict(sfx=sfx) if alpha else ""
+    ah = "run_anyhit" if alpha else "nullptr"
+    return anyhit + """
+namespace ref_rtp%(sfx)s_chit {
+void traceRayEXT(accelerationStructureEXT &as, uint flags, uint cull_mask, uint sbt_offset, uint sbt_stride, uint miss_index, vec3 origin, float tmin, vec3 dir,
+                 float tmax, int payload_loc) {      // the shadow ray: payload location 1, miss index 1, closest-hit shader skipped
+    const RayHit h = trace_query(as, flags, origin, tmin, dir, tmax, (flags & gl_RayFlagsNoOpaqueEXT) ? %(ah)s : nullptr);
+    if (!h.hit) { ref_rtp%(sfx)s_smiss::payload = shadow_payload; ref_rtp%(sfx)s_smiss::shader_main(); shadow_payload = ref_rtp%(sfx)s_smiss::payload; }
+}
+}
+namespace ref_rtp%(sfx)s_raygen {
+void traceRayEXT(accelerationStructureEXT &as, uint flags, uint cull_mask, uint sbt_offset, uint sbt_stride, uint miss_index, vec3 origin, float tmin, vec3 dir,
+                 float tmax, int payload_loc) {
+    const RayHit h = trace_query(as, flags, origin, tmin, dir, tmax, (flags & gl_RayFlagsNoOpaqueEXT) ? %(ah)s : nullptr);
+    if (!h.hit) { ref_rtp%(sfx)s_miss::payload = payload; ref_rtp%(sfx)s_miss::shader_main(); payload = ref_rtp%(sfx)s_miss::payload; return; }
+    namespace Hs = ref_rtp%(sfx)s_chit;
+    Hs::gl_GeometryIndexEXT = h.geometry_index; Hs::gl_PrimitiveID = h.primitive_id;
+    Hs::hit_attribs = vec3(h.attribs, 0.0f);
+    Hs::payload = payload;
+    Hs::shader_main();
+    payload = Hs::payload;
+}
+}
+extern "C" void vr_raytraced%(sfx)s(const void *scene, void *trace_any, void *trace_closest, void *trace_closest_filtered, const void *pfd, int W, int H, uint8_t *out_bgra8,
+                               const void *vertices, const uint32_t *indices, const void *primitives, const vr_texture *textures, int n_textures) {
+    using namespace glsl;
+    ImageDesc dout = {out_bgra8, out_bgra8, W, H, FMT_B8G8R8A8_UNORM};     // "RaytracedOutput" (raytraced_render_path.cpp:15; the shader says rgba8)
+    // textures[]: slot -1 (a material without a base-colour texture; the alpha-tested shaders index it unconditionally, which is undefined in the
+    // reference) holds one opaque white texel
+    static const uint8_t white[4] = {255, 255, 255, 255};
+    std::vector<ImageDesc> tdesc(n_textures + 1);
+    std::vector<sampler2D> tsamp(n_textures + 1);
+    tdesc[0] = ImageDesc{white, nullptr, 1, 1, FMT_R8G8B8A8_UNORM}; tsamp[0].d = &tdesc[0];
+    for (int i = 0; i < n_textures; ++i) {
+        tdesc[i + 1] = ImageDesc{textures[i].rgba, nullptr, textures[i].w, textures[i].h, textures[i].vk_format};
+        tsamp[i + 1].d = &tdesc[i + 1]; tsamp[i + 1].mag = textures[i].mag; tsamp[i + 1].min = textures[i].min; tsamp[i + 1].wrap_u = textures[i].wrap_u; tsamp[i + 1].wrap_v = textures[i].wrap_v;
+    }
+#pragma omp parallel
+    {
+        namespace R = ref_rtp%(sfx)s_raygen;
+        namespace Hs = ref_rtp%(sfx)s_chit;
+        accelerationStructureEXT as;
+        as.scene = scene;
+        as.trace_any = (int (*)(const void *, const float *, const float *, float, float))trace_any;
+        as.trace_closest = (int (*)(const void *, const float *, const float *, float, float, double *, uint32_t *))trace_closest;
+        as.trace_closest_filtered = (int (*)(const void *, const float *, const float *, float, float, int (*)(void *, uint32_t, uint32_t, double, double), void *, double *, uint32_t *))trace_closest_filtered;
+        std::memcpy(&R::pfd, pfd, sizeof(R::pfd)); std::memcpy(&Hs::pfd, pfd, sizeof(Hs::pfd));
+        R::TLAS = as; Hs::TLAS = as;
+        R::output_image.d = &dout;
+        Hs::vertices = (const Hs::Vertex *)vertices; Hs::indices = indices; Hs::primitives = (const Hs::Primitive *)primitives; Hs::textures = tsamp.data() + 1;
+%(ahbind)s
+        R::gl_LaunchSizeEXT.set(W, H, 1);
+#pragma omp for schedule(dynamic, 1)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                R::gl_LaunchIDEXT.set(x, y, 0);
+                R::shader_main();
+            }
+    }
+}
+""" % dict(sfx=sfx, ah=ah, ahbind=("        { namespace A = ref_rtp%s_ahit; A::vertices = (const A::Vertex *)vertices; A::indices = indices; A::primitives = (const A::Primitive *)primitives; A::textures = tsamp.data() + 1; }" % sfx) if alpha else "")
+
+
 def generate():
     os.makedirs(GEN_DIR, exist_ok=True)
     units = []   # (file name, text)
@@ -515,6 +591,15 @@ def generate():
     rhit, _ = shader_unit(H + "reflection_hit.rchit", "ref_reflection_hit", fwd=TRACE_FWD)
     rgen, _ = shader_unit(H + "raygen.rgen", "ref_raygen", fwd=TRACE_FWD)
     units.append(("ref_raygen.cpp", "#include <vector>\n" + miss + rmiss + rhit + rgen + HARNESS_RAYGEN))
+    P = "raytraced_render_path/"
+    tex_struct = "#include <cstdint>\nstruct vr_texture { const uint8_t *rgba; int w, h, vk_format, mag, min, wrap_u, wrap_v; };\n"
+    for sfx, alpha in (("", False), ("_alpha", True)):
+        parts = [shader_unit(P + "miss.rmiss", f"ref_rtp{sfx}_miss")[0], shader_unit(P + "shadow_miss.rmiss", f"ref_rtp{sfx}_smiss")[0]]
+        if alpha:
+            parts.append(shader_unit(P + "shadow_anyhit.rahit", f"ref_rtp{sfx}_ahit")[0])
+        parts.append(shader_unit(P + ("closesthit_test_alpha.rchit" if alpha else "closesthit.rchit"), f"ref_rtp{sfx}_chit", fwd=TRACE_FWD)[0])
+        parts.append(shader_unit(P + ("raygen_test_alpha.rgen" if alpha else "raygen.rgen"), f"ref_rtp{sfx}_raygen", fwd=TRACE_FWD)[0])
+        units.append((f"ref_raytraced{sfx}.cpp", "#include <vector>\n" + tex_struct + "".join(parts) + harness_raytraced(sfx, alpha)))
     paths = []
     for name, text in units:
         p = os.path.join(GEN_DIR, name)

@@ -495,6 +495,20 @@ int vo_trace_closest(const vo_scene *s_, const float *o, const float *d, float t
     return 1;
 }
 
+// Closest hit with an any-hit stage supplied by the caller (oracle/_ref runs the reference's shadow_anyhit.rahit through it):
+// accept(user, geometry index, primitive id, u, v) != 0 keeps the candidate, 0 = ignoreIntersectionEXT.
+typedef int (*vo_anyhit_fn)(void *user, uint32_t geometry_index, uint32_t primitive_id, double u, double v);
+int vo_trace_closest_filtered(const vo_scene *s_, const float *o, const float *d, float tmin, float tmax, vo_anyhit_fn accept, void *user, double *t_u_v,
+                              uint32_t *geom_prim) {
+    const Scene &s = *reinterpret_cast<const Scene *>(s_);
+    Hit h;
+    auto f = [&](uint32_t tri, double u, double v) { return !accept || accept(user, s.tri_geom[tri], s.tri_prim[tri], u, v) != 0; };
+    if (!trace_closest_filtered(s, v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), tmin, tmax, h, f)) return 0;
+    t_u_v[0] = h.t; t_u_v[1] = h.u; t_u_v[2] = h.v;
+    geom_prim[0] = s.tri_geom[h.tri]; geom_prim[1] = s.tri_prim[h.tri];
+    return 1;
+}
+
 // raygen.rgen:14-66. Rows [y0, y1) only (bounded samples for the CPU baseline). `ao_spp` = 2 in the
 // reference (:45,55); `flags` bit0 = trace shadow, bit1 = trace AO, bit2 = trace reflections (all set = reference).
 // Optional outputs: refl_t (float per pixel: closest-hit distance of the reflection ray, -1 = miss / sky),

@@ -79,6 +79,8 @@ def _declare(L):
     L.vr_ssr.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp, vp, vp]
     L.vr_composition.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]
     L.vr_raygen.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    for name in ("vr_raytraced", "vr_raytraced_alpha"):
+        getattr(L, name).argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int]
 
 
 def svgf_temporal(pfd, normals, motion, rt, prev_normals, history, moments_in):
@@ -171,6 +173,31 @@ def composition(pfd, albedo, normals, motion, depth, rt, shadow_mode=0, ao_mode=
 class _VrTexture(C.Structure):
     _fields_ = [("rgba", C.c_void_p), ("w", C.c_int), ("h", C.c_int), ("vk_format", C.c_int), ("mag", C.c_int), ("min", C.c_int), ("wrap_u", C.c_int),
                 ("wrap_v", C.c_int)]
+
+
+def _scene_arrays(scene):
+    v = np.ascontiguousarray(scene.vertices)
+    i = np.ascontiguousarray(scene.indices, np.uint32)
+    p = np.ascontiguousarray(scene.primitives)
+    texs = list(getattr(scene, "textures", []))
+    keep = [np.ascontiguousarray(t.rgba, np.uint8) for t in texs]
+    arr = (_VrTexture * max(len(texs), 1))()
+    for k, t in enumerate(texs):
+        mag, mn, wu, wv = (1, 1, 0, 0) if t.sampler is None else [int(x) for x in t.sampler]
+        arr[k] = _VrTexture(keep[k].ctypes.data, keep[k].shape[1], keep[k].shape[0], int(t.format), mag, mn, wu, wv)
+    return v, i, p, arr, len(texs), keep
+
+
+def raytraced(scene, oracle_scene, pfd, W, H, alpha_test=False):
+    """vkCmdTraceRaysKHR of the fully ray-traced path's "Raytracing Pipeline" compiled from the reference's raytraced_render_path/*.rgen / .rchit /
+    .rahit / .rmiss: [H, W, 4] uint8 B8G8R8A8_UNORM "RaytracedOutput". traceRayEXT queries `oracle_scene`."""
+    out = np.zeros((H, W, 4), np.uint8)
+    v, i, p, arr, n, keep = _scene_arrays(scene)
+    OL = O.lib()
+    fn = lib().vr_raytraced_alpha if alpha_test else lib().vr_raytraced
+    fn(oracle_scene._s, C.cast(OL.vo_trace_any, C.c_void_p), C.cast(OL.vo_trace_closest, C.c_void_p), C.cast(OL.vo_trace_closest_filtered, C.c_void_p),
+       _p(pfd), W, H, _p(out), _p(v), _p(i), _p(p), C.cast(arr, C.c_void_p), n)
+    return out
 
 
 def raygen(scene, oracle_scene, pfd, depth, normals, rows=None):

@@ -43,6 +43,17 @@ inline vec<N, T, Q> abs(detail::_swizzle<N, T, Q, E0, E1, E2, E3> const &s) { re
 template <int N, typename T, qualifier Q, int E0, int E1, int E2, int E3>
 inline vec<N, T, Q> normalize(detail::_swizzle<N, T, Q, E0, E1, E2, E3> const &s) { return normalize(s()); }
 
+// binary built-ins with a swizzle proxy on one side (cross(n, t.xyz), dot(t.xyz, n))
+#define VHR_REF_SWZ_BINARY(fn, ret)                                                                                                          \
+    template <int N, typename T, qualifier Q, int E0, int E1, int E2, int E3>                                                                \
+    inline ret fn(vec<N, T, Q> const &a, detail::_swizzle<N, T, Q, E0, E1, E2, E3> const &b) { return fn(a, b()); }                        \
+    template <int N, typename T, qualifier Q, int E0, int E1, int E2, int E3>                                                                \
+    inline ret fn(detail::_swizzle<N, T, Q, E0, E1, E2, E3> const &a, vec<N, T, Q> const &b) { return fn(a(), b); }
+#define VHR_REF_COMMA ,
+VHR_REF_SWZ_BINARY(cross, vec<N VHR_REF_COMMA T VHR_REF_COMMA Q>)
+VHR_REF_SWZ_BINARY(dot, T)
+#undef VHR_REF_SWZ_BINARY
+#undef VHR_REF_COMMA
 template <length_t L, qualifier Q> inline vec<L, float, Q> to_float(vec<L, int, Q> const &v) { return vec<L, float, Q>(v); }
 // ivec (op) vec, vec (op) ivec
 #define VHR_REF_MIXED(op)                                                                                                                   \
@@ -209,11 +220,25 @@ struct accelerationStructureEXT {
     const void *scene = nullptr;
     int (*trace_any)(const void *scene, const float *o, const float *d, float tmin, float tmax) = nullptr;
     int (*trace_closest)(const void *scene, const float *o, const float *d, float tmin, float tmax, double *t_u_v, uint32_t *geom_prim) = nullptr;
+    // closest hit with an any-hit stage: accept(user, geometry index, primitive id, u, v) == 0 <=> ignoreIntersectionEXT
+    int (*trace_closest_filtered)(const void *scene, const float *o, const float *d, float tmin, float tmax,
+                                  int (*accept)(void *user, uint32_t geometry_index, uint32_t primitive_id, double u, double v), void *user, double *t_u_v,
+                                  uint32_t *geom_prim) = nullptr;
 };
 struct RayHit { bool hit = false; float t = 0.0f; vec2 attribs = vec2(0.0f); int geometry_index = 0, primitive_id = 0; };
-inline RayHit trace_query(const accelerationStructureEXT &as, uint flags, vec3 o, float tmin, vec3 d, float tmax) {
+// `anyhit` != nullptr: the hit group's any-hit shader runs on every candidate (gl_RayFlagsNoOpaqueEXT geometry)
+inline RayHit trace_query(const accelerationStructureEXT &as, uint flags, vec3 o, float tmin, vec3 d, float tmax,
+                          int (*anyhit)(void *, uint32_t, uint32_t, double, double) = nullptr, void *user = nullptr) {
     RayHit r;
     const float of[3] = {o.x, o.y, o.z}, df[3] = {d.x, d.y, d.z};
+    if (anyhit) {
+        double tuv[3]; uint32_t gp[2];
+        if (as.trace_closest_filtered(as.scene, of, df, tmin, tmax, anyhit, user, tuv, gp)) {
+            r.hit = true; r.t = (float)tuv[0]; r.attribs = vec2((float)tuv[1], (float)tuv[2]);
+            r.geometry_index = (int)gp[0]; r.primitive_id = (int)gp[1];
+        }
+        return r;
+    }
     if (flags & gl_RayFlagsTerminateOnFirstHitEXT) {
         r.hit = as.trace_any(as.scene, of, df, tmin, tmax) != 0;
     } else {
