@@ -138,6 +138,15 @@ int vhr_set_partition(vhr_context *ctx, const vhr_partition *p) {
         if (p->world > 1 && p->band_begin[r + 1] < p->band_begin[r] + 64)
             return fail(VHR_ERR_INVALID, "partition: band %u has %d rows; every band must hold at least 64 (halos never skip a rank)", r,
                         (int)p->band_begin[r + 1] - (int)p->band_begin[r]);
+    // copy-free blits (VHR_OPT_BLIT_ALIAS) are suspended while a partition is installed — the peers hold mappings of fixed buffers — so every
+    // image that still shares a buffer with a blit partner gets its own copy now
+    if (ctx->device >= 0) {
+        for (auto &kv : ctx->transient)
+            if (int rc = make_writable(ctx, &kv.second, false)) return rc;
+        for (auto &im : ctx->storage)
+            if (im.used)
+                if (int rc = make_writable(ctx, &im, false)) return rc;
+    }
     Partition pt;
     pt.enabled = true; pt.world = (int)p->world; pt.rank = (int)p->rank;
     for (uint32_t r = 0; r <= p->world; ++r) pt.band_begin[r] = (int)p->band_begin[r];
@@ -153,12 +162,14 @@ int vhr_image_export_ipc(vhr_context *ctx, const char *name, void *handle) {
     VHR_NEED_DEVICE(ctx);
     Image *im = transient(ctx, name);
     if (!im || !handle) return fail(VHR_ERR_INVALID, "export: unknown image '%s'", name ? name : "(null)");
+    if (int rc = make_writable(ctx, im, false)) return rc;        // a buffer shared with a blit partner is not this image's to hand out
     return export_ptr(im->ptr, handle);
 }
 int vhr_storage_image_export_ipc(vhr_context *ctx, int slot, void *handle, void *twin_handle) {
     VHR_NEED_DEVICE(ctx);
     Image *im = storage_slot(ctx, slot);
     if (!im || !handle) return fail(VHR_ERR_INVALID, "export: storage image %d does not exist", slot);
+    if (int rc = make_writable(ctx, im, false)) return rc;
     if (int rc = export_ptr(im->ptr, handle)) return rc;
     if (twin_handle) {
         if (!im->twin) {
