@@ -1,7 +1,8 @@
 """oracle/make_ref.py — TEST INFRASTRUCTURE ONLY. Builds oracle/_ref/libvhr_ref.so = the REFERENCE'S OWN SHADERS compiled for the CPU.
 
 The GLSL files are read from /root/reference/data/shaders (and src/rendering_backend/glsl_common.h) where they lie, at build
-time; nothing is copied into this repository and the generated C++ goes to oracle/_ref/gen/ (git-ignored, like the .so).
+time; nothing is copied into this repository: the generated C++ lives in oracle/_ref/gen/ (git-ignored) only while it is being compiled
+(`--keep` on the command line leaves it there for debugging) and what stays is oracle/_ref/libvhr_ref.so.
 Every shader becomes a C++ namespace whose body is the shader's text after a purely lexical translation:
 
   * `#include` resolved textually, `#version` / `#extension` dropped, glsl_common.h taken on its GLSL (`#ifndef __cplusplus`) side;
@@ -573,8 +574,8 @@ extern "C" void vr_raytraced%(sfx)s(const void *scene, void *trace_any, void *tr
 
 
 def generate():
-    os.makedirs(GEN_DIR, exist_ok=True)
-    units = []   # (file name, text)
+    """The translation units as (file name, C++ text); nothing is written here."""
+    units = []
     H = "hybrid_render_path/"
     svgf, _ = shader_unit(H + "svgf.comp", "ref_svgf")
     atrous, _ = shader_unit(H + "svgf_atrous_filter.comp", "ref_atrous")
@@ -600,44 +601,56 @@ def generate():
         parts.append(shader_unit(P + ("closesthit_test_alpha.rchit" if alpha else "closesthit.rchit"), f"ref_rtp{sfx}_chit", fwd=TRACE_FWD)[0])
         parts.append(shader_unit(P + ("raygen_test_alpha.rgen" if alpha else "raygen.rgen"), f"ref_rtp{sfx}_raygen", fwd=TRACE_FWD)[0])
         units.append((f"ref_raytraced{sfx}.cpp", "#include <vector>\n" + tex_struct + "".join(parts) + harness_raytraced(sfx, alpha)))
-    paths = []
-    for name, text in units:
-        p = os.path.join(GEN_DIR, name)
-        old = open(p).read() if os.path.exists(p) else None
-        if old != text:
-            with open(p, "w") as f:
-                f.write(text)
-        paths.append(p)
-    return paths
+    return units
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, keep_generated=False):
     """Builds oracle/_ref/libvhr_ref.so when /root/reference is present; returns its path, or None when neither the reference nor a
-    prebuilt library exists (the GPU box only ever sees the prebuilt one)."""
+    prebuilt library exists (the GPU box only ever sees the prebuilt one). The generated C++ (which carries the reference's shader text) only
+    exists in oracle/_ref/gen/ for the duration of the compile: what stays is the library and a hash of its inputs (gen.stamp)."""
+    import hashlib
+    import shutil
     if not reference_available():
         return LIB if os.path.exists(LIB) else None
-    srcs = generate()
-    deps = srcs + [os.path.join(HERE, "ref_shim.h"), os.path.abspath(__file__)]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+    units = generate()
+    h = hashlib.sha256()
+    for name, text in units:
+        h.update(name.encode()); h.update(text.encode())
+    for dep in (os.path.join(HERE, "ref_shim.h"), os.path.abspath(__file__)):
+        with open(dep, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(CXXFLAGS).encode())
+    stamp, digest = os.path.join(OUT_DIR, "gen.stamp"), h.hexdigest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
+    os.makedirs(GEN_DIR, exist_ok=True)
     objs, procs = [], []
-    for s in srcs:
-        o = s[:-4] + ".o"
-        objs.append(o)
-        procs.append((s, subprocess.Popen([CXX] + CXXFLAGS + ["-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    failed = False
-    for s, p in procs:
-        out, _ = p.communicate()
-        if p.returncode != 0:
-            failed = True
-            sys.stderr.write(f"--- {s}\n{out}\n")
-        elif verbose and out:
-            print(out)
-    if failed:
-        raise RuntimeError("oracle/_ref: compiling the reference shaders failed")
-    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs, check=True)
+    try:
+        for name, text in units:
+            s = os.path.join(GEN_DIR, name)
+            with open(s, "w") as f:
+                f.write(text)
+            o = s[:-4] + ".o"
+            objs.append(o)
+            procs.append((s, subprocess.Popen([CXX] + CXXFLAGS + ["-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        failed = False
+        for s, p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                failed = True
+                sys.stderr.write(f"--- {s}\n{out}\n")
+            elif verbose and out:
+                print(out)
+        if failed:
+            raise RuntimeError("oracle/_ref: compiling the reference shaders failed")
+        subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + objs, check=True)
+        with open(stamp, "w") as f:
+            f.write(digest + "\n")
+    finally:
+        if not keep_generated:
+            shutil.rmtree(GEN_DIR, ignore_errors=True)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, keep_generated="--keep" in sys.argv))
