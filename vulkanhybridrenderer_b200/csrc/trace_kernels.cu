@@ -529,7 +529,7 @@ __device__ __forceinline__ bool trace_any_sorted(const SceneRefs &scene, const R
 //   1 (variant 3): no cap, 117 registers / 4 blocks — 1.16 / 3.39 ms (fewer warps to hide the node fetches);
 //   BATCHED (variant 4): trace_batched — 1.00 / 2.57 ms: postponing leaves costs the any-hit rays more node steps than the fuller
 //   triangle block saves. Same images in every variant.
-template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4, bool SORT_AO = false, bool PACKED = false>
+template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4, bool SORT_AO = false, bool PACKED = false, bool MERGED = false>
 __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     static_assert(!SORT_AO || WPB == 4, "the AO sort works on 128-thread CTAs");
     int x, y;
@@ -569,9 +569,28 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
     ray.tmin = 0.01f;
     Hit hit;
 
+    float rnd1, rnd2, shadow = 1.0f, ao = 0.0f;
+    if constexpr (MERGED) {
+        // MERGED: the shadow ray and the AO rays go through ONE inlined copy of the any-hit traversal (a loop over the ray kinds) instead of
+        // two: half the hot code in the instruction cache. Same rays, same RNG order.
+#pragma unroll 1
+        for (int k = 0; k <= p.ao_spp; ++k) {
+            rnd1 = random01(rng);
+            rnd2 = random01(rng);
+            const bool is_shadow = k == 0;
+            const bool enabled = is_shadow ? (p.flags & 1) != 0 : (p.flags & 2) != 0;
+            bool occluded = false;
+            if (enabled) {
+                ray.d = is_shadow ? onb_apply(L, normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f))) : onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
+                ray.tmax = is_shadow ? 10000.0f : 5.0f;
+                occluded = trace<true, AcceptAll, PACKED>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+            }
+            if (is_shadow) shadow = occluded ? 0.0f : 1.0f;
+            else ao = add_rn(ao, occluded ? 0.0f : 1.0f);
+        }
+    } else {
     // shadow (raygen.rgen:32-41; the 4x loop re-traces one ray, Q3)
-    float rnd1 = random01(rng), rnd2 = random01(rng);
-    float shadow = 1.0f;
+    rnd1 = random01(rng); rnd2 = random01(rng);
     if (p.flags & 1) {
         const float3 cone = normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f));
         ray.d = onb_apply(L, cone);
@@ -581,7 +600,6 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
         shadow = occluded ? 0.0f : 1.0f;
     }
     // ambient occlusion (raygen.rgen:44-55)
-    float ao = 0.0f;
     for (int i = 0; i < p.ao_spp; ++i) {
         rnd1 = random01(rng);
         rnd2 = random01(rng);
@@ -601,6 +619,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
             ao = add_rn(ao, 1.0f);
         }
     }
+    }   // !MERGED
     ao = __fdiv_rn(ao, (float)p.ao_spp);
     if (lit && !(p.flags & 8)) out_sa[pix] = pack_rg16f(shadow, ao);      // bit 3: another kernel owns the shadow / AO texel (variant 9)
 
@@ -1393,6 +1412,7 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
         case 12:                                                                                 // 4-byte stack entries (trees below 2^23 wide nodes)
             if (ctx->bvh.n_wide < (1u << 23)) { raygen_kernel<8, false, 4, false, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break; }
             raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;
+        case 13: raygen_kernel<8, false, 4, false, false, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;   // one inlined any-hit traversal for shadow + AO
         case 10: raygen_kernel<10><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;        // 48 registers, 10 blocks / SM
         case 11: raygen_kernel<12><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;        // 40 registers, 12 blocks / SM
         default: raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;         // 64 registers, 8 blocks / SM
