@@ -841,3 +841,84 @@ def test_pixel_ray_regenerator_reproduces_the_masks_and_brute_force_agrees_with_
                         checked += 1
         assert np.array_equal(got.astype(np.float16), ref.astype(np.float16)), f"regenerated rays give another image (ao_spp {spp})"
         assert checked > 100
+
+
+def test_ssao_kernel_shortcuts_restated_in_numpy():
+    """The two exact shortcuts of ssao_kernels.cu's sample loop, restated in numpy against the oracle's formulas (ssao.comp:36-44).
+    sample_depth_fixed: texel and weight from the integer floor(fma(t, 256, 0.5)) are bit-identical to bilinear_setup's float formula
+    for |t| < 2^14. sincos_turn: within one ulp of the correctly rounded sine / cosine on the angles random01 * 2 * PI can take."""
+    f32 = np.float32
+    rng = np.random.default_rng(1)
+
+    def oracle_setup(u, n):
+        uu = ((u * f32(n)).astype(f32) - f32(0.5)).astype(f32)
+        s = (np.floor(((uu * f32(256)).astype(f32) + f32(0.5)).astype(f32)) * f32(0.00390625)).astype(f32)
+        fl = np.floor(s)
+        return fl.astype(np.int64), (s - fl).astype(f32), uu
+
+    def kernel_setup(t):
+        k = np.floor((t.astype(np.float64) * 256 + 0.5).astype(f32)).astype(np.int64)         # F2I.FLOOR(fma(t, 256, 0.5))
+        magic = (np.uint32(0x4B000000) | (k & 255).astype(np.uint32)).view(f32)
+        return k >> 8, (magic.astype(np.float64) * 0.00390625 - 32768.0).astype(f32)           # fma(magic, 1/256, -2^15)
+
+    for n in (1920, 1080, 101, 59, 3840):
+        u = np.concatenate([rng.uniform(-2, 3, 400_000).astype(f32), (np.arange(0, n * 4) / f32(n * 2)).astype(f32),
+                            rng.uniform(-1e-3, 1e-3, 50_000).astype(f32), rng.uniform(-8, 8, 50_000).astype(f32)])
+        i0, a, t = oracle_setup(u, n)
+        j0, b = kernel_setup(t)
+        ok = np.abs(t) < 16384
+        assert ok.sum() > 0.9 * ok.size and (i0[ok] == j0[ok]).all() and (a[ok] == b[ok]).all(), n
+
+    def fma(a, b, c):
+        return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(f32)
+
+    r = (rng.integers(0, 1 << 23, 1_000_000).astype(np.uint32) | np.uint32(0x3F800000)).view(f32) - f32(1)
+    ang = ((r * f32(2)).astype(f32) * f32(np.pi)).astype(f32)
+    assert (ang == (r * f32(2.0 * float(f32(np.pi)))).astype(f32)).all()                          # fl(fl(2 r) PI) = fl(r (2 PI))
+    m = fma(ang, f32(0.636619772), f32(12582912.0))
+    q = m.view(np.int32) & 3
+    qf = (m - f32(12582912.0)).astype(f32)
+    f = fma(qf, f32(-1.57079637), ang)
+    f = fma(qf, f32(4.37113883e-8), f)
+    f2 = (f * f).astype(f32)
+    sp = fma(fma(fma(f2, f32(-1.9515295891e-4), f32(8.3321608736e-3)), f2, f32(-1.6666654611e-1)), (f * f2).astype(f32), f)
+    cp = fma(fma(fma(fma(f2, f32(2.443315711809948e-5), f32(-1.388731625493765e-3)), f2, f32(4.166664568298827e-2)), f2, f32(-0.5)), f2, f32(1.0))
+    s = np.where(q & 1, cp, sp)
+    c = np.where(q & 1, sp, cp)
+    s = np.where(q & 2, -s, s)
+    c = np.where((q + 1) & 2, -c, c)
+    for got, want in ((s, np.sin(ang.astype(np.float64))), (c, np.cos(ang.astype(np.float64)))):
+        assert np.abs(got - want).max() < 1.2e-7 * 0.75
+        ulps = np.abs(got.view(np.int32).astype(np.int64) - want.astype(f32).view(np.int32))
+        big = np.abs(want) > 1e-3                                                                  # next to a zero one ulp is tiny
+        assert ulps[big].max() <= 1
+
+
+def test_shared_reciprocal_division_restated_in_numpy():
+    """div_exact of vhr_common.cuh (the screen-space kernels' a / w without __fdiv_rn's slow path), restated in numpy: one Newton step on
+    a reciprocal that is up to one ulp off, the quotient, one residual correction — against numpy's correctly rounded float32 division
+    on 2e7 operand pairs with exponents in [-30, 30]; and the zero / infinite / NaN operand rule a * rcp(w)."""
+    f32 = np.float32
+    rng = np.random.default_rng(5)
+    N = 20_000_000
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+    a = (rng.standard_normal(N) * np.exp2(rng.integers(-30, 30, N))).astype(f32)
+    w = (rng.standard_normal(N) * np.exp2(rng.integers(-30, 30, N))).astype(f32)
+    w[w == 0] = 1
+    r0 = (f32(1) / w).astype(f32)
+    pert = rng.integers(-1, 2, N)
+    r0 = np.where(pert == 0, r0, np.nextafter(r0, np.where(pert > 0, f32(np.inf), f32(-np.inf)).astype(f32))).astype(f32)
+    r = fma(r0, fma(-w, r0, np.ones(N, f32)), r0)
+    q0 = (a * r).astype(f32)
+    q = fma(r, fma(-w, q0, a), q0)
+    assert (q == (a / w).astype(f32)).all()
+    with np.errstate(all="ignore"):
+        sa = np.array([0.0, 1.5, -2.0, np.inf, -np.inf, np.nan, 0.0, -0.0, 3.0, np.inf], f32)
+        sw = np.array([0.0, 0.0, 0.0, 0.0, np.inf, 1.0, np.inf, np.inf, -np.inf, np.inf], f32)
+        rcp = (f32(1) / sw).astype(f32)
+        got, want = (sa * rcp).astype(f32), (sa / sw).astype(f32)
+    assert (np.isnan(got) == np.isnan(want)).all() and (got[~np.isnan(want)] == want[~np.isnan(want)]).all()
+    assert (np.signbit(got[~np.isnan(want)]) == np.signbit(want[~np.isnan(want)])).all()

@@ -11,7 +11,7 @@ import numpy as np
 from . import types as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvhr_b200.so")
+LIB_PATH = os.environ.get("VHR_LIB_PATH") or os.path.join(_HERE, "libvhr_b200.so")      # VHR_LIB_PATH: development aid (A/B of two builds)
 
 # every symbol include/vhr_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [

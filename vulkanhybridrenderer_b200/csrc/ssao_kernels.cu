@@ -7,6 +7,7 @@
 // software with the Vulkan spec's float weights — CUDA texture units filter with 8-bit fixed-point weights, which
 // would not match the CPU oracle.
 #include <algorithm>
+#include <cstdlib>
 
 #include "vhr_internal.h"
 
@@ -16,6 +17,8 @@ struct SsaoParams {
     int W, H;
     int x_end, y_begin, y_end;
     float radius;
+    float Wf, Hf;             // (float)W, (float)H
+    const float4 *quads;      // (d[y][x], d[y][x+1], d[y+1][x], d[y+1][x+1]) per texel, REPEAT-wrapped (depth_quads_kernel); or nullptr
     const uint2 *normals;     // binding 0 (RGBA16F, sampled)
     const float *depth;       // binding 1 (D32F, sampled)
     uint2 *out;               // binding 2 (RGBA16F)
@@ -40,30 +43,114 @@ __device__ __forceinline__ float sample_depth(const SsaoParams &p, float u, floa
     return bilerp_rn(a, b, t00, t10, t01, t11);
 }
 
-// get_view_space_position (glsl_common.h:111-116) for the 16 SAMPLES of a pixel. What must stay exact in this kernel is the sample POSITION
-// (su, sv): the texture unit holds the filter coordinate with 8 fractional bits, so the depth tap is a step function of it — that is the
-// centre unprojection (-> perspective radius), the RNG and sincosf, all kept as in the oracle. The unprojected sample itself only enters
-// the occlusion sum continuously, so here the three IEEE divisions by w become one MUFU reciprocal + one Newton step (<= 1 ulp) and three
-// products, and with PERSPECTIVE (the inverse projection has the sparsity of an inverse perspective matrix: only m00, m11, m23, m32, m33
-// non-zero — checked on the host) the 16 products of the matrix-vector product that multiply exact zeros are not issued (same values: the
-// pairwise sum of glm's mat4 * vec4 with zero terms is the remaining term).
-template <bool PERSPECTIVE>
+// get_view_space_position (glsl_common.h:111-116) for the 16 SAMPLES of a pixel. With PERSPECTIVE (the inverse projection has the
+// sparsity of an inverse perspective matrix: only m00, m11, m23, m32, m33 non-zero — checked on the host) the products of the
+// matrix-vector product that multiply exact zeros are not issued: glm's pairwise sum (c0 x + c1 y) + (c2 z + c3 w) with zero terms IS the
+// remaining term, so the values are the oracle's. FAST (study switch): one MUFU reciprocal and three products instead of the three IEEE
+// divisions by w.
+template <bool PERSPECTIVE, bool FAST>
 __device__ __forceinline__ float3 unproject_sample(const float *inv, float depth, float u, float v) {
-    const float x = sub_rn(mul_rn(u, 2.0f), 1.0f), y = sub_rn(mul_rn(v, 2.0f), 1.0f);
+    const float x = fmaf(u, 2.0f, -1.0f), y = fmaf(v, 2.0f, -1.0f);      // = fl(fl(2 u) - 1): the doubling is exact
     float4 q;
     if (PERSPECTIVE) {
         q = make_float4(mul_rn(inv[0], x), mul_rn(inv[5], y), inv[14], add_rn(mul_rn(inv[11], depth), inv[15]));
     } else {
         q = mul44_rn(inv, make_float4(x, y, depth, 1.0f));
     }
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q.w));
-    const float rn = fmaf(r, fmaf(-q.w, r, 1.0f), r);        // one Newton step
-    r = (q.w == 0.0f) ? r : rn;                              // w = 0 (a sky sample): x * (1 / 0) = x / 0 = +-inf or NaN, as the division gives
-    return make_float3(q.x * r, q.y * r, q.z * r);
+    if (FAST) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q.w));
+        return make_float3(q.x * r, q.y * r, q.z * r);
+    }
+    const ExactDivisor dw = exact_divisor(q.w);       // the three IEEE quotients (vhr_common.cuh)
+    return make_float3(div_exact(q.x, dw), div_exact(q.y, dw), div_exact(q.z, dw));
 }
 
-template <bool PERSPECTIVE>
+// texture(depth, (u, v)).x of a SAMPLE, in two halves so that the loads of several samples are in flight together.
+// tap_setup: the tap selection and the two filter weights, exactly the oracle's (bilinear_setup): with t = fl(fl(u n) - 0.5) the snapped
+// coordinate floor(t 256 + 0.5) / 256 is the integer k = floor(fma(t, 256, 0.5)) (the product by 256 is exact and for |t| < 2^14 so is
+// the sum), texel = k >> 8, weight = (k & 255) / 256 — one F2I instead of two FRND + F2I + the float fraction. Returns the texel index
+// y0 W + x0, or -1 for anything unusual (texel outside the image, |t| >= 2^14, NaN): those samples take the general path.
+// The four taps then come as ONE 16-byte load from the quad image (QUADS) — a gather at 32 unrelated places costs the L1 about two
+// cycles per 128-byte line and load instruction (tools/probes/probe_tld4.cu: 33 M footprints in 114 us as quads, 238 us as four 4-byte
+// loads, 121 us as texture gathers), and it is this, not the arithmetic, that bounds the kernel once the instructions are cut.
+struct Tap { int idx; float a, b; };
+template <bool QUADS>
+__device__ __forceinline__ Tap tap_setup(const SsaoParams &p, float u, float v) {
+    Tap t;
+    t.idx = -1; t.a = 0.0f; t.b = 0.0f;
+    const float tu = sub_rn(mul_rn(u, p.Wf), 0.5f), tv = sub_rn(mul_rn(v, p.Hf), 0.5f);
+    if (fabsf(tu) < 16384.0f && fabsf(tv) < 16384.0f) {
+        const int ku = __float2int_rd(fmaf(tu, 256.0f, 0.5f)), kv = __float2int_rd(fmaf(tv, 256.0f, 0.5f));
+        int x0 = ku >> 8, y0 = kv >> 8;
+        // the quad image has the REPEAT wrap of the right / bottom neighbour built in; without it both taps must be inside.
+        // One period of REPEAT is applied here (QUADS): the samples of a pixel within a radius of the image border fall outside by the
+        // dozen, and the general path for one lane is paid by the whole warp (ncu: 197 executed instructions per sample against
+        // ~125 in the listing before this was added)
+        if (QUADS) {
+            x0 += x0 < 0 ? p.W : 0; x0 -= x0 >= p.W ? p.W : 0;
+            y0 += y0 < 0 ? p.H : 0; y0 -= y0 >= p.H ? p.H : 0;
+        }
+        if ((unsigned)x0 < (unsigned)(p.W - (QUADS ? 0 : 1)) && (unsigned)y0 < (unsigned)(p.H - (QUADS ? 0 : 1))) {
+            // (2^23 + m) / 256 - 2^15 = m / 256 exactly: the weight without an integer-to-float conversion
+            t.a = fmaf(__uint_as_float(0x4B000000u | (uint32_t)(ku & 255)), 0.00390625f, -32768.0f);
+            t.b = fmaf(__uint_as_float(0x4B000000u | (uint32_t)(kv & 255)), 0.00390625f, -32768.0f);
+            t.idx = y0 * p.W + x0;
+        }
+    }
+    return t;
+}
+template <bool QUADS>
+__device__ __forceinline__ float4 tap_load(const SsaoParams &p, const Tap &t) {
+    const int i = t.idx < 0 ? 0 : t.idx;       // a sample on the general path loads texel 0 and ignores it
+    if (QUADS) return __ldg(p.quads + i);
+    const float *r0 = p.depth + i;
+    return make_float4(__ldg(r0), __ldg(r0 + 1), __ldg(r0 + p.W), __ldg(r0 + p.W + 1));
+}
+// (kept out of line: taken by the few taps on the REPEAT seam; inlined copies would triple the unrolled sample loop)
+__device__ __noinline__ float sample_depth_general(const SsaoParams &p, float u, float v) { return sample_depth(p, u, v); }
+
+// Pre-pass of the SSAO dispatch: the bilinear footprint of every depth texel as one float4 (8 MB read, 33 MB written at 1080p)
+__global__ void __launch_bounds__(256) depth_quads_kernel(const float *__restrict__ depth, float4 *__restrict__ quads, int W, int H) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int x1 = x + 1 == W ? 0 : x + 1, y1 = y + 1 == H ? 0 : y + 1;
+    const float *r0 = depth + (size_t)y * W, *r1 = depth + (size_t)y1 * W;
+    quads[(size_t)y * W + x] = make_float4(__ldg(r0 + x), __ldg(r0 + x1), __ldg(r1 + x), __ldg(r1 + x1));
+}
+
+// sin and cos of an angle in [0, 2 pi] (ssao.comp:38: random01 * 2 * PI): quadrant by the 1.5 * 2^23 rounding constant, two-term
+// Cody-Waite reduction to |f| <= pi / 4, degree-7 / degree-8 minimax polynomials (the single-precision cephes coefficients). Within one
+// ulp of the correctly rounded value on all 2^23 angles the RNG can produce (tests/test_oracle_cpu.py restates it in numpy), at a third
+// of sincosf's instructions — and NOT the default (study switch VHR_SSAO_VARIANT bit 2): it differs from the C library's correctly
+// rounded value on 12-17 % of the angles where sincosf almost never does, which moves 1e-5 of the samples across a 1/256 filter step:
+// 0.05-0.13 % of the pixels of the small test images beyond the 1e-3 bar (measured), against 0.002 % with sincosf.
+__device__ __forceinline__ void sincos_turn(float x, float &s, float &c) {
+    const float m = fmaf(x, 0.636619772f, 12582912.0f);
+    const uint32_t q = __float_as_uint(m);
+    const float qf = m - 12582912.0f;
+    float f = fmaf(qf, -1.57079637f, x);
+    f = fmaf(qf, 4.37113883e-8f, f);
+    const float f2 = f * f;
+    float sp = fmaf(f2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, f2, -1.6666654611e-1f);
+    const float sn = fmaf(f * f2, sp, f);
+    float cp = fmaf(f2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, f2, 4.166664568298827e-2f);
+    cp = fmaf(cp, f2, -0.5f);
+    const float cs = fmaf(cp, f2, 1.0f);
+    const bool odd = (q & 1u) != 0u;
+    s = __uint_as_float(__float_as_uint(odd ? cs : sn) ^ ((q << 30) & 0x80000000u));
+    c = __uint_as_float(__float_as_uint(odd ? sn : cs) ^ (((q + 1u) << 30) & 0x80000000u));
+}
+
+// VARIANT (study switch VHR_SSAO_VARIANT): 0 = default: fixed-point filter coordinate, the four taps of a sample as one load from the
+// quad image, four samples' loads in flight, everything else in the oracle's operations and order (same bits as the loop of rounds 1-2,
+// 255 -> ~160 instructions per sample); bit 0 = that older loop; bit 1 = four 4-byte tap loads instead of the quad image; bit 2 =
+// sincos_turn instead of sincosf; bit 3 = the continuous part (interpolation, division by w, occlusion term) on fused / approximate
+// operations — ~110 instructions per sample, but Q - P cancels eight digits for a sample next to the pixel, so one ulp of Q moves
+// that sample's term by up to 1e-2: 0.05-0.13 % of the pixels of the small test images beyond the 1e-3 bar (PSNR 80 dB; measured).
+template <bool PERSPECTIVE, int VARIANT>
 __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoParams p, const __grid_constant__ PerFrameData pfd) {
     const int gx = blockIdx.x * 32 + threadIdx.x;
     const int gy = p.y_begin + blockIdx.y * 8 + threadIdx.y;
@@ -94,20 +181,62 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
     float perspective_radius = __fdiv_rn(p.radius, P.z);
     uint32_t rng = seed_thread(((uint32_t)gy * (uint32_t)pfd.display_size[1] + (uint32_t)gx) * pfd.frame_index);
     float sum = 0.0f;
-    for (int i = 0; i < 16; ++i) {
-        float ang = mul_rn(mul_rn(random01(rng), 2.0f), VHR_PI);
-        float dist = mul_rn(random01(rng), perspective_radius);
-        // full-precision sincosf: MUFU sin / cos (abs error ~5e-7) was measured to break the 1e-3 parity bar — across a depth edge the
-        // bilinear depth tap is unprojected through znear / depth, which amplifies a 1e-6 shift of the tap (1.5e-3 on one pixel of
-        // tests/test_ssao_gpu.py)
-        float s, c;
-        sincosf(ang, &s, &c);
-        float su = add_rn(cu, mul_rn(c, dist)), sv = add_rn(cv, mul_rn(s, dist));
-        float3 Q = unproject_sample<PERSPECTIVE>(pfd.camera_proj_inverse, sample_depth(p, su, sv), su, sv);
-        float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
-        // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
-        float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
-        sum = add_rn(sum, __fdiv_rn(num, add_rn(dot3_rn(V, V), 1e-4f)));
+    if (VARIANT & 1) {
+        for (int i = 0; i < 16; ++i) {
+            float ang = mul_rn(mul_rn(random01(rng), 2.0f), VHR_PI);
+            float dist = mul_rn(random01(rng), perspective_radius);
+            float s, c;
+            sincosf(ang, &s, &c);
+            float su = add_rn(cu, mul_rn(c, dist)), sv = add_rn(cv, mul_rn(s, dist));
+            float3 Q = unproject_sample<PERSPECTIVE, false>(pfd.camera_proj_inverse, sample_depth(p, su, sv), su, sv);
+            float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
+            // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
+            float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
+            sum = add_rn(sum, __fdiv_rn(num, add_rn(dot3_rn(V, V), 1e-4f)));
+        }
+    } else {
+        constexpr bool QUADS = !(VARIANT & 2), FAST = (VARIANT & 8) != 0;
+        constexpr int G = (VARIANT & 16) ? 4 : 1;  // samples whose taps are loaded together (bit 4: four; the kernel is issue-bound, it does not pay)
+#pragma unroll(G == 1 ? 4 : 1)
+        for (int i = 0; i < 16; i += G) {
+            float su[G], sv[G];
+            Tap tap[G];
+            float4 q[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                // fl(fl(r * 2) * PI) = fl(r * (2 PI)): the doubling is exact
+                const float ang = mul_rn(random01(rng), 2.0f * VHR_PI);
+                const float dist = mul_rn(random01(rng), perspective_radius);
+                float s, c;
+                if (VARIANT & 4) sincos_turn(ang, s, c);
+                else sincosf(ang, &s, &c);
+                su[j] = add_rn(cu, mul_rn(c, dist)); sv[j] = add_rn(cv, mul_rn(s, dist));
+                tap[j] = tap_setup<QUADS>(p, su[j], sv[j]);
+                q[j] = tap_load<QUADS>(p, tap[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                float d;
+                if (tap[j].idx < 0) d = sample_depth_general(p, su[j], sv[j]);
+                else if (FAST) {
+                    const float top = fmaf(tap[j].a, q[j].y - q[j].x, q[j].x), bot = fmaf(tap[j].a, q[j].w - q[j].z, q[j].z);
+                    d = fmaf(tap[j].b, bot - top, top);
+                } else d = bilerp_rn(tap[j].a, tap[j].b, q[j].x, q[j].y, q[j].z, q[j].w);
+                const float3 Q = unproject_sample<PERSPECTIVE, FAST>(pfd.camera_proj_inverse, d, su[j], sv[j]);
+                // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
+                if (FAST) {
+                    const float3 V = make_float3(Q.x - P.x, Q.y - P.y, Q.z - P.z);
+                    const float num = fmaxf(fmaf(V.x, N.x, fmaf(V.y, N.y, fmaf(V.z, N.z, -1e-4f))), 0.0f);
+                    float r;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(V.x, V.x, fmaf(V.y, V.y, fmaf(V.z, V.z, 1e-4f)))));
+                    sum = fmaf(num, r, sum);
+                } else {
+                    const float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
+                    const float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
+                    sum = add_rn(sum, div_exact(num, exact_divisor(add_rn(dot3_rn(V, V), 1e-4f))));
+                }
+            }
+        }
     }
     float ao = fmaxf(sub_rn(1.0f, mul_rn(0.125f, sum)), 0.0f);
     ssao_store(p, gy, pix, pack_rgba16f(make_float4(ao, ao, ao, ao)));
@@ -178,6 +307,7 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     p.W = (int)normals->width; p.H = (int)normals->height;
     if (!dispatch_range(ctx, normals, xg, yg, p.x_end, p.y_begin, p.y_end)) return VHR_OK;
     p.radius = radius;
+    p.Wf = (float)p.W; p.Hf = (float)p.H;
     p.normals = (const uint2 *)normals->ptr; p.depth = (const float *)depth->ptr; p.out = (uint2 *)out->ptr;
     // multi-GPU (row bands; every rank holds the full depth / normal G-buffer the samples reach into): the 13x13 blur on the
     // neighbours reads 6 rows of this output beyond their band -> pushed by this kernel, then the flag-word round trip
@@ -189,8 +319,28 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     bool perspective = true;
     for (int i = 0; i < 16; ++i)
         if (i != 0 && i != 5 && i != 11 && i != 14 && i != 15 && ctx->pfd.camera_proj_inverse[i] != 0.0f) perspective = false;
-    if (perspective) ssao_kernel<true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
-    else ssao_kernel<false><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    static const int variant = [] { const char *e = getenv("VHR_SSAO_VARIANT"); return e ? atoi(e) : 0; }();
+    p.quads = nullptr;
+    if (!(variant & 1) && !(variant & 2)) {
+        const size_t texels = (size_t)p.W * p.H;
+        if (ctx->depth_quads_texels < texels) {
+            if (ctx->d_depth_quads) { VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_depth_quads); ctx->d_depth_quads = nullptr; }
+            VHR_CUDA_CHECK(cudaMalloc(&ctx->d_depth_quads, texels * sizeof(float4)));
+            ctx->depth_quads_texels = texels;
+        }
+        // the samples of a row band reach any row of the depth image: the whole quad image on every rank
+        depth_quads_kernel<<<dim3((p.W + 31) / 32, (p.H + 7) / 8), block, 0, ctx->stream>>>(p.depth, ctx->d_depth_quads, p.W, p.H);
+        VHR_CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        p.quads = ctx->d_depth_quads;
+    }
+#define VHR_SSAO_CASE(V) case V: if (perspective) ssao_kernel<true, V><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); \
+                                 else ssao_kernel<false, V><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;
+    switch (variant) {
+        VHR_SSAO_CASE(0) VHR_SSAO_CASE(1) VHR_SSAO_CASE(2) VHR_SSAO_CASE(4) VHR_SSAO_CASE(8) VHR_SSAO_CASE(12) VHR_SSAO_CASE(16) VHR_SSAO_CASE(24)
+        default: return fail(VHR_ERR_INVALID, "VHR_SSAO_VARIANT = %d (0, 1, 2, 4, 8, 12, 16 or 24)", variant);
+    }
+#undef VHR_SSAO_CASE
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return p.push.rows ? peer_sync_neighbours(ctx) : VHR_OK;

@@ -17,12 +17,17 @@
 
 #include "vhr_internal.h"
 
+#ifndef VHR_SSR_STEPS_PER_ROUND
+#define VHR_SSR_STEPS_PER_ROUND 2
+#endif
+
 namespace vhr {
 
 struct SsrParams {
     int W, H;
     int x_end, y_begin, y_end;
     float step_size, thickness;
+    float Wf, Hf;              // (float)W, (float)H
     int n_steps;               // int(ray_distance / step_size), ssr.comp:89
     int bsearch_steps;
     const uint32_t *albedo;    // binding 0 (BGRA8, sampled)
@@ -42,8 +47,8 @@ struct Taps {
 __device__ __forceinline__ Taps taps_for(const SsrParams &p, float u, float v) {
     int x0, x1, y0, y1;
     Taps t;
-    bilinear_setup(u, p.W, x0, x1, t.a);
-    bilinear_setup(v, p.H, y0, y1, t.b);
+    bilinear_setup(u, p.W, p.Wf, x0, x1, t.a);
+    bilinear_setup(v, p.H, p.Hf, y0, y1, t.b);
     t.i00 = (size_t)y0 * p.W + x0; t.i10 = (size_t)y0 * p.W + x1;
     t.i01 = (size_t)y1 * p.W + x0; t.i11 = (size_t)y1 * p.W + x1;
     return t;
@@ -76,19 +81,28 @@ __device__ __forceinline__ float3 sample_albedo(const uint32_t *img, const Taps 
 }
 __device__ __forceinline__ float distance_rn(float3 a, float3 b) {
     const float3 d = make_float3(sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z));
-    return sqrtf(dot3_rn(d, d));
+    return sqrt_exact(dot3_rn(d, d));
 }
 
 // One probe of the march / the binary search (ssr.comp:90-99, 115-123): delta_distance at `offset` along the ray and
-// the uv the ray point projects to.
+// the uv the ray point projects to. Same operations and order as the oracle; the five IEEE divisions (two by clip.w, three by the
+// unprojection's w) and the two square roots go through div_exact / sqrt_exact (vhr_common.cuh): same bits, but a ray point or a depth
+// tap on the sky (w = 0, distances inf / NaN — most rays end there) no longer sends the warp through the library's slow paths, which
+// was more than half of this kernel's time. clip.z is never formed.
 __device__ __forceinline__ float probe(const SsrParams &p, const PerFrameData &pfd, float3 P, float3 dir, float3 cam, float offset,
                                        float &su, float &sv) {
     const float3 rp = make_float3(add_rn(P.x, mul_rn(dir.x, offset)), add_rn(P.y, mul_rn(dir.y, offset)), add_rn(P.z, mul_rn(dir.z, offset)));
     const float distance_to_ray = distance_rn(cam, rp);
-    const float4 clip = mul44_rn(p.pv, make_float4(rp.x, rp.y, rp.z, 1.0f));
-    su = add_rn(mul_rn(__fdiv_rn(clip.x, clip.w), 0.5f), 0.5f);
-    sv = add_rn(mul_rn(__fdiv_rn(clip.y, clip.w), 0.5f), 0.5f);
-    const float3 sp = unproject_rn(pfd.camera_viewproj_inverse, sample_depth(p, su, sv), su, sv);
+    const float *m = p.pv;
+    const float cx = dot4_rn(m[0], rp.x, m[4], rp.y, m[8], rp.z, m[12], 1.0f);
+    const float cy = dot4_rn(m[1], rp.x, m[5], rp.y, m[9], rp.z, m[13], 1.0f);
+    const float cw = dot4_rn(m[3], rp.x, m[7], rp.y, m[11], rp.z, m[15], 1.0f);
+    const ExactDivisor dw = exact_divisor(cw);
+    su = add_rn(mul_rn(div_exact(cx, dw), 0.5f), 0.5f);
+    sv = add_rn(mul_rn(div_exact(cy, dw), 0.5f), 0.5f);
+    const float4 q = mul44_rn(pfd.camera_viewproj_inverse, make_float4(sub_rn(mul_rn(su, 2.0f), 1.0f), sub_rn(mul_rn(sv, 2.0f), 1.0f), sample_depth(p, su, sv), 1.0f));
+    const ExactDivisor dq = exact_divisor(q.w);
+    const float3 sp = make_float3(div_exact(q.x, dq), div_exact(q.y, dq), div_exact(q.z, dq));
     return sub_rn(distance_to_ray, distance_rn(cam, sp));
 }
 
@@ -115,19 +129,30 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
 
     bool found = false;
     float prev_step = 0.0f, final_step = 0.0f;
-    float su, sv;
     // A sky pixel (depth 0 -> w = 0) has a non-finite P: every distance along its ray is inf or NaN, the window test
     // 0.3 < delta < thickness can never pass, so the march is skipped (same result as walking all of it).
     const bool finite_p = fabsf(P.x) <= 3.0e38f && fabsf(P.y) <= 3.0e38f && fabsf(P.z) <= 3.0e38f;
-    for (int i = 0; finite_p && i < p.n_steps; ++i) {                                            // ssr.comp:89-108
-        const float offset = mul_rn(p.step_size, (float)i);
-        const float delta = probe(p, pfd, P, dir, cam, offset, su, sv);
-        if (delta > 0.3f && delta < p.thickness) {
-            final_step = offset;
-            found = true;
-            break;
+    // The march, K steps per round: the K probes of a round are independent (address arithmetic, depth taps and the long division /
+    // square-root chains of K ray points overlap), then they are examined in order exactly as ssr.comp:89-108 walks them — the first
+    // step inside the window wins, later probes of the round are discarded (at most K - 1 wasted probes per pixel).
+    constexpr int K = VHR_SSR_STEPS_PER_ROUND;
+    for (int i = 0; finite_p && !found && i < p.n_steps; i += K) {
+        float delta[K], off[K], pu[K], pv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            off[k] = mul_rn(p.step_size, (float)(i + k));
+            delta[k] = probe(p, pfd, P, dir, cam, off[k], pu[k], pv[k]);
         }
-        prev_step = offset;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (found || i + k >= p.n_steps) break;
+            if (delta[k] > 0.3f && delta[k] < p.thickness) {
+                final_step = off[k];
+                found = true;
+            } else {
+                prev_step = off[k];
+            }
+        }
     }
     if (!found) {                                                                    // ssr.comp:110-112
         p.out[pix] = zero;
@@ -186,6 +211,7 @@ int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstant
     p.y_end = ctx->opt.row_end < 0 ? y_cov : std::min(y_cov, ctx->opt.row_end);
     if (p.x_end <= 0 || p.y_end <= p.y_begin) return VHR_OK;
     p.step_size = pc.step_size; p.thickness = pc.thickness;
+    p.Wf = (float)p.W; p.Hf = (float)p.H;
     p.n_steps = q < 0.0f ? 0 : (int)q;
     p.bsearch_steps = pc.bsearch_steps;
     p.albedo = (const uint32_t *)b[0]->ptr; p.normals = (const uint2 *)b[1]->ptr; p.motion = (const uint2 *)b[2]->ptr;

@@ -116,6 +116,8 @@ struct vhr_context {
     float *d_texel_lut = nullptr;                  // 512 floats: UNORM8 -> float, sRGB8 -> linear float
     float *d_refl_t = nullptr;                     // optional debug image: reflection-ray hit distance per pixel
     uint32_t *d_ray_queue = nullptr;               // head of the persistent ray kernel's pixel queue
+    float4 *d_depth_quads = nullptr;               // ssao.comp: the 2x2 bilinear footprint of every depth texel, one 16-byte word (ssao_kernels.cu)
+    size_t depth_quads_texels = 0;
     int raygen_blocks = 0;                         // resident grid of the persistent ray kernel (SMs x blocks/SM)
     vhr::Bvh bvh;
     vhr::Options opt;
