@@ -12,6 +12,16 @@ from vulkanhybridrenderer_b200 import camera, capi, gltf_export, host_api, scene
 from vulkanhybridrenderer_b200 import types as T
 
 
+@pytest.fixture(autouse=True, params=["cgltf", "own"])
+def parser(request, monkeypatch):
+    """Every test of this file runs twice: through the reference's vendored cgltf.h (the default when libvhr_host.so was built next to the
+    reference tree) and through the loader's own JSON / .glb / accessor reader (VHR_GLTF_PARSER=own, the only one otherwise)."""
+    if request.param == "cgltf" and not host_api.has_cgltf():
+        pytest.skip("libvhr_host.so was built without the reference's vendored cgltf.h")
+    monkeypatch.setenv("VHR_GLTF_PARSER", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def scene():
     sc = scenes.add_procedural_textures(scenes.sponza_like(3000, seed=5, width=96, height=64, n_clutter=10), size=32)
@@ -255,3 +265,29 @@ def test_jpeg_textures_load_through_the_vendored_stb_image(tmp_path, scene):
         assert min(errs) < 2.0, errs
         matched += 1
     assert matched == len(scene.textures)
+
+
+def _same_parse(a, b):
+    for key in ("vertices", "indices", "primitives", "prims_per_mesh", "camera", "light"):
+        assert np.array_equal(np.ascontiguousarray(a[key]).view(np.uint8), np.ascontiguousarray(b[key]).view(np.uint8)), key
+    assert len(a["textures"]) == len(b["textures"])
+    for ta, tb in zip(a["textures"], b["textures"]):
+        assert np.array_equal(ta.rgba, tb.rgba) and ta.format == tb.format and tuple(ta.sampler) == tuple(tb.sampler)
+
+
+@pytest.mark.parametrize("name,embed", [("scene.gltf", False), ("embedded.gltf", True), ("scene.glb", False)])
+def test_cgltf_and_the_own_reader_agree_byte_for_byte(tmp_path, scene, monkeypatch, name, embed):
+    """The two parsers behind SceneLoader::ParseScene hand back identical bytes: vertices, indices, primitives (transforms from
+    cgltf_node_transform_world against the loader's own TRS product), camera, light, decoded textures, formats and samplers — on the
+    exported procedural scene in its three containers and on the hand-built file with interleaved views and a node hierarchy."""
+    if not host_api.has_cgltf():
+        pytest.skip("libvhr_host.so was built without the reference's vendored cgltf.h")
+    paths = [gltf_export.export(scene, tmp_path / name, embed=embed)]
+    if not embed and name.endswith(".gltf"):
+        paths += [_hand_built_gltf(tmp_path, t)[0] for t in (5121, 5125)]
+    for path in paths:
+        monkeypatch.setenv("VHR_GLTF_PARSER", "cgltf")
+        a = host_api.parse_gltf(path)
+        monkeypatch.setenv("VHR_GLTF_PARSER", "own")
+        b = host_api.parse_gltf(path)
+        _same_parse(a, b)

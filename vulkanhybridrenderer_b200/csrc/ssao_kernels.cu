@@ -65,6 +65,30 @@ __device__ __forceinline__ float3 unproject_sample(const float *inv, float depth
     const ExactDivisor dw = exact_divisor(q.w);       // the three IEEE quotients (vhr_common.cuh)
     return make_float3(div_exact(q.x, dw), div_exact(q.y, dw), div_exact(q.z, dw));
 }
+__device__ __noinline__ float occlusion_term_library(float4 q, float3 P, float3 N) {
+    const float3 Q = make_float3(__fdiv_rn(q.x, q.w), __fdiv_rn(q.y, q.w), __fdiv_rn(q.z, q.w));
+    const float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
+    return __fdiv_rn(fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f), add_rn(dot3_rn(V, V), 1e-4f));
+}
+// One sample's occlusion term max(dot(V, N) - beta, 0) / (dot(V, V) + 1e-4), V = view-space sample - P (ssao.comp:42-44), in the oracle's
+// operations. The four IEEE divisions share two refined reciprocals and ONE fall-back branch (div_exact_flag).
+template <bool PERSPECTIVE>
+__device__ __forceinline__ float occlusion_term(const float *inv, float depth, float u, float v, float3 P, float3 N) {
+    const float x = fmaf(u, 2.0f, -1.0f), y = fmaf(v, 2.0f, -1.0f);      // = fl(fl(2 u) - 1): the doubling is exact
+    float4 q;
+    if (PERSPECTIVE) q = make_float4(mul_rn(inv[0], x), mul_rn(inv[5], y), inv[14], add_rn(mul_rn(inv[11], depth), inv[15]));
+    else q = mul44_rn(inv, make_float4(x, y, depth, 1.0f));
+    bool rare = false;
+    const ExactDivisor dw = exact_divisor(q.w);
+    const float3 Q = make_float3(div_exact_flag(q.x, dw, rare), div_exact_flag(q.y, dw, rare), div_exact_flag(q.z, dw, rare));
+    const float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
+    // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
+    const float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
+    const float den = add_rn(dot3_rn(V, V), 1e-4f);
+    float term = div_exact_flag(num, exact_divisor(den), rare);
+    if (rare) term = occlusion_term_library(q, P, N);       // a finite operand outside 2^+-40
+    return term;
+}
 
 // texture(depth, (u, v)).x of a SAMPLE, in two halves so that the loads of several samples are in flight together.
 // tap_setup: the tap selection and the two filter weights, exactly the oracle's (bilinear_setup): with t = fl(fl(u n) - 0.5) the snapped
@@ -222,18 +246,15 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
                     const float top = fmaf(tap[j].a, q[j].y - q[j].x, q[j].x), bot = fmaf(tap[j].a, q[j].w - q[j].z, q[j].z);
                     d = fmaf(tap[j].b, bot - top, top);
                 } else d = bilerp_rn(tap[j].a, tap[j].b, q[j].x, q[j].y, q[j].z, q[j].w);
-                const float3 Q = unproject_sample<PERSPECTIVE, FAST>(pfd.camera_proj_inverse, d, su[j], sv[j]);
-                // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
                 if (FAST) {
+                    const float3 Q = unproject_sample<PERSPECTIVE, true>(pfd.camera_proj_inverse, d, su[j], sv[j]);
                     const float3 V = make_float3(Q.x - P.x, Q.y - P.y, Q.z - P.z);
                     const float num = fmaxf(fmaf(V.x, N.x, fmaf(V.y, N.y, fmaf(V.z, N.z, -1e-4f))), 0.0f);
                     float r;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(V.x, V.x, fmaf(V.y, V.y, fmaf(V.z, V.z, 1e-4f)))));
                     sum = fmaf(num, r, sum);
                 } else {
-                    const float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
-                    const float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
-                    sum = add_rn(sum, div_exact(num, exact_divisor(add_rn(dot3_rn(V, V), 1e-4f))));
+                    sum = add_rn(sum, occlusion_term<PERSPECTIVE>(pfd.camera_proj_inverse, d, su[j], sv[j], P, N));
                 }
             }
         }

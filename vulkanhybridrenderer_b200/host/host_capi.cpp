@@ -147,6 +147,7 @@ int vhrh_load_gltf(vhrh_renderer *r, const char *path) {
 }
 // wh[2] receives the extent; rgba (capacity bytes) the RGBA8 texels when large enough
 int vhrh_has_stb_image(void) { return SceneLoader::HasStbImage() ? 1 : 0; }
+int vhrh_has_cgltf(void) { return SceneLoader::HasCgltf() ? 1 : 0; }
 
 int vhrh_decode_png(const uint8_t *data, size_t size, uint32_t *wh, uint8_t *rgba, size_t capacity) {
     if (!data || !wh) return VHR_ERR_INVALID;

@@ -5,6 +5,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
 
@@ -31,7 +32,31 @@
 #endif
 #endif
 
+// Document parsing = the reference's own parser, cgltf.h (scene_loader.cpp:233-235, 338-341: cgltf_parse_file / cgltf_load_buffers, the
+// accessor readers and cgltf_node_transform_world), taken the same way: through the include path, nothing copied. Without it (or with
+// VHR_GLTF_PARSER=own in the environment) this file's own JSON / .glb / accessor reader does the same job; tests/test_scene_loader_cpu.py
+// runs every case through both and compares the results field by field.
+#if defined(__has_include)
+#if __has_include("cgltf/cgltf.h")
+#define VHR_HAVE_CGLTF 1
+#define CGLTF_IMPLEMENTATION
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wunused-function"
+#pragma GCC diagnostic ignored "-Wsign-compare"
+#pragma GCC diagnostic ignored "-Wmissing-field-initializers"
+#include "cgltf/cgltf.h"
+#pragma GCC diagnostic pop
+#endif
+#endif
+
 namespace SceneLoader {
+bool HasCgltf() {
+#ifdef VHR_HAVE_CGLTF
+    return true;
+#else
+    return false;
+#endif
+}
 bool HasStbImage() {
 #ifdef VHR_HAVE_STB_IMAGE
     return true;
@@ -592,6 +617,97 @@ VkSamplerAddressMode GetVkAddressMode(int mode) {
     }
 }
 
+// scene_loader.cpp:43-72: the camera node
+void setup_camera(Scene &scene, const Mat4 &M, float yfov, float aspect, float znear) {
+    // VkUtils::InfiniteReverseDepthProjection (vulkan_utils.h:494-503)
+    const float scale = 1.0f / tanf(yfov * 0.5f);
+    Camera &c = scene.camera;
+    memset(c.perspective, 0, sizeof(c.perspective));
+    c.perspective[0] = scale / aspect; c.perspective[5] = scale; c.perspective[11] = -1.0f; c.perspective[14] = znear;
+    // glm::extractEulerAngleYXZ, then transform = T * glm::yawPitchRoll(yaw, pitch, roll) (drops any scale)
+    const float T1 = atan2f(M.m[8], M.m[10]);
+    const float C2 = sqrtf(M.m[1] * M.m[1] + M.m[5] * M.m[5]);
+    const float T2 = atan2f(-M.m[9], C2);
+    const float S1 = sinf(T1), C1 = cosf(T1);
+    const float T3 = atan2f(S1 * M.m[6] - C1 * M.m[4], C1 * M.m[0] - S1 * M.m[2]);
+    const float ch = cosf(T1), sh = sinf(T1), cp = cosf(T2), sp = sinf(T2), cb = cosf(T3), sb = sinf(T3);
+    Mat4 R = identity();
+    R.m[0] = ch * cb + sh * sp * sb; R.m[1] = sb * cp; R.m[2] = -sh * cb + ch * sp * sb;
+    R.m[4] = -ch * sb + sh * sp * cb; R.m[5] = cb * cp; R.m[6] = sb * sh + ch * sp * cb;
+    R.m[8] = sh * cp; R.m[9] = -sp; R.m[10] = ch * cp;
+    Mat4 Tm = identity();
+    Tm.m[12] = M.m[12]; Tm.m[13] = M.m[13]; Tm.m[14] = M.m[14];
+    const Mat4 TR = mul(Tm, R), view = inverse_rigid(TR);
+    memcpy(c.transform, TR.m, sizeof(TR.m));
+    memcpy(c.view, view.m, sizeof(view.m));
+    c.yaw = T1; c.pitch = T2; c.roll = T3;
+}
+
+// scene_loader.cpp:74-100: a KHR_lights_punctual directional light
+void setup_directional_light(Scene &scene, const Mat4 &M, const float col[3]) {
+    // glm::decompose -> rotation; direction = normalize(rot * (0,0,-1)) = minus the normalised third basis vector
+    float d[3] = {-M.m[8], -M.m[9], -M.m[10]};
+    const float len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (len > 0) { d[0] /= len; d[1] /= len; d[2] /= len; }
+    DirectionalLight &dl = scene.directional_light;
+    // glm::ortho(-8, 8, -8, 8, 12, 0.1) with GLM_FORCE_DEPTH_ZERO_TO_ONE (right-handed, depth 0..1; pch.h:39)
+    Mat4 P = identity();
+    const float l = -8, r = 8, b = -8, t = 8, zn = 12.0f, zf = 0.1f;
+    P.m[0] = 2 / (r - l); P.m[5] = 2 / (t - b); P.m[10] = -1 / (zf - zn);
+    P.m[12] = -(r + l) / (r - l); P.m[13] = -(t + b) / (t - b); P.m[14] = -zn / (zf - zn);
+    // glm::lookAt(-dir * 12, 0, (0,1,0)), right-handed
+    const float eye[3] = {-d[0] * 12.0f, -d[1] * 12.0f, -d[2] * 12.0f};
+    float f[3] = {-eye[0], -eye[1], -eye[2]};
+    const float fl = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    for (float &v : f) v /= fl;
+    const float up[3] = {0, 1, 0};
+    float s[3] = {f[1] * up[2] - f[2] * up[1], f[2] * up[0] - f[0] * up[2], f[0] * up[1] - f[1] * up[0]};
+    const float sl = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+    for (float &v : s) v /= sl;
+    const float u[3] = {s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]};
+    Mat4 V = identity();
+    V.m[0] = s[0]; V.m[4] = s[1]; V.m[8] = s[2];
+    V.m[1] = u[0]; V.m[5] = u[1]; V.m[9] = u[2];
+    V.m[2] = -f[0]; V.m[6] = -f[1]; V.m[10] = -f[2];
+    V.m[12] = -(s[0] * eye[0] + s[1] * eye[1] + s[2] * eye[2]);
+    V.m[13] = -(u[0] * eye[0] + u[1] * eye[1] + u[2] * eye[2]);
+    V.m[14] = f[0] * eye[0] + f[1] * eye[1] + f[2] * eye[2];
+    const Mat4 PV = mul(P, V);
+    memcpy(dl.projview, PV.m, sizeof(PV.m));
+    dl.direction[0] = d[0]; dl.direction[1] = d[1]; dl.direction[2] = d[2]; dl.direction[3] = 0.0f;
+    dl.color[0] = col[0]; dl.color[1] = col[1]; dl.color[2] = col[2]; dl.color[3] = 1.0f;
+    const float intensity = scene.name == "Pica.glb" ? 2.0f : 30.0f;                  // :98 (the glTF intensity is ignored)
+    for (float &v : dl.intensity) v = intensity;
+}
+
+// scene_loader.cpp:317-329: no directional light in the file
+void default_directional_light(Scene &scene) {
+    DirectionalLight &dl = scene.directional_light;
+    dl = DirectionalLight{};
+    dl.direction[0] = 0.0f; dl.direction[1] = -1.0f; dl.direction[2] = 0.01f; dl.direction[3] = 0.0f;
+    dl.color[0] = dl.color[1] = dl.color[2] = 1.0f; dl.color[3] = 0.0f;
+}
+
+// scene_loader.cpp:284-290: four channels whatever the file holds
+void decode_image(const std::vector<uint8_t> &bytes, ParsedTexture &pt, const std::string &what) {
+    std::string err;
+    bool decoded = false;
+#ifdef VHR_HAVE_STB_IMAGE
+    {
+        int x = 0, y = 0, n = 0;
+        if (uint8_t *px = stbi_load_from_memory(bytes.data(), (int)bytes.size(), &x, &y, &n, STBI_rgb_alpha)) {
+            pt.width = (uint32_t)x; pt.height = (uint32_t)y;
+            pt.rgba.assign(px, px + (size_t)x * y * 4);
+            stbi_image_free(px);
+            decoded = true;
+        } else {
+            err = std::string("stb_image: ") + (stbi_failure_reason() ? stbi_failure_reason() : "unknown failure");
+        }
+    }
+#endif
+    if (!decoded && !DecodePNG(bytes.data(), bytes.size(), pt.width, pt.height, pt.rgba, err)) bad(what + ": " + err);
+}
+
 int texture_of(const Json *info) {      // textureInfo object -> texture index or -1
     if (!info || info->type != Json::Object) return -1;
     return info->integer("index", -1);
@@ -599,7 +715,7 @@ int texture_of(const Json *info) {      // textureInfo object -> texture index o
 
 }  // namespace
 
-void ParseScene(const char *path, ParsedScene &out) {
+static void ParseSceneOwn(const char *path, ParsedScene &out) {
     Document doc;
     load_document(path, doc);
     out = ParsedScene();
@@ -649,22 +765,7 @@ void ParseScene(const char *path, ParsedScene &out) {
             bytes.assign(p, p + len);
         }
         ParsedTexture pt;
-        std::string err;
-        bool decoded = false;
-#ifdef VHR_HAVE_STB_IMAGE
-        {   // scene_loader.cpp:284-290: four channels whatever the file holds
-            int x = 0, y = 0, n = 0;
-            if (uint8_t *px = stbi_load_from_memory(bytes.data(), (int)bytes.size(), &x, &y, &n, STBI_rgb_alpha)) {
-                pt.width = (uint32_t)x; pt.height = (uint32_t)y;
-                pt.rgba.assign(px, px + (size_t)x * y * 4);
-                stbi_image_free(px);
-                decoded = true;
-            } else {
-                err = std::string("stb_image: ") + (stbi_failure_reason() ? stbi_failure_reason() : "unknown failure");
-            }
-        }
-#endif
-        if (!decoded && !DecodePNG(bytes.data(), bytes.size(), pt.width, pt.height, pt.rgba, err)) bad("image " + std::to_string(img) + ": " + err);
+        decode_image(bytes, pt, "image " + std::to_string(img));
         pt.format = tu.second;
         pt.name = image.str("name", image.str("uri"));
         const int smp = tex.integer("sampler", -1);
@@ -698,29 +799,7 @@ void ParseScene(const char *path, ParsedScene &out) {
             if (cam.str("type") != "perspective") bad("only perspective cameras are supported (scene_loader.cpp:44)");
             const Json &persp = cam.at("perspective");
             const float yfov = (float)persp.num("yfov", 1.0), aspect = (float)persp.num("aspectRatio", 1.0), znear = (float)persp.num("znear", 0.1);
-            // VkUtils::InfiniteReverseDepthProjection (vulkan_utils.h:494-503)
-            const float scale = 1.0f / tanf(yfov * 0.5f);
-            Camera &c = scene.camera;
-            memset(c.perspective, 0, sizeof(c.perspective));
-            c.perspective[0] = scale / aspect; c.perspective[5] = scale; c.perspective[11] = -1.0f; c.perspective[14] = znear;
-            const Mat4 M = node_world(doc, (int)ni);
-            // glm::extractEulerAngleYXZ, then transform = T * glm::yawPitchRoll(yaw, pitch, roll) (drops any scale)
-            const float T1 = atan2f(M.m[8], M.m[10]);
-            const float C2 = sqrtf(M.m[1] * M.m[1] + M.m[5] * M.m[5]);
-            const float T2 = atan2f(-M.m[9], C2);
-            const float S1 = sinf(T1), C1 = cosf(T1);
-            const float T3 = atan2f(S1 * M.m[6] - C1 * M.m[4], C1 * M.m[0] - S1 * M.m[2]);
-            const float ch = cosf(T1), sh = sinf(T1), cp = cosf(T2), sp = sinf(T2), cb = cosf(T3), sb = sinf(T3);
-            Mat4 R = identity();
-            R.m[0] = ch * cb + sh * sp * sb; R.m[1] = sb * cp; R.m[2] = -sh * cb + ch * sp * sb;
-            R.m[4] = -ch * sb + sh * sp * cb; R.m[5] = cb * cp; R.m[6] = sb * sh + ch * sp * cb;
-            R.m[8] = sh * cp; R.m[9] = -sp; R.m[10] = ch * cp;
-            Mat4 Tm = identity();
-            Tm.m[12] = M.m[12]; Tm.m[13] = M.m[13]; Tm.m[14] = M.m[14];
-            const Mat4 TR = mul(Tm, R), view = inverse_rigid(TR);
-            memcpy(c.transform, TR.m, sizeof(TR.m));
-            memcpy(c.view, view.m, sizeof(view.m));
-            c.yaw = T1; c.pitch = T2; c.roll = T3;
+            setup_camera(scene, node_world(doc, (int)ni), yfov, aspect, znear);
             continue;
         }
         int light_index = -1;
@@ -728,42 +807,9 @@ void ParseScene(const char *path, ParsedScene &out) {
             if (const Json *lp = ext->find("KHR_lights_punctual")) light_index = lp->integer("light", -1);
         if (light_index >= 0 && lights && (size_t)light_index < lights->size() && lights->array[light_index].str("type") == "directional") {   // :74-100
             const Json &light = lights->array[light_index];
-            const Mat4 M = node_world(doc, (int)ni);
-            // glm::decompose -> rotation; direction = normalize(rot * (0,0,-1)) = minus the normalised third basis vector
-            float d[3] = {-M.m[8], -M.m[9], -M.m[10]};
-            const float len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            if (len > 0) { d[0] /= len; d[1] /= len; d[2] /= len; }
-            DirectionalLight &dl = scene.directional_light;
-            // glm::ortho(-8, 8, -8, 8, 12, 0.1) with GLM_FORCE_DEPTH_ZERO_TO_ONE (right-handed, depth 0..1; pch.h:39)
-            Mat4 P = identity();
-            const float l = -8, r = 8, b = -8, t = 8, zn = 12.0f, zf = 0.1f;
-            P.m[0] = 2 / (r - l); P.m[5] = 2 / (t - b); P.m[10] = -1 / (zf - zn);
-            P.m[12] = -(r + l) / (r - l); P.m[13] = -(t + b) / (t - b); P.m[14] = -zn / (zf - zn);
-            // glm::lookAt(-dir * 12, 0, (0,1,0)), right-handed
-            const float eye[3] = {-d[0] * 12.0f, -d[1] * 12.0f, -d[2] * 12.0f};
-            float f[3] = {-eye[0], -eye[1], -eye[2]};
-            const float fl = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
-            for (float &v : f) v /= fl;
-            const float up[3] = {0, 1, 0};
-            float s[3] = {f[1] * up[2] - f[2] * up[1], f[2] * up[0] - f[0] * up[2], f[0] * up[1] - f[1] * up[0]};
-            const float sl = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
-            for (float &v : s) v /= sl;
-            const float u[3] = {s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]};
-            Mat4 V = identity();
-            V.m[0] = s[0]; V.m[4] = s[1]; V.m[8] = s[2];
-            V.m[1] = u[0]; V.m[5] = u[1]; V.m[9] = u[2];
-            V.m[2] = -f[0]; V.m[6] = -f[1]; V.m[10] = -f[2];
-            V.m[12] = -(s[0] * eye[0] + s[1] * eye[1] + s[2] * eye[2]);
-            V.m[13] = -(u[0] * eye[0] + u[1] * eye[1] + u[2] * eye[2]);
-            V.m[14] = f[0] * eye[0] + f[1] * eye[1] + f[2] * eye[2];
-            const Mat4 PV = mul(P, V);
-            memcpy(dl.projview, PV.m, sizeof(PV.m));
-            dl.direction[0] = d[0]; dl.direction[1] = d[1]; dl.direction[2] = d[2]; dl.direction[3] = 0.0f;
             float col[3] = {1, 1, 1};
             if (const Json *c = light.find("color")) for (int i = 0; i < 3 && i < (int)c->size(); ++i) col[i] = (float)c->array[i].number;
-            dl.color[0] = col[0]; dl.color[1] = col[1]; dl.color[2] = col[2]; dl.color[3] = 1.0f;
-            const float intensity = scene.name == "Pica.glb" ? 2.0f : 30.0f;                  // :98 (the glTF intensity is ignored)
-            for (float &v : dl.intensity) v = intensity;
+            setup_directional_light(scene, node_world(doc, (int)ni), col);
             have_directional_light = true;
             continue;
         }
@@ -835,12 +881,160 @@ void ParseScene(const char *path, ParsedScene &out) {
         }
         scene.meshes.push_back(std::move(mesh));
     }
-    if (!have_directional_light) {                                                             // :317-329
-        DirectionalLight &dl = scene.directional_light;
-        dl = DirectionalLight{};
-        dl.direction[0] = 0.0f; dl.direction[1] = -1.0f; dl.direction[2] = 0.01f; dl.direction[3] = 0.0f;
-        dl.color[0] = dl.color[1] = dl.color[2] = 1.0f; dl.color[3] = 0.0f;
+    if (!have_directional_light) default_directional_light(scene);                             // :317-329
+}
+
+#ifdef VHR_HAVE_CGLTF
+// ---------------------------------------------------------------------------------------------------------------------
+// The same flattening on cgltf's document (the reference's ParseglTF / ParseNode, scene_loader.cpp:40-334)
+// ---------------------------------------------------------------------------------------------------------------------
+static void ParseSceneCgltf(const char *path, ParsedScene &out) {
+    cgltf_options options{};
+    cgltf_data *data = nullptr;
+    const cgltf_result pr = cgltf_parse_file(&options, path, &data);                              // :338-341
+    if (pr != cgltf_result_success) bad(pr == cgltf_result_file_not_found ? std::string("cannot open '") + path + "'" : "cgltf_parse_file: error " + std::to_string((int)pr));
+    struct Guard { cgltf_data *d; ~Guard() { cgltf_free(d); } } guard{data};
+    const cgltf_result lr = cgltf_load_buffers(&options, data, path);                             // :234-235
+    if (lr != cgltf_result_success) bad("cgltf_load_buffers: error " + std::to_string((int)lr));
+    if (cgltf_validate(data) != cgltf_result_success) bad("cgltf_validate: accessor / buffer view / index out of range");
+    out = ParsedScene();
+    Scene &scene = out.scene;
+    scene.name = file_name(path);                                                                 // :338
+    const std::string dir = parent_dir(path);
+
+    // ---- textures to upload and their formats (:239-275): base colour sRGB, everything else UNORM; the first use decides
+    std::vector<std::pair<const cgltf_texture *, VkFormat>> to_upload;
+    auto want = [&](const cgltf_texture *tex, VkFormat fmt) {
+        if (!tex) return;
+        for (auto &t : to_upload)
+            if (t.first == tex) return;
+        to_upload.emplace_back(tex, fmt);
+    };
+    for (cgltf_size i = 0; i < data->meshes_count; ++i)
+        for (cgltf_size j = 0; j < data->meshes[i].primitives_count; ++j) {
+            const cgltf_material *mat = data->meshes[i].primitives[j].material;
+            if (!mat) continue;
+            if (mat->has_pbr_metallic_roughness) {
+                want(mat->pbr_metallic_roughness.base_color_texture.texture, VK_FORMAT_R8G8B8A8_SRGB);
+                want(mat->pbr_metallic_roughness.metallic_roughness_texture.texture, VK_FORMAT_R8G8B8A8_UNORM);
+            }
+            want(mat->normal_texture.texture, VK_FORMAT_R8G8B8A8_UNORM);
+        }
+    // ---- decode + describe (:277-309); the lookup table is keyed by the IMAGE, as in the reference
+    std::map<const cgltf_image *, int> slot_of_image;
+    for (auto &tu : to_upload) {
+        const cgltf_texture *tex = tu.first;
+        const cgltf_image *image = tex->image;
+        if (!image) bad("texture without a valid image source");
+        std::vector<uint8_t> bytes;
+        if (image->uri) bytes = load_uri(image->uri, dir);
+        else if (image->buffer_view && image->buffer_view->buffer && image->buffer_view->buffer->data) {
+            const uint8_t *p = (const uint8_t *)image->buffer_view->buffer->data + image->buffer_view->offset;
+            bytes.assign(p, p + image->buffer_view->size);
+        } else bad("image without uri or bufferView");
+        ParsedTexture pt;
+        decode_image(bytes, pt, "image " + std::to_string((int)(image - data->images)));
+        pt.format = tu.second;
+        pt.name = image->name ? image->name : (image->uri ? image->uri : "");
+        if (const cgltf_sampler *smp = tex->sampler)
+            pt.sampler = SamplerInfo{GetVkFilter(smp->mag_filter), GetVkFilter(smp->min_filter), GetVkAddressMode(smp->wrap_s), GetVkAddressMode(smp->wrap_t)};
+        slot_of_image[image] = (int)out.textures.size();
+        out.textures.push_back(std::move(pt));
     }
+    auto slot_for = [&](const cgltf_texture *tex) -> int {
+        if (!tex) return -1;
+        auto it = slot_of_image.find(tex->image);
+        return it == slot_of_image.end() ? -1 : it->second;
+    };
+
+    // ---- nodes in file order (:311-315 -> ParseNode :40-231)
+    bool have_directional_light = false;
+    for (cgltf_size ni = 0; ni < data->nodes_count; ++ni) {
+        const cgltf_node &node = data->nodes[ni];
+        Mat4 world;
+        cgltf_node_transform_world(&node, world.m);
+        if (node.camera) {                                                                        // :43-72
+            if (node.camera->type != cgltf_camera_type_perspective) bad("only perspective cameras are supported (scene_loader.cpp:44)");
+            const cgltf_camera_perspective &pc = node.camera->data.perspective;
+            setup_camera(scene, world, pc.yfov, pc.aspect_ratio != 0.0f ? pc.aspect_ratio : 1.0f, pc.znear);
+            continue;
+        }
+        if (node.light && node.light->type == cgltf_light_type_directional) {                     // :74-100
+            setup_directional_light(scene, world, node.light->color);
+            have_directional_light = true;
+            continue;
+        }
+        if (!node.mesh) continue;                                                                 // :102-104
+        Mesh mesh;
+        for (cgltf_size pi = 0; pi < node.mesh->primitives_count; ++pi) {
+            const cgltf_primitive &prim = node.mesh->primitives[pi];
+            if (prim.type != cgltf_primitive_type_triangles) bad("only triangle-list primitives are supported (scene_loader.cpp:112)");
+            const uint32_t vertex_offset = (uint32_t)out.vertices.size(), index_offset = (uint32_t)out.indices.size();
+            const cgltf_accessor *pos = nullptr, *nrm = nullptr, *tan = nullptr, *uv0 = nullptr, *uv1 = nullptr;
+            for (cgltf_size a = 0; a < prim.attributes_count; ++a) {                             // :123-147
+                const cgltf_attribute &at = prim.attributes[a];
+                auto expect = [&](cgltf_type t, const char *name) { if (at.data->type != t) bad(std::string(name) + ": unexpected accessor type"); };
+                if (at.type == cgltf_attribute_type_position) { expect(cgltf_type_vec3, "POSITION"); pos = at.data; }
+                else if (at.type == cgltf_attribute_type_normal) { expect(cgltf_type_vec3, "NORMAL"); nrm = at.data; }
+                else if (at.type == cgltf_attribute_type_tangent) { expect(cgltf_type_vec4, "TANGENT"); tan = at.data; }
+                else if (at.type == cgltf_attribute_type_texcoord && at.index == 0) { expect(cgltf_type_vec2, "TEXCOORD_0"); uv0 = at.data; }
+                else if (at.type == cgltf_attribute_type_texcoord && at.index == 1) { expect(cgltf_type_vec2, "TEXCOORD_1"); uv1 = at.data; }
+            }
+            if (!pos) bad("primitive without POSITION (scene_loader.cpp:149)");
+            if (pos->is_sparse || (nrm && nrm->is_sparse) || (tan && tan->is_sparse) || (uv0 && uv0->is_sparse) || (uv1 && uv1->is_sparse))
+                bad("sparse accessors are not supported");
+            for (cgltf_size j = 0; j < pos->count; ++j) {                                         // :150-173
+                Vertex v{};
+                cgltf_accessor_read_float(pos, j, v.pos, 3);
+                if (nrm && j < nrm->count) cgltf_accessor_read_float(nrm, j, v.normal, 3);
+                if (tan && j < tan->count) cgltf_accessor_read_float(tan, j, v.tangent, 4);
+                if (uv0 && j < uv0->count) cgltf_accessor_read_float(uv0, j, v.uv0, 2);
+                if (uv1 && j < uv1->count) cgltf_accessor_read_float(uv1, j, v.uv1, 2);
+                out.vertices.push_back(v);
+            }
+            if (!prim.indices) bad("primitive without indices (scene_loader.cpp:175)");
+            if (prim.indices->component_type != cgltf_component_type_r_8u && prim.indices->component_type != cgltf_component_type_r_16u &&
+                prim.indices->component_type != cgltf_component_type_r_32u)
+                bad("index accessor must be UNSIGNED_BYTE / SHORT / INT");
+            for (cgltf_size j = 0; j < prim.indices->count; ++j) {
+                const uint32_t k = (uint32_t)cgltf_accessor_read_index(prim.indices, j);
+                if (k >= pos->count) bad("index exceeds the primitive's vertex count");
+                out.indices.push_back(k);
+            }
+            Material material{{1.0f, 1.0f, 1.0f, 1.0f}, -1, -1, -1, 1.0f, 1.0f, 0, 0.0f};        // :182-218
+            if (const cgltf_material *mat = prim.material) {
+                const cgltf_pbr_metallic_roughness &pbr = mat->pbr_metallic_roughness;        // cgltf fills the defaults: factors 1
+                if (pbr.base_color_texture.texture) material.base_color_texture = slot_for(pbr.base_color_texture.texture);
+                else if (mat->has_pbr_metallic_roughness) memcpy(material.base_color, pbr.base_color_factor, sizeof(material.base_color));
+                if (pbr.metallic_roughness_texture.texture) material.metallic_roughness_texture = slot_for(pbr.metallic_roughness_texture.texture);
+                if (mat->has_pbr_metallic_roughness) { material.metallic_factor = pbr.metallic_factor; material.roughness_factor = pbr.roughness_factor; }
+                if (mat->normal_texture.texture) {
+                    material.normal_map = slot_for(mat->normal_texture.texture);
+                    if (!tan) bad("normal map without vertex tangents (scene_loader.cpp:212-213)");
+                }
+                if (mat->alpha_mode == cgltf_alpha_mode_mask) {
+                    material.alpha_mask = 1;
+                    material.alpha_cutoff = mat->alpha_cutoff;
+                }
+            }
+            Primitive p{};
+            memcpy(p.transform, world.m, sizeof(p.transform));
+            p.material = material;
+            p.vertex_offset = vertex_offset; p.index_offset = index_offset; p.index_count = (uint32_t)prim.indices->count;
+            mesh.primitives.push_back(p);
+        }
+        scene.meshes.push_back(std::move(mesh));
+    }
+    if (!have_directional_light) default_directional_light(scene);                                // :317-329
+}
+#endif
+
+void ParseScene(const char *path, ParsedScene &out) {
+#ifdef VHR_HAVE_CGLTF
+    const char *which = getenv("VHR_GLTF_PARSER");
+    if (!which || strcmp(which, "own") != 0) { ParseSceneCgltf(path, out); return; }
+#endif
+    ParseSceneOwn(path, out);
 }
 
 Scene LoadScene(ResourceManager &resource_manager, const char *path) {

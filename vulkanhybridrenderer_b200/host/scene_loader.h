@@ -4,9 +4,9 @@
 // ParseNode :40-231): same flattening of nodes -> meshes -> primitives into the global Vertex[] / uint32 indices[] /
 // Primitive[] arrays ResourceManager::UpdateGeometry consumes, same material mapping, same texture formats (base colour
 // sRGB, the rest UNORM) and glTF-sampler -> SamplerInfo mapping, same camera and directional-light set-up.
-// The reference parses with cgltf and decodes images with stb_image (third-party, vendored there, not copied here):
-// this file has its own small JSON / .glb / accessor reader and a PNG decoder on zlib. JPEG images are rejected with an
-// error message (stb decodes them; convert to PNG).
+// The reference parses with cgltf and decodes images with stb_image (third-party, vendored there, not copied here): both are used
+// through the include path when the library is built next to the reference tree (HasCgltf / HasStbImage); the loader also has its
+// own small JSON / .glb / accessor reader and a PNG decoder on zlib, which are the fall-back and the cross-check of the tests.
 //
 // Parsing is split from uploading so the loader can be exercised without a GPU:
 //   ParseScene(path, out)          file -> ParsedScene (pure host work)
@@ -18,6 +18,9 @@
 #include "render_graph.h"
 
 namespace SceneLoader {
+// true when the library was built against the reference's vendored cgltf.h: ParseScene then parses with it (VHR_GLTF_PARSER=own in the
+// environment selects this file's own reader instead; without cgltf.h that reader is the only one)
+bool HasCgltf();
 // true when the library was built against the reference's vendored stb_image.h (JPEG / PNG / ... textures); false: own PNG decoder only
 bool HasStbImage();
 

@@ -175,6 +175,14 @@ def has_stb_image():
     return bool(L.vhrh_has_stb_image())
 
 
+def has_cgltf():
+    """True when libvhr_host.so was built against the reference's vendored cgltf.h: parse_gltf then parses with it (VHR_GLTF_PARSER=own in the
+    environment selects the loader's own reader)."""
+    L = lib()
+    L.vhrh_has_cgltf.restype = C.c_int
+    return bool(L.vhrh_has_cgltf())
+
+
 def decode_png(data):
     """SceneLoader::DecodePNG: bytes -> [H, W, 4] uint8."""
     buf = np.frombuffer(bytes(data), np.uint8)
