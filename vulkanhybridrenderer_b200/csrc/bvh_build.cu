@@ -64,7 +64,13 @@ __global__ void extract_triangles_kernel(const Vertex *__restrict__ verts, const
         TriRef r;
         r.v0 = make_float4(v[0].x, v[0].y, v[0].z, __uint_as_float(g));
         r.v1 = make_float4(v[1].x, v[1].y, v[1].z, __uint_as_float(k));
-        r.v2 = make_float4(v[2].x, v[2].y, v[2].z, 0.0f);
+        // v2.w: 1 = a candidate hit on this triangle has to go through the any-hit stage (gbuf.frag's discards / shadow_anyhit.rahit):
+        // an alpha-masked material, a base-colour texture index (its texel's alpha may be 0 or below the cutoff; the image may arrive
+        // after this build) or a base colour with alpha 0. 0 = every any-hit stage of the path accepts it without looking the material up —
+        // the closest-hit traversals test the flag in the register the vertex came in instead of chasing triangle -> primitive -> material
+        // for every candidate.
+        const bool any_hit_stage = p.material.alpha_mask == 1 || p.material.base_color_texture >= 0 || p.material.base_color[3] == 0.0f;
+        r.v2 = make_float4(v[2].x, v[2].y, v[2].z, __uint_as_float(any_hit_stage ? 1u : 0u));
         out[t] = r;
         mn[0] = fminf(v[0].x, fminf(v[1].x, v[2].x)); mx[0] = fmaxf(v[0].x, fmaxf(v[1].x, v[2].x));
         mn[1] = fminf(v[0].y, fminf(v[1].y, v[2].y)); mx[1] = fmaxf(v[0].y, fmaxf(v[1].y, v[2].y));

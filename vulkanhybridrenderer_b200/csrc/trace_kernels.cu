@@ -211,6 +211,7 @@ __device__ __forceinline__ void expand_leaves(const WideNode *__restrict__ nodes
 
 // while-while traversal (Aila & Laine 2009) over the 8-wide nodes, one ray per lane; every lane of the warp calls
 // trace() together (`alive` = this lane really has a ray) so callers never diverge before the loop.
+// (a triangle whose record says no any-hit stage can reject it — v2.w = 0, bvh_build.cu — is accepted without the call)
 // `accept(tri, u, v)` is the any-hit stage: a candidate it rejects is ignored and the traversal goes on (the G-buffer
 // producer's alpha test, gbuf.frag:27-32). The hybrid path's own rays are gl_RayFlagsOpaqueEXT (raygen.rgen:39,51,64):
 // AcceptAll, which compiles to nothing.
@@ -261,7 +262,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
                 const float4 *tp = tris + (size_t)(tri_base + j) * 3;
                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
                 float t, u, v;
-                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && accept(tri_base + j, u, v)) {
+                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && (__float_as_uint(v2.w) == 0u || accept(tri_base + j, u, v))) {
                     if (ANY) return true;
                     tmax = t;
                     hit.t = t; hit.u = u; hit.v = v; hit.tri = tri_base + j;
@@ -331,7 +332,7 @@ __device__ __forceinline__ bool trace_batched(const WideNode *__restrict__ nodes
                 const float4 *tp = tris + (size_t)(tri_base + j) * 3;
                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
                 float t, u, v;
-                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && accept(tri_base + j, u, v)) {
+                if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && (__float_as_uint(v2.w) == 0u || accept(tri_base + j, u, v))) {
                     found = true;
                     if (ANY) { done = true; break; }
                     tmax = t;
