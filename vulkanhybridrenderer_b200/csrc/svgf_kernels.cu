@@ -147,7 +147,10 @@ __device__ __forceinline__ TemporalOut temporal_pixel(const TemporalParams &p, i
     return r;
 }
 
-__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ TemporalParams p) {
+#ifndef VHR_TEMPORAL_MIN_BLOCKS
+#define VHR_TEMPORAL_MIN_BLOCKS 1      // 6 / 8 (40 / 32 registers, spills) measured 2-4 us slower than the natural 48 registers / 5 blocks
+#endif
+__global__ void __launch_bounds__(256, VHR_TEMPORAL_MIN_BLOCKS) svgf_temporal_kernel(const __grid_constant__ TemporalParams p) {
     const int cx = blockIdx.x * 32 + threadIdx.x;
     const int cy = p.y_begin + blockIdx.y * 8 + threadIdx.y;
     if (cx >= p.x_end || cy >= p.y_end) return;
