@@ -245,3 +245,50 @@ def test_config5_view_batch_is_partitioned_exactly_and_views_render():
             assert np.isfinite(den).all() and 0.0 <= den[..., :2].min() and den[..., :2].max() <= 1.0 + 1e-3
             sums.append(float(den[..., :2].sum()))
     assert len(set(round(s, 1) for s in sums)) == len(sums), "different views must give different frames"
+
+
+# ---- the rows around the path at the size the metric is quoted on -------------------------------------------------
+def test_next_rows_1080p_260k():
+    """ssao.comp + ssao_blur.comp (whole frame), ssr.comp (a 96-row band: 250 march steps per pixel on the CPU) and composition.frag (whole
+    frame, screen-space modes) at 1920x1080 on the 260 k-triangle scene, from the G-buffer the CUDA producer wrote, against the
+    reference's own shaders compiled for the CPU (checker). The small-size tests pin the arithmetic; this is the same comparison at
+    the BASELINE size, where sample radii, march lengths and REPEAT wrap-arounds are those of a real frame."""
+    W, H = 1920, 1080
+    sc = scenes.sponza_like(260_000, seed=1, width=W, height=H)
+    seq = camera.FrameSequencer(W, H, sc.light)
+    seq.next(sc.camera)
+    cam = sc.camera
+    cam.set_pose(cam.position + np.array([0.03, 0.0, 0.01]), cam.yaw + 0.002, cam.pitch)
+    pfd = seq.next(cam)
+    with capi.Context(W, H) as ctx:
+        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+        path = HP.HybridRenderPath(ctx, W, H, ssao=True, composition=F4, shadow_map_size=(64, 64))
+        g = _gbuffer_on_gpu(ctx, path, pfd, W, H)
+        g["albedo"] = ctx.image_download(path.gsets[0][HP.N_ALBEDO])
+        path.ssao_passes()
+        raw, blur = ctx.image_download(HP.N_SSAO_RAW), ctx.image_download(HP.N_SSAO)
+        path.ssr_pass()
+        ssr = ctx.image_download(HP.N_SSR)
+        # composition in the screen-space modes (shadow mode 2 = off: no shadow map on this path): consumes the SSAO and SSR images above
+        zero_rt = np.zeros((H, W, 2), np.float16)
+        ctx.image_upload(HP.N_RT, zero_rt)
+        path.composition_pass(2, 1, 1, denoised=False)
+        comp = ctx.image_download(HP.N_RENDER_OUTPUT).astype(np.float32)
+    ref_raw = O.ssao(pfd, g["depth"], g["normals"], 0.75)
+    Hh.assert_parity(raw, ref_raw, "next rows 1080p: ssao raw", outlier_frac=1e-4)
+    Hh.assert_parity(blur, O.ssao_blur(pfd, raw), "next rows 1080p: ssao blur (of the CUDA raw image)")
+    y0, y1 = 600, 696
+    ref_ssr = O.ssr(pfd, g["albedo"], g["normals"], g["motion"], g["depth"], rows=(y0, y1))
+    o, r = ssr[y0:y1].astype(np.float32), ref_ssr[y0:y1].astype(np.float32)
+    fo, fr = o[..., 3] > 0, r[..., 3] > 0
+    both = fo & fr
+    err = np.abs(o[both][:, :3] - r[both][:, :3]) / np.maximum(1.0, np.abs(r[both][:, :3]))
+    exact = float(np.mean(np.all(ssr[y0:y1].view(np.uint16) == ref_ssr[y0:y1].view(np.uint16), axis=-1)))
+    print(f"[parity] next rows 1080p: ssr rows {y0}..{y1}: found {fr.mean()*100:.1f}%, mask agreement {np.mean(fo == fr)*100:.4f}%, bit-exact {exact*100:.4f}%")
+    assert fr.mean() > 0.02 and np.mean(fo == fr) >= 0.999 and (not both.any() or np.mean(np.all(err <= 2e-3, axis=-1)) >= 0.999)
+    ref_comp = O.composition(pfd, g["albedo"], g["normals"], g["motion"], g["depth"], zero_rt, 2, 1, 1, ssao_img=blur, ssr_img=ssr,
+                             refl=np.zeros((H, W, 4), np.float16), shadow_map=np.zeros((64, 64), np.float32)).astype(np.float32)
+    d = np.abs(comp - ref_comp)
+    bad = d > 1e-3 * np.maximum(1.0, np.abs(ref_comp))
+    print(f"[parity] next rows 1080p: composition (2, 1, 1): max_abs={d.max():.3e} exact={np.mean(comp == ref_comp)*100:.2f}% beyond tolerance: {int(bad.sum())}")
+    assert np.isfinite(ref_comp).all() and np.isfinite(comp).all() and not bad.any()
