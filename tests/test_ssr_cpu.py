@@ -201,3 +201,43 @@ def test_ssr_properties(frame):
     top = O.ssr(*args, ray_distance=8.0, step_size=0.1, thickness=0.5, bsearch_steps=6, rows=(0, 24))
     bot = O.ssr(*args, ray_distance=8.0, step_size=0.1, thickness=0.5, bsearch_steps=6, rows=(24, H))
     assert np.array_equal(np.concatenate([top[:24], bot[24:]]).view(np.uint16), base.view(np.uint16))
+
+
+def test_window_estimate_stays_inside_its_error_bound():
+    """ssr_kernels.cu decides the two comparisons of a march step from an ESTIMATE of delta (MUFU reciprocal, fused dot products, rsqrt
+    instead of three IEEE quotients and two correctly rounded square roots) whenever the estimate is further than 32 * 2^-24 * (d1 + d2 +
+    |sp|_1) from both thresholds. Restated in numpy with worst-case MUFU errors (reciprocal +-1 ulp, rsqrt +-2 ulp) on random probes at
+    four scene scales: the estimate never leaves 8 * 2^-24 * (...) of the oracle-order value — a quarter of the band the kernel uses."""
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    N = 1_000_000
+
+    def r32(x):
+        return x.astype(f32)
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+    def pert(x, ulps):
+        return (x.view(np.int32) + rng.integers(-ulps, ulps + 1, x.shape).astype(np.int32)).view(f32)
+
+    def dist_rn(a, b):
+        d = r32(a - b)
+        s = r32(r32(r32(d[:, 0] * d[:, 0]) + r32(d[:, 1] * d[:, 1])) + r32(d[:, 2] * d[:, 2]))
+        return r32(np.sqrt(s.astype(np.float64)))
+
+    for scale in (1e-2, 1.0, 30.0, 1000.0):
+        cam = r32(rng.standard_normal((N, 3)) * scale)
+        rp = r32(cam + rng.standard_normal((N, 3)) * scale * rng.uniform(0.001, 3, (N, 1)))
+        w = r32(rng.uniform(1e-4, 10, N) * rng.choice([-1, 1], N))
+        q = r32(r32(cam + rng.standard_normal((N, 3)) * scale * rng.uniform(0.001, 3, (N, 1))) * w[:, None])
+        exact = r32(dist_rn(cam, rp) - dist_rn(cam, r32(q / w[:, None])))
+        s = r32(q * pert(r32(1.0 / w.astype(np.float64)), 1)[:, None])
+        e, f = r32(cam - s), r32(cam - rp)
+        d2q = fma(e[:, 0], e[:, 0], fma(e[:, 1], e[:, 1], r32(e[:, 2] * e[:, 2])))
+        d1q = fma(f[:, 0], f[:, 0], fma(f[:, 1], f[:, 1], r32(f[:, 2] * f[:, 2])))
+        d2 = r32(d2q * pert(r32(1 / np.sqrt(d2q.astype(np.float64))), 2))
+        d1 = r32(d1q * pert(r32(1 / np.sqrt(d1q.astype(np.float64))), 2))
+        est = r32(d1 - d2)
+        unit = (d1 + d2 + np.abs(s).sum(1)).astype(np.float64) * 2.0 ** -24
+        assert (np.abs(est.astype(np.float64) - exact.astype(np.float64)) <= 8 * unit).all(), scale

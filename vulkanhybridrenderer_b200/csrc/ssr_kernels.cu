@@ -17,9 +17,6 @@
 
 #include "vhr_internal.h"
 
-#ifndef VHR_SSR_STEPS_PER_ROUND
-#define VHR_SSR_STEPS_PER_ROUND 1      // 2 / 4 measured: 4.89 / 5.66 ms against 4.84 (the kernel is issue-bound, not latency-bound)
-#endif
 
 namespace vhr {
 
@@ -84,15 +81,30 @@ __device__ __forceinline__ float distance_rn(float3 a, float3 b) {
     return sqrt_exact(dot3_rn(d, d));
 }
 
-// One probe of the march / the binary search (ssr.comp:90-99, 115-123): delta_distance at `offset` along the ray and
-// the uv the ray point projects to. Same operations and order as the oracle; the five IEEE divisions (two by clip.w, three by the
-// unprojection's w) and the two square roots go through div_exact / sqrt_exact (vhr_common.cuh): same bits, but a ray point or a depth
-// tap on the sky (w = 0, distances inf / NaN — most rays end there) no longer sends the warp through the library's slow paths, which
-// was more than half of this kernel's time. clip.z is never formed.
-__device__ __forceinline__ float probe(const SsrParams &p, const PerFrameData &pfd, float3 P, float3 dir, float3 cam, float offset,
-                                       float &su, float &sv) {
+// The tail of a probe in the oracle's operations: three IEEE quotients, two correctly rounded square roots (ssr.comp:92-99). Out of line:
+// in_window() below only comes here when its cheap estimate of delta is within the error bound of a threshold.
+__device__ __noinline__ float delta_exact_tail(float3 cam, float3 rp, float4 q) {
+    const ExactDivisor dq = exact_divisor(q.w);
+    const float3 sp = make_float3(div_exact(q.x, dq), div_exact(q.y, dq), div_exact(q.z, dq));
+    return sub_rn(distance_rn(cam, rp), distance_rn(cam, sp));
+}
+
+// One probe of the march / the binary search (ssr.comp:90-99, 115-123): is delta_distance at `offset` along the ray inside the window
+// (0.3, thickness)? — and the uv the ray point projects to. EXACT decisions at a fraction of the exact arithmetic:
+//   * everything that selects the depth taps is computed in the oracle's operations and order: the ray point, clip.x / .y / .w (clip.z is
+//     never formed), the two IEEE quotients (div_exact), su / sv, the fixed-point filter coordinate, the rounded bilinear interpolation
+//     and the 4 x 4 unprojection product q — these are the oracle's bits;
+//   * the rest of the oracle's probe (three quotients q.xyz / q.w, two distances with correctly rounded square roots, their difference)
+//     only feeds two comparisons, so it is ESTIMATED: one MUFU reciprocal, fused dot products, rsqrt — each within a few ulps of the
+//     rounded operation it replaces: |estimate - oracle's delta| stays below 8 * 2^-24 * (d1 + d2 + |sp.x| + |sp.y| + |sp.z|) (sum of the
+//     per-operation bounds; 0.74 of it is the largest deviation on 1.6e7 random probes with worst-case MUFU errors,
+//     tests/test_ssr_cpu.py), and the band used is four times that. When the estimate is further than the band from both thresholds the
+//     comparisons are decided; otherwise (about one probe in 10^4, and NaN estimates) the oracle's tail is evaluated;
+//   * q.w = 0 exactly — a tap on the sky, where most rays end — makes the oracle's quotients +-inf or NaN, its delta -inf or NaN and both
+//     comparisons false: decided without arithmetic (q.w is the oracle's own value).
+__device__ __forceinline__ bool in_window(const SsrParams &p, const PerFrameData &pfd, float3 P, float3 dir, float3 cam, float offset,
+                                          float &su, float &sv) {
     const float3 rp = make_float3(add_rn(P.x, mul_rn(dir.x, offset)), add_rn(P.y, mul_rn(dir.y, offset)), add_rn(P.z, mul_rn(dir.z, offset)));
-    const float distance_to_ray = distance_rn(cam, rp);
     const float *m = p.pv;
     const float cx = dot4_rn(m[0], rp.x, m[4], rp.y, m[8], rp.z, m[12], 1.0f);
     const float cy = dot4_rn(m[1], rp.x, m[5], rp.y, m[9], rp.z, m[13], 1.0f);
@@ -101,9 +113,24 @@ __device__ __forceinline__ float probe(const SsrParams &p, const PerFrameData &p
     su = add_rn(mul_rn(div_exact(cx, dw), 0.5f), 0.5f);
     sv = add_rn(mul_rn(div_exact(cy, dw), 0.5f), 0.5f);
     const float4 q = mul44_rn(pfd.camera_viewproj_inverse, make_float4(sub_rn(mul_rn(su, 2.0f), 1.0f), sub_rn(mul_rn(sv, 2.0f), 1.0f), sample_depth(p, su, sv), 1.0f));
-    const ExactDivisor dq = exact_divisor(q.w);
-    const float3 sp = make_float3(div_exact(q.x, dq), div_exact(q.y, dq), div_exact(q.z, dq));
-    return sub_rn(distance_to_ray, distance_rn(cam, sp));
+    if (q.w == 0.0f) return false;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q.w));
+    const float sx = q.x * r, sy = q.y * r, sz = q.z * r;
+    const float ex = cam.x - sx, ey = cam.y - sy, ez = cam.z - sz;
+    const float fx = sub_rn(cam.x, rp.x), fy = sub_rn(cam.y, rp.y), fz = sub_rn(cam.z, rp.z);
+    const float d2q = fmaf(ex, ex, fmaf(ey, ey, ez * ez)), d1q = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+    float i2, i1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(i2) : "f"(d2q));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(d1q));
+    const float d2 = d2q * i2, d1 = d1q * i1;
+    const float delta = d1 - d2;
+    const float bound = (d1 + d2 + fabsf(sx) + fabsf(sy) + fabsf(sz)) * 1.9073486e-6f;      // 32 * 2^-24
+    const float lo = delta - 0.3f, hi = p.thickness - delta;
+    if (lo > bound && hi > bound) return true;
+    if (lo < -bound || hi < -bound) return false;
+    const float exact = delta_exact_tail(cam, rp, q);           // undecided (or NaN: 0 * inf, a zero distance)
+    return exact > 0.3f && exact < p.thickness;
 }
 
 }  // namespace
@@ -132,27 +159,17 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
     // A sky pixel (depth 0 -> w = 0) has a non-finite P: every distance along its ray is inf or NaN, the window test
     // 0.3 < delta < thickness can never pass, so the march is skipped (same result as walking all of it).
     const bool finite_p = fabsf(P.x) <= 3.0e38f && fabsf(P.y) <= 3.0e38f && fabsf(P.z) <= 3.0e38f;
-    // The march, K steps per round: the K probes of a round are independent (address arithmetic, depth taps and the long division /
-    // square-root chains of K ray points overlap), then they are examined in order exactly as ssr.comp:89-108 walks them — the first
-    // step inside the window wins, later probes of the round are discarded (at most K - 1 wasted probes per pixel).
-    constexpr int K = VHR_SSR_STEPS_PER_ROUND;
-    for (int i = 0; finite_p && !found && i < p.n_steps; i += K) {
-        float delta[K], off[K], pu[K], pv[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            off[k] = mul_rn(p.step_size, (float)(i + k));
-            delta[k] = probe(p, pfd, P, dir, cam, off[k], pu[k], pv[k]);
+    // (two and four probes per round, examined in order afterwards, were measured: 4.89 / 5.66 ms against 4.84 — the kernel is bound by
+    // instruction issue, not by latency)
+    for (int i = 0; finite_p && i < p.n_steps; ++i) {                                            // ssr.comp:89-108
+        const float offset = mul_rn(p.step_size, (float)i);
+        float pu, pv;
+        if (in_window(p, pfd, P, dir, cam, offset, pu, pv)) {
+            final_step = offset;
+            found = true;
+            break;
         }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (found || i + k >= p.n_steps) break;
-            if (delta[k] > 0.3f && delta[k] < p.thickness) {
-                final_step = off[k];
-                found = true;
-            } else {
-                prev_step = off[k];
-            }
-        }
+        prev_step = offset;
     }
     if (!found) {                                                                    // ssr.comp:110-112
         p.out[pix] = zero;
@@ -161,8 +178,7 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
     float mid_step = mul_rn(add_rn(prev_step, final_step), 0.5f);                    // ssr.comp:115-135
     float fu = 0.0f, fv = 0.0f;
     for (int i = 0; i < p.bsearch_steps; ++i) {
-        const float delta = probe(p, pfd, P, dir, cam, mid_step, fu, fv);
-        if (delta > 0.3f && delta < p.thickness) {
+        if (in_window(p, pfd, P, dir, cam, mid_step, fu, fv)) {
             mid_step = mul_rn(add_rn(prev_step, mid_step), 0.5f);
         } else {
             const float tmp = mid_step;
