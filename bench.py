@@ -865,8 +865,8 @@ def run_gpu(args):
                              "coordinate is quantised to 1/256 texel; the occlusion term cancels eight digits next to the pixel): issue-bound (89 %), "
                              "the depth gather at 47 % of the L1"),
                     "ssao_blur": ("ssao_blur_kernel", px * HP.BYTES_SSAO_BLUR, None),
-                    "ssr": ("ssr_kernel", px * HP.BYTES_SSR, "up to 250 march steps + 10 bisection steps per pixel, each one re-projection + bilinear "
-                            "depth tap in exactly rounded arithmetic: instruction-bound, the HBM fraction is tiny by construction"),
+                    "ssr": ("ssr_kernel", px * HP.BYTES_SSR, "up to 250 march steps + 10 bisection steps per pixel, each one re-projection + bilinear depth tap in the oracle's "
+                            "operations (the two comparisons decided from a bounded estimate): instruction-bound, the HBM fraction is tiny by construction"),
                     "gbuffer": ("gbuffer_kernel", px * 28, "primary closest-hit rays on the BVH (traversal-bound); 28 B/px of G-buffer written")}
             line["next_rows"] = {}
             for key, ms_ in next_ms.items():

@@ -14,6 +14,7 @@
 // of world_space_to_uv (ssr.comp:22-26, GLSL evaluates it left to right) is formed once per dispatch.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "vhr_internal.h"
 
@@ -135,6 +136,39 @@ __device__ __forceinline__ bool in_window(const SsrParams &p, const PerFrameData
 
 }  // namespace
 
+// ssr.comp:62-86 for one pixel: the fragment's world position and the reflected direction. False (nothing to march): a sky pixel (depth
+// 0 -> w = 0) has a non-finite P — every distance along its ray is inf or NaN, the window test can never pass — the output is zero.
+__device__ __forceinline__ bool pixel_setup(const SsrParams &p, const PerFrameData &pfd, int gx, int gy, float3 cam, float3 &P, float3 &dir) {
+    const float cu = mul_rn((float)gx, pfd.display_size_inverse[0]);                 // texel corner (ssr.comp:68)
+    const float cv = mul_rn((float)gy, pfd.display_size_inverse[1]);
+    const Taps t0 = taps_for(p, cu, cv);
+    const float fragment_depth = bilerp_rn(t0.a, t0.b, __ldg(&p.depth[t0.i00]), __ldg(&p.depth[t0.i10]), __ldg(&p.depth[t0.i01]), __ldg(&p.depth[t0.i11]));
+    P = unproject_rn(pfd.camera_viewproj_inverse, fragment_depth, cu, cv);
+    const float3 N = sample_xyz16(p.normals, t0);
+    const float3 I = normalize_rn(make_float3(sub_rn(P.x, cam.x), sub_rn(P.y, cam.y), sub_rn(P.z, cam.z)));
+    const float k2 = mul_rn(2.0f, dot3_rn(N, I));
+    dir = normalize_rn(make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2))));
+    return fabsf(P.x) <= 3.0e38f && fabsf(P.y) <= 3.0e38f && fabsf(P.z) <= 3.0e38f;
+}
+
+// compute_lighting(final_uv), ssr.comp:29-59
+__device__ __forceinline__ uint2 lighting(const SsrParams &p, const PerFrameData &pfd, float3 cam, float fu, float fv) {
+    const Taps t = taps_for(p, fu, fv);
+    const float3 albedo = sample_albedo(p.albedo, t);
+    const float d = bilerp_rn(t.a, t.b, __ldg(&p.depth[t.i00]), __ldg(&p.depth[t.i10]), __ldg(&p.depth[t.i01]), __ldg(&p.depth[t.i11]));
+    const float3 position = unproject_rn(pfd.camera_viewproj_inverse, d, fu, fv);
+    const float2 mr = sample_zw16(p.motion, t);
+    const float3 V = normalize_rn(make_float3(sub_rn(cam.x, position.x), sub_rn(cam.y, position.y), sub_rn(cam.z, position.z)));
+    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
+    const float3 Nh = sample_xyz16(p.normals, t);
+    const float3 H = normalize_rn(make_float3(add_rn(L.x, V.x), add_rn(L.y, V.y), add_rn(L.z, V.z)));
+    const float3 c = shade_direct_rn(albedo, mr.x, mr.y, Nh, V, L, H, pfd.directional_light.intensity, pfd.directional_light.color);
+    return pack_rgba16f(make_float4(c.x, c.y, c.z, 1.0f));
+}
+
+// Variant 0 (default): one thread per pixel in 8x4-pixel warp tiles, the shader's control flow as written. A pixel that finds its hit
+// after 20 steps idles while a neighbour walks all 250: 20 of 32 lanes are active on average (ncu) — and still the faster kernel, because
+// the 32 lanes probe the SAME step of nearly parallel rays, so the four depth taps of a probe fall into a few cache lines.
 __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrParams p, const __grid_constant__ PerFrameData pfd) {
     // 16x8 block of four 8x4 warp tiles
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,22 +177,11 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
     if (gx >= p.x_end || gy >= p.y_end) return;
     const size_t pix = (size_t)gy * p.W + gx;
     const uint2 zero = make_uint2(0u, 0u);                                           // ssr.comp:62-66
-    const float cu = mul_rn((float)gx, pfd.display_size_inverse[0]);                 // texel corner (ssr.comp:68)
-    const float cv = mul_rn((float)gy, pfd.display_size_inverse[1]);
-    const Taps t0 = taps_for(p, cu, cv);
-    const float fragment_depth = bilerp_rn(t0.a, t0.b, __ldg(&p.depth[t0.i00]), __ldg(&p.depth[t0.i10]), __ldg(&p.depth[t0.i01]), __ldg(&p.depth[t0.i11]));
     const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
-    const float3 P = unproject_rn(pfd.camera_viewproj_inverse, fragment_depth, cu, cv);
-    const float3 N = sample_xyz16(p.normals, t0);
-    const float3 I = normalize_rn(make_float3(sub_rn(P.x, cam.x), sub_rn(P.y, cam.y), sub_rn(P.z, cam.z)));
-    const float k2 = mul_rn(2.0f, dot3_rn(N, I));
-    const float3 dir = normalize_rn(make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2))));
-
+    float3 P, dir;
+    const bool finite_p = pixel_setup(p, pfd, gx, gy, cam, P, dir);
     bool found = false;
     float prev_step = 0.0f, final_step = 0.0f;
-    // A sky pixel (depth 0 -> w = 0) has a non-finite P: every distance along its ray is inf or NaN, the window test
-    // 0.3 < delta < thickness can never pass, so the march is skipped (same result as walking all of it).
-    const bool finite_p = fabsf(P.x) <= 3.0e38f && fabsf(P.y) <= 3.0e38f && fabsf(P.z) <= 3.0e38f;
     // (two and four probes per round, examined in order afterwards, were measured: 4.89 / 5.66 ms against 4.84 — the kernel is bound by
     // instruction issue, not by latency)
     for (int i = 0; finite_p && i < p.n_steps; ++i) {                                            // ssr.comp:89-108
@@ -186,18 +209,93 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
             prev_step = tmp;
         }
     }
-    // compute_lighting(final_uv), ssr.comp:29-59
-    const Taps t = taps_for(p, fu, fv);
-    const float3 albedo = sample_albedo(p.albedo, t);
-    const float d = bilerp_rn(t.a, t.b, __ldg(&p.depth[t.i00]), __ldg(&p.depth[t.i10]), __ldg(&p.depth[t.i01]), __ldg(&p.depth[t.i11]));
-    const float3 position = unproject_rn(pfd.camera_viewproj_inverse, d, fu, fv);
-    const float2 mr = sample_zw16(p.motion, t);
-    const float3 V = normalize_rn(make_float3(sub_rn(cam.x, position.x), sub_rn(cam.y, position.y), sub_rn(cam.z, position.z)));
-    const float3 L = make_float3(-pfd.directional_light.direction[0], -pfd.directional_light.direction[1], -pfd.directional_light.direction[2]);
-    const float3 Nh = sample_xyz16(p.normals, t);
-    const float3 H = normalize_rn(make_float3(add_rn(L.x, V.x), add_rn(L.y, V.y), add_rn(L.z, V.z)));
-    const float3 c = shade_direct_rn(albedo, mr.x, mr.y, Nh, V, L, H, pfd.directional_light.intensity, pfd.directional_light.color);
-    p.out[pix] = pack_rgba16f(make_float4(c.x, c.y, c.z, 1.0f));
+    p.out[pix] = lighting(p, pfd, cam, fu, fv);
+}
+
+// Variant 1 (VHR_SSR_VARIANT=1, study): the same per-pixel computation with LANE REFILL. A warp owns a 32 x 8-pixel region (eight 8x4 tiles, walked in
+// order) and keeps a pixel in every lane: a lane whose pixel is finished takes the next one of the region instead of idling until the
+// slowest pixel of its tile has walked its 250 steps. Every lane runs the same loop body — one probe per round, of the march or of the
+// binary search, which differ in how the offset is formed and what the answer updates (a per-lane state, ssr.comp:89-135 unrolled into
+// MARCH / BSEARCH) — so unlike ray traversal there are no divergent phases to serialise; the two heavy one-off pieces (pixel set-up,
+// ~300 instructions; lighting, ~250) run for the lanes that wait for them once GATHER have gathered or nothing else is left to do.
+// Bit-identical images, and 6.7-7.5 ms against 4.1 ms for every region size and gather threshold tried (2 / 4 / 8 tiles, 4 / 8 lanes,
+// profiles/r02/ssr_variants.log): lanes at different march steps probe different places, the tap loads of a warp spread over up to 32
+// cache lines each, and the L1 pays more than the idle lanes cost.
+template <int TX, int TY, int GATHER>
+__global__ void __launch_bounds__(128) ssr_refill_kernel(const __grid_constant__ SsrParams p, const __grid_constant__ PerFrameData pfd) {
+    enum : int { NEW = 0, MARCH = 1, BSEARCH = 2, LIGHT = 3, DONE = 4 };
+    constexpr int REGION = 32 * TX * TY;          // TX x TY tiles of 8 x 4 pixels per warp
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rx0 = (blockIdx.x * 2 + (warp & 1)) * (8 * TX), ry0 = p.y_begin + (blockIdx.y * 2 + (warp >> 1)) * (4 * TY);
+    if (rx0 >= p.x_end || ry0 >= p.y_end) return;                                    // warp-uniform
+    const float3 cam = make_float3(pfd.camera_view_inverse[12], pfd.camera_view_inverse[13], pfd.camera_view_inverse[14]);
+    int k = lane, next = 32, phase = NEW;
+    int gx = 0, gy = 0, i = 0;
+    float3 P = make_float3(0.0f, 0.0f, 0.0f), dir = P;
+    float prev_step = 0.0f, mid_step = 0.0f, fu = 0.0f, fv = 0.0f;
+    while (true) {
+        unsigned m_run = __ballot_sync(FULL, phase == MARCH || phase == BSEARCH);
+        const unsigned m_new = __ballot_sync(FULL, phase == NEW);
+        if (m_new && (__popc(m_new) >= GATHER || !m_run)) {
+            if (phase == NEW) {
+                const int tile = k >> 5, l = k & 31;
+                gx = rx0 + (tile % TX) * 8 + (l & 7);
+                gy = ry0 + (tile / TX) * 4 + (l >> 3);
+                phase = DONE;
+                if (gx < p.x_end && gy < p.y_end) {
+                    if (pixel_setup(p, pfd, gx, gy, cam, P, dir) && p.n_steps > 0) {
+                        phase = MARCH; i = 0; prev_step = 0.0f;
+                    } else {
+                        p.out[(size_t)gy * p.W + gx] = make_uint2(0u, 0u);               // ssr.comp:62-66, 110-112
+                    }
+                }
+            }
+            m_run = __ballot_sync(FULL, phase == MARCH || phase == BSEARCH);
+        }
+        const unsigned m_light = __ballot_sync(FULL, phase == LIGHT);
+        if (m_light && (__popc(m_light) >= GATHER || !m_run)) {
+            if (phase == LIGHT) {
+                p.out[(size_t)gy * p.W + gx] = lighting(p, pfd, cam, fu, fv);
+                phase = DONE;
+            }
+        }
+        const unsigned m_done = __ballot_sync(FULL, phase == DONE);
+        if (m_done && next < REGION) {
+            const int kk = next + __popc(m_done & ((1u << lane) - 1u));
+            if (phase == DONE && kk < REGION) { k = kk; phase = NEW; }
+            next += __popc(m_done);
+        }
+        if (__all_sync(FULL, phase == DONE)) break;
+        if (phase == MARCH || phase == BSEARCH) {
+            const float offset = phase == MARCH ? mul_rn(p.step_size, (float)i) : mid_step;
+            float pu, pv;
+            const bool hit = in_window(p, pfd, P, dir, cam, offset, pu, pv);
+            if (phase == MARCH) {                                                     // ssr.comp:89-112
+                if (hit) {
+                    mid_step = mul_rn(add_rn(prev_step, offset), 0.5f);              // ssr.comp:115
+                    fu = 0.0f; fv = 0.0f; i = 0;
+                    phase = p.bsearch_steps > 0 ? BSEARCH : LIGHT;
+                } else {
+                    prev_step = offset;
+                    if (++i >= p.n_steps) {
+                        p.out[(size_t)gy * p.W + gx] = make_uint2(0u, 0u);
+                        phase = DONE;
+                    }
+                }
+            } else {                                                                 // ssr.comp:116-135
+                fu = pu; fv = pv;
+                if (hit) {
+                    mid_step = mul_rn(add_rn(prev_step, mid_step), 0.5f);
+                } else {
+                    const float tmp = mid_step;
+                    mid_step = add_rn(mid_step, sub_rn(mid_step, prev_step));
+                    prev_step = tmp;
+                }
+                if (++i >= p.bsearch_steps) phase = LIGHT;
+            }
+        }
+    }
 }
 
 int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc) {
@@ -244,8 +342,20 @@ int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstant
             }
             p.pv[c * 4 + r] = acc;
         }
-    dim3 block(128), grid((p.x_end + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
-    ssr_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    static const int variant = [] { const char *e = getenv("VHR_SSR_VARIANT"); return e ? atoi(e) : 0; }();
+    if (variant != 1) {
+        dim3 block(128), grid((p.x_end + 15) / 16, (p.y_end - p.y_begin + 7) / 8);
+        ssr_kernel<<<grid, block, 0, ctx->stream>>>(p, ctx->pfd);
+    } else {
+        // four warps per block, a (8 TX) x (4 TY)-pixel region each
+        static const int region = [] { const char *e = getenv("VHR_SSR_REGION"); return e ? atoi(e) : 42; }();
+#define VHR_SSR_CASE(ID, TX, TY, G) case ID: ssr_refill_kernel<TX, TY, G><<<dim3((p.x_end + 16 * TX - 1) / (16 * TX), (p.y_end - p.y_begin + 8 * TY - 1) / (8 * TY)), 128, 0, ctx->stream>>>(p, ctx->pfd); break;
+        switch (region) {       // tiles across, tiles down, lanes gathered before a set-up / lighting round
+            VHR_SSR_CASE(21, 2, 1, 8) VHR_SSR_CASE(22, 2, 1, 4) VHR_SSR_CASE(41, 4, 1, 8) VHR_SSR_CASE(42, 4, 1, 4) VHR_SSR_CASE(81, 4, 2, 8) VHR_SSR_CASE(82, 4, 2, 4) VHR_SSR_CASE(44, 2, 2, 4)
+            default: return fail(VHR_ERR_INVALID, "VHR_SSR_REGION = %d", region);
+        }
+#undef VHR_SSR_CASE
+    }
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     return VHR_OK;
