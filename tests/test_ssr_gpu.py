@@ -48,7 +48,7 @@ def test_ssr_vs_oracle(size, params):
         pc = np.array(params, T.SSRPushConstants)
         n0 = ctx.kernel_launches
         ctx.dispatch(HP.SHADER_SSR, HP.groups(W), HP.groups(H), 1, pc)
-        assert ctx.kernel_launches == n0 + 1
+        assert ctx.kernel_launches == n0 + 2          # the depth quad-image pre-pass + the march
         out = ctx.image_download(HP.N_SSR)
         # push-constant size is checked like the reference's assert (compute_execution_context.h:23)
         with pytest.raises(capi.VhrError):

@@ -312,6 +312,20 @@ static bool dispatch_range(vhr_context *ctx, const Image *ref, uint32_t xg, uint
     return x_end > 0 && y1 > y0;
 }
 
+// The quad image of a depth image (screen-space passes: ssao.comp, ssr.comp), rebuilt by every dispatch that gathers from it.
+int build_depth_quads(vhr_context *ctx, const float *depth, int W, int H) {
+    const size_t texels = (size_t)W * H;
+    if (ctx->depth_quads_texels < texels) {
+        if (ctx->d_depth_quads) { VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_depth_quads); ctx->d_depth_quads = nullptr; }
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_depth_quads, texels * sizeof(float4)));
+        ctx->depth_quads_texels = texels;
+    }
+    depth_quads_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(depth, ctx->d_depth_quads, W, H);
+    VHR_CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    return VHR_OK;
+}
+
 int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     // descriptor set 3 of the "SSAO Pass" (hybrid_render_path.cpp:143-150): 0 normals, 1 depth, 2 raw output
     if (ctx->n_bound < 3) return fail(VHR_ERR_STATE, "ssao.comp: pass images not bound (need bindings 0..2)");
@@ -343,16 +357,8 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     static const int variant = [] { const char *e = getenv("VHR_SSAO_VARIANT"); return e ? atoi(e) : 0; }();
     p.quads = nullptr;
     if (!(variant & 1) && !(variant & 2)) {
-        const size_t texels = (size_t)p.W * p.H;
-        if (ctx->depth_quads_texels < texels) {
-            if (ctx->d_depth_quads) { VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_depth_quads); ctx->d_depth_quads = nullptr; }
-            VHR_CUDA_CHECK(cudaMalloc(&ctx->d_depth_quads, texels * sizeof(float4)));
-            ctx->depth_quads_texels = texels;
-        }
         // the samples of a row band reach any row of the depth image: the whole quad image on every rank
-        depth_quads_kernel<<<dim3((p.W + 31) / 32, (p.H + 7) / 8), block, 0, ctx->stream>>>(p.depth, ctx->d_depth_quads, p.W, p.H);
-        VHR_CUDA_CHECK(cudaGetLastError());
-        ctx->launches++;
+        if (int rc = build_depth_quads(ctx, p.depth, p.W, p.H)) return rc;
         p.quads = ctx->d_depth_quads;
     }
 #define VHR_SSAO_CASE(V) case V: if (perspective) ssao_kernel<true, V><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); \

@@ -161,6 +161,7 @@ int fail(int status, const char *fmt, ...);
 int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
 int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
 int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius);
+int build_depth_quads(vhr_context *ctx, const float *depth, int W, int H);     // -> ctx->d_depth_quads (ssao_kernels.cu)
 int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg);
 int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc);
 int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height);
