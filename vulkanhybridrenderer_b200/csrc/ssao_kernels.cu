@@ -7,6 +7,7 @@
 // software with the Vulkan spec's float weights — CUDA texture units filter with 8-bit fixed-point weights, which
 // would not match the CPU oracle.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "vhr_internal.h"
@@ -71,8 +72,11 @@ __device__ __noinline__ float occlusion_term_library(float4 q, float3 P, float3 
     return __fdiv_rn(fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f), add_rn(dot3_rn(V, V), 1e-4f));
 }
 // One sample's occlusion term max(dot(V, N) - beta, 0) / (dot(V, V) + 1e-4), V = view-space sample - P (ssao.comp:42-44), in the oracle's
-// operations. The four IEEE divisions share two refined reciprocals and ONE fall-back branch (div_exact_flag).
-template <bool PERSPECTIVE>
+// operations. The four IEEE divisions share two refined reciprocals and ONE fall-back branch (div_exact_flag). BOUNDED (PERSPECTIVE only):
+// the caller vouches for the three dividends of the unprojection — the host has checked |m00|, |m11| in [2^-14, 2^8] and |m23| in
+// [2^-38, 2^38], and the sample went through the fixed-point tap path (|u n| < 2^14), so x = 2u - 1 is zero or in [2^-24, 2^15] — and
+// their range tests are not issued.
+template <bool PERSPECTIVE, bool BOUNDED>
 __device__ __forceinline__ float occlusion_term(const float *inv, float depth, float u, float v, float3 P, float3 N) {
     const float x = fmaf(u, 2.0f, -1.0f), y = fmaf(v, 2.0f, -1.0f);      // = fl(fl(2 u) - 1): the doubling is exact
     float4 q;
@@ -80,7 +84,9 @@ __device__ __forceinline__ float occlusion_term(const float *inv, float depth, f
     else q = mul44_rn(inv, make_float4(x, y, depth, 1.0f));
     bool rare = false;
     const ExactDivisor dw = exact_divisor(q.w);
-    const float3 Q = make_float3(div_exact_flag(q.x, dw, rare), div_exact_flag(q.y, dw, rare), div_exact_flag(q.z, dw, rare));
+    const float3 Q = (PERSPECTIVE && BOUNDED)
+                         ? make_float3(div_exact_flag_bounded(q.x, dw, rare), div_exact_flag_bounded(q.y, dw, rare), div_exact_flag_bounded(q.z, dw, rare))
+                         : make_float3(div_exact_flag(q.x, dw, rare), div_exact_flag(q.y, dw, rare), div_exact_flag(q.z, dw, rare));
     const float3 V = make_float3(sub_rn(Q.x, P.x), sub_rn(Q.y, P.y), sub_rn(Q.z, P.z));
     // fmaxf returns the non-NaN operand, like the GLSL max() on NVIDIA hardware the oracle restates
     const float num = fmaxf(sub_rn(dot3_rn(V, N), 1e-4f), 0.0f);
@@ -89,6 +95,8 @@ __device__ __forceinline__ float occlusion_term(const float *inv, float depth, f
     if (rare) term = occlusion_term_library(q, P, N);       // a finite operand outside 2^+-40
     return term;
 }
+struct SsaoParams;
+__device__ __noinline__ float occlusion_term_general_tap(const SsaoParams &p, const float *inv, float u, float v, float3 P, float3 N);
 
 // texture(depth, (u, v)).x of a SAMPLE, in two halves so that the loads of several samples are in flight together.
 // tap_setup: the tap selection and the two filter weights, exactly the oracle's (bilinear_setup): with t = fl(fl(u n) - 0.5) the snapped
@@ -133,6 +141,11 @@ __device__ __forceinline__ float4 tap_load(const SsaoParams &p, const Tap &t) {
 }
 // (kept out of line: taken by the few taps on the REPEAT seam; inlined copies would triple the unrolled sample loop)
 __device__ __noinline__ float sample_depth_general(const SsaoParams &p, float u, float v) { return sample_depth(p, u, v); }
+// a sample off the fixed-point tap path (|u n| >= 2^14, NaN): general tap, general matrix product (same values as the sparse form), every
+// range test
+__device__ __noinline__ float occlusion_term_general_tap(const SsaoParams &p, const float *inv, float u, float v, float3 P, float3 N) {
+    return occlusion_term<false, false>(inv, sample_depth(p, u, v), u, v, P, N);
+}
 
 // Pre-pass of the SSAO dispatch: the bilinear footprint of every depth texel as one float4 (8 MB read, 33 MB written at 1080p)
 __global__ void __launch_bounds__(256) depth_quads_kernel(const float *__restrict__ depth, float4 *__restrict__ quads, int W, int H) {
@@ -240,21 +253,24 @@ __global__ void __launch_bounds__(256) ssao_kernel(const __grid_constant__ SsaoP
             }
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                float d;
-                if (tap[j].idx < 0) d = sample_depth_general(p, su[j], sv[j]);
-                else if (FAST) {
-                    const float top = fmaf(tap[j].a, q[j].y - q[j].x, q[j].x), bot = fmaf(tap[j].a, q[j].w - q[j].z, q[j].z);
-                    d = fmaf(tap[j].b, bot - top, top);
-                } else d = bilerp_rn(tap[j].a, tap[j].b, q[j].x, q[j].y, q[j].z, q[j].w);
                 if (FAST) {
+                    float d;
+                    if (tap[j].idx < 0) d = sample_depth_general(p, su[j], sv[j]);
+                    else {
+                        const float top = fmaf(tap[j].a, q[j].y - q[j].x, q[j].x), bot = fmaf(tap[j].a, q[j].w - q[j].z, q[j].z);
+                        d = fmaf(tap[j].b, bot - top, top);
+                    }
                     const float3 Q = unproject_sample<PERSPECTIVE, true>(pfd.camera_proj_inverse, d, su[j], sv[j]);
                     const float3 V = make_float3(Q.x - P.x, Q.y - P.y, Q.z - P.z);
                     const float num = fmaxf(fmaf(V.x, N.x, fmaf(V.y, N.y, fmaf(V.z, N.z, -1e-4f))), 0.0f);
                     float r;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(V.x, V.x, fmaf(V.y, V.y, fmaf(V.z, V.z, 1e-4f)))));
                     sum = fmaf(num, r, sum);
+                } else if (tap[j].idx < 0) {
+                    sum = add_rn(sum, occlusion_term_general_tap(p, pfd.camera_proj_inverse, su[j], sv[j], P, N));
                 } else {
-                    sum = add_rn(sum, occlusion_term<PERSPECTIVE>(pfd.camera_proj_inverse, d, su[j], sv[j], P, N));
+                    const float d = bilerp_rn(tap[j].a, tap[j].b, q[j].x, q[j].y, q[j].z, q[j].w);
+                    sum = add_rn(sum, occlusion_term<PERSPECTIVE, true>(pfd.camera_proj_inverse, d, su[j], sv[j], P, N));
                 }
             }
         }
@@ -411,6 +427,12 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     bool perspective = true;
     for (int i = 0; i < 16; ++i)
         if (i != 0 && i != 5 && i != 11 && i != 14 && i != 15 && ctx->pfd.camera_proj_inverse[i] != 0.0f) perspective = false;
+    // ... and its coefficients in the range occlusion_term<.., BOUNDED> relies on (any real camera: m00, m11 = tan(fov / 2) terms, m23 = -1)
+    {
+        const float *m = ctx->pfd.camera_proj_inverse;
+        const float a0 = std::fabs(m[0]), a5 = std::fabs(m[5]), a14 = std::fabs(m[14]);
+        if (!(a0 >= 6.1035156e-5f && a0 <= 256.0f && a5 >= 6.1035156e-5f && a5 <= 256.0f && a14 >= 3.6379788e-12f && a14 <= 2.7487791e11f)) perspective = false;
+    }
     static const int variant = [] { const char *e = getenv("VHR_SSAO_VARIANT"); return e ? atoi(e) : 0; }();
     p.quads = nullptr;
     if (!(variant & 1) && !(variant & 2)) {
