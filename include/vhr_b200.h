@@ -295,7 +295,8 @@ typedef enum vhr_option {
                                       9: two-phase kernel — the shadow + AO rays of a 16 x 8 pixel block are generated into shared memory, then traversed with
                                          RAY-level lane refill from that queue (ao_spp 1, 2 or 4; reflections through variant 0 afterwards);
                                       10 / 11: variant 0 built for 10 / 12 resident blocks per SM (48 / 40 registers); 12: 4-byte traversal-stack entries;
-                                      13: the shadow ray and the AO rays through one inlined copy of the any-hit traversal.
+                                      13: the shadow ray and the AO rays through one inlined copy of the any-hit traversal;
+                                      14 / 15: the first 8 / 12 traversal-stack entries of a thread in shared memory.
                                       Same images in every variant; all measured equal to or slower than 0 on B200, kept for study */
     VHR_OPT_RAYTRACED_ALPHA_TEST = 11,/* the fully ray-traced path's use_anyhit_shader (raytraced_render_path.h:14): 1 selects the pipeline
                                       raygen_test_alpha.rgen + closesthit_test_alpha.rchit + shadow_anyhit.rahit */

@@ -287,7 +287,7 @@ def test_ray_queue_variant_matches_per_pixel_kernel(ao_spp, shadows, ao, refl, b
         assert len(np.unique(outs[1][0][rows, :, 1].astype(np.float32))) >= 2 and len(np.unique(outs[1][0][rows, :, 0].astype(np.float32))) == 2
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 6, 7, 8, 10, 11, 12, 13])
+@pytest.mark.parametrize("variant", [2, 3, 4, 6, 7, 8, 10, 11, 12, 13, 14, 15])
 def test_raygen_kernel_variants_match_default(variant):
     """VHR_OPT_RAYGEN_VARIANT 2 / 3 (other register budgets), 4 (postponed leaves: the warp runs the triangle block together) trace the
     same rays against the same tree: shadow / AO masks are identical; the closest-hit ray may report another triangle only on exact ties."""

@@ -220,15 +220,22 @@ struct AcceptAll {
 };
 // PACKED: stack entries of 4 bytes, (child base << 9) | (reverse bit << 8) | hit mask, instead of 8 (wide trees below 2^23 nodes): the
 // per-thread stacks live in local memory, i.e. in L1 next to the nodes — 12 levels x 32 warps x 256 B = 98 KB per SM with 8-byte entries.
-template <bool ANY, class Accept = AcceptAll, bool PACKED = false>
+// SS > 0: the first SS stack entries of a thread live in SHARED memory (entry i of thread t at vhr_sstack[i * threads + t]: a warp's
+// accesses fall into 32 different banks), deeper entries in local memory as before — the kernel is launched with SS * 8 * threads bytes of
+// dynamic shared memory. The stack traffic of the default kernel is a third of its L1 sector traffic (ncu: 9.8 M local load + 11.4 M local
+// store sectors against 44.8 M global), with write-allocate misses going to L2.
+extern __shared__ uint2 vhr_sstack[];
+template <bool ANY, class Accept = AcceptAll, bool PACKED = false, int SS = 0>
 __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n_wide,
                                       uint32_t bias, const Ray &ray, bool alive, Hit &hit, const Accept accept = Accept()) {
     if (!alive || n_wide == 0) return false;
     const RayPre r = prepare(ray);
     float tmax = ray.tmax;
     bool found = false;
-    uint2 stack[PACKED ? 1 : kStackSize];
+    uint2 stack[PACKED ? 1 : kStackSize - SS];
     uint32_t stack32[PACKED ? kStackSize : 1];
+    uint2 *const sstack = vhr_sstack + (threadIdx.y * blockDim.x + threadIdx.x);
+    const int sstride = blockDim.x * blockDim.y;
     int sp = 0;
     uint2 group = make_uint2(0u, 1u);   // (child_base, hit mask over child ordinals): the root
     while (true) {
@@ -237,6 +244,9 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
             if (PACKED) {
                 const uint32_t e = stack32[--sp];
                 group = make_uint2((e >> 9) | ((e & 0x100u) << 23), e & 0xffu);
+            } else if (SS > 0) {
+                --sp;
+                group = sp < SS ? sstack[sp * sstride] : stack[sp - SS];
             } else {
                 group = stack[--sp];
             }
@@ -244,7 +254,10 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
         const uint32_t k = pop_child<ANY>(group);
         if (group.y != 0u && sp < kStackSize) {
             if (PACKED) stack32[sp++] = ((group.x & 0x7fffffffu) << 9) | ((group.x >> 31) << 8) | group.y;
-            else stack[sp++] = group;
+            else if (SS > 0) {
+                if (sp < SS) sstack[sp * sstride] = group; else stack[sp - SS] = group;
+                ++sp;
+            } else stack[sp++] = group;
         }
         const uint32_t node = (ANY ? group.x : (group.x & 0x7fffffffu)) + k;
         uint32_t child_base, child_hits, leaf_hits;
@@ -530,7 +543,7 @@ __device__ __forceinline__ bool trace_any_sorted(const SceneRefs &scene, const R
 //   1 (variant 3): no cap, 117 registers / 4 blocks — 1.16 / 3.39 ms (fewer warps to hide the node fetches);
 //   BATCHED (variant 4): trace_batched — 1.00 / 2.57 ms: postponing leaves costs the any-hit rays more node steps than the fuller
 //   triangle block saves. Same images in every variant.
-template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4, bool SORT_AO = false, bool PACKED = false, bool MERGED = false>
+template <int MIN_BLOCKS, bool BATCHED = false, int WPB = 4, bool SORT_AO = false, bool PACKED = false, bool MERGED = false, int SS = 0>
 __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(const __grid_constant__ RaygenParams p, const __grid_constant__ PerFrameData pfd) {
     static_assert(!SORT_AO || WPB == 4, "the AO sort works on 128-thread CTAs");
     int x, y;
@@ -584,7 +597,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
             if (enabled) {
                 ray.d = is_shadow ? onb_apply(L, normalize_rn(uniform_sample_cone(rnd1, rnd2, 0.999995f))) : onb_apply(N, uniform_sample_cosine_weighted_hemisphere(rnd1, rnd2));
                 ray.tmax = is_shadow ? 10000.0f : 5.0f;
-                occluded = trace<true, AcceptAll, PACKED>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+                occluded = trace<true, AcceptAll, PACKED, SS>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
             }
             if (is_shadow) shadow = occluded ? 0.0f : 1.0f;
             else ao = add_rn(ao, occluded ? 0.0f : 1.0f);
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
         ray.d = onb_apply(L, cone);
         ray.tmax = 10000.0f;
         const bool occluded = BATCHED ? trace_batched<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
-                                      : trace<true, AcceptAll, PACKED>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+                                      : trace<true, AcceptAll, PACKED, SS>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
         shadow = occluded ? 0.0f : 1.0f;
     }
     // ambient occlusion (raygen.rgen:44-55)
@@ -613,7 +626,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
                 occluded = trace_any_sorted(p.scene, ray, lit, ao_sort);
             } else {
                 occluded = BATCHED ? trace_batched<true>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
-                                   : trace<true, AcceptAll, PACKED>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+                                   : trace<true, AcceptAll, PACKED, SS>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
             }
             ao = add_rn(ao, occluded ? 0.0f : 1.0f);
         } else {
@@ -634,7 +647,7 @@ __global__ void __launch_bounds__(32 * WPB, MIN_BLOCKS * 4 / WPB) raygen_kernel(
         ray.d = make_float3(sub_rn(I.x, mul_rn(N.x, k2)), sub_rn(I.y, mul_rn(N.y, k2)), sub_rn(I.z, mul_rn(N.z, k2)));
         ray.tmax = 10000.0f;
         const bool refl_hit = BATCHED ? trace_batched<false>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit, p.leaf_batch)
-                                      : trace<false, AcceptAll, PACKED>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
+                                      : trace<false, AcceptAll, PACKED, SS>(p.scene.nodes, p.scene.tris, p.scene.n_wide, p.scene.bias, ray, lit, hit);
         if (refl_hit && lit) {
             payload = reflection_hit(p.scene, pfd, hit);
             rt = hit.t;
@@ -1414,6 +1427,8 @@ int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height) {
             if (ctx->bvh.n_wide < (1u << 23)) { raygen_kernel<8, false, 4, false, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break; }
             raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;
         case 13: raygen_kernel<8, false, 4, false, false, true><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;   // one inlined any-hit traversal for shadow + AO
+        case 14: raygen_kernel<8, false, 4, false, false, false, 8><<<grid, block, 8 * sizeof(uint2) * 128, ctx->stream>>>(p, ctx->pfd); break;     // first 8 stack entries in shared memory
+        case 15: raygen_kernel<8, false, 4, false, false, false, 12><<<grid, block, 12 * sizeof(uint2) * 128, ctx->stream>>>(p, ctx->pfd); break;   // first 12
         case 10: raygen_kernel<10><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;        // 48 registers, 10 blocks / SM
         case 11: raygen_kernel<12><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;        // 40 registers, 12 blocks / SM
         default: raygen_kernel<8><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;         // 64 registers, 8 blocks / SM

@@ -848,7 +848,7 @@ int vhr_set_option(vhr_context *ctx, int option, int64_t value) {
             ctx->opt.atrous_variant = (int)value; return VHR_OK;
         case VHR_OPT_RAYTRACED_ALPHA_TEST: ctx->opt.raytraced_alpha_test = value != 0; return VHR_OK;
         case VHR_OPT_RAYGEN_VARIANT:
-            if (value < 0 || value > 13 || value == 5) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);
+            if (value < 0 || value > 15 || value == 5) return fail(VHR_ERR_INVALID, "raygen variant %lld", (long long)value);
             ctx->opt.raygen_variant = (int)value; return VHR_OK;
         case VHR_OPT_DEBUG_REFLECTION_T:
             ctx->opt.debug_refl_t = value != 0;
