@@ -29,8 +29,13 @@ struct __align__(16) WideNode {
     uint8_t meta[8];
     uint8_t qlo[3][8];
     uint8_t qhi[3][8];
+#ifdef VHR_NODE_PAD_BYTES      // study: 48 pads a node to one 128-byte cache line (measured: see DESIGN.md section 7)
+    uint8_t pad[VHR_NODE_PAD_BYTES];
+#endif
 };
+#ifndef VHR_NODE_PAD_BYTES
 static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+#endif
 
 constexpr int kMaxLeafTris = 3;
 
