@@ -292,3 +292,56 @@ def test_next_rows_1080p_260k():
     bad = d > 1e-3 * np.maximum(1.0, np.abs(ref_comp))
     print(f"[parity] next rows 1080p: composition (2, 1, 1): max_abs={d.max():.3e} exact={np.mean(comp == ref_comp)*100:.2f}% beyond tolerance: {int(bad.sum())}")
     assert np.isfinite(ref_comp).all() and np.isfinite(comp).all() and not bad.any()
+
+
+# ---- the workload bench.py quotes its headline on ---------------------------------------------------------------------------------------
+def test_bench_workload_frames_match_the_checker_on_a_band():
+    """`hybrid_frame_1080p_3Mtri` exactly as bench.py drives it — its scene (2.997 M triangles), its two camera poses, its options (shadow
+    1 + AO 1 spp, no reflections, copy-free blits), G-buffers from the CUDA producer, frame indices 3, 4, ...: the shadow / AO masks of the
+    first two timed frames agree with the checker on a 64-row band (every mismatching pixel re-traced by brute force and classified), and
+    the denoised image of the first frame (no history yet) is within the SVGF bar on that band. The number the bench reports is computed on
+    these images."""
+    import bench
+    wl = "hybrid_frame_1080p_3Mtri"
+    W, H, _, ao_spp, refl = bench.WORKLOADS[wl]
+    sc, poses = bench.make_scene(wl)
+    osc = O.OracleScene(sc)
+    seq = camera.FrameSequencer(W, H, sc.light)
+    cam = sc.camera
+    rows = (520, 584)
+    band = slice(*rows)
+    with capi.Context(W, H) as ctx:
+        ctx.update_geometry(sc.vertices, sc.indices, sc.primitives)
+        ctx.set_option(capi.OPT_TRACE_SHADOWS, 1); ctx.set_option(capi.OPT_TRACE_AO, 1)
+        ctx.set_option(capi.OPT_AO_SPP, ao_spp); ctx.set_option(capi.OPT_TRACE_REFLECTIONS, refl)
+        path = HP.HybridRenderPath(ctx, W, H, gbuffer_sets=2, blit_alias=True)
+        pfds, gs = [None, None], [None, None]
+        for s in (1, 0, 1):                       # bench.GpuFrameLoop: pose 1 first, so each pose's previous camera is the other pose
+            cam.set_pose(*poses[s])
+            pfds[s] = seq.next(cam)
+            gs[s] = _gbuffer_on_gpu(ctx, path, pfds[s], W, H, gset=s)
+        for k in range(2):
+            s = k & 1
+            pfd = pfds[s]
+            pfd["frame_index"] = 3 + k
+            path.frame(pfd, gset=s)
+            rt, den = ctx.image_download(HP.N_RT), ctx.image_download(HP.N_DENOISED)
+            g = gs[s]
+            ref = osc.raygen(pfd, g["depth"], g["normals"], ao_spp=ao_spp, flags=3, rows=rows)
+            agree = float(np.mean(np.all(rt[band] == ref["shadow_ao"][band], axis=-1)))
+            print(f"[bench workload] frame {k}: mask agreement on rows {rows}: {agree * 100:.4f}%")
+            assert agree >= MASK_MIN
+            full_gpu, full_ref = np.ones_like(rt), np.ones_like(rt)
+            full_gpu[band], full_ref[band] = rt[band], ref["shadow_ao"][band]
+            Hh.classify_mask_mismatches(osc, pfd, g["depth"], g["normals"], full_gpu, full_ref, ao_spp, f"bench workload frame {k} rows {rows}")
+            if k == 0:
+                m = 72
+                sub_ = slice(rows[0] - m, rows[1] + m)
+                bpfd = pfd.copy()
+                bpfd["display_size"] = (W, sub_.stop - sub_.start)
+                bpfd["display_size_inverse"] = (np.float32(1) / np.float32(W), np.float32(1) / np.float32(sub_.stop - sub_.start))
+                st = O.SvgfState(W, sub_.stop - sub_.start)
+                den_ref, _, _ = st.run(bpfd, np.ascontiguousarray(g["normals"][sub_]), np.ascontiguousarray(g["motion"][sub_]),
+                                       np.ascontiguousarray(rt[sub_]), want_iters=False)
+                Hh.assert_parity(den[band], den_ref[m:-m], f"bench workload frame {k} denoised, rows {rows}")
+            assert np.isfinite(den.astype(np.float32)).all()
