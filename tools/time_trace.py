@@ -28,7 +28,7 @@ def main(tris=260_000, W=1920, H=1080, reps=10):
         st = ctx.bvh_stats()
         print(f"update_geometry {time.time()-t0:.3f}s wall; build {st.build_ms:.2f} ms device; wide nodes {st.n_wide_nodes}; depth {st.wide_depth}; slots in use {st.n_used_slots / max(8 * st.n_wide_nodes, 1) * 100:.1f}%; sah {st.sah_cost:.1f}")
         ctx.update_per_frame_ubo(pfd)
-        ctx.set_option(capi.OPT_RAYGEN_VARIANT, int(os.environ.get('VHR_RAYGEN_VARIANT', '1')))
+        ctx.set_option(capi.OPT_RAYGEN_VARIANT, int(os.environ.get('VHR_RAYGEN_VARIANT', '0')))
         for n, f in GB.items():
             ctx.actualize_image(n, f)
         ctx.actualize_image("Raytraced Shadows and Ambient Occlusion", F2)

@@ -113,6 +113,23 @@ __device__ __forceinline__ bool intersect_tri(const RayPre &r, float tmin, float
 __device__ __forceinline__ float byte_biased(uint32_t w, int i, uint32_t bias) {
     return __uint_as_float(__byte_perm(w, bias, 0x7604u | ((uint32_t)i << 4)));
 }
+// Triangle records: 144 MB at 3 M triangles against 27 MB of nodes. VHR_TRI_LOAD_MODE (study, build-time): 0 = __ldg (default); 1 = __ldcs
+// (evict-first: the records should not push the nodes out of L1 / L2); 2 = L1::no_allocate.
+#ifndef VHR_TRI_LOAD_MODE
+#define VHR_TRI_LOAD_MODE 0
+#endif
+__device__ __forceinline__ float4 tri_load_na(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+#if VHR_TRI_LOAD_MODE == 1
+#define VHR_TRI_LOAD(p) __ldcs(p)
+#elif VHR_TRI_LOAD_MODE == 2
+#define VHR_TRI_LOAD(p) tri_load_na(p)
+#else
+#define VHR_TRI_LOAD(p) __ldg(p)
+#endif
 struct Hit {
     float t, u, v;
     uint32_t tri;
@@ -273,7 +290,7 @@ __device__ __forceinline__ bool trace(const WideNode *__restrict__ nodes, const 
                 const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
                 tri_hits &= tri_hits - 1u;
                 const float4 *tp = tris + (size_t)(tri_base + j) * 3;
-                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                const float4 v0 = VHR_TRI_LOAD(tp), v1 = VHR_TRI_LOAD(tp + 1), v2 = VHR_TRI_LOAD(tp + 2);
                 float t, u, v;
                 if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && (__float_as_uint(v2.w) == 0u || accept(tri_base + j, u, v))) {
                     if (ANY) return true;
@@ -343,7 +360,7 @@ __device__ __forceinline__ bool trace_batched(const WideNode *__restrict__ nodes
                 const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
                 tri_hits &= tri_hits - 1u;
                 const float4 *tp = tris + (size_t)(tri_base + j) * 3;
-                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                const float4 v0 = VHR_TRI_LOAD(tp), v1 = VHR_TRI_LOAD(tp + 1), v2 = VHR_TRI_LOAD(tp + 2);
                 float t, u, v;
                 if (intersect_tri(r, ray.tmin, tmax, v0, v1, v2, t, u, v) && (__float_as_uint(v2.w) == 0u || accept(tri_base + j, u, v))) {
                     found = true;
@@ -849,7 +866,7 @@ __global__ void __launch_bounds__(128) raygen_persistent_kernel(const __grid_con
                         const uint32_t j = (uint32_t)__ffs((int)tri_hits) - 1u;
                         tri_hits &= tri_hits - 1u;
                         const float4 *tp = tris + (size_t)(tri_base + j) * 3;
-                        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                        const float4 v0 = VHR_TRI_LOAD(tp), v1 = VHR_TRI_LOAD(tp + 1), v2 = VHR_TRI_LOAD(tp + 2);
                         float t, u, v;
                         if (intersect_tri(r, tmin, tmax, v0, v1, v2, t, u, v)) {
                             if (!closest) { occluded = true; done = true; break; }
@@ -1002,7 +1019,7 @@ __global__ void __launch_bounds__(128, 8) raygen_queue_kernel(const __grid_const
                         const uint32_t jt = (uint32_t)__ffs((int)tri_hits) - 1u;
                         tri_hits &= tri_hits - 1u;
                         const float4 *tp = tris + (size_t)(tri_base + jt) * 3;
-                        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                        const float4 v0 = VHR_TRI_LOAD(tp), v1 = VHR_TRI_LOAD(tp + 1), v2 = VHR_TRI_LOAD(tp + 2);
                         float tt, uu, vv;
                         if (intersect_tri(r, 0.01f, tmax, v0, v1, v2, tt, uu, vv)) { hit_any = true; done = true; break; }
                     } while (tri_hits);
