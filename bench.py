@@ -130,7 +130,18 @@ class CpuArm:
         self.seq = camera.FrameSequencer(self.W, self.H, self.sc.light)
         self.rows = min(band_rows, self.H)
         self.y0 = (self.H - self.rows) // 2
-        self.state = O.SvgfState(self.W, self.rows)
+        # The SVGF pass (svgf.comp + five svgf_atrous_filter.comp dispatches, ~85 % of this arm's time) runs the REFERENCE'S OWN SHADERS compiled for
+        # the CPU (oracle/_ref, built by oracle/make_ref.py where /root/reference exists; it travels to the GPU box as a built library) when that
+        # library is there, else the hand-written port (bit-identical to it). The rays always go through the port's BVH: the reference's
+        # traceRayEXT is the Vulkan driver, there is no reference CPU implementation of it.
+        self.svgf_impl, self.kind = O, "port"
+        try:
+            import ref_lib
+            if ref_lib.available():
+                self.svgf_impl, self.kind = ref_lib, "reference"
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench.py: oracle/_ref not usable ({e}); the CPU arm runs the port\n")
+        self.state = self.svgf_impl.SvgfState(self.W, self.rows)
         self.g = None
         self.k = 0
 
@@ -165,14 +176,21 @@ class CpuArm:
         rays = nonsky * (1 + self.ao_spp + self.refl)
         return t2 - t0, rays, t1 - t0, t2 - t1
 
+    def use_port_svgf(self):
+        self.svgf_impl = self.O
+        self.state = self.O.SvgfState(self.W, self.rows)
+
     def sample_desc(self):
-        return (f"a {self.rows}-ROW BAND, rows [{self.y0},{self.y0 + self.rows}) of the {self.W}x{self.H} frame (not a whole frame): oracle raygen (shadow 1 + AO "
-                f"{self.ao_spp} spp{' + reflection' if self.refl else ''}) + oracle SVGF pass on that band, OpenMP {self.cores} threads")
+        svgf = ("the reference's own svgf.comp + svgf_atrous_filter.comp compiled for the CPU (oracle/_ref)" if self.kind == "reference"
+                else "the oracle port of the SVGF pass")
+        return (f"a {self.rows}-ROW BAND, rows [{self.y0},{self.y0 + self.rows}) of the {self.W}x{self.H} frame (not a whole frame): ray generation + CPU BVH "
+                f"traversal of the oracle port (shadow 1 + AO {self.ao_spp} spp{' + reflection' if self.refl else ''}; the reference's traceRayEXT is the "
+                f"Vulkan driver) + {svgf} on that band, OpenMP {self.cores} threads")
 
     def full_frame_svgf_ms(self):
         """One actual full-frame SVGF pass of the oracle (the band figure extrapolates linearly; this one is measured)."""
         pfd, g = self.frames[0]
-        st = self.O.SvgfState(self.W, self.H)
+        st = self.svgf_impl.SvgfState(self.W, self.H)
         rt = np.zeros((self.H, self.W, 2), np.float16)
         rt[..., 0] = (np.arange(self.W)[None, :] // 7 + np.arange(self.H)[:, None] // 5) % 2
         rt[..., 1] = 0.5
@@ -197,6 +215,15 @@ def run_reference(args):
     val = tot_rays / tot_s / 1e6
     W, H, tris, ao, refl = WORKLOADS[args.workload]
     full_svgf_ms = arm.full_frame_svgf_ms()
+    port_val = val
+    if arm.kind == "reference":          # the same steps with the port's SVGF pass (the faster, conservative CPU figure)
+        arm.use_port_svgf()
+        arm.step()
+        ps, pr = 0.0, 0
+        for _ in range(args.steps):
+            s, r, _, _ = arm.step()
+            ps += s; pr += r
+        port_val = pr / ps / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "metric_note": f"CPU arm: each step is a {arm.rows}-ROW BAND of the frame, not a frame; the rate (rays / second) is scale-free",
         "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -204,16 +231,18 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {**config_dict(args.workload, arm.sc.num_triangles), "frames_in_flight": args.frames_in_flight},
-        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": arm.cores, "kind": "port", "sample": arm.sample_desc(),
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind, "sample": arm.sample_desc(), "port_value": port_val,
                          "raygen_s_per_step": rt_s / args.steps, "svgf_s_per_step": svgf_s / args.steps,
                          "svgf_ms_per_full_frame_extrapolated": svgf_s / args.steps * 1e3 * H / arm.rows,
                          "svgf_ms_per_full_frame_measured": full_svgf_ms},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the hand-written CPU port of the reference shaders (oracle/, OpenMP). oracle/_ref — the reference's own GLSL compiled for the CPU — holds this "
-                "port bit-identical (tests/test_ref_pinning_cpu.py) but cannot run this configuration: raygen.rgen is hard-wired to 2 AO samples, the "
-                "reflection ray and a 4x shadow loop; it also runs 1.7-3x SLOWER than the port (glm temporaries, generic image access), so the port is "
-                "the conservative baseline. The reference program itself needs Win32 + Vulkan ray tracing + glslang and cannot run here",
+        "note": "SVGF pass (about 85 % of this arm's time): the reference's own svgf.comp / svgf_atrous_filter.comp compiled for the CPU (oracle/_ref, kind "
+                "'reference') when that library is present, else the hand-written port, which is bit-identical to it and 1.7-3x faster (no glm temporaries, "
+                "no generic image access) — cpu_baseline.port_value is the same sample with the port's SVGF pass, the conservative figure. The rays go through "
+                "the port's ray generation and CPU BVH in both cases: raygen.rgen is hard-wired to 2 AO samples, a reflection ray and a 4x shadow loop, so "
+                "it cannot run this configuration, and the reference's traceRayEXT is the Vulkan driver. The reference program itself needs Win32 + Vulkan "
+                "ray tracing + glslang and cannot run here",
     }
     print(json.dumps(line))
 
@@ -882,7 +911,7 @@ def run_gpu(args):
             while n < 3 or (t_s < 8.0 and n < 10):
                 s_, r_, _, b_ = arm.step()
                 t_s += s_; t_r += r_; svgf_s += b_; n += 1
-            line["cpu_baseline"] = {"value": t_r / t_s / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
+            line["cpu_baseline"] = {"value": t_r / t_s / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind,
                                     "sample": arm.sample_desc() + f", {n} samples",
                                     "svgf_ms_per_full_frame_extrapolated": svgf_s / n * 1e3 * H / arm.rows,
                                     "svgf_ms_per_full_frame_measured": arm.full_frame_svgf_ms()}
