@@ -386,16 +386,18 @@ static bool dispatch_range(vhr_context *ctx, const Image *ref, uint32_t xg, uint
 }
 
 // The quad image of a depth image (screen-space passes: ssao.comp, ssr.comp), rebuilt by every dispatch that gathers from it.
-int build_depth_quads(vhr_context *ctx, const float *depth, int W, int H) {
+int build_depth_quads(vhr_context *ctx, const float *depth, int W, int H, const float4 **quads) {
+    const int q = ctx->stream == ctx->queue[1] && ctx->queue[1] != nullptr ? 1 : 0;       // the selected queue's own buffer
     const size_t texels = (size_t)W * H;
-    if (ctx->depth_quads_texels < texels) {
-        if (ctx->d_depth_quads) { VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_depth_quads); ctx->d_depth_quads = nullptr; }
-        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_depth_quads, texels * sizeof(float4)));
-        ctx->depth_quads_texels = texels;
+    if (ctx->depth_quads_texels[q] < texels) {
+        if (ctx->d_depth_quads[q]) { VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_depth_quads[q]); ctx->d_depth_quads[q] = nullptr; }
+        VHR_CUDA_CHECK(cudaMalloc(&ctx->d_depth_quads[q], texels * sizeof(float4)));
+        ctx->depth_quads_texels[q] = texels;
     }
-    depth_quads_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(depth, ctx->d_depth_quads, W, H);
+    depth_quads_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(depth, ctx->d_depth_quads[q], W, H);
     VHR_CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
+    *quads = ctx->d_depth_quads[q];
     return VHR_OK;
 }
 
@@ -437,8 +439,7 @@ int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius) {
     p.quads = nullptr;
     if (!(variant & 1) && !(variant & 2)) {
         // the samples of a row band reach any row of the depth image: the whole quad image on every rank
-        if (int rc = build_depth_quads(ctx, p.depth, p.W, p.H)) return rc;
-        p.quads = ctx->d_depth_quads;
+        if (int rc = build_depth_quads(ctx, p.depth, p.W, p.H, &p.quads)) return rc;
     }
 #define VHR_SSAO_CASE(V) case V: if (perspective) ssao_kernel<true, V><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); \
                                  else ssao_kernel<false, V><<<grid, block, 0, ctx->stream>>>(p, ctx->pfd); break;

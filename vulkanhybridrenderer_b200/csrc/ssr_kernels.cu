@@ -337,8 +337,7 @@ int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstant
     p.bsearch_steps = pc.bsearch_steps;
     p.albedo = (const uint32_t *)b[0]->ptr; p.normals = (const uint2 *)b[1]->ptr; p.motion = (const uint2 *)b[2]->ptr;
     p.depth = (const float *)b[3]->ptr; p.out = (uint2 *)b[4]->ptr;
-    if (int rc = build_depth_quads(ctx, p.depth, p.W, p.H)) return rc;
-    p.quads = ctx->d_depth_quads;
+    if (int rc = build_depth_quads(ctx, p.depth, p.W, p.H, &p.quads)) return rc;
     // camera_proj * camera_view, each element a left-to-right sum of rounded products (volatile keeps the host compiler from
     // contracting or reassociating; the oracle forms the same product)
     const float *A = ctx->pfd.camera_proj, *B = ctx->pfd.camera_view;

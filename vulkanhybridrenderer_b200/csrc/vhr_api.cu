@@ -223,7 +223,7 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->d_normal_mats) cudaFree(ctx->d_normal_mats);
     if (ctx->d_refl_t) cudaFree(ctx->d_refl_t);
     if (ctx->d_ray_queue) cudaFree(ctx->d_ray_queue);
-    if (ctx->d_depth_quads) cudaFree(ctx->d_depth_quads);
+    for (float4 *q : ctx->d_depth_quads) if (q) cudaFree(q);
     for (TextureDesc &t : ctx->textures) if (t.texels) cudaFree((void *)t.texels);
     if (ctx->d_textures) cudaFree(ctx->d_textures);
     if (ctx->d_texel_lut) cudaFree(ctx->d_texel_lut);

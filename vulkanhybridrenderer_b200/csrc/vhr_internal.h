@@ -116,8 +116,10 @@ struct vhr_context {
     float *d_texel_lut = nullptr;                  // 512 floats: UNORM8 -> float, sRGB8 -> linear float
     float *d_refl_t = nullptr;                     // optional debug image: reflection-ray hit distance per pixel
     uint32_t *d_ray_queue = nullptr;               // head of the persistent ray kernel's pixel queue
-    float4 *d_depth_quads = nullptr;               // ssao.comp: the 2x2 bilinear footprint of every depth texel, one 16-byte word (ssao_kernels.cu)
-    size_t depth_quads_texels = 0;
+    // ssao.comp / ssr.comp: the 2x2 bilinear footprint of every depth texel, one 16-byte word (ssao_kernels.cu); one buffer per queue, so
+    // that a screen-space pass recorded on queue 1 does not rebuild the image a pass on queue 0 is still gathering from
+    float4 *d_depth_quads[2] = {nullptr, nullptr};
+    size_t depth_quads_texels[2] = {0, 0};
     int raygen_blocks = 0;                         // resident grid of the persistent ray kernel (SMs x blocks/SM)
     vhr::Bvh bvh;
     vhr::Options opt;
@@ -161,7 +163,7 @@ int fail(int status, const char *fmt, ...);
 int launch_svgf_temporal(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
 int launch_svgf_atrous(vhr_context *ctx, uint32_t xg, uint32_t yg, const SVGFPushConstants &pc);
 int launch_ssao(vhr_context *ctx, uint32_t xg, uint32_t yg, float radius);
-int build_depth_quads(vhr_context *ctx, const float *depth, int W, int H);     // -> ctx->d_depth_quads (ssao_kernels.cu)
+int build_depth_quads(vhr_context *ctx, const float *depth, int W, int H, const float4 **quads);     // -> the selected queue's quad image (ssao_kernels.cu)
 int launch_ssao_blur(vhr_context *ctx, uint32_t xg, uint32_t yg);
 int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc);
 int launch_trace_rays(vhr_context *ctx, uint32_t width, uint32_t height);
