@@ -166,7 +166,9 @@ int vhr_bind_pass_images(vhr_context *ctx, const char *const *names_by_binding, 
  * x_groups*8 by y_groups*8 pixels clipped to the image. `push_constants` is SVGFPushConstants (24 B,
  * glsl_common.h:31-39) for the two SVGF kernels, SSAOPushConstants (4 B, :48-50) or NULL (radius 0.75) for SSAO and
  * SSRPushConstants (16 B, :41-46; bound images 0 albedo, 1 normals, 2 motion/metallic-roughness, 3 depth, 4 output) for SSR;
- * a size that does not match fails like the reference's assert (compute_execution_context.h:23). */
+ * a size that does not match fails like the reference's assert (compute_execution_context.h:23).
+ * The ssao.comp and ssr.comp dispatches first rewrite a scratch image of the library (16 bytes per texel of the depth image, one per
+ * queue, allocated on first use): the 2 x 2 bilinear footprint of every depth texel, which their depth taps read with one load. */
 int vhr_dispatch(vhr_context *ctx, const char *shader_path, uint32_t x_groups, uint32_t y_groups, uint32_t z_groups,
                  const void *push_constants, size_t push_constants_size);
 
