@@ -19,6 +19,10 @@
 #include "vhr_internal.h"
 
 
+#ifndef VHR_SSR_SKIP_COOLDOWN
+#define VHR_SSR_SKIP_COOLDOWN 7
+#endif
+
 namespace vhr {
 
 struct SsrParams {
@@ -33,6 +37,11 @@ struct SsrParams {
     const uint2 *motion;       // binding 2 (.zw = metallic, roughness)
     const float *depth;        // binding 3
     const float4 *quads;       // the 2 x 2 bilinear footprint of every depth texel as one 16-byte word (build_depth_quads, ssao_kernels.cu)
+    const float2 *tiles;       // (min, max) depth over texels [8 i - 2, 8 i + 10) x [8 j - 2, 8 j + 10) (REPEAT-wrapped) of tile (i, j), or nullptr: no skipping
+    int tiles_w, tiles_h;
+    float margin0;             // 1e-5 + 4e-6 |camera position|_1
+    float pi14sq;
+    float pi0, pi5, pi14, pi11, pi15;   // camera_proj_inverse entries m00, m11, m23, m32, m33 (column-major indices 0, 5, 14, 11, 15)
     uint2 *out;                // binding 4 (RGBA16F)
     float pv[16];              // camera_proj * camera_view, column-major
 };
@@ -87,6 +96,79 @@ __device__ __forceinline__ float3 sample_albedo(const uint32_t *img, const Taps 
 __device__ __forceinline__ float distance_rn(float3 a, float3 b) {
     const float3 d = make_float3(sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z));
     return sqrt_exact(dot3_rn(d, d));
+}
+
+// (min, max) of the depth image over every 8 x 8-texel tile plus a 2-texel apron, REPEAT-wrapped like the sampler.
+__global__ void __launch_bounds__(128) depth_tiles_kernel(const float *__restrict__ depth, float2 *__restrict__ tiles, int W, int H, int tw, int th) {
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= tw * th) return;
+    const int ti = t % tw, tj = t / tw;
+    float mn = 3.0e38f, mx = -3.0e38f;
+    for (int k = lane; k < 144; k += 32) {
+        int x = ti * 8 - 2 + k % 12, y = tj * 8 - 2 + k / 12;
+        x = x < 0 ? x + W : (x >= W ? x - W : x);
+        y = y < 0 ? y + H : (y >= H ? y - H : y);
+        if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
+            const float d = __ldg(depth + (size_t)y * W + x);
+            mn = fminf(mn, d); mx = fmaxf(mx, d);
+            if (!(d == d)) { mn = -3.0e38f; mx = 3.0e38f; }      // a NaN texel: the tile decides nothing
+        } else { mn = -3.0e38f; mx = 3.0e38f; }                  // image smaller than the apron
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) tiles[t] = make_float2(mn, mx);
+}
+
+// Can the march step at `offset` be decided WITHOUT evaluating it? The window test compares delta = |cam - rp| - |cam - sp|, where sp is
+// the surface point under the ray point's screen position. For a perspective camera |cam - sp| = L(uv) / w(depth) with L = |(m00 x, m11 y,
+// m23)| and w = m32 depth + m33 (the view-space form of the oracle's unprojection: the host has checked that camera_viewproj_inverse is
+// camera_view_inverse * camera_proj_inverse with a rigid view and an inverse-perspective projection, m32 > 0, m33 >= 0), decreasing in
+// depth. The depth the oracle samples is a convex combination of four texels of the tile the (approximate) uv falls in — the tile's
+// 2-texel apron absorbs the difference between this approximate uv and the oracle's — so it lies in the tile's [min, max], and delta in
+// [d1 - L / w(min), d1 - L / w(max)]. If that interval lies below 0.3 or above `thickness` by a margin of 1e-4 (d1 + d2) + 1e-5 + 4e-6 |cam|
+// (a hundred times the rounding of both evaluations) the step is outside the window whatever the exact numbers are. ~45 instructions against
+// ~200 for the probe; most steps of most rays are in open space in front of the geometry or well behind it.
+__device__ __forceinline__ bool step_is_outside_window(const SsrParams &p, float3 P, float3 dir, float3 cam, float offset) {
+    const float rx = fmaf(dir.x, offset, P.x), ry = fmaf(dir.y, offset, P.y), rz = fmaf(dir.z, offset, P.z);
+    const float *m = p.pv;
+    const float cx = fmaf(m[0], rx, fmaf(m[4], ry, fmaf(m[8], rz, m[12])));
+    const float cy = fmaf(m[1], rx, fmaf(m[5], ry, fmaf(m[9], rz, m[13])));
+    const float cw = fmaf(m[3], rx, fmaf(m[7], ry, fmaf(m[11], rz, m[15])));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(cw));
+    const float x = cx * r, y = cy * r;                              // NDC = 2 uv - 1
+    // texel coordinate u W = (x + 1) W / 2; one period of REPEAT, anything further out is left to the probe
+    int tx = __float2int_rd(fmaf(x, 0.5f * p.Wf, 0.5f * p.Wf)), ty = __float2int_rd(fmaf(y, 0.5f * p.Hf, 0.5f * p.Hf));
+    tx += tx < 0 ? p.W : 0; tx -= tx >= p.W ? p.W : 0;
+    ty += ty < 0 ? p.H : 0; ty -= ty >= p.H ? p.H : 0;
+    if (!((unsigned)tx < (unsigned)p.W && (unsigned)ty < (unsigned)p.H)) return false;      // also NaN / inf coordinates
+    const float2 mm = __ldg(p.tiles + (ty >> 3) * p.tiles_w + (tx >> 3));
+    if (!(mm.x >= 0.0f)) return false;
+    const float lx = p.pi0 * x, ly = p.pi5 * y;
+    const float Lq = fmaf(lx, lx, fmaf(ly, ly, p.pi14sq));
+    float Li;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(Li) : "f"(Lq));
+    const float L = Lq * Li;                                         // Lq >= m23^2 > 0
+    const float w_far = fmaf(p.pi11, mm.x, p.pi15), w_near = fmaf(p.pi11, mm.y, p.pi15);
+    float rf, rn;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(w_far));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(w_near));
+    const float d2_far = L * rf, d2_near = L * rn;                   // w_far = 0 (sky in the tile): +inf
+    const float fx = cam.x - rx, fy = cam.y - ry, fz = cam.z - rz;
+    const float d1q = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+    float d1i;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(d1i) : "f"(d1q));
+    const float d1 = d1q * d1i;                                      // d1q = 0 (the ray point is the camera): NaN, nothing is decided
+    // margins: 1e-4 of the distances involved + 4e-6 of the camera's distance from the origin (the oracle subtracts world-space points)
+    const float m_near = fmaf(1e-4f, d1 + fminf(d2_near, 1e30f), p.margin0), m_far = fmaf(1e-4f, d1 + fminf(d2_far, 1e30f), p.margin0);
+    // in front of (or not far enough behind) the nearest surface of the tile: delta <= d1 - d2_near < 0.3 (an all-sky tile: d2_near = inf)
+    if (d1 + m_near - 0.3f < d2_near) return true;
+    // behind the farthest surface of the tile by more than the thickness (never with sky in the tile: d2_far = inf)
+    if (d1 - p.thickness - m_far > d2_far) return true;
+    return false;
 }
 
 // The tail of a probe in the oracle's operations: three IEEE quotients, two correctly rounded square roots (ssr.comp:92-99). Out of line:
@@ -191,10 +273,21 @@ __global__ void __launch_bounds__(128) ssr_kernel(const __grid_constant__ SsrPar
     float prev_step = 0.0f, final_step = 0.0f;
     // (two and four probes per round, examined in order afterwards, were measured: 4.89 / 5.66 ms against 4.84 — the kernel is bound by
     // instruction issue, not by latency)
+    // The skip test only pays when the whole warp can skip the step (a probe issued for one lane costs as much as for 32): after a round
+    // in which some lane needed its probe the warp goes `VHR_SSR_SKIP_COOLDOWN` rounds without testing (a warp-uniform counter; which
+    // steps are tested changes nothing in the result, only how many probes are evaluated).
+    int cooldown = 0;
     for (int i = 0; finite_p && i < p.n_steps; ++i) {                                            // ssr.comp:89-108
         const float offset = mul_rn(p.step_size, (float)i);
         float pu, pv;
-        if (in_window(p, pfd, P, dir, cam, offset, pu, pv)) {
+        bool skip = false;
+        if (p.tiles) {
+            if (cooldown == 0) {
+                skip = step_is_outside_window(p, P, dir, cam, offset);
+                if (!__all_sync(__activemask(), skip)) cooldown = VHR_SSR_SKIP_COOLDOWN;
+            } else --cooldown;
+        }
+        if (!skip && in_window(p, pfd, P, dir, cam, offset, pu, pv)) {
             final_step = offset;
             found = true;
             break;
@@ -305,6 +398,35 @@ __global__ void __launch_bounds__(128) ssr_refill_kernel(const __grid_constant__
     }
 }
 
+// Does step_is_outside_window's bound hold for these matrices? camera_proj_inverse with the sparsity of an inverse perspective projection
+// (m32 > 0, m33 >= 0: w = m32 depth + m33 grows with depth and is not negative), camera_view_inverse rigid, camera_viewproj_inverse their
+// product (to 1e-4 of the largest entry) — then the distance from the camera to the oracle's unprojected point equals the length of the
+// view-space point. Anything else (a hand-made test matrix, an orthographic camera): no skipping, every step is probed.
+static bool skip_bound_applies(const PerFrameData &pfd) {
+    const float *pi = pfd.camera_proj_inverse, *vi = pfd.camera_view_inverse, *vpi = pfd.camera_viewproj_inverse;
+    for (int i = 0; i < 16; ++i)
+        if (i != 0 && i != 5 && i != 11 && i != 14 && i != 15 && pi[i] != 0.0f) return false;
+    if (!(pi[11] > 0.0f) || !(pi[15] >= 0.0f) || !(pi[0] != 0.0f) || !(pi[5] != 0.0f) || !(pi[14] != 0.0f)) return false;
+    if (vi[3] != 0.0f || vi[7] != 0.0f || vi[11] != 0.0f || vi[15] != 1.0f) return false;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            double d = 0.0;
+            for (int k = 0; k < 3; ++k) d += (double)vi[a * 4 + k] * vi[b * 4 + k];      // columns of the rotation are orthonormal
+            if (std::fabs(d - (a == b ? 1.0 : 0.0)) > 1e-4) return false;
+        }
+    double big = 0.0, prod[16];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += (double)vi[k * 4 + r] * pi[c * 4 + k];
+            prod[c * 4 + r] = acc;
+            big = std::max(big, std::fabs(acc));
+        }
+    for (int i = 0; i < 16; ++i)
+        if (!(std::fabs(prod[i] - (double)vpi[i]) <= 1e-4 * big)) return false;
+    return true;
+}
+
 int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstants &pc) {
     // descriptor set 3 of the "SSR Pass" (hybrid_render_path.cpp:211-219): 0 albedo, 1 normals, 2 motion, 3 depth, 4 output
     if (ctx->n_bound < 5) return fail(VHR_ERR_STATE, "ssr.comp: pass images not bound (need bindings 0..4)");
@@ -338,6 +460,30 @@ int launch_ssr(vhr_context *ctx, uint32_t xg, uint32_t yg, const SSRPushConstant
     p.albedo = (const uint32_t *)b[0]->ptr; p.normals = (const uint2 *)b[1]->ptr; p.motion = (const uint2 *)b[2]->ptr;
     p.depth = (const float *)b[3]->ptr; p.out = (uint2 *)b[4]->ptr;
     if (int rc = build_depth_quads(ctx, p.depth, p.W, p.H, &p.quads)) return rc;
+    // conservative step skipping (step_is_outside_window): only for a camera whose matrices have the structure the bound relies on
+    p.tiles = nullptr; p.tiles_w = (p.W + 7) / 8; p.tiles_h = (p.H + 7) / 8;
+    // Off by default (VHR_SSR_SKIP=1 turns it on): 79 % of the lane-steps of the bench frame can be skipped but only 41 % of the warp-steps
+    // (a probe issued for one lane costs as much as for 32), and the test itself is a ~100-instruction dependent chain with a tile load
+    // in the middle: 3.37 ms without, 3.83 / 3.49 / 3.31 / 3.22 ms with a cooldown of 0 / 1 / 3 / 7 rounds (profiles/r02/ssr_variants.log).
+    // Bit-identical images either way.
+    static const bool skip_enabled = [] { const char *e = getenv("VHR_SSR_SKIP"); return e && atoi(e) != 0; }();
+    if (skip_enabled && p.W >= 16 && p.H >= 16 && skip_bound_applies(ctx->pfd)) {
+        const int q = ctx->stream == ctx->queue[1] && ctx->queue[1] != nullptr ? 1 : 0;
+        const size_t count = (size_t)p.tiles_w * p.tiles_h;
+        if (ctx->depth_tiles_count[q] < count) {
+            if (ctx->d_depth_tiles[q]) { VHR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_depth_tiles[q]); ctx->d_depth_tiles[q] = nullptr; }
+            VHR_CUDA_CHECK(cudaMalloc(&ctx->d_depth_tiles[q], count * sizeof(float2)));
+            ctx->depth_tiles_count[q] = count;
+        }
+        depth_tiles_kernel<<<(unsigned)((count + 3) / 4), 128, 0, ctx->stream>>>(p.depth, ctx->d_depth_tiles[q], p.W, p.H, p.tiles_w, p.tiles_h);
+        VHR_CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        p.tiles = ctx->d_depth_tiles[q];
+        const float *pi = ctx->pfd.camera_proj_inverse;
+        p.pi0 = pi[0]; p.pi5 = pi[5]; p.pi14 = pi[14]; p.pi11 = pi[11]; p.pi15 = pi[15]; p.pi14sq = pi[14] * pi[14];
+        const float *vi = ctx->pfd.camera_view_inverse;
+        p.margin0 = 1e-5f + 4e-6f * (std::fabs(vi[12]) + std::fabs(vi[13]) + std::fabs(vi[14]));
+    }
     // camera_proj * camera_view, each element a left-to-right sum of rounded products (volatile keeps the host compiler from
     // contracting or reassociating; the oracle forms the same product)
     const float *A = ctx->pfd.camera_proj, *B = ctx->pfd.camera_view;

@@ -224,6 +224,7 @@ void vhr_context_destroy(vhr_context *ctx) {
     if (ctx->d_refl_t) cudaFree(ctx->d_refl_t);
     if (ctx->d_ray_queue) cudaFree(ctx->d_ray_queue);
     for (float4 *q : ctx->d_depth_quads) if (q) cudaFree(q);
+    for (float2 *q : ctx->d_depth_tiles) if (q) cudaFree(q);
     for (TextureDesc &t : ctx->textures) if (t.texels) cudaFree((void *)t.texels);
     if (ctx->d_textures) cudaFree(ctx->d_textures);
     if (ctx->d_texel_lut) cudaFree(ctx->d_texel_lut);

@@ -120,6 +120,9 @@ struct vhr_context {
     // that a screen-space pass recorded on queue 1 does not rebuild the image a pass on queue 0 is still gathering from
     float4 *d_depth_quads[2] = {nullptr, nullptr};
     size_t depth_quads_texels[2] = {0, 0};
+    // ssr.comp: (min, max) depth over every 8 x 8-texel tile + a 2-texel apron (ssr_kernels.cu: conservative skip of march steps)
+    float2 *d_depth_tiles[2] = {nullptr, nullptr};
+    size_t depth_tiles_count[2] = {0, 0};
     int raygen_blocks = 0;                         // resident grid of the persistent ray kernel (SMs x blocks/SM)
     vhr::Bvh bvh;
     vhr::Options opt;
